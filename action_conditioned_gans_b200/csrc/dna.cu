@@ -1,0 +1,276 @@
+// Dynamic Neural Advection (DNA) transform, forward and backward, for sm_100a.
+//
+// Replaces models.py:60-72 of the reference (tf.nn.softmax over the K*K logits of every pixel,
+// tf.extract_image_patches of the input frame with SAME zero padding, stack/multiply/reduce_sum)
+// and TF's autodiff of that sub-graph.  The reference materialises the [B,64,64,K*K,3] patch tensor
+// and a 3x stacked softmax in HBM (~15x the algorithmic traffic); here one persistent kernel streams
+// each band of 4 image rows exactly once:
+//
+//   * thread 0 of the CTA is the producer: per band it issues ONE bulk-copy (TMA engine, SASS UBLKCP)
+//     for the band's contiguous logits and one per image row of the band + halo into a padded
+//     shared-memory tile, all completing on the stage's mbarrier (expect_tx byte counting);
+//   * 256 consumer threads (one pixel each) read their K*K logits from shared memory (stride K*K words
+//     -> conflict free for K=5), do max / exp / sum in registers, accumulate the K*K x 3 weighted
+//     neighbourhood from the padded image tile (stride-3 words -> conflict free) and normalise once;
+//   * the backward kernel recomputes the softmax, forms g_p = <dy, x_p>, writes
+//     dz_p = s_p (g_p - sum_q s_q g_q) IN PLACE over the staged logits and ships the band back to HBM
+//     with one shared->global bulk store.
+//
+// HBM traffic per pixel (fp32): forward (K*K + 3 + 3)*4 B, backward (2*K*K + 3 + 3)*4 B plus the
+// halo rows (served from L2: the neighbouring band's CTA has just read them).
+#include "common.cuh"
+
+namespace acg {
+namespace {
+
+constexpr int kRows = 4;                 // image rows per band
+constexpr int kMaxW = 64;
+constexpr int kThreads = kRows * kMaxW;  // one pixel per thread
+constexpr int kPadCols = 4;              // zero columns left and right (4*12 B keeps rows 16 B aligned)
+constexpr int kRowStride = (kMaxW + 2 * kPadCols) * 3;  // floats per staged image row
+
+template <int K, typename LT, bool BWD> struct StageLayout {
+    static constexpr int KK = K * K;
+    static constexpr int NR = kRows + K - 1;  // band rows + halo
+    static constexpr int logits_bytes = kThreads * KK * (int)sizeof(LT);
+    static constexpr int img_bytes = NR * kRowStride * 4;
+    static constexpr int dy_bytes = BWD ? kThreads * 3 * 4 : 0;
+    static constexpr int off_img = logits_bytes;
+    static constexpr int off_dy = off_img + img_bytes;
+    static constexpr int bytes = ((off_dy + dy_bytes + 127) / 128) * 128;
+};
+
+template <int K, typename LT, bool BWD, int STAGES>
+__global__ void __launch_bounds__(kThreads)
+dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const float* __restrict__ dy,
+           float* __restrict__ out, LT* __restrict__ dlogits, int B, int H, int W) {
+    using L = StageLayout<K, LT, BWD>;
+    constexpr int KK = K * K;
+    constexpr int PB = (K - 1) / 2;  // TF SAME: pad_before = (K-1)/2, the odd element goes after
+    // forward keeps STAGES-1 bands in flight; backward one fewer so that the bulk store of the
+    // previous band may still be reading its stage while the next load is issued.
+    constexpr int PREFETCH = BWD ? STAGES - 2 : STAGES - 1;
+    static_assert(PREFETCH >= 1, "need a deeper ring");
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES];
+
+    const int tid = threadIdx.x;
+    const int bands_per_img = H / kRows;
+    const int nbands = B * bands_per_img;
+    const int npx = kRows * W;
+    const uint32_t lbytes = (uint32_t)(npx * KK * sizeof(LT));
+    const uint32_t rbytes = (uint32_t)(W * 3 * 4);
+
+    // zero the pad columns of every staged image row once (bulk copies never touch them)
+    for (int idx = tid; idx < STAGES * L::NR * 2 * kPadCols * 3; idx += kThreads) {
+        int s = idx / (L::NR * 2 * kPadCols * 3);
+        int rem = idx % (L::NR * 2 * kPadCols * 3);
+        int r = rem / (2 * kPadCols * 3);
+        int c = rem % (2 * kPadCols * 3);
+        float* row = reinterpret_cast<float*>(smem + (size_t)s * L::bytes + L::off_img) + r * kRowStride;
+        int col = c < kPadCols * 3 ? c : (kPadCols + W) * 3 + (c - kPadCols * 3);
+        row[col] = 0.f;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int band, int stage) {
+        unsigned char* st = smem + (size_t)stage * L::bytes;
+        const int b = band / bands_per_img;
+        const int r0 = (band % bands_per_img) * kRows;
+        int valid = 0;
+        for (int t = 0; t < L::NR; ++t) {
+            int row = r0 - PB + t;
+            valid += (row >= 0 && row < H);
+        }
+        uint32_t total = lbytes + (uint32_t)valid * rbytes + (BWD ? (uint32_t)npx * 12u : 0u);
+        mbar_expect_tx(&full_bar[stage], total);
+        bulk_g2s(st, logits + (size_t)band * npx * KK, lbytes, &full_bar[stage]);
+        for (int t = 0; t < L::NR; ++t) {
+            int row = r0 - PB + t;
+            if (row >= 0 && row < H)
+                bulk_g2s(reinterpret_cast<float*>(st + L::off_img) + t * kRowStride + kPadCols * 3,
+                         img + ((size_t)(b * H + row) * W) * 3, rbytes, &full_bar[stage]);
+        }
+        if (BWD) bulk_g2s(st + L::off_dy, dy + (size_t)band * npx * 3, (uint32_t)npx * 12u, &full_bar[stage]);
+    };
+
+    if (tid == 0) {
+        for (int p = 0; p < PREFETCH; ++p) {
+            int band = blockIdx.x + p * gridDim.x;
+            if (band < nbands) issue(band, p % STAGES);
+        }
+    }
+
+    const int il = tid / W;   // row of this thread's pixel inside the band
+    const int j = tid - il * W;
+    const bool active = tid < npx;
+
+    for (int it = 0;; ++it) {
+        const int band = blockIdx.x + it * gridDim.x;
+        if (band >= nbands) break;
+        const int stage = it % STAGES;
+        if (tid == 0) {
+            int nb = band + PREFETCH * gridDim.x;
+            if (nb < nbands) {
+                if (BWD) bulk_wait_read<1>();  // the store that last read this stage has drained
+                issue(nb, (it + PREFETCH) % STAGES);
+            }
+        }
+        mbar_wait(&full_bar[stage], (uint32_t)((it / STAGES) & 1));
+
+        unsigned char* st = smem + (size_t)stage * L::bytes;
+        LT* lg = reinterpret_cast<LT*>(st);
+        const float* tile = reinterpret_cast<const float*>(st + L::off_img);
+        const int r0 = (band % bands_per_img) * kRows;
+
+        if (active) {
+            float e[KK];
+            float m = -INFINITY;
+#pragma unroll
+            for (int p = 0; p < KK; ++p) {
+                e[p] = ld_as_float<LT>(lg, (size_t)tid * KK + p);
+                m = fmaxf(m, e[p]);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int p = 0; p < KK; ++p) {
+                e[p] = __expf(e[p] - m);
+                sum += e[p];
+            }
+            const float inv = 1.f / sum;
+            if (!BWD) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+                for (int a = 0; a < K; ++a) {
+                    const int row = r0 + il + a - PB;
+                    if (row < 0 || row >= H) continue;  // uniform per warp pair: SAME zero rows
+                    const float* rp = tile + (il + a) * kRowStride + (kPadCols + j - PB) * 3;
+#pragma unroll
+                    for (int c = 0; c < K; ++c) {
+                        const float wgt = e[a * K + c];
+                        a0 = fmaf(wgt, rp[c * 3 + 0], a0);
+                        a1 = fmaf(wgt, rp[c * 3 + 1], a1);
+                        a2 = fmaf(wgt, rp[c * 3 + 2], a2);
+                    }
+                }
+                float* o = out + ((size_t)band * npx + tid) * 3;
+                o[0] = a0 * inv;
+                o[1] = a1 * inv;
+                o[2] = a2 * inv;
+            } else {
+                const float* dyt = reinterpret_cast<const float*>(st + L::off_dy) + tid * 3;
+                const float d0 = dyt[0], d1 = dyt[1], d2 = dyt[2];
+                float g[KK];
+                float dot = 0.f;
+#pragma unroll
+                for (int a = 0; a < K; ++a) {
+                    const int row = r0 + il + a - PB;
+                    const bool rv = (row >= 0 && row < H);
+                    const float* rp = tile + (il + a) * kRowStride + (kPadCols + j - PB) * 3;
+#pragma unroll
+                    for (int c = 0; c < K; ++c) {
+                        float gv = 0.f;
+                        if (rv) gv = fmaf(d0, rp[c * 3 + 0], fmaf(d1, rp[c * 3 + 1], d2 * rp[c * 3 + 2]));
+                        g[a * K + c] = gv;
+                        e[a * K + c] *= inv;
+                        dot = fmaf(e[a * K + c], gv, dot);
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < KK; ++p) st_from_float<LT>(lg, (size_t)tid * KK + p, e[p] * (g[p] - dot));
+                fence_proxy_async();  // make the in-place dlogits visible to the bulk-copy engine
+            }
+        }
+        __syncthreads();  // every thread is done with this stage
+        if (BWD && tid == 0) {
+            bulk_s2g(dlogits + (size_t)band * npx * KK, lg, lbytes);
+            bulk_commit();
+        }
+    }
+    if (BWD && tid == 0) bulk_wait<0>();  // smem must stay alive until the last store has read it
+}
+
+template <int K, typename LT, bool BWD, int STAGES>
+int launch(const void* logits, const float* img, const float* dy, float* out, void* dlogits, int B, int H,
+           int W, cudaStream_t stream) {
+    using L = StageLayout<K, LT, BWD>;
+    auto kern = dna_kernel<K, LT, BWD, STAGES>;
+    const int smem = STAGES * L::bytes;
+    static int occ = 0;  // per template instance
+    if (occ == 0) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+            cudaError_t e = cudaGetLastError();
+            set_error("acg_dna: cannot set %d B dynamic smem: %s", smem, cudaGetErrorString(e));
+            return ACG_ERR_CUDA;
+        }
+        int o = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kern, kThreads, smem) != cudaSuccess || o < 1) {
+            cudaGetLastError();
+            o = 1;
+        }
+        occ = o;
+    }
+    const int nbands = B * (H / kRows);
+    int grid = num_sms() * occ;
+    if (grid > nbands) grid = nbands;
+    kern<<<grid, kThreads, smem, stream>>>(static_cast<const LT*>(logits), img, dy, out,
+                                           static_cast<LT*>(dlogits), B, H, W);
+    return check_launch(BWD ? "acg_dna_bwd" : "acg_dna_fwd");
+}
+
+int validate(const void* logits, const float* img, int B, int H, int W, int C, int K, int dtype) {
+    ACG_REQUIRE(logits && img, ACG_ERR_INVALID, "acg_dna: null pointer");
+    ACG_REQUIRE(B > 0 && H > 0 && W > 0, ACG_ERR_INVALID, "acg_dna: non-positive size");
+    ACG_REQUIRE(C == 3, ACG_ERR_UNSUPPORTED, "acg_dna: C=%d (only 3 colour channels)", C);
+    ACG_REQUIRE(K == 5 || K == 6, ACG_ERR_UNSUPPORTED, "acg_dna: K=%d (only 5 or 6)", K);
+    ACG_REQUIRE(W <= kMaxW && W % 4 == 0 && H % kRows == 0, ACG_ERR_UNSUPPORTED,
+                "acg_dna: H=%d W=%d (need H%%4==0, W%%4==0, W<=64)", H, W);
+    ACG_REQUIRE(dtype == ACG_F32 || dtype == ACG_BF16, ACG_ERR_UNSUPPORTED, "acg_dna: logits dtype %d", dtype);
+    ACG_REQUIRE(((uintptr_t)logits % 16) == 0 && ((uintptr_t)img % 16) == 0, ACG_ERR_INVALID,
+                "acg_dna: buffers must be 16-byte aligned");
+    return ACG_OK;
+}
+
+}  // namespace
+}  // namespace acg
+
+extern "C" {
+
+int acg_dna_fwd(const void* logits, int logits_dtype, const float* img, float* out, int B, int H, int W, int C,
+                int K, void* stream) {
+    using namespace acg;
+    int rc = validate(logits, img, B, H, W, C, K, logits_dtype);
+    if (rc) return rc;
+    ACG_REQUIRE(out, ACG_ERR_INVALID, "acg_dna_fwd: null out");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (logits_dtype == ACG_F32) {
+        if (K == 5) return launch<5, float, false, 3>(logits, img, nullptr, out, nullptr, B, H, W, s);
+        return launch<6, float, false, 2>(logits, img, nullptr, out, nullptr, B, H, W, s);
+    }
+    if (K == 5) return launch<5, __nv_bfloat16, false, 3>(logits, img, nullptr, out, nullptr, B, H, W, s);
+    return launch<6, __nv_bfloat16, false, 3>(logits, img, nullptr, out, nullptr, B, H, W, s);
+}
+
+int acg_dna_bwd(const void* logits, int logits_dtype, const float* img, const float* dy, void* dlogits, int B,
+                int H, int W, int C, int K, void* stream) {
+    using namespace acg;
+    int rc = validate(logits, img, B, H, W, C, K, logits_dtype);
+    if (rc) return rc;
+    ACG_REQUIRE(dy && dlogits, ACG_ERR_INVALID, "acg_dna_bwd: null pointer");
+    ACG_REQUIRE(((uintptr_t)dy % 16) == 0 && ((uintptr_t)dlogits % 16) == 0, ACG_ERR_INVALID,
+                "acg_dna_bwd: buffers must be 16-byte aligned");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (logits_dtype == ACG_F32) {
+        if (K == 5) return launch<5, float, true, 3>(logits, img, dy, nullptr, dlogits, B, H, W, s);
+        return launch<6, float, true, 3>(logits, img, dy, nullptr, dlogits, B, H, W, s);
+    }
+    if (K == 5) return launch<5, __nv_bfloat16, true, 3>(logits, img, dy, nullptr, dlogits, B, H, W, s);
+    return launch<6, __nv_bfloat16, true, 3>(logits, img, dy, nullptr, dlogits, B, H, W, s);
+}
+
+}  // extern "C"

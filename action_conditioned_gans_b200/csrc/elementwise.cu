@@ -1,0 +1,291 @@
+// Batch-norm moments / apply / backward, activations, channel-slice copies and the action-tile concat.
+//
+// Replaces slim.batch_norm (arg_scope at models.py:11,32,81; slim defaults: batch statistics in train AND
+// test, biased variance, epsilon 1e-3, beta only), tf.nn.relu / ops.lrelu (ops.py:22-26) / tf.tanh,
+// tf.concat (models.py:16,38,84; train.py:64,68) and tf.tile (train.py:48-50), plus TF autodiff of them.
+// All tensors are [rows, C] views of NHWC buffers with an explicit row stride so that producers can write
+// straight into the wider concat buffers and consumers can read a channel slice.
+#include "common.cuh"
+
+namespace acg {
+namespace {
+
+constexpr int kTX = 32, kTY = 8;
+
+__device__ __forceinline__ float ldx(const void* p, int dt, size_t i) {
+    return dt == ACG_F32 ? static_cast<const float*>(p)[i]
+                         : __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void stx(void* p, int dt, size_t i, float v) {
+    if (dt == ACG_F32) static_cast<float*>(p)[i] = v;
+    else static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16_rn(v);
+}
+
+// column-wise two-moment reduction shared by bn_stats and bn_act_bwd_reduce.
+// MODE 0: (z, z^2).  MODE 1: (dzh, dzh*xhat) with dzh = dA*act'(u).
+template <int MODE>
+__global__ void __launch_bounds__(kTX* kTY)
+col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void* __restrict__ dA,
+                  const void* __restrict__ dA2, int d_dt, int ld_d, long long rows_per_group, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
+                  const float* __restrict__ shift, int act, double* __restrict__ out) {
+    const int c = blockIdx.x * kTX + threadIdx.x;
+    const int g = blockIdx.z;
+    const long long r_begin = (long long)g * rows_per_group;
+    float s0 = 0.f, s1 = 0.f;
+    double d0 = 0.0, d1 = 0.0;
+    if (c < C) {
+        float mu = 0.f, rs = 1.f, sh = 0.f;
+        if (MODE == 1) {
+            if (mean) mu = mean[g * C + c];
+            if (rstd) rs = rstd[g * C + c];
+            if (shift) sh = shift[g * C + c];
+        }
+        int k = 0;
+        for (long long r = (long long)blockIdx.y * kTY + threadIdx.y; r < rows_per_group;
+             r += (long long)gridDim.y * kTY) {
+            const float zv = ldx(z, z_dt, (size_t)(r_begin + r) * ld_z + c);
+            if (MODE == 0) {
+                s0 += zv;
+                s1 += zv * zv;
+            } else {
+                const float u = zv * rs + sh;
+                float dav = ldx(dA, d_dt, (size_t)(r_begin + r) * ld_d + c);
+                if (dA2) dav += ldx(dA2, d_dt, (size_t)(r_begin + r) * ld_d + c);
+                const float dzh = dav * act_bwd(u, act);
+                s0 += dzh;
+                s1 += dzh * ((zv - mu) * rs);
+            }
+            if (++k == 64) {  // flush fp32 partials into fp64 regularly
+                d0 += s0; d1 += s1; s0 = s1 = 0.f; k = 0;
+            }
+        }
+        d0 += s0;
+        d1 += s1;
+    }
+    __shared__ double sh0[kTY][kTX], sh1[kTY][kTX];
+    sh0[threadIdx.y][threadIdx.x] = d0;
+    sh1[threadIdx.y][threadIdx.x] = d1;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+        for (int y = 0; y < kTY; ++y) { t0 += sh0[y][threadIdx.x]; t1 += sh1[y][threadIdx.x]; }
+        atomicAdd(&out[(size_t)g * 2 * C + c], t0);
+        atomicAdd(&out[(size_t)g * 2 * C + C + c], t1);
+    }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ beta,
+                                   long long rows_per_group, int C, int groups, float eps, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= groups * C) return;
+    const int g = i / C, c = i % C;
+    const double inv = 1.0 / (double)rows_per_group;
+    const double mu = stats[(size_t)g * 2 * C + c] * inv;
+    double var = stats[(size_t)g * 2 * C + C + c] * inv - mu * mu;  // biased
+    if (var < 0.0) var = 0.0;
+    const float rs = (float)(1.0 / sqrt(var + (double)eps));
+    const float b = beta ? beta[c] : 0.f;
+    mean[i] = (float)mu;
+    rstd[i] = rs;
+    scale[i] = rs;
+    shift[i] = b - (float)mu * rs;
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const void* __restrict__ z, int z_dt, long long rows, int C, int ld_in, long long rows_per_group,
+                  const float* __restrict__ scale, const float* __restrict__ shift, int act, void* __restrict__ out,
+                  int o_dt, int ld_out) {
+    const long long total = rows * C;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / C;
+        const int c = (int)(idx - r * C);
+        const int gc = (int)(r / rows_per_group) * C + c;
+        float u = ldx(z, z_dt, (size_t)r * ld_in + c);
+        if (scale) u *= scale[gc];
+        if (shift) u += shift[gc];
+        stx(out, o_dt, (size_t)r * ld_out + c, act_fwd(u, act));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict__ dA2, int d_dt, int ld_d, const void* __restrict__ z, int z_dt,
+                        int ld_z, long long rows, int C, int groups, long long rows_per_group,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ shift, int act, int has_bn, const double* __restrict__ red,
+                        void* __restrict__ dz, int dz_dt, float* __restrict__ dbeta, long long norm_rows,
+                        float dbeta_scale) {
+    const long long total = rows * C;
+    const float inv_r = 1.f / (float)norm_rows;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / C;
+        const int c = (int)(idx - r * C);
+        const int g = (int)(r / rows_per_group);
+        const int gc = g * C + c;
+        const float mu = mean ? mean[gc] : 0.f;
+        const float rs = rstd ? rstd[gc] : 1.f;
+        const float sh = shift ? shift[gc] : 0.f;
+        const float zv = ldx(z, z_dt, (size_t)r * ld_z + c);
+        const float u = zv * rs + sh;
+        float d = ldx(dA, d_dt, (size_t)r * ld_d + c);
+        if (dA2) d += ldx(dA2, d_dt, (size_t)r * ld_d + c);
+        d *= act_bwd(u, act);
+        if (has_bn) {
+            const float m0 = (float)red[(size_t)g * 2 * C + c] * inv_r;
+            const float m1 = (float)red[(size_t)g * 2 * C + C + c] * inv_r;
+            d = rs * (d - m0 - (zv - mu) * rs * m1);
+        }
+        stx(dz, dz_dt, (size_t)r * C + c, d);
+    }
+    if (dbeta && blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            double t = 0.0;
+            for (int g = 0; g < groups; ++g) t += red[(size_t)g * 2 * C + c];
+            dbeta[c] += dbeta_scale * (float)t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+copy_channels_kernel(const void* __restrict__ src, int s_dt, int ld_src, int off_src, void* __restrict__ dst,
+                     int d_dt, int ld_dst, int off_dst, long long rows, int n) {
+    const long long total = rows * n;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / n;
+        const int c = (int)(idx - r * n);
+        stx(dst, d_dt, (size_t)r * ld_dst + off_dst + c, ldx(src, s_dt, (size_t)r * ld_src + off_src + c));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+tile_actions_kernel(const float* __restrict__ actions, int B, int hw, int A, void* __restrict__ dst, int d_dt,
+                    int ld_dst, int off) {
+    const long long total = (long long)B * hw * A;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / A;
+        const int a = (int)(idx - r * A);
+        const int b = (int)(r / hw);
+        stx(dst, d_dt, (size_t)r * ld_dst + off + a, actions[b * A + a]);
+    }
+}
+
+int ew_grid(long long total) {
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+dim3 reduce_grid(long long rows_per_group, int C, int groups) {
+    const int gx = (C + kTX - 1) / kTX;
+    long long gy = (rows_per_group + kTY * 8 - 1) / (kTY * 8);  // >= 8 rows per thread
+    long long cap = ((long long)num_sms() * 8) / ((long long)gx * groups);
+    if (cap < 1) cap = 1;
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    return dim3(gx, (unsigned)gy, groups);
+}
+
+bool dt_ok(int dt) { return dt == ACG_F32 || dt == ACG_BF16; }
+
+}  // namespace
+}  // namespace acg
+
+extern "C" {
+
+int acg_bn_stats(const void* z, int dtype, long long rows, int C, int ld, int groups, double* stats, void* stream) {
+    using namespace acg;
+    ACG_REQUIRE(z && stats, ACG_ERR_INVALID, "acg_bn_stats: null pointer");
+    ACG_REQUIRE(rows > 0 && C > 0 && ld >= C && groups > 0 && rows % groups == 0, ACG_ERR_INVALID,
+                "acg_bn_stats: rows=%lld C=%d ld=%d groups=%d", rows, C, ld, groups);
+    ACG_REQUIRE(dt_ok(dtype), ACG_ERR_UNSUPPORTED, "acg_bn_stats: dtype %d", dtype);
+    const long long rpg = rows / groups;
+    col_reduce_kernel<0><<<reduce_grid(rpg, C, groups), dim3(kTX, kTY), 0, static_cast<cudaStream_t>(stream)>>>(
+        z, dtype, ld, nullptr, nullptr, 0, 0, rpg, C, nullptr, nullptr, nullptr, 0, stats);
+    return check_launch("acg_bn_stats");
+}
+
+int acg_bn_finalize(const double* stats, const float* beta, long long rows_per_group, int C, int groups, float eps,
+                    float* mean, float* rstd, float* scale, float* shift, void* stream) {
+    using namespace acg;
+    ACG_REQUIRE(stats && mean && rstd && scale && shift, ACG_ERR_INVALID, "acg_bn_finalize: null pointer");
+    ACG_REQUIRE(rows_per_group > 0 && C > 0 && groups > 0, ACG_ERR_INVALID, "acg_bn_finalize: bad size");
+    const int n = C * groups;
+    bn_finalize_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        stats, beta, rows_per_group, C, groups, eps, mean, rstd, scale, shift);
+    return check_launch("acg_bn_finalize");
+}
+
+int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in, int groups, const float* scale,
+                   const float* shift, int act, void* out, int out_dtype, int ld_out, void* stream) {
+    using namespace acg;
+    ACG_REQUIRE(z && out, ACG_ERR_INVALID, "acg_bn_act_fwd: null pointer");
+    ACG_REQUIRE(rows > 0 && C > 0 && ld_in >= C && ld_out >= C && groups > 0 && rows % groups == 0,
+                ACG_ERR_INVALID, "acg_bn_act_fwd: bad size");
+    ACG_REQUIRE(dt_ok(z_dtype) && dt_ok(out_dtype), ACG_ERR_UNSUPPORTED, "acg_bn_act_fwd: dtype");
+    bn_act_fwd_kernel<<<ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        z, z_dtype, rows, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
+    return check_launch("acg_bn_act_fwd");
+}
+
+int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype, int ld_z,
+                          long long rows, int C, int groups, const float* mean, const float* rstd,
+                          const float* shift, int act, double* red, void* stream) {
+    using namespace acg;
+    ACG_REQUIRE(dA && z && red, ACG_ERR_INVALID, "acg_bn_act_bwd_reduce: null pointer");
+    ACG_REQUIRE(rows > 0 && C > 0 && ld_d >= C && ld_z >= C && groups > 0 && rows % groups == 0,
+                ACG_ERR_INVALID, "acg_bn_act_bwd_reduce: bad size");
+    ACG_REQUIRE(dt_ok(d_dtype) && dt_ok(z_dtype), ACG_ERR_UNSUPPORTED, "acg_bn_act_bwd_reduce: dtype");
+    const long long rpg = rows / groups;
+    col_reduce_kernel<1><<<reduce_grid(rpg, C, groups), dim3(kTX, kTY), 0, static_cast<cudaStream_t>(stream)>>>(
+        z, z_dtype, ld_z, dA, dA2, d_dtype, ld_d, rpg, C, mean, rstd, shift, act, red);
+    return check_launch("acg_bn_act_bwd_reduce");
+}
+
+int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype, int ld_z,
+                         long long rows, int C, int groups, const float* mean, const float* rstd,
+                         const float* shift, int act, int has_bn, const double* red, void* dz, int dz_dtype,
+                         float* dbeta, long long norm_rows, float dbeta_scale, void* stream) {
+    using namespace acg;
+    ACG_REQUIRE(dA && z && red && dz, ACG_ERR_INVALID, "acg_bn_act_bwd_apply: null pointer");
+    ACG_REQUIRE(rows > 0 && C > 0 && ld_d >= C && ld_z >= C && groups > 0 && rows % groups == 0,
+                ACG_ERR_INVALID, "acg_bn_act_bwd_apply: bad size");
+    ACG_REQUIRE(dt_ok(d_dtype) && dt_ok(z_dtype) && dt_ok(dz_dtype), ACG_ERR_UNSUPPORTED,
+                "acg_bn_act_bwd_apply: dtype");
+    bn_act_bwd_apply_kernel<<<ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, rows, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
+        dz, dz_dtype, dbeta, norm_rows > 0 ? norm_rows : rows / groups, dbeta_scale);
+    return check_launch("acg_bn_act_bwd_apply");
+}
+
+int acg_copy_channels(const void* src, int src_dtype, int ld_src, int off_src, void* dst, int dst_dtype,
+                      int ld_dst, int off_dst, long long rows, int n, void* stream) {
+    using namespace acg;
+    ACG_REQUIRE(src && dst, ACG_ERR_INVALID, "acg_copy_channels: null pointer");
+    ACG_REQUIRE(rows > 0 && n > 0 && off_src >= 0 && off_dst >= 0 && off_src + n <= ld_src && off_dst + n <= ld_dst,
+                ACG_ERR_INVALID, "acg_copy_channels: bad slice");
+    ACG_REQUIRE(dt_ok(src_dtype) && dt_ok(dst_dtype), ACG_ERR_UNSUPPORTED, "acg_copy_channels: dtype");
+    copy_channels_kernel<<<ew_grid(rows * n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, src_dtype, ld_src, off_src, dst, dst_dtype, ld_dst, off_dst, rows, n);
+    return check_launch("acg_copy_channels");
+}
+
+int acg_tile_actions(const float* actions, int B, int hw, int A, void* dst, int dst_dtype, int ld_dst, int off,
+                     void* stream) {
+    using namespace acg;
+    ACG_REQUIRE(actions && dst, ACG_ERR_INVALID, "acg_tile_actions: null pointer");
+    ACG_REQUIRE(B > 0 && hw > 0 && A > 0 && off >= 0 && off + A <= ld_dst, ACG_ERR_INVALID,
+                "acg_tile_actions: bad size");
+    ACG_REQUIRE(dt_ok(dst_dtype), ACG_ERR_UNSUPPORTED, "acg_tile_actions: dtype");
+    tile_actions_kernel<<<ew_grid((long long)B * hw * A), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        actions, B, hw, A, dst, dst_dtype, ld_dst, off);
+    return check_launch("acg_tile_actions");
+}
+
+}  // extern "C"

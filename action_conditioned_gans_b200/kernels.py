@@ -1,0 +1,153 @@
+"""Thin Python shims over the C-ABI (one function per entry point of include/acg_b200.h).
+
+Every function takes CUDA torch tensors (used only as device storage), enqueues the kernel on torch's current
+stream and returns immediately.  Nothing here computes on the CPU or through torch ops.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_IDS, ConvShape, TcFusion, call, dtype_id, ptr, stream
+
+
+def same_pad(n_in, k, s):
+    """TF SAME: out=ceil(n/s), pad_total=max((out-1)s+k-n,0), before=total//2 (odd element after)."""
+    out = -(-n_in // s)
+    total = max((out - 1) * s + k - n_in, 0)
+    return out, total // 2
+
+
+def conv_shape(B, H, W, Cin, Cout, k, stride, padding="SAME"):
+    """acg_conv_shape of a forward convolution with TF padding semantics."""
+    if padding == "SAME":
+        OH, pt = same_pad(H, k, stride)
+        OW, pl = same_pad(W, k, stride)
+    elif padding == "VALID":
+        OH, OW, pt, pl = (H - k) // stride + 1, (W - k) // stride + 1, 0, 0
+    else:
+        raise ValueError("padding must be SAME or VALID")
+    return ConvShape(B, H, W, Cin, OH, OW, Cout, k, k, stride, pt, pl)
+
+
+# ---- DNA ------------------------------------------------------------------------------------
+def dna_fwd(logits, img, out, K):
+    B, H, W, Cc = img.shape
+    call("acg_dna_fwd", ptr(logits), dtype_id(logits), ptr(img), ptr(out), B, H, W, Cc, K, stream())
+
+
+def dna_bwd(logits, img, dy, dlogits, K):
+    B, H, W, Cc = img.shape
+    if dlogits.dtype != logits.dtype:
+        raise RuntimeError("dlogits must have the dtype of logits")
+    call("acg_dna_bwd", ptr(logits), dtype_id(logits), ptr(img), ptr(dy), ptr(dlogits), B, H, W, Cc, K, stream())
+
+
+# ---- convolutions -----------------------------------------------------------------------------
+def conv_fprop_f32(shape, x, w, y):
+    call("acg_conv_fprop_f32", C.byref(shape), ptr(x), ptr(w), ptr(y), stream())
+
+
+def conv_dgrad_f32(shape, dy, w, dx):
+    call("acg_conv_dgrad_f32", C.byref(shape), ptr(dy), ptr(w), ptr(dx), stream())
+
+
+def conv_wgrad_f32(shape, x, dy, dw):
+    call("acg_conv_wgrad_f32", C.byref(shape), ptr(x), ptr(dy), ptr(dw), stream())
+
+
+def tc_supported(shape, which):
+    return bool(_lib.load().acg_conv_tc_supported(C.byref(shape), which))
+
+
+def _fusion(in_scale=None, in_shift=None, in_act=None, bias=None, stats=None, out_dtype=_lib.BF16, out_act=None):
+    return TcFusion(ptr(in_scale), ptr(in_shift), ACT_IDS[in_act], ptr(bias), ptr(stats), out_dtype,
+                    ACT_IDS[out_act])
+
+
+def conv_fprop_tc(shape, x, w_pack, y, **fusion):
+    f = _fusion(out_dtype=dtype_id(y), **fusion)
+    call("acg_conv_fprop_tc", C.byref(shape), ptr(x), ptr(w_pack), ptr(y), C.byref(f), stream())
+
+
+def conv_dgrad_tc(shape, dy, w_pack, dx, **fusion):
+    f = _fusion(out_dtype=dtype_id(dx), **fusion)
+    call("acg_conv_dgrad_tc", C.byref(shape), ptr(dy), ptr(w_pack), ptr(dx), C.byref(f), stream())
+
+
+def conv_wgrad_tc(shape, x, dy, dw, **fusion):
+    f = _fusion(out_dtype=_lib.F32, **fusion)
+    call("acg_conv_wgrad_tc", C.byref(shape), ptr(x), ptr(dy), ptr(dw), C.byref(f), stream())
+
+
+def pack_weights(w, taps, Cin, Cout, pack_fprop, pack_dgrad):
+    call("acg_pack_weights", ptr(w), taps, Cin, Cout, ptr(pack_fprop), ptr(pack_dgrad), stream())
+
+
+# ---- batch-norm / activation / concat -------------------------------------------------------------
+def bn_stats(z, rows, Cc, ld, groups, stats):
+    call("acg_bn_stats", ptr(z), dtype_id(z), rows, Cc, ld, groups, ptr(stats), stream())
+
+
+def bn_finalize(stats, beta, rows_per_group, Cc, groups, mean, rstd, scale, shift, eps=1e-3):
+    call("acg_bn_finalize", ptr(stats), ptr(beta), rows_per_group, Cc, groups, eps, ptr(mean), ptr(rstd),
+         ptr(scale), ptr(shift), stream())
+
+
+def bn_act_fwd(z, rows, Cc, ld_in, groups, scale, shift, act, out, ld_out):
+    call("acg_bn_act_fwd", ptr(z), dtype_id(z), rows, Cc, ld_in, groups, ptr(scale), ptr(shift), ACT_IDS[act],
+         ptr(out), dtype_id(out), ld_out, stream())
+
+
+def bn_act_bwd_reduce(dA, dA2, ld_d, z, ld_z, rows, Cc, groups, mean, rstd, shift, act, red):
+    call("acg_bn_act_bwd_reduce", ptr(dA), ptr(dA2), dtype_id(dA), ld_d, ptr(z), dtype_id(z), ld_z, rows, Cc,
+         groups, ptr(mean), ptr(rstd), ptr(shift), ACT_IDS[act], ptr(red), stream())
+
+
+def bn_act_bwd_apply(dA, dA2, ld_d, z, ld_z, rows, Cc, groups, mean, rstd, shift, act, has_bn, red, dz, dbeta,
+                     norm_rows=0, dbeta_scale=1.0):
+    call("acg_bn_act_bwd_apply", ptr(dA), ptr(dA2), dtype_id(dA), ld_d, ptr(z), dtype_id(z), ld_z, rows, Cc,
+         groups, ptr(mean), ptr(rstd), ptr(shift), ACT_IDS[act], int(has_bn), ptr(red), ptr(dz), dtype_id(dz),
+         ptr(dbeta), norm_rows, dbeta_scale, stream())
+
+
+def copy_channels(src, ld_src, off_src, dst, ld_dst, off_dst, rows, n):
+    call("acg_copy_channels", ptr(src), dtype_id(src), ld_src, off_src, ptr(dst), dtype_id(dst), ld_dst, off_dst,
+         rows, n, stream())
+
+
+def tile_actions(actions, B, hw, dst, ld_dst, off):
+    A = actions.shape[1]
+    call("acg_tile_actions", ptr(actions), B, hw, A, ptr(dst), dtype_id(dst), ld_dst, off, stream())
+
+
+# ---- losses -------------------------------------------------------------------------------------
+def frame_losses(g, n, sums, dg=None, w_l1=0.0, w_gdl=0.0, dadv=None, ld_adv=0, adv_off=0):
+    B, H, W, _ = g.shape
+    call("acg_frame_losses", ptr(g), ptr(n), B, H, W, ptr(sums), ptr(dg), w_l1, w_gdl, ptr(dadv), ld_adv, adv_off,
+         stream())
+
+
+def dlogit_loss(x, n, kind, label_or_sign, grad_scale, loss_out, dlogits=None):
+    if kind not in ("bce", "wass"):
+        raise ValueError("unexpected loss argument")
+    call("acg_dlogit_loss", ptr(x), n, _lib.LOSS_BCE if kind == "bce" else _lib.LOSS_WASS, label_or_sign,
+         grad_scale, ptr(loss_out), ptr(dlogits), stream())
+
+
+def state_loss(s, t, n, inv_batch, grad_scale, loss_out, dstate=None):
+    call("acg_state_loss", ptr(s), ptr(t), n, inv_batch, grad_scale, ptr(loss_out), ptr(dstate), stream())
+
+
+# ---- optimizers -----------------------------------------------------------------------------------
+NO_CLIP = (1.0, -1.0)  # lo > hi disables the clip
+
+
+def adam_step(p, g, m, v, lr_t, b1=0.9, b2=0.999, eps=1e-8, clip=NO_CLIP, grad_scale=1.0):
+    call("acg_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr_t, b1, b2, eps, clip[0], clip[1],
+         grad_scale, stream())
+
+
+def rmsprop_step(p, g, ms, lr, decay=0.9, eps=1e-10, clip=NO_CLIP, grad_scale=1.0):
+    call("acg_rmsprop_step", ptr(p), ptr(g), ptr(ms), p.numel(), lr, decay, eps, clip[0], clip[1], grad_scale,
+         stream())

@@ -1,0 +1,259 @@
+"""`Trainer`: the step wrappers of train.py:27-176 on top of the acg_b200 engine.
+
+Same constructor flags and methods as the reference (`Trainer(sess, arg_adv, arg_loss, arg_opt, arg_transform)`,
+`pretrain_g`, `train_g`, `train_d`, `test`, `test_sequence`); `sess` is accepted and ignored (there is no TF
+session -- each method enqueues one device step).  Repairs R1-R6 of SURVEY.md section 0 are applied; the D step
+is update-THEN-clip (the reference leaves the order of train.py:140,143 unspecified).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import engine as E
+from . import kernels as K
+
+BATCH_SIZE = 64      # train.py:19
+L2_WEIGHT = 0.05     # train.py:22
+DNA_KSIZE = 6        # train.py:53-54 passes ksize=6
+
+SUMMARY_KEYS = ["discriminator_direct_loss", "discriminator_gen_loss", "discriminator_loss", "g_loss",
+                "g_l2_loss", "g_adv_loss", "g_psnr"]
+
+
+class DataParallel:
+    """Batch-sharded data parallelism (one process per GPU, torch.distributed for the plumbing).
+    Collectives on the path: the flat gradient bucket of the network being updated, the per-layer batch-norm
+    moment vectors (SyncBN: the reference normalises over the WHOLE batch) and the loss sums."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def allreduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+
+class Trainer:
+    def __init__(self, sess=None, arg_adv=True, arg_loss="bce", arg_opt="adam", arg_transform=True,
+                 batch_size=BATCH_SIZE, ksize=DNA_KSIZE, device=None, params=None, seed=7, dp=None):
+        if arg_loss not in ("bce", "wass"):
+            raise ValueError("unexpected loss argument")          # ops.py:35,47
+        if arg_opt not in ("adam", "rmsprop"):
+            raise ValueError("unexpected opt argument")           # train.py:98
+        if not torch.cuda.is_available():
+            raise RuntimeError("acg_b200 needs a CUDA device: there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda")
+        self.arg_adv, self.arg_loss, self.arg_opt, self.arg_transform = arg_adv, arg_loss, arg_opt, arg_transform
+        self.B = batch_size                      # LOCAL batch (per rank)
+        self.dp = dp
+        self.world = dp.world if dp is not None else 1
+        self.GB = self.B * self.world            # global batch: every normaliser of the losses uses this
+        self.ksize = ksize
+        self.precision = "fp32"
+        g_spec = E.g_dna_spec(ksize) if arg_transform else E.g_direct_spec()
+        d_spec = E.d_spec()
+        if params is None:
+            rng = np.random.RandomState(seed)    # train.py:14 seeds NumPy with 7
+            params = E.xavier_init(g_spec, rng)
+            params.update(E.xavier_init(d_spec, rng))
+        dev = self.device
+        self.g_store = E.ParamStore(g_spec, dev, params)
+        self.d_store = E.ParamStore(d_spec, dev, params)
+        self.g_run = E.GeneratorRun(self.g_store, self.B, dev, arg_transform, ksize, dp)
+        self.d_gen = E.DiscriminatorRun(self.d_store, self.B, dev, dp)
+        self.d_real = E.DiscriminatorRun(self.d_store, self.B, dev, dp)
+        self.g_opt = E.TFOptimizer(self.g_store, arg_opt)            # train.py:100
+        self.g_pretrain_opt = E.TFOptimizer(self.g_store, arg_opt)   # train.py:101
+        self.d_opt = E.TFOptimizer(self.d_store, arg_opt)            # train.py:102
+        # device-resident scalars: fsum = [sum|g-n|, sum(g-n)^2, gdl]; sc = [adv, d_direct, d_gen, state]
+        self.fsum = torch.zeros(3, dtype=torch.float64, device=dev)
+        self.sc = torch.zeros(4, dtype=torch.float32, device=dev)
+        self.zero_state = torch.zeros(self.B, E.STATE_DIM, device=dev)
+        self._have = set()
+
+    # ---- feeds -----------------------------------------------------------------------------------
+    def _dev(self, a, shape):
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=torch.float32, non_blocking=True)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(self.device,
+                                                                                          non_blocking=True)
+        t = t.reshape(shape).contiguous()
+        return t
+
+    def _feed(self, img, nxt, act, state=None):
+        B = self.B
+        img = self._dev(img, (B, E.IMG, E.IMG, 3))
+        nxt = self._dev(nxt, (B, E.IMG, E.IMG, 3))
+        act = self._dev(act, (B, E.ACTION_DIM))
+        st = self._dev(state, (B, E.STATE_DIM)) if state is not None else self.zero_state
+        return img, nxt, act, st
+
+    # ---- shared pieces -----------------------------------------------------------------------------
+    def _g_losses(self, nxt, state_gt, want_grad, with_adv_grad):
+        """Frame / state / adversarial generator losses (train.py:72-83) and, when want_grad, dL/dg_out and
+        dL/dstate.  with_adv_grad: back-propagate g_adv_loss through D(gen) first (train_g)."""
+        g = self.g_run
+        self._have = {"g"}
+        dadv = None
+        w_l1 = (L2_WEIGHT if self.arg_transform else 1.0) / self.GB
+        if with_adv_grad:
+            sign_or_label = 1.0                                     # bce: labels = ones; wass: +mean
+            K.dlogit_loss(self.d_gen.logits, self.d_gen.n_logits, self.arg_loss, sign_or_label,
+                          1.0 / self.world, self.sc[0:1], self.d_gen.dlogits)
+            dadv = self.d_gen.backward(need_dw=False, need_dinput=True)
+        elif self.arg_adv:
+            K.dlogit_loss(self.d_gen.logits, self.d_gen.n_logits, self.arg_loss, 1.0, 1.0, self.sc[0:1], None)
+        self.fsum.zero_()
+        K.frame_losses(g.g_out, nxt, self.fsum, g.dg_out if want_grad else None, w_l1,
+                       1.0 if with_adv_grad else 0.0, dadv, 6, 3)
+        if self.arg_transform:
+            K.state_loss(g.state, state_gt, self.B * E.STATE_DIM, 1.0 / self.GB, 1.0, self.sc[3:4],
+                         g.dstate if want_grad else None)
+
+    def _scalars(self):
+        """Host values of the loss scalars of the last step (synchronises; logging only)."""
+        fs = self.fsum.clone()
+        sc = self.sc.clone().double()
+        if self.dp is not None:
+            self.dp.allreduce_sum(fs)
+            loc = sc.clone()
+            loc[:3] /= self.world        # means over the local logits -> global mean
+            # the state loss is a norm over the GLOBAL batch: combine squared local norms
+            loc[3] = (sc[3] * self.GB) ** 2
+            self.dp.allreduce_sum(loc)
+            loc[3] = torch.sqrt(loc[3]) / self.GB
+            sc = loc
+        fs = fs.cpu().numpy()
+        sc = sc.cpu().numpy()
+        n_el = self.GB * E.IMG * E.IMG * 3
+        out = {}
+        l2 = fs[0] / self.GB
+        if self.arg_transform:
+            l2 = l2 * L2_WEIGHT + sc[3]
+        out["g_l2_loss"] = float(l2)
+        out["g_psnr"] = float(10.0 * math.log10(1.0 / max(fs[1] / n_el, 1e-300)))
+        if self.arg_adv:
+            out["g_adv_loss"] = float(sc[0])
+            out["g_loss"] = float(l2 + sc[0] + fs[2])              # train.py:81 (gdl is a SUM)
+        else:
+            out["g_loss"] = float(l2)
+        if "d" in self._have:
+            out["discriminator_direct_loss"] = float(sc[1])
+            out["discriminator_gen_loss"] = float(sc[2])
+            out["discriminator_loss"] = float(sc[1] + sc[2])
+        return out
+
+    def summaries(self):
+        s = self._scalars()
+        return {k: s[k] for k in SUMMARY_KEYS if k in s}
+
+    def _sync_grads(self, store):
+        if self.dp is not None:
+            self.dp.allreduce_sum(store.grad)
+
+    # ---- train.py:114-121 -------------------------------------------------------------------------------
+    def pretrain_g(self, input_images, next_frame, actions, state):
+        img, nxt, act, st = self._feed(input_images, next_frame, actions, state)
+        self.enqueue_pretrain_g(img, nxt, act, st)
+        return self._scalars()["g_loss"]
+
+    def enqueue_pretrain_g(self, img, nxt, act, st):
+        self.g_store.grad.zero_()
+        g_out, _ = self.g_run.forward(img, act)
+        self.d_gen.forward(img, g_out, act)          # self.g_loss is fetched -> D(gen) forward runs too
+        self._g_losses(nxt, st, want_grad=True, with_adv_grad=False)
+        self.g_run.backward(with_state=self.arg_transform)
+        self._sync_grads(self.g_store)
+        self.g_pretrain_opt.step()
+
+    # ---- train.py:123-130 -------------------------------------------------------------------------------
+    def train_g(self, input_images, next_frame, actions, state):
+        img, nxt, act, st = self._feed(input_images, next_frame, actions, state)
+        self.enqueue_train_g(img, nxt, act, st)
+        return self.g_run.g_out.cpu().numpy()
+
+    def enqueue_train_g(self, img, nxt, act, st):
+        self.g_store.grad.zero_()
+        g_out, _ = self.g_run.forward(img, act)
+        if self.arg_adv:
+            self.d_gen.forward(img, g_out, act)
+        self._g_losses(nxt, st, want_grad=True, with_adv_grad=self.arg_adv)
+        self.g_run.backward(with_state=self.arg_transform)
+        self._sync_grads(self.g_store)
+        self.g_opt.step()
+
+    # ---- train.py:132-144 -------------------------------------------------------------------------------
+    def train_d(self, input_images, next_frame, actions, summarize=False):
+        img, nxt, act, st = self._feed(input_images, next_frame, actions, None)
+        self.enqueue_train_d(img, nxt, act)
+        if summarize:
+            # merged_summaries also holds the generator scalars (train.py:112,140)
+            self._g_losses(nxt, st, want_grad=False, with_adv_grad=False)
+            self._have = {"g", "d"}
+            return self.summaries()
+        return None
+
+    def enqueue_train_d(self, img, nxt, act):
+        self.d_store.grad.zero_()
+        g_out, _ = self.g_run.forward(img, act)
+        self.d_gen.forward(img, g_out, act)
+        self.d_real.forward(img, nxt, act)
+        gs = 1.0 / self.world
+        if self.arg_loss == "bce":                                   # ops.py:38-42
+            K.dlogit_loss(self.d_real.logits, self.d_real.n_logits, "bce", 0.9, gs, self.sc[1:2], self.d_real.dlogits)
+            K.dlogit_loss(self.d_gen.logits, self.d_gen.n_logits, "bce", 0.0, gs, self.sc[2:3], self.d_gen.dlogits)
+        else:                                                        # ops.py:43-45
+            K.dlogit_loss(self.d_real.logits, self.d_real.n_logits, "wass", 1.0, gs, self.sc[1:2], self.d_real.dlogits)
+            K.dlogit_loss(self.d_gen.logits, self.d_gen.n_logits, "wass", -1.0, gs, self.sc[2:3], self.d_gen.dlogits)
+        self.d_real.backward(need_dw=True, need_dinput=False)
+        self.d_gen.backward(need_dw=True, need_dinput=False)
+        self._sync_grads(self.d_store)
+        self.d_opt.step(clip=(-0.01, 0.01))                          # train.py:89, update then clip
+        self._have = {"d"}
+
+    # ---- train.py:146-155 -------------------------------------------------------------------------------
+    def test(self, input_images, next_frame, actions):
+        img, nxt, act, st = self._feed(input_images, next_frame, actions, None)
+        g_out, g_state = self.enqueue_test(img, nxt, act, st)
+        state = g_state.cpu().numpy() if g_state is not None else None
+        return g_out.cpu().numpy(), state, self.summaries()
+
+    def enqueue_test(self, img, nxt, act, st):
+        g_out, g_state = self.g_run.forward(img, act)
+        self.d_gen.forward(img, g_out, act)
+        self.d_real.forward(img, nxt, act)
+        self._g_losses(nxt, st, want_grad=False, with_adv_grad=False)
+        if self.arg_loss == "bce":
+            K.dlogit_loss(self.d_real.logits, self.d_real.n_logits, "bce", 0.9, 1.0, self.sc[1:2], None)
+            K.dlogit_loss(self.d_gen.logits, self.d_gen.n_logits, "bce", 0.0, 1.0, self.sc[2:3], None)
+        else:
+            K.dlogit_loss(self.d_real.logits, self.d_real.n_logits, "wass", 1.0, 1.0, self.sc[1:2], None)
+            K.dlogit_loss(self.d_gen.logits, self.d_gen.n_logits, "wass", -1.0, 1.0, self.sc[2:3], None)
+        self._have = {"g", "d"}
+        return g_out, g_state
+
+    # ---- train.py:157-176 -------------------------------------------------------------------------------
+    def test_sequence(self, input_images, test_next_frame, test_actions):
+        """6-step recursive rollout; frames and the predicted state stay on the device between steps
+        (the reference round-trips host<->device every step)."""
+        B = self.B
+        seq = self._dev(input_images, (B, -1, E.IMG, E.IMG, 3))
+        nxt = self._dev(test_next_frame, (B, -1, E.IMG, E.IMG, 3))
+        acts = self._dev(test_actions, (B, -1, E.ACTION_DIM))
+        predicted = torch.empty(6, B, E.IMG, E.IMG, 3, device=self.device)
+        current_frame = seq[:, 0].contiguous()
+        current_state = acts[:, 0, 5:].contiguous()
+        for j in range(6):
+            acs = torch.cat((acts[:, j * 2, :5], current_state), dim=1).contiguous()   # train.py:163
+            g_out, g_state = self.enqueue_test(current_frame, nxt[:, j * 2].contiguous(), acs, self.zero_state)
+            predicted[j].copy_(g_out)
+            current_frame = predicted[j]
+            if g_state is not None:                    # R5: the direct generator keeps the fed state
+                current_state = g_state.clone()
+        pred = predicted.permute(1, 0, 2, 3, 4).contiguous().cpu().numpy()
+        return pred, current_frame[1:7].cpu().numpy()

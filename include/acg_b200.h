@@ -1,0 +1,193 @@
+/*
+ * acg_b200.h -- C-ABI of the B200-native hot path of action_conditioned_GANs.
+ *
+ * The reference (TensorFlow 1.0 graph code) has NO native layer to mirror: every device op is a
+ * library call inside TF.  These entry points are therefore the boundary a
+ * maintainer of the reference would bind instead of the TF ops at the cited call sites; the
+ * binding stub is shown in INTEGRATION.md.  One entry point per kernel family.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*.
+ *  - tensors are NHWC, weights HWIO ([kh,kw,Cin,Cout]); transposed-conv weights are
+ *    [kh,kw,Cout,Cin] exactly as slim.conv2d_transpose stores them.
+ *  - the caller owns all buffers; nothing here allocates device memory; workspaces are passed in.
+ *  - every call only ENQUEUES work on `stream` (a cudaStream_t cast to void*), never synchronises,
+ *    and is CUDA-graph capturable.
+ *  - return value: 0 on success, negative on failure (ACG_ERR_*); acg_last_error() gives the text.
+ *    There is no CPU fallback: without a CUDA device every compute call fails with ACG_ERR_CUDA.
+ */
+#ifndef ACG_B200_H_
+#define ACG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACG_OK 0
+#define ACG_ERR_INVALID (-1)     /* bad argument (null pointer, non-positive size, ...) */
+#define ACG_ERR_UNSUPPORTED (-2) /* shape / dtype outside what the kernels were built for */
+#define ACG_ERR_CUDA (-3)        /* a CUDA runtime call or launch failed */
+
+/* element types of activation / logit buffers */
+#define ACG_F32 0
+#define ACG_BF16 1
+
+/* activations (ops.py:22-26 lrelu; tf.nn.relu / tf.tanh at models.py:10,20,31,80) */
+#define ACG_ACT_NONE 0
+#define ACG_ACT_RELU 1
+#define ACG_ACT_LRELU 2 /* leak 0.2 */
+#define ACG_ACT_TANH 3
+
+/* adversarial loss kinds (ops.py:28-50) */
+#define ACG_LOSS_BCE 0
+#define ACG_LOSS_WASS 1
+
+int acg_version(void);
+const char* acg_last_error(void);
+/* number of kernel launches enqueued through this library since load (for bench.py's gpu_launches) */
+long long acg_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * DNA transform: replaces tf.nn.softmax + tf.extract_image_patches + stack/mul/reduce_sum at
+ * models.py:60-72 (forward) and TF autodiff of it (backward w.r.t. the logits).
+ *   logits [B,H,W,K*K] (f32 or bf16), img [B,H,W,C] f32, out [B,H,W,C] f32.
+ *   y[b,i,j,c] = sum_p softmax(logits[b,i,j,:])_p * img[b, i+p/K-pb, j+p%K-pb, c], pb=(K-1)/2,
+ *   zero outside the frame (TF SAME: K=5 pads 2/2, K=6 pads 2/3).
+ * K in {5,6}, C == 3, W <= 64 and (W*C) % 4 == 0, H % 4 == 0.
+ * ------------------------------------------------------------------------------------------ */
+int acg_dna_fwd(const void* logits, int logits_dtype, const float* img, float* out,
+                int B, int H, int W, int C, int K, void* stream);
+/* dlogits (same dtype as logits) = s_p * (g_p - sum_q s_q g_q), g_p = sum_c dy_c * img_{p,c}.
+ * img is a fed placeholder in the reference (train.py:31-34) so no image gradient is produced. */
+int acg_dna_bwd(const void* logits, int logits_dtype, const float* img, const float* dy,
+                void* dlogits, int B, int H, int W, int C, int K, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution family: replaces slim.conv2d (models.py:12-15,34-37,42-51,82-88),
+ * slim.conv2d_transpose (models.py:17-21,39-40,53-59) and their TF-autodiff gradients.
+ * The shape always describes the FORWARD CONVOLUTION x[B,H,W,Cin] -> y[B,OH,OW,Cout]:
+ *     y[b,oh,ow,co] = sum_{a,c,ci} x[b, oh*stride+a-pad_t, ow*stride+c-pad_l, ci] * w[a,c,ci,co]
+ * (cross-correlation, zero padding).  conv2d_transpose IS acg_conv_dgrad of that convolution
+ * (exact adjoint, which is how TF defines it), its data gradient is acg_conv_fprop and its weight
+ * gradient acg_conv_wgrad with the roles of x / y swapped by the caller.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct acg_conv_shape {
+    int B, H, W, Cin;     /* conv input */
+    int OH, OW, Cout;     /* conv output */
+    int KH, KW, stride;   /* filter, stride (1 or 2) */
+    int pad_t, pad_l;     /* zero padding before (TF SAME puts the odd element after) */
+} acg_conv_shape;
+
+/* fp32 SIMT implicit-GEMM kernels (thin layers + high-precision device reference) */
+int acg_conv_fprop_f32(const acg_conv_shape* s, const float* x, const float* w, float* y, void* stream);
+int acg_conv_dgrad_f32(const acg_conv_shape* s, const float* dy, const float* w, float* dx, void* stream);
+/* dw += sum over the batch (caller zeroes dw; split over the batch with fp32 atomics) */
+int acg_conv_wgrad_f32(const acg_conv_shape* s, const float* x, const float* dy, float* dw, void* stream);
+
+/* tcgen05 / TMEM implicit-GEMM kernels (bf16 operands, fp32 accumulate in tensor memory).
+ *   x / dy operands are bf16 NHWC; weights are the bf16 GEMM-ready packs made by acg_pack_weights.
+ *   `scale`/`shift` (per input channel, may be NULL) and `act` fuse the producer layer's
+ *   batch-norm apply + activation into the operand staging:  operand = act(x*scale+shift).
+ *   `bias` (per output channel, may be NULL) is added in the epilogue; `stats` (may be NULL) receives
+ *   per-output-channel [sum, sum of squares] fp64 partials of the fp32 accumulators (batch-norm
+ *   moments of THIS layer) accumulated with atomics; out_dtype selects bf16 or f32 output. */
+typedef struct acg_tc_fusion {
+    const float* in_scale;  /* [Cin-of-operand] or NULL */
+    const float* in_shift;  /* [Cin-of-operand] or NULL */
+    int in_act;             /* ACG_ACT_* applied after scale/shift */
+    const float* bias;      /* [N] or NULL */
+    double* stats;          /* [2*N] or NULL */
+    int out_dtype;          /* ACG_F32 | ACG_BF16 */
+    int out_act;            /* ACG_ACT_NONE | ACG_ACT_TANH (models.py:20) */
+} acg_tc_fusion;
+
+int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w_pack, void* y,
+                      const acg_tc_fusion* f, void* stream);
+int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* w_pack, void* dx,
+                      const acg_tc_fusion* f, void* stream);
+int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* dy_bf16, float* dw,
+                      const acg_tc_fusion* f, void* stream);
+/* fp32 HWIO weights -> bf16 packs: fwd pack [tap][Cout][Cin] (K-major B operand of fprop) and
+ * bwd pack [tap][Cin][Cout] (K-major B operand of dgrad).  Either output may be NULL. */
+int acg_pack_weights(const float* w, int taps, int Cin, int Cout, void* pack_fprop, void* pack_dgrad,
+                     void* stream);
+/* 1 when the tcgen05 kernels accept the shape (channel multiples etc.), 0 otherwise */
+int acg_conv_tc_supported(const acg_conv_shape* s, int which /*0 fprop,1 dgrad,2 wgrad*/);
+
+/* ------------------------------------------------------------------------------------------
+ * Batch-norm (slim.batch_norm defaults: batch statistics always, biased variance, eps 1e-3, beta
+ * only; models.py:11,32,81), activations and the action-tile concat (train.py:48-50,
+ * models.py:16,38,84).  `rows` = B*H*W; tensors are [rows, C] with row stride ld (in elements).
+ * ------------------------------------------------------------------------------------------ */
+/* stats[0:C] += sum_r z, stats[C:2C] += sum_r z^2   (fp64 accumulators, caller zeroes).
+ * `groups` splits rows into equal contiguous groups with independent statistics
+ * (stats is [groups][2][C]) -- the two discriminator applications of train.py:63-70. */
+int acg_bn_stats(const void* z, int dtype, long long rows, int C, int ld, int groups, double* stats,
+                 void* stream);
+/* mean/rstd/scale/shift [groups][C] from stats; rows_per_group rows each.  With beta==NULL it is 0.
+ * scale = rstd, shift = beta - mean*rstd so that bn(z) = z*scale + shift. */
+int acg_bn_finalize(const double* stats, const float* beta, long long rows_per_group, int C, int groups,
+                    float eps, float* mean, float* rstd, float* scale, float* shift, void* stream);
+/* a[r, 0:C] = act(z[r,0:C]*scale + shift) written with row stride ld_out at channel offset 0;
+ * scale==NULL means identity scale; shift==NULL means 0 (bias layers pass shift = biases). */
+int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in, int groups,
+                   const float* scale, const float* shift, int act, void* out, int out_dtype,
+                   int ld_out, void* stream);
+/* backward, pass 1: dzh = (dA + dA2) * act'(z*scale+shift)   (dA2 may be NULL; it is the second consumer's
+ * gradient where the graph forks -- g/tconv2 feeds both g/tconv3 and g/sconv3, models.py:40-53); red[0:C] += sum dzh, red[C:2C] += sum dzh*xhat
+ * (xhat = (z-mean)*rstd; fp64, caller zeroes; [groups][2][C]). */
+int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype, int ld_z,
+                          long long rows, int C, int groups, const float* mean, const float* rstd,
+                          const float* shift, int act, double* red, void* stream);
+/* backward, pass 2: dz = rstd*(dzh - red0/R - xhat*red1/R) when has_bn, else dz = dzh, with
+ * R = norm_rows (0 -> rows/groups; data-parallel SyncBN passes the GLOBAL row count after all-reducing red).
+ * dbeta[c] += dbeta_scale * sum over groups of red0 (also the bias gradient of non-BN layers). */
+int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype, int ld_z,
+                         long long rows, int C, int groups, const float* mean, const float* rstd,
+                         const float* shift, int act, int has_bn, const double* red, void* dz,
+                         int dz_dtype, float* dbeta, long long norm_rows, float dbeta_scale, void* stream);
+/* dst[r, off_dst:off_dst+n] = src[r, off_src:off_src+n]  (channel-slice copy with dtype conversion) */
+int acg_copy_channels(const void* src, int src_dtype, int ld_src, int off_src, void* dst, int dst_dtype,
+                      int ld_dst, int off_dst, long long rows, int n, void* stream);
+/* dst[(b*hw + p), off:off+A] = actions[b, 0:A]  (tf.tile of the [B,1,1,A] action map) */
+int acg_tile_actions(const float* actions, int B, int hw, int A, void* dst, int dst_dtype, int ld_dst,
+                     int off, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Losses (ops.py:19-50,100-120; train.py:72-85)
+ * ------------------------------------------------------------------------------------------ */
+/* frame losses in one pass over g_out / next_frame [B,H,W,3] f32:
+ *   sums[0] = sum|g-n| (tf.norm ord=1, train.py:73), sums[1] = sum (g-n)^2 (build_psnr),
+ *   sums[2] = gdl(next, g) (ops.py:100-120, alpha=1).   sums is fp64[3], caller zeroes.
+ *   dg (may be NULL) = w_l1*sign(g-n) + w_gdl*dGDL/dg + (dadv ? dadv[..., adv_off:adv_off+3] : 0)
+ *   where dadv has row stride ld_adv (the discriminator's input gradient, [B,H,W,6]). */
+int acg_frame_losses(const float* g, const float* n, int B, int H, int W, double* sums, float* dg,
+                     float w_l1, float w_gdl, const float* dadv, int ld_adv, int adv_off, void* stream);
+/* discriminator-logit losses (tf.losses.sigmoid_cross_entropy / reduce_mean; ops.py:28-50).
+ *   loss_out[0] = mean over n of  bce: max(x,0) - x*label + log1p(exp(-|x|));  wass: sign*x
+ *   dlogits (may be NULL) = grad_scale * d loss / d x.   label is 1, 0.9 or 0; sign is +1/-1. */
+int acg_dlogit_loss(const float* x, int n, int kind, float label_or_sign, float grad_scale,
+                    float* loss_out, float* dlogits, void* stream);
+/* state loss ||s - t||_F / B (train.py:77) over [B,5]; dstate (may be NULL) = grad_scale * d/ds. */
+int acg_state_loss(const float* s, const float* t, int n, float inv_batch, float grad_scale,
+                   float* loss_out, float* dstate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimizers: tf.train.AdamOptimizer / RMSPropOptimizer as TF 1.0 implements them
+ * (train.py:91-102) with the weight clip of train.py:89 fused (update, THEN clip).
+ * Flat fp32 buffers of n elements; clip_lo > clip_hi disables the clip.
+ * ------------------------------------------------------------------------------------------ */
+/* lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller (host scalar) */
+int acg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1,
+                  float b2, float eps, float clip_lo, float clip_hi, float grad_scale, void* stream);
+/* ms starts at ONE; p -= lr*g/sqrt(ms+eps) */
+int acg_rmsprop_step(float* p, const float* g, float* ms, long long n, float lr, float decay, float eps,
+                     float clip_lo, float clip_hi, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACG_B200_H_ */

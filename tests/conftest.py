@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """The in-tree C-ABI library (built on demand; nvcc cross-compiles without a GPU)."""
+    from action_conditioned_gans_b200 import _build, _lib
+    _build.build()
+    return _lib.load()
+
+
+@pytest.fixture(scope="session")
+def cuda(built_lib):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")

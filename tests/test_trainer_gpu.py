@@ -1,0 +1,138 @@
+"""Whole training steps (train.py:114-176) on the GPU engine vs the CPU oracle Trainer (oracle/torch_ref.py, fp64)
+on identical weights and feeds: per-step losses, generated frames and every updated variable."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_ref, torch_ref
+from tests._gates import device_gates
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _clear_gates():
+    yield
+    torch_ref.GATES = None
+
+
+def _gates(trn):
+    """The oracle applies G, then D(gen), then D(real) (torch_ref.Trainer._forward)."""
+    torch_ref.GATES = device_gates(trn.g_run, trn.d_gen, trn.d_real)
+
+
+def _feeds(B, seed):
+    rng = np.random.RandomState(seed)
+    img = rng.uniform(-1, 1, (B, 64, 64, 3)).astype(np.float32)
+    nxt = np.clip(img + 0.1 * rng.randn(B, 64, 64, 3), -1, 1).astype(np.float32)
+    act = rng.randn(B, 10).astype(np.float32)
+    state = rng.randn(B, 5).astype(np.float32)
+    return img, nxt, act, state
+
+
+def _params(dna, ksize, seed=7):
+    rng = np.random.RandomState(seed)
+    p = np_ref.init_params(np_ref.g_dna_spec(ksize) if dna else np_ref.g_direct_spec(), rng)
+    p.update(np_ref.init_params(np_ref.d_spec(), rng))
+    # non-zero beta / biases so that their gradients and the clip are exercised
+    for k in p:
+        if not k.endswith("weights"):
+            p[k] = (rng.randn(*p[k].shape) * 0.05).astype(np.float32)
+    return p
+
+
+def _compare_params(got, ref, tol, what, outliers=1e-3):
+    """Updated variables.  Adam's first steps move every weight by ~lr*sign(g), so an element whose gradient is
+    within fp32 rounding of zero may legitimately land 2*lr away: allow 0.1 % such elements per variable."""
+    for k, v in ref.items():
+        d = np.abs(got[k] - v)
+        assert (d > tol).mean() <= outliers, "%s: %s differs (max %g, %.4f%% above %g)" % (
+            what, k, d.max(), 100 * (d > tol).mean(), tol)
+
+
+def _compare_grads(store, ora, scope, what, l2_only=False):
+    """l2_only: train_g's loss holds sign() kinks of its own (L1 and the |.| chain of build_gdl, ops.py:100-120);
+    one element of g_out within fp32 rounding of a tie flips a +-1 term of dL/dg_out, which moves every generator
+    gradient by ~1/sqrt(#pixels).  The per-element checks of that gradient live in test_frame_losses and of the
+    network backward in test_networks_gpu; here the whole-step gradient is checked in the Frobenius norm."""
+    got = store.grads_numpy()
+    for k, g in ora.last_grads.items():
+        if not k.startswith(scope):
+            continue
+        ref = g.numpy()
+        if l2_only:
+            rel = np.linalg.norm(got[k] - ref) / max(np.linalg.norm(ref), 1e-12)
+            assert rel <= 2e-2, "%s: grad of %s differs by %g in relative L2" % (what, k, rel)
+            continue
+        d = np.abs(got[k] - ref).max()
+        assert d <= 5e-4 * max(np.abs(ref).max(), 1e-3), "%s: grad of %s differs by %g (scale %g)" % (
+            what, k, d, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("dna,loss,opt", [(True, "bce", "adam"), (True, "wass", "rmsprop"), (False, "bce", "adam")])
+def test_step_sequence_matches_oracle(cuda, dna, loss, opt):
+    from action_conditioned_gans_b200.trainer import Trainer
+    B, ksize = 4, 6
+    params = _params(dna, ksize)
+    ora = torch_ref.Trainer(params, True, loss, opt, dna, ksize=ksize)
+    trn = Trainer(None, True, loss, opt, dna, batch_size=B, ksize=ksize, params=params)
+    img, nxt, act, state = _feeds(B, 1)
+
+    # pretrain_g (train.py:114-121)
+    gl = trn.pretrain_g(img, nxt, act, state)
+    _gates(trn)
+    gl_ref = ora.pretrain_g(img, nxt, act, state)
+    assert abs(gl - gl_ref) <= 2e-4 * abs(gl_ref)
+    _compare_grads(trn.g_store, ora, "g/", "pretrain_g")
+    _compare_params(trn.g_store.numpy(), {k: v for k, v in ora.numpy_params().items() if k.startswith("g/")},
+                    5e-5, "pretrain_g")
+
+    # train_d with summaries (train.py:132-144), then train_g (train.py:123-130)
+    img, nxt, act, state = _feeds(B, 2)
+    s = trn.train_d(img, nxt, act, summarize=True)
+    _gates(trn)
+    s_ref = ora.train_d(img, nxt, act, summarize=True)
+    for k in ("discriminator_direct_loss", "discriminator_gen_loss", "discriminator_loss"):
+        assert abs(s[k] - s_ref[k]) <= 2e-4 * max(1.0, abs(s_ref[k])), k
+    _compare_grads(trn.d_store, ora, "d/", "train_d")
+    _compare_params(trn.d_store.numpy(), {k: v for k, v in ora.numpy_params().items() if k.startswith("d/")},
+                    5e-5, "train_d")
+    assert max(np.abs(v).max() for v in trn.d_store.numpy().values()) <= 0.01 + 1e-7   # clip (train.py:89)
+
+    frames = trn.train_g(img, nxt, act, state)
+    _gates(trn)
+    frames_ref = ora.train_g(img, nxt, act, state)
+    # the two parameter sets already differ by Adam's +-2*lr on the few sign-flipped elements (see _compare_params)
+    assert np.abs(frames - frames_ref).max() <= 2e-3
+    _compare_grads(trn.g_store, ora, "g/", "train_g", l2_only=True)
+    sg, sg_ref = trn.summaries(), ora.summaries()
+    for k in ("g_loss", "g_l2_loss", "g_adv_loss", "g_psnr"):
+        assert abs(sg[k] - sg_ref[k]) <= 2e-4 * max(1.0, abs(sg_ref[k])), k
+    _compare_params(trn.g_store.numpy(), {k: v for k, v in ora.numpy_params().items() if k.startswith("g/")},
+                    1e-4, "train_g", outliers=1e-2)
+
+
+def test_rollout_matches_oracle(cuda):
+    """test_sequence (train.py:157-176): 6 recursive steps, DNA and direct (R5) generators."""
+    from action_conditioned_gans_b200.trainer import Trainer
+    B = 7
+    rng = np.random.RandomState(3)
+    seq = rng.uniform(-1, 1, (B, 13, 64, 64, 3)).astype(np.float32)
+    acts = rng.randn(B, 13, 10).astype(np.float32)
+    for dna in (True, False):
+        params = _params(dna, 6)
+        ora = torch_ref.Trainer(params, True, "bce", "adam", dna, ksize=6)
+        trn = Trainer(None, True, "bce", "adam", dna, batch_size=B, ksize=6, params=params)
+        p_ref, tail_ref = ora.test_sequence(seq, seq, acts)
+        p, tail = trn.test_sequence(seq, seq, acts)
+        assert p.shape == p_ref.shape == (B, 6, 64, 64, 3)
+        assert np.abs(p - p_ref).max() <= 1e-3
+        assert np.abs(tail - tail_ref).max() <= 1e-3
+
+
+def test_bad_flags_raise(cuda):
+    from action_conditioned_gans_b200.trainer import Trainer
+    with pytest.raises(ValueError, match="unexpected loss argument"):
+        Trainer(None, True, "hinge", "adam", True, batch_size=2)
+    with pytest.raises(ValueError, match="unexpected opt argument"):
+        Trainer(None, True, "bce", "sgd", True, batch_size=2)
