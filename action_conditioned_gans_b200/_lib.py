@@ -23,14 +23,15 @@ class ConvShape(C.Structure):
                 ("B", "H", "W", "Cin", "OH", "OW", "Cout", "KH", "KW", "stride", "pad_t", "pad_l")]
 
 
-class TcFusion(C.Structure):
-    _fields_ = [("in_scale", C.c_void_p), ("in_shift", C.c_void_p), ("in_act", C.c_int),
-                ("bias", C.c_void_p), ("stats", C.c_void_p), ("out_dtype", C.c_int), ("out_act", C.c_int)]
+class TcArgs(C.Structure):
+    """struct acg_tc_args"""
+    _fields_ = [("ld_in", C.c_int), ("ld_out", C.c_int), ("bias", C.c_void_p), ("out_dtype", C.c_int),
+                ("out_act", C.c_int)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _SP = C.POINTER(ConvShape)
-_FP = C.POINTER(TcFusion)
+_FP = C.POINTER(TcArgs)
 
 # name -> argtypes; must list every function include/acg_b200.h declares (tests/test_abi.py checks this)
 SIGNATURES = {
@@ -42,7 +43,7 @@ SIGNATURES = {
     "acg_conv_fprop_tc": [_SP, _P, _P, _P, _FP, _P],
     "acg_conv_dgrad_tc": [_SP, _P, _P, _P, _FP, _P],
     "acg_conv_wgrad_tc": [_SP, _P, _P, _P, _FP, _P],
-    "acg_pack_weights": [_P, _I, _I, _I, _P, _P, _P],
+    "acg_pack_weights": [_SP, _P, _I, _I, _P, _P],
     "acg_conv_tc_supported": [_SP, _I],
     "acg_bn_stats": [_P, _I, _L, _I, _I, _I, _P, _P],
     "acg_bn_finalize": [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _P],
@@ -60,7 +61,7 @@ SIGNATURES = {
 }
 # calls that return a plain value instead of a status
 PLAIN = {"acg_version": ([], C.c_int), "acg_last_error": ([], C.c_char_p),
-         "acg_launch_count": ([], C.c_longlong)}
+         "acg_launch_count": ([], C.c_longlong), "acg_pack_size": ([_SP, _I, _I], C.c_longlong)}
 
 _lib = None
 

@@ -8,7 +8,7 @@ import ctypes as C
 import torch
 
 from . import _lib
-from ._lib import ACT_IDS, ConvShape, TcFusion, call, dtype_id, ptr, stream
+from ._lib import ACT_IDS, ConvShape, TcArgs, call, dtype_id, ptr, stream
 
 
 def same_pad(n_in, k, s):
@@ -60,28 +60,34 @@ def tc_supported(shape, which):
     return bool(_lib.load().acg_conv_tc_supported(C.byref(shape), which))
 
 
-def _fusion(in_scale=None, in_shift=None, in_act=None, bias=None, stats=None, out_dtype=_lib.BF16, out_act=None):
-    return TcFusion(ptr(in_scale), ptr(in_shift), ACT_IDS[in_act], ptr(bias), ptr(stats), out_dtype,
-                    ACT_IDS[out_act])
+def _tc_args(ld_in, ld_out, bias, out, out_act):
+    return TcArgs(ld_in, ld_out, ptr(bias), dtype_id(out), ACT_IDS[out_act])
 
 
-def conv_fprop_tc(shape, x, w_pack, y, **fusion):
-    f = _fusion(out_dtype=dtype_id(y), **fusion)
-    call("acg_conv_fprop_tc", C.byref(shape), ptr(x), ptr(w_pack), ptr(y), C.byref(f), stream())
+def conv_fprop_tc(shape, x, w_pack, y, ld_in, ld_out, bias=None, out_act=None):
+    t = _tc_args(ld_in, ld_out, bias, y, out_act)
+    call("acg_conv_fprop_tc", C.byref(shape), ptr(x), ptr(w_pack), ptr(y), C.byref(t), stream())
 
 
-def conv_dgrad_tc(shape, dy, w_pack, dx, **fusion):
-    f = _fusion(out_dtype=dtype_id(dx), **fusion)
-    call("acg_conv_dgrad_tc", C.byref(shape), ptr(dy), ptr(w_pack), ptr(dx), C.byref(f), stream())
+def conv_dgrad_tc(shape, dy, w_pack, dx, ld_in, ld_out, bias=None, out_act=None):
+    t = _tc_args(ld_in, ld_out, bias, dx, out_act)
+    call("acg_conv_dgrad_tc", C.byref(shape), ptr(dy), ptr(w_pack), ptr(dx), C.byref(t), stream())
 
 
-def conv_wgrad_tc(shape, x, dy, dw, **fusion):
-    f = _fusion(out_dtype=_lib.F32, **fusion)
-    call("acg_conv_wgrad_tc", C.byref(shape), ptr(x), ptr(dy), ptr(dw), C.byref(f), stream())
+def conv_wgrad_tc(shape, x, dy, dw, ld_x, ld_dy):
+    t = TcArgs(ld_x, ld_dy, None, _lib.F32, 0)
+    call("acg_conv_wgrad_tc", C.byref(shape), ptr(x), ptr(dy), ptr(dw), C.byref(t), stream())
 
 
-def pack_weights(w, taps, Cin, Cout, pack_fprop, pack_dgrad):
-    call("acg_pack_weights", ptr(w), taps, Cin, Cout, ptr(pack_fprop), ptr(pack_dgrad), stream())
+def pack_size(shape, which, ld_k):
+    n = int(_lib.load().acg_pack_size(C.byref(shape), which, ld_k))
+    if n < 0:
+        raise RuntimeError("acg_pack_size: invalid arguments")
+    return n
+
+
+def pack_weights(shape, w, which, ld_k, pack):
+    call("acg_pack_weights", C.byref(shape), ptr(w), which, ld_k, ptr(pack), stream())
 
 
 # ---- batch-norm / activation / concat -------------------------------------------------------------

@@ -87,35 +87,36 @@ int acg_conv_dgrad_f32(const acg_conv_shape* s, const float* dy, const float* w,
 /* dw += sum over the batch (caller zeroes dw; split over the batch with fp32 atomics) */
 int acg_conv_wgrad_f32(const acg_conv_shape* s, const float* x, const float* dy, float* dw, void* stream);
 
-/* tcgen05 / TMEM implicit-GEMM kernels (bf16 operands, fp32 accumulate in tensor memory).
- *   x / dy operands are bf16 NHWC; weights are the bf16 GEMM-ready packs made by acg_pack_weights.
- *   `scale`/`shift` (per input channel, may be NULL) and `act` fuse the producer layer's
- *   batch-norm apply + activation into the operand staging:  operand = act(x*scale+shift).
- *   `bias` (per output channel, may be NULL) is added in the epilogue; `stats` (may be NULL) receives
- *   per-output-channel [sum, sum of squares] fp64 partials of the fp32 accumulators (batch-norm
- *   moments of THIS layer) accumulated with atomics; out_dtype selects bf16 or f32 output. */
-typedef struct acg_tc_fusion {
-    const float* in_scale;  /* [Cin-of-operand] or NULL */
-    const float* in_shift;  /* [Cin-of-operand] or NULL */
-    int in_act;             /* ACG_ACT_* applied after scale/shift */
-    const float* bias;      /* [N] or NULL */
-    double* stats;          /* [2*N] or NULL */
-    int out_dtype;          /* ACG_F32 | ACG_BF16 */
-    int out_act;            /* ACG_ACT_NONE | ACG_ACT_TANH (models.py:20) */
-} acg_tc_fusion;
+/* tcgen05 / TMEM implicit-GEMM kernels (bf16 operands, fp32 accumulation in tensor memory).
+ *   Operands are bf16 NHWC with an explicit channel stride (ld_in, a multiple of 8; the channels between the real
+ *   count and ld_in must be zero) so that concat buffers and channel-padded thin layers (3 -> 16) are consumed in
+ *   place.  Weights are the bf16 GEMM-ready packs made by acg_pack_weights with the SAME ld (the packed K dimension
+ *   is taps x ld).  The output is written for ru16(N) channels (pad channels come out as exact zeros) with row
+ *   stride ld_out, as bf16 or f32; `bias` (real channel count entries, may be NULL) and tanh (models.py:20) are
+ *   applied in the epilogue. */
+typedef struct acg_tc_args {
+    int ld_in;          /* channel stride of the gathered operand */
+    int ld_out;         /* channel stride of the output rows, >= ru16(output channels) */
+    const float* bias;  /* [output channels] or NULL */
+    int out_dtype;      /* ACG_F32 | ACG_BF16 */
+    int out_act;        /* ACG_ACT_NONE | ACG_ACT_TANH */
+} acg_tc_args;
 
+/* y = conv(x): x [B,H,W,ld_in] -> y [B,OH,OW,ld_out]; w_pack = acg_pack_weights(which=0, ld_k=ld_in) */
 int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w_pack, void* y,
-                      const acg_tc_fusion* f, void* stream);
+                      const acg_tc_args* t, void* stream);
+/* dx = conv^T(dy): dy [B,OH,OW,ld_in] -> dx [B,H,W,ld_out]; w_pack = acg_pack_weights(which=1, ld_k=ld_in) */
 int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* w_pack, void* dx,
-                      const acg_tc_fusion* f, void* stream);
+                      const acg_tc_args* t, void* stream);
+/* dw[a,c,ci,co] += sum x*dy over the batch: x [B,H,W,ld_in], dy [B,OH,OW,ld_out] (both bf16); dw fp32 HWIO */
 int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* dy_bf16, float* dw,
-                      const acg_tc_fusion* f, void* stream);
-/* fp32 HWIO weights -> bf16 packs: fwd pack [tap][Cout][Cin] (K-major B operand of fprop) and
- * bwd pack [tap][Cin][Cout] (K-major B operand of dgrad).  Either output may be NULL. */
-int acg_pack_weights(const float* w, int taps, int Cin, int Cout, void* pack_fprop, void* pack_dgrad,
-                     void* stream);
-/* 1 when the tcgen05 kernels accept the shape (channel multiples etc.), 0 otherwise */
-int acg_conv_tc_supported(const acg_conv_shape* s, int which /*0 fprop,1 dgrad,2 wgrad*/);
+                      const acg_tc_args* t, void* stream);
+/* fp32 HWIO weights -> bf16 pack.  which=0: fprop pack [ru16(Cout)][tap][ld_k>=Cin]; which=1: dgrad pack, one
+ * [ru16(Cin)][class taps][ld_k>=Cout] matrix per output-parity class.  acg_pack_size gives the element count. */
+long long acg_pack_size(const acg_conv_shape* s, int which, int ld_k);
+int acg_pack_weights(const acg_conv_shape* s, const float* w, int which, int ld_k, void* pack, void* stream);
+/* 1 when the tcgen05 kernels accept the shape, 0 otherwise (which: 0 fprop, 1 dgrad, 2 wgrad) */
+int acg_conv_tc_supported(const acg_conv_shape* s, int which);
 
 /* ------------------------------------------------------------------------------------------
  * Batch-norm (slim.batch_norm defaults: batch statistics always, biased variance, eps 1e-3, beta

@@ -1,0 +1,109 @@
+"""tcgen05 implicit-GEMM convolution kernels vs the CPU oracle on bf16-rounded operands (fp32 accumulation, so
+the only difference left is summation order): conv2d forward, conv2d_transpose forward (== dgrad), both data
+gradients, channel padding / concat strides, ragged tiles."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_ref, torch_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def ru(v, m):
+    return (v + m - 1) // m * m
+
+
+def _bf16_round(a):
+    return torch.from_numpy(a.astype(np.float32)).to(torch.bfloat16).float().numpy().astype(np.float64)
+
+
+def _pad_channels(a, ld, cuda):
+    """[B,H,W,C] float64 -> bf16 CUDA tensor [B,H,W,ld] with zero pad channels"""
+    B, H, W, C = a.shape
+    t = torch.zeros(B, H, W, ld, dtype=torch.bfloat16, device=cuda)
+    t[..., :C] = torch.from_numpy(a.astype(np.float32)).to(cuda).to(torch.bfloat16)
+    return t
+
+
+# (B, H, W, Cin, Cout, k, stride, padding)
+CASES = [
+    (2, 8, 8, 64, 64, 1, 1, "SAME"),       # plain GEMM through the conv path: M=128, K=64, N=64
+    (2, 16, 16, 64, 128, 5, 2, "SAME"),    # g/conv3-like
+    (3, 64, 64, 3, 32, 5, 2, "SAME"),      # g/conv1: Cin 3 padded to 16
+    (2, 16, 16, 138, 128, 5, 2, "SAME"),   # d/conv3: concat channels 138 -> ld 144
+    (5, 8, 8, 128, 256, 5, 2, "SAME"),     # d/conv4: two N tiles, partial M tile
+    (2, 64, 64, 36, 128, 5, 2, "SAME"),    # adjoint of g/tconv4 (ksize 6)
+    (3, 8, 8, 272, 128, 5, 2, "SAME"),     # adjoint of g/tconv1 with the action concat (266 -> 272)
+    (2, 16, 16, 128, 32, 3, 2, "SAME"),    # g/sconv3
+    (1, 7, 9, 24, 40, 5, 2, "SAME"),       # odd extents, ragged N
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_conv_fprop_tc(cuda, case, out_dtype):
+    from action_conditioned_gans_b200 import kernels as Kn
+    B, H, W, Cin, Cout, k, s, padding = case
+    rng = np.random.RandomState(sum(case[:7]))
+    x = _bf16_round(rng.randn(B, H, W, Cin))
+    w = rng.randn(k, k, Cin, Cout) / np.sqrt(k * k * Cin)
+    bias = rng.randn(Cout)
+    shape = Kn.conv_shape(B, H, W, Cin, Cout, k, s, padding)
+    ld_in, ld_out = ru(Cin, 16), ru(Cout, 16) + 16
+    y_ref = np_ref.conv2d(x, _bf16_round(w), s, padding) + bias
+    wt = torch.from_numpy(w.astype(np.float32)).to(cuda)
+    pack = torch.empty(Kn.pack_size(shape, 0, ld_in), dtype=torch.bfloat16, device=cuda)
+    Kn.pack_weights(shape, wt, 0, ld_in, pack)
+    y = torch.full((B, shape.OH, shape.OW, ld_out), 7.0, dtype=out_dtype, device=cuda)
+    Kn.conv_fprop_tc(shape, _pad_channels(x, ld_in, cuda), pack, y, ld_in, ld_out,
+                     bias=torch.from_numpy(bias.astype(np.float32)).to(cuda))
+    torch.cuda.synchronize()
+    got = y.float().cpu().numpy()
+    tol = 2e-3 if out_dtype == torch.float32 else 1.2e-2
+    assert np.abs(got[..., :Cout] - y_ref).max() <= tol * max(1.0, np.abs(y_ref).max())
+    assert np.abs(got[..., Cout:ru(Cout, 16)]).max(initial=0.0) == 0.0      # pad channels are exact zeros
+    assert (got[..., ru(Cout, 16):] == 7.0).all()                            # beyond ru16(Cout): untouched
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_dgrad_tc(cuda, case):
+    """dgrad == conv2d_transpose forward: checked against the independent torch restatement's autograd."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    B, H, W, Cin, Cout, k, s, padding = case
+    rng = np.random.RandomState(sum(case[:7]) + 1)
+    shape = Kn.conv_shape(B, H, W, Cin, Cout, k, s, padding)
+    dy = _bf16_round(rng.randn(B, shape.OH, shape.OW, Cout))
+    w = rng.randn(k, k, Cin, Cout) / np.sqrt(k * k * Cout)
+    xt = torch.zeros(B, H, W, Cin, dtype=torch.float64, requires_grad=True)
+    yt = torch_ref.conv2d(xt, torch.tensor(_bf16_round(w)), s, padding)
+    (dx_ref,) = torch.autograd.grad(yt, [xt], torch.tensor(dy))
+    dx_ref = dx_ref.numpy()
+    ld_in, ld_out = ru(Cout, 8), ru(Cin, 16)
+    wt = torch.from_numpy(w.astype(np.float32)).to(cuda)
+    pack = torch.empty(Kn.pack_size(shape, 1, ld_in), dtype=torch.bfloat16, device=cuda)
+    Kn.pack_weights(shape, wt, 1, ld_in, pack)
+    dx = torch.full((B, H, W, ld_out), float("nan"), dtype=torch.float32, device=cuda)
+    Kn.conv_dgrad_tc(shape, _pad_channels(dy, ld_in, cuda), pack, dx, ld_in, ld_out)
+    torch.cuda.synchronize()
+    got = dx.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got[..., :Cin] - dx_ref).max() <= 2e-3 * max(1.0, np.abs(dx_ref).max())
+    assert np.abs(got[..., Cin:]).max(initial=0.0) == 0.0
+
+
+def test_conv_tc_matches_simt_at_full_size(cuda):
+    """Largest layer of the DNA generator (tconv3 as a dgrad, B=64): tensor-core path vs the fp32 SIMT kernel."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    B = 64
+    shape = Kn.conv_shape(B, 32, 32, 128, 128, 5, 2, "SAME")
+    g = torch.Generator(device=cuda).manual_seed(1)
+    dy = torch.randn(B, 16, 16, 128, device=cuda, generator=g).to(torch.bfloat16)
+    w = (torch.randn(5, 5, 128, 128, device=cuda, generator=g) / 40).to(torch.bfloat16).float()
+    ref = torch.empty(B, 32, 32, 128, device=cuda)
+    Kn.conv_dgrad_f32(shape, dy.float(), w, ref)
+    pack = torch.empty(Kn.pack_size(shape, 1, 128), dtype=torch.bfloat16, device=cuda)
+    Kn.pack_weights(shape, w, 1, 128, pack)
+    out = torch.empty(B, 32, 32, 128, device=cuda)
+    Kn.conv_dgrad_tc(shape, dy, pack, out, 128, 128)
+    assert (out - ref).abs().max() <= 2e-3 * ref.abs().max()
