@@ -70,16 +70,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 64 bf16 (128 B), 8-row atoms of 1024 B.
-__device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t smem_addr) {
+// shared-memory matrix descriptor with 128-byte swizzle (atoms of 8 rows x 128 B = 1024 B, 1024 B aligned).
+//   K-major : a row is 64 consecutive K elements of one M/N index; SBO = stride between 8-row (M/N) groups;
+//             LBO is unused.
+//   MN-major: a row is 64 consecutive M/N elements of one K index; SBO = stride between 8-row (K) groups;
+//             LBO = stride between 64-element M/N atoms.
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
-    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next 8-row group
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;  // stride byte offset
     d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
     d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
     return d;
 }
+__device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t smem_addr) { return sw128_desc(smem_addr, 16, 1024); }
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N runtime
 __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -274,6 +279,137 @@ conv_tc_kernel(const Params p) {
     }
 }
 
+
+// ---- wgrad ---------------------------------------------------------------------------------------------------
+// dW[tap][ci][co] += sum_pix x[pix @ tap][ci] * dy[pix][co]   as   D[m = co][n = (tap, ci)] = sum_k A[m][k] B[n][k]
+// with k = output pixel.  Both operands are channel-contiguous in NHWC, i.e. MN-major for this GEMM: a stage holds
+// [64-channel atom][64 pixels][128 B] per operand and the instruction descriptor sets a_major = b_major = MN.
+// grid = (N tiles over taps x ld_x, M tiles over Cout, pixel splits); partial sums are reduced with fp32 RED.
+struct WgradParams {
+    const __nv_bfloat16* x;
+    const __nv_bfloat16* dy;
+    float* dw;
+    int B, H, W, OH, OW, KH, KW, stride, pad_t, pad_l;
+    int Cin, Cout, ldx, ldy;
+    int k_chunk;     // pixels per split (multiple of BK)
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+conv_wgrad_tc_kernel(const WgradParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
+    __shared__ uint32_t tmem_base_sh;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smemA = smem_base, smemB = smem_base + STAGES * kStageA;
+
+    const int Ntot = p.KH * p.KW * p.ldx;
+    const int n0 = blockIdx.x * BN;
+    const int n_cta = min(BN, Ntot - n0);
+    const int co0 = blockIdx.y * BM;
+    const int Kd = p.B * p.OH * p.OW;
+    const int k_begin = blockIdx.z * p.k_chunk;
+    const int k_end = min(Kd, k_begin + p.k_chunk);
+    const int nkb = k_end > k_begin ? (k_end - k_begin + BK - 1) / BK : 0;
+    if (nkb == 0) return;
+
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], kProducers); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&acc_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp < 4) {
+        // producers: thread = (16-byte channel chunk c16 of the 128-wide tile, pixel slot)
+        const int c16 = tid & 15, pslot = tid >> 4;
+        const int atom = c16 >> 3, jc = c16 & 7;
+        // A: dy channels co0 + c16*8 .. +8
+        const int a_ch = co0 + c16 * 8;
+        const bool a_ch_ok = a_ch + 8 <= p.ldy;
+        // B: n = n0 + c16*8 -> (tap, ci) fixed for the whole kernel
+        const int nn = n0 + c16 * 8;
+        const bool b_ch_ok = c16 * 8 < n_cta;
+        const int tap = nn / p.ldx, ci = nn - tap * p.ldx;
+        const int ta = tap / p.KW, tcc = tap - ta * p.KW;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int stage = kb % STAGES;
+            if (kb >= STAGES) mbar_wait(&empty_bar[stage], (uint32_t)(((kb / STAGES) - 1) & 1));
+            const uint32_t dstA = smemA + stage * kStageA + atom * (BK * 128);
+            const uint32_t dstB = smemB + stage * kStageB + atom * (BK * 128);
+#pragma unroll
+            for (int i = 0; i < BK / 8; ++i) {
+                const int k = pslot + 8 * i;
+                const int pix = k_begin + kb * BK + k;
+                const bool pv = pix < k_end;
+                const uint32_t soff = k * 128 + ((jc ^ (k & 7)) << 4);
+                const bool aok = pv && a_ch_ok;
+                cp_async16(dstA + soff, aok ? (const void*)(p.dy + (long long)pix * p.ldy + a_ch) : (const void*)p.dy,
+                           aok ? 16u : 0u);
+                bool bok = false;
+                long long boff = 0;
+                if (pv && b_ch_ok) {
+                    const int b = pix / (p.OH * p.OW), r = pix - b * p.OH * p.OW;
+                    const int oh = r / p.OW, ow = r - oh * p.OW;
+                    const int ih = oh * p.stride + ta - p.pad_t, iw = ow * p.stride + tcc - p.pad_l;
+                    bok = (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+                    boff = ((long long)(b * p.H + ih) * p.W + iw) * p.ldx + ci;
+                }
+                cp_async16(dstB + soff, bok ? (const void*)(p.x + boff) : (const void*)p.x, bok ? 16u : 0u);
+            }
+            cp_async_arrive_noinc(&full_bar[stage]);
+        }
+    } else if (lane == 0) {
+        const uint32_t idesc = make_idesc(n_cta, 1, 1);
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int stage = kb % STAGES;
+            mbar_wait(&full_bar[stage], (uint32_t)((kb / STAGES) & 1));
+            tc_fence_after();
+            const uint32_t aaddr = smemA + stage * kStageA, baddr = smemB + stage * kStageB;
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)   // 16 pixels = two 8-row groups further down each atom
+                tc_mma(tmem_base, sw128_desc(aaddr + k * 2048, BK * 128, 1024), sw128_desc(baddr + k * 2048, BK * 128, 1024),
+                       idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit(&empty_bar[stage]);
+        }
+        tc_commit(&acc_bar);
+    }
+
+    if (warp < 4) {
+        mbar_wait(&acc_bar, 0);
+        tc_fence_after();
+        const int co = co0 + warp * 32 + lane;
+        for (int cb = 0; cb < n_cta; cb += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + cb, v);
+            if (co < p.Cout) {
+                const int nn = n0 + cb;
+                const int tap = nn / p.ldx, ci0 = nn - tap * p.ldx;   // 16-column groups never straddle a tap (ldx % 16 == 0)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int ci = ci0 + i;
+                    if (ci < p.Cin) atomicAdd(p.dw + ((size_t)tap * p.Cin + ci) * p.Cout + co, __uint_as_float(v[i]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
 // ---- weight packing ------------------------------------------------------------------------------------------
 // HWIO fp32 w[a][c][ci][co] -> CONV pack bf16 Wf[n = co (N rows, zero padded)][tap][cis (zero padded)]
 __global__ void __launch_bounds__(256)
@@ -397,7 +533,6 @@ int acg_pack_weights(const acg_conv_shape* s, const float* w, int which, int ld_
 int acg_conv_tc_supported(const acg_conv_shape* s, int which) {
     if (!s) return 0;
     if (s->stride != 1 && s->stride != 2) return 0;
-    if (which == 2) return 0;   // wgrad: not yet
     return 1;
 }
 
@@ -458,9 +593,41 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     return check_launch("acg_conv_dgrad_tc");
 }
 
-int acg_conv_wgrad_tc(const acg_conv_shape*, const void*, const void*, float*, const acg_tc_args*, void*) {
-    acg::set_error("acg_conv_wgrad_tc: not built yet");
-    return ACG_ERR_UNSUPPORTED;
+int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* dy_bf16, float* dw, const acg_tc_args* t,
+                      void* stream) {
+    using namespace acg;
+    using namespace acg::tc;
+    ACG_REQUIRE(s && t && x_bf16 && dy_bf16 && dw, ACG_ERR_INVALID, "acg_conv_wgrad_tc: null pointer");
+    ACG_REQUIRE(s->stride == 1 || s->stride == 2, ACG_ERR_UNSUPPORTED, "acg_conv_wgrad_tc: stride %d", s->stride);
+    ACG_REQUIRE(t->ld_in % 16 == 0 && t->ld_in >= s->Cin, ACG_ERR_UNSUPPORTED,
+                "acg_conv_wgrad_tc: ld_x=%d must be a multiple of 16 and >= Cin", t->ld_in);
+    ACG_REQUIRE(t->ld_out % 8 == 0 && t->ld_out >= s->Cout, ACG_ERR_UNSUPPORTED,
+                "acg_conv_wgrad_tc: ld_dy=%d must be a multiple of 8 and >= Cout", t->ld_out);
+    ACG_REQUIRE((long long)s->B * s->H * s->W * (long long)t->ld_in < (1ll << 40) &&
+                    (long long)s->B * s->OH * s->OW < (1ll << 31),
+                ACG_ERR_UNSUPPORTED, "acg_conv_wgrad_tc: tensor too large");
+    static bool ready = false;
+    if (!ready) { int rc = set_smem((const void*)conv_wgrad_tc_kernel); if (rc) return rc; ready = true; }
+    WgradParams p{};
+    p.x = static_cast<const __nv_bfloat16*>(x_bf16); p.dy = static_cast<const __nv_bfloat16*>(dy_bf16); p.dw = dw;
+    p.B = s->B; p.H = s->H; p.W = s->W; p.OH = s->OH; p.OW = s->OW; p.KH = s->KH; p.KW = s->KW;
+    p.stride = s->stride; p.pad_t = s->pad_t; p.pad_l = s->pad_l;
+    p.Cin = s->Cin; p.Cout = s->Cout; p.ldx = t->ld_in; p.ldy = t->ld_out;
+    const int Ntot = s->KH * s->KW * t->ld_in;
+    const int gx = (Ntot + BN - 1) / BN, gy = (s->Cout + BM - 1) / BM;
+    const long long Kd = (long long)s->B * s->OH * s->OW;
+    // split the pixel reduction so that ~2 waves of CTAs exist, at least 4 K blocks per split
+    long long splits = ((long long)num_sms() * 4 + (long long)gx * gy - 1) / ((long long)gx * gy);
+    const long long max_splits = (Kd + 4 * BK - 1) / (4 * BK);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    long long chunk = (Kd + splits - 1) / splits;
+    chunk = (chunk + BK - 1) / BK * BK;
+    splits = (Kd + chunk - 1) / chunk;
+    p.k_chunk = (int)chunk;
+    dim3 grid(gx, gy, (unsigned)splits);
+    conv_wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+    return check_launch("acg_conv_wgrad_tc");
 }
 
 }  // extern "C"

@@ -107,3 +107,27 @@ def test_conv_tc_matches_simt_at_full_size(cuda):
     out = torch.empty(B, 32, 32, 128, device=cuda)
     Kn.conv_dgrad_tc(shape, dy, pack, out, 128, 128)
     assert (out - ref).abs().max() <= 2e-3 * ref.abs().max()
+
+
+@pytest.mark.parametrize("case", CASES + [(16, 32, 32, 32, 64, 5, 2, "SAME"), (4, 32, 32, 128, 48, 5, 2, "SAME")])
+def test_conv_wgrad_tc(cuda, case):
+    """dW[a,c,ci,co] = sum x*dy (MN-major operands, split over pixels with fp32 atomics) vs oracle autograd."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    B, H, W, Cin, Cout, k, s, padding = case
+    rng = np.random.RandomState(sum(case[:7]) + 2)
+    shape = Kn.conv_shape(B, H, W, Cin, Cout, k, s, padding)
+    x = _bf16_round(rng.randn(B, H, W, Cin))
+    dy = _bf16_round(rng.randn(B, shape.OH, shape.OW, Cout))
+    wt = torch.zeros(k, k, Cin, Cout, dtype=torch.float64, requires_grad=True)
+    yt = torch_ref.conv2d(torch.tensor(x), wt, s, padding)
+    (dw_ref,) = torch.autograd.grad(yt, [wt], torch.tensor(dy))
+    dw_ref = dw_ref.numpy()
+    ld_x, ld_dy = ru(Cin, 16), ru(Cout, 8)
+    dw = torch.zeros(k, k, Cin, Cout, device=cuda)
+    Kn.conv_wgrad_tc(shape, _pad_channels(x, ld_x, cuda), _pad_channels(dy, ld_dy, cuda), dw, ld_x, ld_dy)
+    torch.cuda.synchronize()
+    got = dw.cpu().numpy()
+    assert np.abs(got - dw_ref).max() <= 2e-3 * max(1.0, np.abs(dw_ref).max())
+    # accumulate semantics: a second call doubles the result
+    Kn.conv_wgrad_tc(shape, _pad_channels(x, ld_x, cuda), _pad_channels(dy, ld_dy, cuda), dw, ld_x, ld_dy)
+    assert np.abs(dw.cpu().numpy() - 2 * dw_ref).max() <= 4e-3 * max(1.0, np.abs(dw_ref).max())
