@@ -49,7 +49,7 @@ SIGNATURES = {
     "acg_bn_finalize": [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _P],
     "acg_bn_act_fwd": [_P, _I, _L, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P],
     "acg_bn_act_bwd_reduce": [_P, _P, _I, _I, _P, _I, _I, _L, _I, _I, _P, _P, _P, _I, _P, _P],
-    "acg_bn_act_bwd_apply": [_P, _P, _I, _I, _P, _I, _I, _L, _I, _I, _P, _P, _P, _I, _I, _P, _P, _I, _P, _L, _F,
+    "acg_bn_act_bwd_apply": [_P, _P, _I, _I, _P, _I, _I, _L, _I, _I, _P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _L, _F,
                              _P],
     "acg_copy_channels": [_P, _I, _I, _I, _P, _I, _I, _I, _L, _I, _P],
     "acg_tile_actions": [_P, _I, _I, _I, _P, _I, _I, _I, _P],

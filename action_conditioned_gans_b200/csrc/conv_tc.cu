@@ -37,6 +37,7 @@ struct Params {
     int ldo;         // channel stride of the output rows (>= N)
     int N;           // GEMM N of this launch (multiple of 16)
     int n_bias;      // bias entries (real output channels)
+    int n_store;     // output channels written per row: min(N, ldo)
     int out_dtype, out_act;
     long long w_class_off[4];   // ADJ: element offset of each parity class' [N][Kc] matrix inside w_pack
 };
@@ -252,21 +253,34 @@ conv_tc_kernel(const Params p) {
                     if (p.bias && n < p.n_bias) f[i] += p.bias[n];
                     if (p.out_act == ACG_ACT_TANH) f[i] = tanhf(f[i]);
                 }
+                const bool full = n0 + cb + 16 <= p.n_store;
                 if (p.out_dtype == ACG_BF16) {
                     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + row_off + n0 + cb;
-                    uint32_t w[8];
+                    if (full && (p.ldo & 7) == 0) {
+                        uint32_t w[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                        w[i] = *reinterpret_cast<uint32_t*>(&h);
+                        for (int i = 0; i < 8; ++i) {
+                            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+                            w[i] = *reinterpret_cast<uint32_t*>(&h);
+                        }
+                        reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n0 + cb + i < p.n_store) o[i] = __float2bfloat16_rn(f[i]);
                     }
-                    reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                    reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
                 } else {
                     float* o = static_cast<float*>(p.out) + row_off + n0 + cb;
+                    if (full && (p.ldo & 3) == 0) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                        for (int i = 0; i < 4; ++i)
+                            reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (n0 + cb + i < p.n_store) o[i] = f[i];
+                    }
                 }
             }
         }
@@ -471,7 +485,7 @@ int check(const acg_conv_shape* s, const acg_tc_args* t, const char* who) {
     ACG_REQUIRE(s->stride == 1 || s->stride == 2, ACG_ERR_UNSUPPORTED, "%s: stride %d", who, s->stride);
     ACG_REQUIRE(t->ld_in % 8 == 0 && t->ld_in > 0, ACG_ERR_UNSUPPORTED, "%s: ld_in=%d must be a multiple of 8", who,
                 t->ld_in);
-    ACG_REQUIRE(t->ld_out % 8 == 0, ACG_ERR_UNSUPPORTED, "%s: ld_out=%d must be a multiple of 8", who, t->ld_out);
+    ACG_REQUIRE(t->ld_out > 0, ACG_ERR_INVALID, "%s: ld_out=%d", who, t->ld_out);
     ACG_REQUIRE(t->out_dtype == ACG_F32 || t->out_dtype == ACG_BF16, ACG_ERR_UNSUPPORTED, "%s: out dtype", who);
     ACG_REQUIRE((long long)s->B * s->H * s->W * (long long)t->ld_in < (1ll << 31) &&
                     (long long)s->B * s->OH * s->OW * (long long)t->ld_in < (1ll << 31) &&
@@ -545,7 +559,7 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     ACG_REQUIRE(x_bf16 && w_pack && y, ACG_ERR_INVALID, "acg_conv_fprop_tc: null pointer");
     ACG_REQUIRE(t->ld_in >= s->Cin, ACG_ERR_INVALID, "acg_conv_fprop_tc: ld_in < Cin");
     const int N = ru(s->Cout, 16);
-    ACG_REQUIRE(t->ld_out >= N, ACG_ERR_INVALID, "acg_conv_fprop_tc: ld_out=%d < padded Cout=%d", t->ld_out, N);
+    ACG_REQUIRE(t->ld_out >= s->Cout, ACG_ERR_INVALID, "acg_conv_fprop_tc: ld_out=%d < Cout=%d", t->ld_out, s->Cout);
     static bool ready = false;
     if (!ready) { rc = set_smem((const void*)conv_tc_kernel<CONV>); if (rc) return rc; ready = true; }
     Params p{};
@@ -553,7 +567,7 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     p.out = y; p.bias = t->bias;
     p.B = s->B; p.H = s->H; p.W = s->W; p.OH = s->OH; p.OW = s->OW; p.KH = s->KH; p.KW = s->KW;
     p.stride = s->stride; p.pad_t = s->pad_t; p.pad_l = s->pad_l;
-    p.lda = t->ld_in; p.ldo = t->ld_out; p.N = N; p.n_bias = s->Cout; p.out_dtype = t->out_dtype; p.out_act = t->out_act;
+    p.lda = t->ld_in; p.ldo = t->ld_out; p.N = N; p.n_bias = s->Cout; p.n_store = N < t->ld_out ? N : t->ld_out; p.out_dtype = t->out_dtype; p.out_act = t->out_act;
     const long long M = (long long)s->B * s->OH * s->OW;
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, 1);
     conv_tc_kernel<CONV><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
@@ -569,7 +583,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     ACG_REQUIRE(dy_bf16 && w_pack && dx, ACG_ERR_INVALID, "acg_conv_dgrad_tc: null pointer");
     ACG_REQUIRE(t->ld_in >= s->Cout, ACG_ERR_INVALID, "acg_conv_dgrad_tc: ld_in < Cout");
     const int N = ru(s->Cin, 16);
-    ACG_REQUIRE(t->ld_out >= N, ACG_ERR_INVALID, "acg_conv_dgrad_tc: ld_out=%d < padded Cin=%d", t->ld_out, N);
+    ACG_REQUIRE(t->ld_out >= s->Cin, ACG_ERR_INVALID, "acg_conv_dgrad_tc: ld_out=%d < Cin=%d", t->ld_out, s->Cin);
     static bool ready = false;
     if (!ready) { rc = set_smem((const void*)conv_tc_kernel<ADJ>); if (rc) return rc; ready = true; }
     Params p{};
@@ -577,7 +591,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     p.out = dx; p.bias = t->bias;
     p.B = s->B; p.H = s->H; p.W = s->W; p.OH = s->OH; p.OW = s->OW; p.KH = s->KH; p.KW = s->KW;
     p.stride = s->stride; p.pad_t = s->pad_t; p.pad_l = s->pad_l;
-    p.lda = t->ld_in; p.ldo = t->ld_out; p.N = N; p.n_bias = s->Cin; p.out_dtype = t->out_dtype; p.out_act = t->out_act;
+    p.lda = t->ld_in; p.ldo = t->ld_out; p.N = N; p.n_bias = s->Cin; p.n_store = N < t->ld_out ? N : t->ld_out; p.out_dtype = t->out_dtype; p.out_act = t->out_act;
     long long off = 0;
     const int ncls = s->stride * s->stride;
     for (int cls = 0; cls < ncls; ++cls) {

@@ -43,7 +43,7 @@ col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void* __
         int k = 0;
         for (long long r = (long long)blockIdx.y * kTY + threadIdx.y; r < rows_per_group;
              r += (long long)gridDim.y * kTY) {
-            const float zv = ldx(z, z_dt, (size_t)(r_begin + r) * ld_z + c);
+            const float zv = z ? ldx(z, z_dt, (size_t)(r_begin + r) * ld_z + c) : 0.f;
             if (MODE == 0) {
                 s0 += zv;
                 s1 += zv * zv;
@@ -115,7 +115,7 @@ bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict__ dA
                         int ld_z, long long rows, int C, int groups, long long rows_per_group,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ shift, int act, int has_bn, const double* __restrict__ red,
-                        void* __restrict__ dz, int dz_dt, float* __restrict__ dbeta, long long norm_rows,
+                        void* __restrict__ dz, int dz_dt, int ld_dz, float* __restrict__ dbeta, long long norm_rows,
                         float dbeta_scale) {
     const long long total = rows * C;
     const float inv_r = 1.f / (float)norm_rows;
@@ -128,7 +128,7 @@ bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict__ dA
         const float mu = mean ? mean[gc] : 0.f;
         const float rs = rstd ? rstd[gc] : 1.f;
         const float sh = shift ? shift[gc] : 0.f;
-        const float zv = ldx(z, z_dt, (size_t)r * ld_z + c);
+        const float zv = z ? ldx(z, z_dt, (size_t)r * ld_z + c) : 0.f;
         const float u = zv * rs + sh;
         float d = ldx(dA, d_dt, (size_t)r * ld_d + c);
         if (dA2) d += ldx(dA2, d_dt, (size_t)r * ld_d + c);
@@ -138,7 +138,7 @@ bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict__ dA
             const float m1 = (float)red[(size_t)g * 2 * C + C + c] * inv_r;
             d = rs * (d - m0 - (zv - mu) * rs * m1);
         }
-        stx(dz, dz_dt, (size_t)r * C + c, d);
+        stx(dz, dz_dt, (size_t)r * ld_dz + c, d);
     }
     if (dbeta && blockIdx.x == 0) {
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -238,8 +238,10 @@ int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d
                           long long rows, int C, int groups, const float* mean, const float* rstd,
                           const float* shift, int act, double* red, void* stream) {
     using namespace acg;
-    ACG_REQUIRE(dA && z && red, ACG_ERR_INVALID, "acg_bn_act_bwd_reduce: null pointer");
-    ACG_REQUIRE(rows > 0 && C > 0 && ld_d >= C && ld_z >= C && groups > 0 && rows % groups == 0,
+    ACG_REQUIRE(dA && red, ACG_ERR_INVALID, "acg_bn_act_bwd_reduce: null pointer");
+    ACG_REQUIRE(z || (!mean && act == ACG_ACT_NONE), ACG_ERR_INVALID,
+                "acg_bn_act_bwd_reduce: z may only be NULL for a layer without batch-norm and activation");
+    ACG_REQUIRE(rows > 0 && C > 0 && ld_d >= C && (!z || ld_z >= C) && groups > 0 && rows % groups == 0,
                 ACG_ERR_INVALID, "acg_bn_act_bwd_reduce: bad size");
     ACG_REQUIRE(dt_ok(d_dtype) && dt_ok(z_dtype), ACG_ERR_UNSUPPORTED, "acg_bn_act_bwd_reduce: dtype");
     const long long rpg = rows / groups;
@@ -251,16 +253,18 @@ int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d
 int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype, int ld_z,
                          long long rows, int C, int groups, const float* mean, const float* rstd,
                          const float* shift, int act, int has_bn, const double* red, void* dz, int dz_dtype,
-                         float* dbeta, long long norm_rows, float dbeta_scale, void* stream) {
+                         int ld_dz, float* dbeta, long long norm_rows, float dbeta_scale, void* stream) {
     using namespace acg;
-    ACG_REQUIRE(dA && z && red && dz, ACG_ERR_INVALID, "acg_bn_act_bwd_apply: null pointer");
-    ACG_REQUIRE(rows > 0 && C > 0 && ld_d >= C && ld_z >= C && groups > 0 && rows % groups == 0,
+    ACG_REQUIRE(dA && red && dz, ACG_ERR_INVALID, "acg_bn_act_bwd_apply: null pointer");
+    ACG_REQUIRE(z || (!has_bn && act == ACG_ACT_NONE), ACG_ERR_INVALID,
+                "acg_bn_act_bwd_apply: z may only be NULL for a layer without batch-norm and activation");
+    ACG_REQUIRE(rows > 0 && C > 0 && ld_d >= C && (!z || ld_z >= C) && ld_dz >= C && groups > 0 && rows % groups == 0,
                 ACG_ERR_INVALID, "acg_bn_act_bwd_apply: bad size");
     ACG_REQUIRE(dt_ok(d_dtype) && dt_ok(z_dtype) && dt_ok(dz_dtype), ACG_ERR_UNSUPPORTED,
                 "acg_bn_act_bwd_apply: dtype");
     bn_act_bwd_apply_kernel<<<ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, rows, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
-        dz, dz_dtype, dbeta, norm_rows > 0 ? norm_rows : rows / groups, dbeta_scale);
+        dz, dz_dtype, ld_dz, dbeta, norm_rows > 0 ? norm_rows : rows / groups, dbeta_scale);
     return check_launch("acg_bn_act_bwd_apply");
 }
 

@@ -118,13 +118,22 @@ class ParamStore:
         self.grad = torch.zeros(off, dtype=torch.float32, device=device)
         self.views = {n: self.flat[o:o + k].view(shape) for n, (o, k, shape) in self.offsets.items()}
         self.gviews = {n: self.grad[o:o + k].view(shape) for n, (o, k, shape) in self.offsets.items()}
+        self.packs = {}      # layer name -> (shape, fwd_which, fwd_ld, fwd_pack, bwd_which, bwd_ld, bwd_pack)
         if init is not None:
             self.load(init)
+
+    def refresh_packs(self):
+        """bf16 GEMM-ready copies of the fp32 master weights (after init / load and after every optimizer step)."""
+        for name, (shape, fw, fld, pf, bw, bld, pb) in self.packs.items():
+            w = self.views[name + "/weights"]
+            K.pack_weights(shape, w, fw, fld, pf)
+            K.pack_weights(shape, w, bw, bld, pb)
 
     def load(self, arrays):
         for name, (o, k, shape) in self.offsets.items():
             a = np.asarray(arrays[name], dtype=np.float32).reshape(shape)
             self.views[name].copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        self.refresh_packs()
 
     def numpy(self):
         return {n: v.detach().cpu().numpy().copy() for n, v in self.views.items()}
@@ -137,23 +146,31 @@ class _LayerState:
     pass
 
 
+def ru16(v):
+    return (v + 15) // 16 * 16
+
+
 class NetRun:
     """Activation / gradient buffers of ONE application of a network at a fixed local batch size.
-    The discriminator is applied twice per step (generated and real pair, train.py:63-70) with shared
-    ParamStore and two NetRuns, which is exactly TF's reuse=True."""
+    The discriminator is applied twice per step (generated and real pair, train.py:63-70) with a shared
+    ParamStore and two NetRuns, which is exactly TF's reuse=True.
 
-    def __init__(self, store, batch, in_hw, device, dp=None):
+    precision 'bf16': every convolution runs on the tcgen05 kernels; activations, raw conv outputs and their
+      gradients are bf16 NHWC with the channel count rounded up to 16 (pad channels are zero), weights are bf16
+      GEMM-ready packs refreshed from the fp32 master copy after every optimizer step.
+    precision 'fp32': fp32 SIMT kernels end to end (the tight-tolerance parity mode)."""
+
+    def __init__(self, store, batch, device, dp=None, precision="bf16"):
         self.store, self.B, self.device, self.dp = store, batch, device, dp
+        self.bf16 = precision == "bf16"
+        self.adt = torch.bfloat16 if self.bf16 else torch.float32
         self.layers = {}
-        n_stat = 0
-        for L in store.spec:
-            n_stat += 4 * L.cout
+        n_stat = sum(4 * L.cout for L in store.spec)
         self.f64 = torch.zeros(n_stat, dtype=torch.float64, device=device)   # [stats | red] per layer
         soff = 0
         for L in store.spec:
             st = _LayerState()
             st.spec = L
-            st.soff = soff
             st.stats = self.f64[soff:soff + 2 * L.cout]
             st.red = self.f64[soff + 2 * L.cout:soff + 4 * L.cout]
             soff += 4 * L.cout
@@ -163,8 +180,18 @@ class NetRun:
             st.shift = torch.zeros(L.cout, device=device)
             self.layers[L.name] = st
 
-    def plan(self, name, h, w):
-        """Fix the geometry of layer `name` for an input of h x w pixels; allocate z / dz.  Returns output hw."""
+    def ld(self, c):
+        """channel stride of a buffer holding c channels"""
+        return ru16(c) if self.bf16 else c
+
+    def act_buffer(self, h, w, c, dtype=None):
+        """zero-initialised so that pad channels stay zero forever (kernels only write the real channels)"""
+        return torch.zeros(self.B, h, w, self.ld(c), dtype=dtype or self.adt, device=self.device)
+
+    def plan(self, name, h, w, ld_in, fused_out=False):
+        """Fix the geometry of layer `name` for an input of h x w pixels with channel stride ld_in.
+        fused_out: (bf16 only) a layer without batch-norm and activation whose bias is added in the conv epilogue,
+        writing the caller's output buffer directly; no raw z is kept."""
         st = self.layers[name]
         L = st.spec
         B = self.B
@@ -177,107 +204,143 @@ class NetRun:
             assert st.shape.OH == h and st.shape.OW == w
         st.in_hw, st.out_hw = (h, w), (oh, ow)
         st.rows = B * oh * ow
-        st.in_rows = B * h * w
-        st.z = torch.empty(B, oh, ow, L.cout, device=self.device)
-        st.dz = torch.empty(B, oh, ow, L.cout, device=self.device)
+        st.ld_in = ld_in
+        st.ldz = self.ld(L.cout)
+        st.fused = bool(fused_out and self.bf16 and not L.bn and L.act == "none")
+        st.z = None if st.fused else torch.empty(B, oh, ow, st.ldz, dtype=self.adt, device=self.device)
+        st.dz = torch.zeros(B, oh, ow, st.ldz, dtype=self.adt, device=self.device)
         st.dx = None
+        if self.bf16 and name not in self.store.packs:
+            # forward / backward-data packs; conv2d_transpose swaps the roles (see include/acg_b200.h)
+            fwd_which, bwd_which = (0, 1) if L.kind == "conv" else (1, 0)
+            pf = torch.empty(K.pack_size(st.shape, fwd_which, ld_in), dtype=torch.bfloat16, device=self.device)
+            pb = torch.empty(K.pack_size(st.shape, bwd_which, st.ldz), dtype=torch.bfloat16, device=self.device)
+            self.store.packs[name] = (st.shape, fwd_which, ld_in, pf, bwd_which, st.ldz, pb)
         return oh, ow
 
     def zero_reductions(self):
         self.f64.zero_()
 
-    # -- one layer forward: conv -> (bias | batch-norm) -> activation ------------------------------
+    # -- convolution dispatch ------------------------------------------------------------------------------
+    def _conv_fwd(self, st, x, out, ld_out, bias=None):
+        L = st.spec
+        if self.bf16:
+            pk = self.store.packs[L.name]
+            fn = K.conv_fprop_tc if L.kind == "conv" else K.conv_dgrad_tc
+            fn(st.shape, x, pk[3], out, st.ld_in, ld_out, bias=bias)
+        else:
+            w = self.store.views[L.name + "/weights"]
+            (K.conv_fprop_f32 if L.kind == "conv" else K.conv_dgrad_f32)(st.shape, x, w, out)
+
+    # -- one layer forward: conv -> (bias | batch-norm) -> activation --------------------------------------
     def layer_fwd(self, name, x, out, ld_out):
         st = self.layers[name]
         L = st.spec
-        w = self.store.views[name + "/weights"]
-        if L.kind == "conv":
-            K.conv_fprop_f32(st.shape, x, w, st.z)
-        else:
-            K.conv_dgrad_f32(st.shape, x, w, st.z)
         st.x = x
+        if st.fused:
+            self._conv_fwd(st, x, out, ld_out, bias=self.store.views[name + "/biases"] if L.bias else None)
+            return
+        self._conv_fwd(st, x, st.z, st.ldz)
         if L.bn:
-            K.bn_stats(st.z, st.rows, L.cout, L.cout, 1, st.stats)
+            K.bn_stats(st.z, st.rows, L.cout, st.ldz, 1, st.stats)
             world = 1
             if self.dp is not None:
                 world = self.dp.world
                 self.dp.allreduce_sum(st.stats)        # SyncBN: statistics over the GLOBAL batch
             K.bn_finalize(st.stats, self.store.views[name + "/BatchNorm/beta"], st.rows * world, L.cout, 1,
                           st.mean, st.rstd, st.scale, st.shift, BN_EPS)
-            K.bn_act_fwd(st.z, st.rows, L.cout, L.cout, 1, st.scale, st.shift, L.act, out, ld_out)
+            K.bn_act_fwd(st.z, st.rows, L.cout, st.ldz, 1, st.scale, st.shift, L.act, out, ld_out)
         else:
             bias = self.store.views[name + "/biases"] if L.bias else None
-            K.bn_act_fwd(st.z, st.rows, L.cout, L.cout, 1, None, bias, L.act, out, ld_out)
+            K.bn_act_fwd(st.z, st.rows, L.cout, st.ldz, 1, None, bias, L.act, out, ld_out)
 
     # -- one layer backward ----------------------------------------------------------------------------
-    def layer_bwd(self, name, dA, ld_d, dA2=None, need_dx=True, need_dw=True):
+    def layer_bwd(self, name, dA, ld_d, dA2=None, need_dx=True, need_dw=True, dx_dtype=None):
         st = self.layers[name]
         L = st.spec
         if L.bn:
             mean, rstd, shift = st.mean, st.rstd, st.shift
         else:
             mean, rstd, shift = None, None, (self.store.views[name + "/biases"] if L.bias else None)
-        K.bn_act_bwd_reduce(dA, dA2, ld_d, st.z, L.cout, st.rows, L.cout, 1, mean, rstd, shift, L.act, st.red)
+        K.bn_act_bwd_reduce(dA, dA2, ld_d, st.z, st.ldz, st.rows, L.cout, 1, mean, rstd, shift, L.act, st.red)
         world = 1
-        if self.dp is not None and L.bn:
+        if self.dp is not None:
             world = self.dp.world
-            self.dp.allreduce_sum(st.red)
+            if L.bn:
+                self.dp.allreduce_sum(st.red)
         dpar = None
         if need_dw:
             dpar = self.store.gviews[name + ("/BatchNorm/beta" if L.bn else "/biases")]
-        K.bn_act_bwd_apply(dA, dA2, ld_d, st.z, L.cout, st.rows, L.cout, 1, mean, rstd, shift, L.act, L.bn,
-                           st.red, st.dz, dpar, norm_rows=st.rows * world, dbeta_scale=1.0 / world)
-        w = self.store.views[name + "/weights"]
+        K.bn_act_bwd_apply(dA, dA2, ld_d, st.z, st.ldz, st.rows, L.cout, 1, mean, rstd, shift, L.act, L.bn,
+                           st.red, st.dz, dpar, norm_rows=st.rows * world,
+                           dbeta_scale=(1.0 / world if L.bn else 1.0), ld_dz=st.ldz)
         if need_dw:
             dw = self.store.gviews[name + "/weights"]
-            if L.kind == "conv":
+            if self.bf16:
+                if L.kind == "conv":
+                    K.conv_wgrad_tc(st.shape, st.x, st.dz, dw, st.ld_in, st.ldz)
+                else:
+                    K.conv_wgrad_tc(st.shape, st.dz, st.x, dw, st.ldz, st.ld_in)
+            elif L.kind == "conv":
                 K.conv_wgrad_f32(st.shape, st.x, st.dz, dw)
             else:
                 K.conv_wgrad_f32(st.shape, st.dz, st.x, dw)
         if need_dx:
             if st.dx is None:
-                st.dx = torch.empty(self.B, st.in_hw[0], st.in_hw[1], L.cin, device=self.device)
-            if L.kind == "conv":
-                K.conv_dgrad_f32(st.shape, st.dz, w, st.dx)
+                st.dx = torch.zeros(self.B, st.in_hw[0], st.in_hw[1], st.ld_in, dtype=dx_dtype or self.adt,
+                                    device=self.device)
+            if self.bf16:
+                pk = self.store.packs[name]
+                fn = K.conv_dgrad_tc if L.kind == "conv" else K.conv_fprop_tc
+                fn(st.shape, st.dz, pk[6], st.dx, st.ldz, st.ld_in)
             else:
-                K.conv_fprop_f32(st.shape, st.dz, w, st.dx)
+                w = self.store.views[name + "/weights"]
+                (K.conv_dgrad_f32 if L.kind == "conv" else K.conv_fprop_f32)(st.shape, st.dz, w, st.dx)
         return st.dx
 
 
 class GeneratorRun(NetRun):
     """One application of the generator (DNA: models.py:24-74, direct: models.py:8-22)."""
 
-    def __init__(self, store, batch, device, dna, ksize, dp=None):
-        super().__init__(store, batch, IMG, device, dp)
+    def __init__(self, store, batch, device, dna, ksize, dp=None, precision="bf16"):
+        super().__init__(store, batch, device, dp, precision)
         self.dna, self.ksize = dna, ksize
         B = batch
+        dev = device
+        Ls = self.layers
+        self.img_in = self.act_buffer(IMG, IMG, 3) if self.bf16 else None       # bf16 copy, 3 -> 16 channels
         h = w = IMG
-        self.enc = ["g/conv1", "g/conv2", "g/conv3", "g/conv4"]
-        self.act_bufs = {}
-        for n in self.enc:
-            h, w = self.plan(n, h, w)
-        c4 = self.layers["g/conv4"].spec.cout
-        self.cat = torch.empty(B, h, w, c4 + ACTION_DIM, device=device)      # models.py:16,38
+        ld = self.ld(3)
+        for n in ["g/conv1", "g/conv2", "g/conv3", "g/conv4"]:
+            h, w = self.plan(n, h, w, ld)
+            ld = self.ld(Ls[n].spec.cout)
+        c4 = Ls["g/conv4"].spec.cout
         self.cat_c = c4
-        h1, w1 = self.plan("g/tconv1", h, w)
-        h2, w2 = self.plan("g/tconv2", h1, w1)
+        self.cat = self.act_buffer(h, w, c4 + ACTION_DIM)                        # models.py:16,38
+        cat_ld = self.cat.shape[3]
+        h1, w1 = self.plan("g/tconv1", h, w, cat_ld)
+        h2, w2 = self.plan("g/tconv2", h1, w1, self.ld(Ls["g/tconv1"].spec.cout))
+        ld2 = self.ld(Ls["g/tconv2"].spec.cout)
         if dna:
-            hs, ws = self.plan("g/sconv3", h2, w2)
-            hs, ws = self.plan("g/sconv4", hs, ws)
-            hs, ws = self.plan("g/sconv5", hs, ws)
+            hs, ws = self.plan("g/sconv3", h2, w2, ld2)
+            hs, ws = self.plan("g/sconv4", hs, ws, self.ld(32))
+            hs, ws = self.plan("g/sconv5", hs, ws, self.ld(16), fused_out=True)
             assert (hs, ws) == (1, 1)
-        h3, w3 = self.plan("g/tconv3", h2, w2)
-        h4, w4 = self.plan("g/tconv4", h3, w3)
+        h3, w3 = self.plan("g/tconv3", h2, w2, ld2)
+        h4, w4 = self.plan("g/tconv4", h3, w3, self.ld(Ls["g/tconv3"].spec.cout), fused_out=dna)
         assert (h4, w4) == (IMG, IMG)
-        for n, st in self.layers.items():
-            if n != "g/conv4":
-                st.a = torch.empty(B, st.out_hw[0], st.out_hw[1], st.spec.cout, device=device)
-        self.g_out = torch.empty(B, IMG, IMG, 3, device=device)
-        self.dg_out = torch.empty(B, IMG, IMG, 3, device=device)
+        for n, st in Ls.items():
+            if n in ("g/conv4", "g/tconv4", "g/sconv5"):
+                continue
+            st.a = self.act_buffer(st.out_hw[0], st.out_hw[1], st.spec.cout)
+        self.g_out = torch.empty(B, IMG, IMG, 3, device=dev)
+        self.dg_out = torch.empty(B, IMG, IMG, 3, device=dev)
         if dna:
-            self.dlogits = torch.empty(B, IMG, IMG, ksize * ksize, device=device)
-            self.state = self.layers["g/sconv5"].a.view(B, STATE_DIM)
-            self.dstate = torch.empty(B, STATE_DIM, device=device)
+            kk = ksize * ksize
+            self.logits = torch.empty(B, IMG, IMG, kk, device=dev)               # fp32, dense: what acg_dna_* reads
+            self.dlogits = torch.empty(B, IMG, IMG, kk, device=dev)
+            self.state = torch.empty(B, STATE_DIM, device=dev)
+            self.dstate = torch.empty(B, STATE_DIM, device=dev)
         else:
             self.state = None
 
@@ -285,26 +348,31 @@ class GeneratorRun(NetRun):
         self.zero_reductions()
         self.img = img
         Ls = self.layers
-        x = img
-        for n in self.enc[:-1]:
-            self.layer_fwd(n, x, Ls[n].a, Ls[n].spec.cout)
+        rows = self.B * IMG * IMG
+        if self.bf16:
+            K.copy_channels(img, 3, 0, self.img_in, self.img_in.shape[3], 0, rows, 3)
+            x = self.img_in
+        else:
+            x = img
+        for n in ["g/conv1", "g/conv2", "g/conv3"]:
+            self.layer_fwd(n, x, Ls[n].a, Ls[n].a.shape[3])
             x = Ls[n].a
         ld = self.cat.shape[3]
         self.layer_fwd("g/conv4", x, self.cat, ld)
         hw = self.cat.shape[1] * self.cat.shape[2]
         K.tile_actions(actions, self.B, hw, self.cat, ld, self.cat_c)            # train.py:48-49
-        self.layer_fwd("g/tconv1", self.cat, Ls["g/tconv1"].a, Ls["g/tconv1"].spec.cout)
-        self.layer_fwd("g/tconv2", Ls["g/tconv1"].a, Ls["g/tconv2"].a, Ls["g/tconv2"].spec.cout)
+        self.layer_fwd("g/tconv1", self.cat, Ls["g/tconv1"].a, Ls["g/tconv1"].a.shape[3])
+        self.layer_fwd("g/tconv2", Ls["g/tconv1"].a, Ls["g/tconv2"].a, Ls["g/tconv2"].a.shape[3])
         t2 = Ls["g/tconv2"].a
         if self.dna:
-            self.layer_fwd("g/sconv3", t2, Ls["g/sconv3"].a, 32)
-            self.layer_fwd("g/sconv4", Ls["g/sconv3"].a, Ls["g/sconv4"].a, 16)
-            self.layer_fwd("g/sconv5", Ls["g/sconv4"].a, Ls["g/sconv5"].a, STATE_DIM)
-        self.layer_fwd("g/tconv3", t2, Ls["g/tconv3"].a, Ls["g/tconv3"].spec.cout)
+            self.layer_fwd("g/sconv3", t2, Ls["g/sconv3"].a, Ls["g/sconv3"].a.shape[3])
+            self.layer_fwd("g/sconv4", Ls["g/sconv3"].a, Ls["g/sconv4"].a, Ls["g/sconv4"].a.shape[3])
+            self.layer_fwd("g/sconv5", Ls["g/sconv4"].a, self.state, STATE_DIM)
+        self.layer_fwd("g/tconv3", t2, Ls["g/tconv3"].a, Ls["g/tconv3"].a.shape[3])
         if self.dna:
             kk = self.ksize * self.ksize
-            self.layer_fwd("g/tconv4", Ls["g/tconv3"].a, Ls["g/tconv4"].a, kk)   # logits (+bias)
-            K.dna_fwd(Ls["g/tconv4"].a, img, self.g_out, self.ksize)             # models.py:60-72
+            self.layer_fwd("g/tconv4", Ls["g/tconv3"].a, self.logits, kk)        # logits (+bias), fp32 dense
+            K.dna_fwd(self.logits, img, self.g_out, self.ksize)                  # models.py:60-72
         else:
             self.layer_fwd("g/tconv4", Ls["g/tconv3"].a, self.g_out, 3)          # tanh image
         return self.g_out, self.state
@@ -313,68 +381,75 @@ class GeneratorRun(NetRun):
         """dg_out (and dstate when with_state) must be filled; accumulates into store.grad."""
         Ls = self.layers
         if self.dna:
-            K.dna_bwd(Ls["g/tconv4"].a, self.img, self.dg_out, self.dlogits, self.ksize)
+            K.dna_bwd(self.logits, self.img, self.dg_out, self.dlogits, self.ksize)
             d = self.layer_bwd("g/tconv4", self.dlogits, self.ksize * self.ksize)
         else:
             d = self.layer_bwd("g/tconv4", self.dg_out, 3)
-        d3 = self.layer_bwd("g/tconv3", d, Ls["g/tconv3"].spec.cout)
+        d3 = self.layer_bwd("g/tconv3", d, d.shape[3])
         d2b = None
         if self.dna and with_state:
             ds = self.layer_bwd("g/sconv5", self.dstate, STATE_DIM)
-            ds = self.layer_bwd("g/sconv4", ds, 16)
-            d2b = self.layer_bwd("g/sconv3", ds, 32)
-        d = self.layer_bwd("g/tconv2", d3, Ls["g/tconv2"].spec.cout, dA2=d2b)
-        d = self.layer_bwd("g/tconv1", d, Ls["g/tconv1"].spec.cout)            # [B,4,4,c4+10]
-        d = self.layer_bwd("g/conv4", d, self.cat.shape[3])                     # first c4 channels
-        d = self.layer_bwd("g/conv3", d, Ls["g/conv3"].spec.cout)
-        d = self.layer_bwd("g/conv2", d, Ls["g/conv2"].spec.cout)
-        self.layer_bwd("g/conv1", d, Ls["g/conv1"].spec.cout, need_dx=False)
+            ds = self.layer_bwd("g/sconv4", ds, ds.shape[3])
+            d2b = self.layer_bwd("g/sconv3", ds, ds.shape[3])
+        d = self.layer_bwd("g/tconv2", d3, d3.shape[3], dA2=d2b)
+        d = self.layer_bwd("g/tconv1", d, d.shape[3])                           # [B,4,4,ld(c4+10)]
+        d = self.layer_bwd("g/conv4", d, d.shape[3])                            # first c4 channels
+        d = self.layer_bwd("g/conv3", d, d.shape[3])
+        d = self.layer_bwd("g/conv2", d, d.shape[3])
+        self.layer_bwd("g/conv1", d, d.shape[3], need_dx=False)
 
 
 class DiscriminatorRun(NetRun):
     """One application of build_discriminator (models.py:76-88) to concat([img, frame], 3)."""
 
-    def __init__(self, store, batch, device, dp=None):
-        super().__init__(store, batch, IMG, device, dp)
+    def __init__(self, store, batch, device, dp=None, precision="bf16"):
+        super().__init__(store, batch, device, dp, precision)
         B = batch
-        self.d_in = torch.empty(B, IMG, IMG, 6, device=device)                   # train.py:64,68
+        Ls = self.layers
+        self.d_in = self.act_buffer(IMG, IMG, 6)                                 # train.py:64,68
         h = w = IMG
-        h, w = self.plan("d/conv1", h, w)
-        h, w = self.plan("d/conv2", h, w)
-        self.cat = torch.empty(B, h, w, 128 + ACTION_DIM, device=device)         # models.py:84 (R3: 16x16)
+        h, w = self.plan("d/conv1", h, w, self.d_in.shape[3])
+        h, w = self.plan("d/conv2", h, w, self.ld(64))
+        self.cat = self.act_buffer(h, w, 128 + ACTION_DIM)                       # models.py:84 (R3: 16x16)
+        ld = self.cat.shape[3]
         for n in ["d/conv3", "d/conv4", "d/conv5", "d/conv6"]:
-            h, w = self.plan(n, h, w)
-        for n, st in self.layers.items():
-            if n != "d/conv2":
-                st.a = torch.empty(B, st.out_hw[0], st.out_hw[1], st.spec.cout, device=device)
-        self.logits = self.layers["d/conv6"].a                                   # [B,2,2,1]
+            h, w = self.plan(n, h, w, ld)
+            ld = self.ld(Ls[n].spec.cout)
+        for n, st in Ls.items():
+            if n in ("d/conv2", "d/conv6"):
+                continue
+            st.a = self.act_buffer(st.out_hw[0], st.out_hw[1], st.spec.cout)
+        self.logits = torch.empty(B, 2, 2, 1, device=device)                     # fp32, dense
         self.n_logits = self.logits.numel()
         self.dlogits = torch.empty(self.n_logits, device=device)
 
     def forward(self, img, frame, actions):
         self.zero_reductions()
         rows = self.B * IMG * IMG
-        K.copy_channels(img, 3, 0, self.d_in, 6, 0, rows, 3)
-        K.copy_channels(frame, 3, 0, self.d_in, 6, 3, rows, 3)
+        ld_in = self.d_in.shape[3]
+        K.copy_channels(img, 3, 0, self.d_in, ld_in, 0, rows, 3)
+        K.copy_channels(frame, 3, 0, self.d_in, ld_in, 3, rows, 3)
         Ls = self.layers
-        self.layer_fwd("d/conv1", self.d_in, Ls["d/conv1"].a, 64)
+        self.layer_fwd("d/conv1", self.d_in, Ls["d/conv1"].a, Ls["d/conv1"].a.shape[3])
         ld = self.cat.shape[3]
         self.layer_fwd("d/conv2", Ls["d/conv1"].a, self.cat, ld)
         K.tile_actions(actions, self.B, self.cat.shape[1] * self.cat.shape[2], self.cat, ld, 128)
         x = self.cat
-        for n in ["d/conv3", "d/conv4", "d/conv5", "d/conv6"]:
-            self.layer_fwd(n, x, Ls[n].a, Ls[n].spec.cout)
+        for n in ["d/conv3", "d/conv4", "d/conv5"]:
+            self.layer_fwd(n, x, Ls[n].a, Ls[n].a.shape[3])
             x = Ls[n].a
+        self.layer_fwd("d/conv6", x, self.logits, 1)
         return self.logits
 
     def backward(self, need_dw, need_dinput):
-        """dlogits must be filled.  Returns d(d_in) [B,64,64,6] when need_dinput."""
+        """dlogits must be filled.  Returns d(d_in) [B,64,64,ld(6)] fp32 when need_dinput."""
         d = self.layer_bwd("d/conv6", self.dlogits, 1, need_dw=need_dw)
-        d = self.layer_bwd("d/conv5", d, 512, need_dw=need_dw)
-        d = self.layer_bwd("d/conv4", d, 256, need_dw=need_dw)
-        d = self.layer_bwd("d/conv3", d, 128, need_dw=need_dw)                   # [B,16,16,138]
-        d = self.layer_bwd("d/conv2", d, self.cat.shape[3], need_dw=need_dw)
-        return self.layer_bwd("d/conv1", d, 64, need_dw=need_dw, need_dx=need_dinput)
+        d = self.layer_bwd("d/conv5", d, d.shape[3], need_dw=need_dw)
+        d = self.layer_bwd("d/conv4", d, d.shape[3], need_dw=need_dw)
+        d = self.layer_bwd("d/conv3", d, d.shape[3], need_dw=need_dw)           # [B,16,16,ld(138)]
+        d = self.layer_bwd("d/conv2", d, d.shape[3], need_dw=need_dw)
+        return self.layer_bwd("d/conv1", d, d.shape[3], need_dw=need_dw, need_dx=need_dinput,
+                              dx_dtype=torch.float32)
 
 
 class TFOptimizer:
@@ -400,3 +475,4 @@ class TFOptimizer:
             K.adam_step(s.flat, s.grad, self.m, self.v, lr_t, clip=clip, grad_scale=grad_scale)
         else:
             K.rmsprop_step(s.flat, s.grad, self.ms, self.lr, clip=clip, grad_scale=grad_scale)
+        s.refresh_packs()

@@ -106,15 +106,16 @@ def bn_act_fwd(z, rows, Cc, ld_in, groups, scale, shift, act, out, ld_out):
 
 
 def bn_act_bwd_reduce(dA, dA2, ld_d, z, ld_z, rows, Cc, groups, mean, rstd, shift, act, red):
-    call("acg_bn_act_bwd_reduce", ptr(dA), ptr(dA2), dtype_id(dA), ld_d, ptr(z), dtype_id(z), ld_z, rows, Cc,
+    call("acg_bn_act_bwd_reduce", ptr(dA), ptr(dA2), dtype_id(dA), ld_d, ptr(z), dtype_id(z) if z is not None else 0,
+         ld_z, rows, Cc,
          groups, ptr(mean), ptr(rstd), ptr(shift), ACT_IDS[act], ptr(red), stream())
 
 
 def bn_act_bwd_apply(dA, dA2, ld_d, z, ld_z, rows, Cc, groups, mean, rstd, shift, act, has_bn, red, dz, dbeta,
-                     norm_rows=0, dbeta_scale=1.0):
-    call("acg_bn_act_bwd_apply", ptr(dA), ptr(dA2), dtype_id(dA), ld_d, ptr(z), dtype_id(z), ld_z, rows, Cc,
-         groups, ptr(mean), ptr(rstd), ptr(shift), ACT_IDS[act], int(has_bn), ptr(red), ptr(dz), dtype_id(dz),
-         ptr(dbeta), norm_rows, dbeta_scale, stream())
+                     norm_rows=0, dbeta_scale=1.0, ld_dz=None):
+    call("acg_bn_act_bwd_apply", ptr(dA), ptr(dA2), dtype_id(dA), ld_d, ptr(z), dtype_id(z) if z is not None else 0,
+         ld_z, rows, Cc, groups, ptr(mean), ptr(rstd), ptr(shift), ACT_IDS[act], int(has_bn), ptr(red), ptr(dz),
+         dtype_id(dz), Cc if ld_dz is None else ld_dz, ptr(dbeta), norm_rows, dbeta_scale, stream())
 
 
 def copy_channels(src, ld_src, off_src, dst, ld_dst, off_dst, rows, n):

@@ -39,7 +39,8 @@ class DataParallel:
 
 class Trainer:
     def __init__(self, sess=None, arg_adv=True, arg_loss="bce", arg_opt="adam", arg_transform=True,
-                 batch_size=BATCH_SIZE, ksize=DNA_KSIZE, device=None, params=None, seed=7, dp=None):
+                 batch_size=BATCH_SIZE, ksize=DNA_KSIZE, device=None, params=None, seed=7, dp=None,
+                 precision="bf16"):
         if arg_loss not in ("bce", "wass"):
             raise ValueError("unexpected loss argument")          # ops.py:35,47
         if arg_opt not in ("adam", "rmsprop"):
@@ -53,7 +54,9 @@ class Trainer:
         self.world = dp.world if dp is not None else 1
         self.GB = self.B * self.world            # global batch: every normaliser of the losses uses this
         self.ksize = ksize
-        self.precision = "fp32"
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' (tcgen05 kernels) or 'fp32' (SIMT kernels)")
+        self.precision = precision
         g_spec = E.g_dna_spec(ksize) if arg_transform else E.g_direct_spec()
         d_spec = E.d_spec()
         if params is None:
@@ -63,9 +66,11 @@ class Trainer:
         dev = self.device
         self.g_store = E.ParamStore(g_spec, dev, params)
         self.d_store = E.ParamStore(d_spec, dev, params)
-        self.g_run = E.GeneratorRun(self.g_store, self.B, dev, arg_transform, ksize, dp)
-        self.d_gen = E.DiscriminatorRun(self.d_store, self.B, dev, dp)
-        self.d_real = E.DiscriminatorRun(self.d_store, self.B, dev, dp)
+        self.g_run = E.GeneratorRun(self.g_store, self.B, dev, arg_transform, ksize, dp, precision)
+        self.d_gen = E.DiscriminatorRun(self.d_store, self.B, dev, dp, precision)
+        self.d_real = E.DiscriminatorRun(self.d_store, self.B, dev, dp, precision)
+        self.g_store.refresh_packs()
+        self.d_store.refresh_packs()
         self.g_opt = E.TFOptimizer(self.g_store, arg_opt)            # train.py:100
         self.g_pretrain_opt = E.TFOptimizer(self.g_store, arg_opt)   # train.py:101
         self.d_opt = E.TFOptimizer(self.d_store, arg_opt)            # train.py:102
@@ -110,7 +115,7 @@ class Trainer:
             K.dlogit_loss(self.d_gen.logits, self.d_gen.n_logits, self.arg_loss, 1.0, 1.0, self.sc[0:1], None)
         self.fsum.zero_()
         K.frame_losses(g.g_out, nxt, self.fsum, g.dg_out if want_grad else None, w_l1,
-                       1.0 if with_adv_grad else 0.0, dadv, 6, 3)
+                       1.0 if with_adv_grad else 0.0, dadv, dadv.shape[3] if dadv is not None else 0, 3)
         if self.arg_transform:
             K.state_loss(g.state, state_gt, self.B * E.STATE_DIM, 1.0 / self.GB, 1.0, self.sc[3:4],
                          g.dstate if want_grad else None)

@@ -145,11 +145,13 @@ int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d
                           const float* shift, int act, double* red, void* stream);
 /* backward, pass 2: dz = rstd*(dzh - red0/R - xhat*red1/R) when has_bn, else dz = dzh, with
  * R = norm_rows (0 -> rows/groups; data-parallel SyncBN passes the GLOBAL row count after all-reducing red).
- * dbeta[c] += dbeta_scale * sum over groups of red0 (also the bias gradient of non-BN layers). */
+ * dbeta[c] += dbeta_scale * sum over groups of red0 (also the bias gradient of non-BN layers).
+ * dz rows have stride ld_dz.  z may be NULL for a layer without batch-norm and activation (dz = dA). */
 int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype, int ld_z,
                          long long rows, int C, int groups, const float* mean, const float* rstd,
                          const float* shift, int act, int has_bn, const double* red, void* dz,
-                         int dz_dtype, float* dbeta, long long norm_rows, float dbeta_scale, void* stream);
+                         int dz_dtype, int ld_dz, float* dbeta, long long norm_rows, float dbeta_scale,
+                         void* stream);
 /* dst[r, off_dst:off_dst+n] = src[r, off_src:off_src+n]  (channel-slice copy with dtype conversion) */
 int acg_copy_channels(const void* src, int src_dtype, int ld_src, int off_src, void* dst, int dst_dtype,
                       int ld_dst, int off_dst, long long rows, int n, void* stream);

@@ -11,6 +11,6 @@ def device_gates(*runs):
                 continue
             k = count.get(name, 0)
             count[name] = k + 1
-            u = st.z * st.scale + st.shift
+            u = st.z[..., :st.spec.cout].float() * st.scale + st.shift
             out["%s#%d" % (name, k)] = (u > 0).cpu().numpy()
     return out
