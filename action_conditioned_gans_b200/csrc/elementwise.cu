@@ -194,6 +194,232 @@ dim3 reduce_grid(long long rows_per_group, int C, int groups) {
 
 bool dt_ok(int dt) { return dt == ACG_F32 || dt == ACG_BF16; }
 
+// ---- 8-channel vectorised variants (bf16 / fp32, 16-byte accesses) -----------------------------------------------
+// Used whenever C % 8 == 0, every row stride is a multiple of 8 and the buffers are 16-byte aligned, i.e. for every
+// layer of the tensor-core path; the scalar kernels above remain for ragged channel counts (3, 5, 25, 36, 138 ...).
+struct F8 { float v[8]; };
+
+__device__ __forceinline__ F8 load8(const void* p, int dt, size_t idx) {
+    F8 r;
+    if (dt == ACG_BF16) {
+        const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p) + idx);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            r.v[2 * i] = __uint_as_float(w[i] << 16);
+            r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    } else {
+        const float4 a = reinterpret_cast<const float4*>(static_cast<const float*>(p) + idx)[0];
+        const float4 b = reinterpret_cast<const float4*>(static_cast<const float*>(p) + idx)[1];
+        r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    }
+    return r;
+}
+__device__ __forceinline__ void store8(void* p, int dt, size_t idx, const F8& f) {
+    if (dt == ACG_BF16) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f.v[2 * i], f.v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p) + idx) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        float4* o = reinterpret_cast<float4*>(static_cast<float*>(p) + idx);
+        o[0] = make_float4(f.v[0], f.v[1], f.v[2], f.v[3]);
+        o[1] = make_float4(f.v[4], f.v[5], f.v[6], f.v[7]);
+    }
+}
+__device__ __forceinline__ F8 load8f(const float* p, int c) {   // per-channel parameter vectors (may be NULL)
+    F8 r;
+    const float4 a = reinterpret_cast<const float4*>(p + c)[0], b = reinterpret_cast<const float4*>(p + c)[1];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+vec_col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void* __restrict__ dA,
+                      const void* __restrict__ dA2, int d_dt, int ld_d, long long rows_per_group, int C,
+                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ shift,
+                      int act, double* __restrict__ out) {
+    __shared__ double sm[16][256];
+    const int bx = blockDim.x, by = blockDim.y;
+    const int tid = threadIdx.y * bx + threadIdx.x;
+    const int nv = C >> 3;
+    const int cv = blockIdx.x * bx + threadIdx.x;
+    const int g = blockIdx.z;
+    const long long r_begin = (long long)g * rows_per_group;
+    float s0[8], s1[8];
+    double d0[8], d1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s0[i] = s1[i] = 0.f; d0[i] = d1[i] = 0.0; }
+    if (cv < nv) {
+        const int c = cv * 8;
+        F8 mu, rs, sh;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { mu.v[i] = 0.f; rs.v[i] = 1.f; sh.v[i] = 0.f; }
+        if (MODE == 1) {
+            if (mean) mu = load8f(mean + (size_t)g * C, c);
+            if (rstd) rs = load8f(rstd + (size_t)g * C, c);
+            if (shift) sh = load8f(shift + (size_t)g * C, c);
+        }
+        int k = 0;
+        for (long long r = (long long)blockIdx.y * by + threadIdx.y; r < rows_per_group; r += (long long)gridDim.y * by) {
+            F8 zv;
+            if (z) zv = load8(z, z_dt, (size_t)(r_begin + r) * ld_z + c);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) zv.v[i] = 0.f;
+            }
+            if (MODE == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { s0[i] += zv.v[i]; s1[i] += zv.v[i] * zv.v[i]; }
+            } else {
+                F8 da = load8(dA, d_dt, (size_t)(r_begin + r) * ld_d + c);
+                if (dA2) {
+                    const F8 db = load8(dA2, d_dt, (size_t)(r_begin + r) * ld_d + c);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) da.v[i] += db.v[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float u = zv.v[i] * rs.v[i] + sh.v[i];
+                    const float dzh = da.v[i] * act_bwd(u, act);
+                    s0[i] += dzh;
+                    s1[i] += dzh * ((zv.v[i] - mu.v[i]) * rs.v[i]);
+                }
+            }
+            if (++k == 32) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { d0[i] += s0[i]; d1[i] += s1[i]; s0[i] = s1[i] = 0.f; }
+                k = 0;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { d0[i] += s0[i]; d1[i] += s1[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sm[i][tid] = d0[i]; sm[8 + i][tid] = d1[i]; }
+    __syncthreads();
+    // thread (x, y) finalises values y, y+by, ... (of 16) of vector column x
+    if (cv < nv) {
+        for (int i = threadIdx.y; i < 16; i += by) {
+            double t = 0.0;
+            for (int y = 0; y < by; ++y) t += sm[i][y * bx + threadIdx.x];
+            const int c = cv * 8 + (i & 7);
+            atomicAdd(&out[(size_t)g * 2 * C + (i < 8 ? 0 : C) + c], t);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+vec_bn_act_fwd_kernel(const void* __restrict__ z, int z_dt, long long rows, int C, int ld_in, long long rows_per_group,
+                      const float* __restrict__ scale, const float* __restrict__ shift, int act, void* __restrict__ out,
+                      int o_dt, int ld_out) {
+    const int nv = C >> 3;
+    const long long total = rows * nv;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / nv;
+        const int c = (int)(idx - r * nv) * 8;
+        const size_t gc = (size_t)(r / rows_per_group) * C + c;
+        F8 u = load8(z, z_dt, (size_t)r * ld_in + c);
+        if (scale) { const F8 sc = load8f(scale, gc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u.v[i] *= sc.v[i]; }
+        if (shift) { const F8 sh = load8f(shift, gc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u.v[i] += sh.v[i]; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u.v[i] = act_fwd(u.v[i], act);
+        store8(out, o_dt, (size_t)r * ld_out + c, u);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+vec_bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict__ dA2, int d_dt, int ld_d,
+                            const void* __restrict__ z, int z_dt, int ld_z, long long rows, int C, int groups,
+                            long long rows_per_group, const float* __restrict__ mean, const float* __restrict__ rstd,
+                            const float* __restrict__ shift, int act, int has_bn, const double* __restrict__ red,
+                            void* __restrict__ dz, int dz_dt, int ld_dz, float* __restrict__ dbeta, long long norm_rows,
+                            float dbeta_scale) {
+    const int nv = C >> 3;
+    const long long total = rows * nv;
+    const float inv_r = 1.f / (float)norm_rows;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / nv;
+        const int c = (int)(idx - r * nv) * 8;
+        const int g = (int)(r / rows_per_group);
+        const size_t gc = (size_t)g * C + c;
+        F8 mu, rs, sh;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { mu.v[i] = 0.f; rs.v[i] = 1.f; sh.v[i] = 0.f; }
+        if (mean) mu = load8f(mean, gc);
+        if (rstd) rs = load8f(rstd, gc);
+        if (shift) sh = load8f(shift, gc);
+        F8 zv;
+        if (z) zv = load8(z, z_dt, (size_t)r * ld_z + c);
+        else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) zv.v[i] = 0.f;
+        }
+        F8 d = load8(dA, d_dt, (size_t)r * ld_d + c);
+        if (dA2) {
+            const F8 d2 = load8(dA2, d_dt, (size_t)r * ld_d + c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d.v[i] += d2.v[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float u = zv.v[i] * rs.v[i] + sh.v[i];
+            float dv = d.v[i] * act_bwd(u, act);
+            if (has_bn) {
+                const float m0 = (float)red[(size_t)g * 2 * C + c + i] * inv_r;
+                const float m1 = (float)red[(size_t)g * 2 * C + C + c + i] * inv_r;
+                dv = rs.v[i] * (dv - m0 - (zv.v[i] - mu.v[i]) * rs.v[i] * m1);
+            }
+            d.v[i] = dv;
+        }
+        store8(dz, dz_dt, (size_t)r * ld_dz + c, d);
+    }
+    if (dbeta && blockIdx.x == 0) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            double t = 0.0;
+            for (int g = 0; g < groups; ++g) t += red[(size_t)g * 2 * C + c];
+            dbeta[c] += dbeta_scale * (float)t;
+        }
+    }
+}
+
+bool al16(const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; }
+
+void vec_reduce_launch_dims(long long rows_per_group, int C, int groups, dim3* grid, dim3* block) {
+    const int nv = C >> 3;
+    int bx = 1;
+    while (bx < nv && bx < 32) bx <<= 1;
+    const int by = 256 / bx;
+    const int gx = (nv + bx - 1) / bx;
+    long long gy = (rows_per_group + (long long)by * 4 - 1) / ((long long)by * 4);   // >= 4 rows per thread
+    long long cap = ((long long)num_sms() * 8) / ((long long)gx * groups);
+    if (cap < 1) cap = 1;
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    *grid = dim3(gx, (unsigned)gy, groups);
+    *block = dim3(bx, by);
+}
+
+int vec_ew_grid(long long total_vec) {
+    long long blocks = (total_vec + 255) / 256;
+    const long long cap = (long long)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+
 }  // namespace
 }  // namespace acg
 
@@ -206,6 +432,13 @@ int acg_bn_stats(const void* z, int dtype, long long rows, int C, int ld, int gr
                 "acg_bn_stats: rows=%lld C=%d ld=%d groups=%d", rows, C, ld, groups);
     ACG_REQUIRE(dt_ok(dtype), ACG_ERR_UNSUPPORTED, "acg_bn_stats: dtype %d", dtype);
     const long long rpg = rows / groups;
+    if (C % 8 == 0 && ld % 8 == 0 && al16(z)) {
+        dim3 grid, block;
+        vec_reduce_launch_dims(rpg, C, groups, &grid, &block);
+        vec_col_reduce_kernel<0><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+            z, dtype, ld, nullptr, nullptr, 0, 0, rpg, C, nullptr, nullptr, nullptr, 0, stats);
+        return check_launch("acg_bn_stats");
+    }
     col_reduce_kernel<0><<<reduce_grid(rpg, C, groups), dim3(kTX, kTY), 0, static_cast<cudaStream_t>(stream)>>>(
         z, dtype, ld, nullptr, nullptr, 0, 0, rpg, C, nullptr, nullptr, nullptr, 0, stats);
     return check_launch("acg_bn_stats");
@@ -229,6 +462,11 @@ int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in,
     ACG_REQUIRE(rows > 0 && C > 0 && ld_in >= C && ld_out >= C && groups > 0 && rows % groups == 0,
                 ACG_ERR_INVALID, "acg_bn_act_fwd: bad size");
     ACG_REQUIRE(dt_ok(z_dtype) && dt_ok(out_dtype), ACG_ERR_UNSUPPORTED, "acg_bn_act_fwd: dtype");
+    if (C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && al16(z) && al16(out) && al16(scale) && al16(shift)) {
+        vec_bn_act_fwd_kernel<<<vec_ew_grid(rows * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            z, z_dtype, rows, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
+        return check_launch("acg_bn_act_fwd");
+    }
     bn_act_fwd_kernel<<<ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         z, z_dtype, rows, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
     return check_launch("acg_bn_act_fwd");
@@ -245,6 +483,14 @@ int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d
                 ACG_ERR_INVALID, "acg_bn_act_bwd_reduce: bad size");
     ACG_REQUIRE(dt_ok(d_dtype) && dt_ok(z_dtype), ACG_ERR_UNSUPPORTED, "acg_bn_act_bwd_reduce: dtype");
     const long long rpg = rows / groups;
+    if (C % 8 == 0 && ld_d % 8 == 0 && (!z || ld_z % 8 == 0) && al16(z) && al16(dA) && al16(dA2) && al16(mean) &&
+        al16(rstd) && al16(shift)) {
+        dim3 grid, block;
+        vec_reduce_launch_dims(rpg, C, groups, &grid, &block);
+        vec_col_reduce_kernel<1><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+            z, z_dtype, ld_z, dA, dA2, d_dtype, ld_d, rpg, C, mean, rstd, shift, act, red);
+        return check_launch("acg_bn_act_bwd_reduce");
+    }
     col_reduce_kernel<1><<<reduce_grid(rpg, C, groups), dim3(kTX, kTY), 0, static_cast<cudaStream_t>(stream)>>>(
         z, z_dtype, ld_z, dA, dA2, d_dtype, ld_d, rpg, C, mean, rstd, shift, act, red);
     return check_launch("acg_bn_act_bwd_reduce");
@@ -262,6 +508,13 @@ int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d,
                 ACG_ERR_INVALID, "acg_bn_act_bwd_apply: bad size");
     ACG_REQUIRE(dt_ok(d_dtype) && dt_ok(z_dtype) && dt_ok(dz_dtype), ACG_ERR_UNSUPPORTED,
                 "acg_bn_act_bwd_apply: dtype");
+    if (C % 8 == 0 && ld_d % 8 == 0 && (!z || ld_z % 8 == 0) && ld_dz % 8 == 0 && al16(z) && al16(dA) && al16(dA2) &&
+        al16(dz) && al16(mean) && al16(rstd) && al16(shift)) {
+        vec_bn_act_bwd_apply_kernel<<<vec_ew_grid(rows * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, rows, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
+            dz, dz_dtype, ld_dz, dbeta, norm_rows > 0 ? norm_rows : rows / groups, dbeta_scale);
+        return check_launch("acg_bn_act_bwd_apply");
+    }
     bn_act_bwd_apply_kernel<<<ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, rows, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
         dz, dz_dtype, ld_dz, dbeta, norm_rows > 0 ? norm_rows : rows / groups, dbeta_scale);
