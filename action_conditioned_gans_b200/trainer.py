@@ -262,3 +262,33 @@ class Trainer:
                 current_state = g_state.clone()
         pred = predicted.permute(1, 0, 2, 3, 4).contiguous().cpu().numpy()
         return pred, current_frame[1:7].cpu().numpy()
+
+    # ---- checkpoints (replaces tf.train.Saver, train.py:215,274 / test.py:29-30) -------------------------------
+    def state_dict(self):
+        """All variables keyed by their TF names (HWIO layouts) + optimizer slots + step counters."""
+        out = {}
+        out.update(self.g_store.numpy())
+        out.update(self.d_store.numpy())
+        for oname, opt in (("g_opt", self.g_opt), ("g_pretrain_opt", self.g_pretrain_opt), ("d_opt", self.d_opt)):
+            out[oname + "/t"] = np.array(opt.t, dtype=np.int64)
+            for slot in ("m", "v", "ms"):
+                if hasattr(opt, slot):
+                    out[oname + "/" + slot] = getattr(opt, slot).cpu().numpy()
+        return out
+
+    def load_state_dict(self, sd):
+        self.g_store.load(sd)
+        self.d_store.load(sd)
+        for oname, opt in (("g_opt", self.g_opt), ("g_pretrain_opt", self.g_pretrain_opt), ("d_opt", self.d_opt)):
+            if oname + "/t" in sd:
+                opt.t = int(sd[oname + "/t"])
+            for slot in ("m", "v", "ms"):
+                if hasattr(opt, slot) and oname + "/" + slot in sd:
+                    getattr(opt, slot).copy_(torch.from_numpy(np.asarray(sd[oname + "/" + slot])))
+
+    def save(self, path):
+        np.savez(path, **self.state_dict())
+
+    def restore(self, path):
+        with np.load(path) as f:
+            self.load_state_dict({k: f[k] for k in f.files})

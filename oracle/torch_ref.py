@@ -292,7 +292,7 @@ class Trainer:
     # -- train.py:114-144 --------------------------------------------------------------
     def pretrain_g(self, img, nxt, act, state):
         out = self._step(img, nxt, act, state, "g_l2_loss", "g/", self.g_pretrain_opt, need_real=False)
-        return float(out["g_loss"])
+        return float(out["g_loss"].detach())
 
     def train_g(self, img, nxt, act, state):
         out = self._step(img, nxt, act, state, "g_loss", "g/", self.g_opt, need_real=False)

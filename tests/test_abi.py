@@ -1,0 +1,76 @@
+"""The C-ABI shared library: builds with nvcc (no GPU needed), loads, exports every symbol include/acg_b200.h
+declares, the ctypes table covers every one of them, and argument validation works without touching the device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "acg_b200.h")
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(acg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_lists_the_expected_families():
+    names = declared_functions()
+    for n in ("acg_dna_fwd", "acg_dna_bwd", "acg_conv_fprop_tc", "acg_conv_dgrad_tc", "acg_conv_wgrad_tc",
+              "acg_conv_fprop_f32", "acg_bn_stats", "acg_frame_losses", "acg_dlogit_loss", "acg_adam_step",
+              "acg_rmsprop_step", "acg_pack_weights"):
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from action_conditioned_gans_b200 import _lib
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (acg_[a-z0-9_]+)", out))
+    declared = set(declared_functions())
+    assert declared <= exported, "declared but not exported: %s" % sorted(declared - exported)
+    assert exported <= declared, "exported but not declared in the header: %s" % sorted(exported - declared)
+    bound = set(_lib.SIGNATURES) | set(_lib.PLAIN)
+    assert bound == declared, "ctypes table mismatch: %s" % sorted(bound ^ declared)
+    assert built_lib.acg_version() >= 100
+
+
+def test_sass_is_blackwell_native(built_lib):
+    """tcgen05.mma -> UTCHMMA, tcgen05.ld -> LDTM, bulk copies (TMA engine) -> UBLKCP, cp.async -> LDGSTS."""
+    from action_conditioned_gans_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if not sass:
+        pytest.skip("cuobjdump unavailable")
+    for mnemonic in ("UTCHMMA", "LDTM", "UBLKCP", "LDGSTS"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass          # no legacy mma.sync path
+
+
+def test_argument_validation_without_a_device(built_lib):
+    """Invalid arguments are rejected before any CUDA call (status < 0 and a message); nothing computes on the CPU."""
+    from action_conditioned_gans_b200 import _lib
+    lib = built_lib
+    assert lib.acg_dna_fwd(None, 0, None, None, 1, 8, 8, 3, 5, None) == -1
+    assert b"null" in lib.acg_last_error()
+    buf = C.create_string_buffer(4096)
+    p = C.cast(C.addressof(buf) + (-C.addressof(buf)) % 16, C.c_void_p)
+    assert lib.acg_dna_fwd(p, 0, p, p, 1, 8, 8, 3, 4, None) == -2          # K must be 5 or 6
+    assert lib.acg_dna_fwd(p, 0, p, p, 1, 8, 8, 4, 5, None) == -2          # C must be 3
+    assert lib.acg_dlogit_loss(p, 4, 7, 1.0, 1.0, p, None, None) == -1     # unknown loss kind
+    assert b"unexpected loss argument" in lib.acg_last_error()
+    shape = _lib.ConvShape(1, 8, 8, 4, 4, 4, 4, 5, 5, 3, 1, 1)             # stride 3
+    assert lib.acg_conv_fprop_f32(C.byref(shape), p, p, p, None) == -2
+    assert lib.acg_adam_step(None, p, p, p, 4, 1e-3, 0.9, 0.999, 1e-8, 1.0, -1.0, 1.0, None) == -1
+    with pytest.raises(RuntimeError, match="acg_dna_fwd failed"):
+        _lib.call("acg_dna_fwd", None, 0, None, None, 1, 8, 8, 3, 5, None)
+
+
+def test_pack_size_is_host_only(built_lib):
+    from action_conditioned_gans_b200 import kernels as K
+    s = K.conv_shape(4, 16, 16, 64, 128, 5, 2, "SAME")
+    assert K.pack_size(s, 0, 64) == 128 * 25 * 64
+    # dgrad pack: 4 parity classes with 3x3 + 3x2 + 2x3 + 2x2 = 25 taps in total
+    assert K.pack_size(s, 1, 128) == 64 * 25 * 128
+    assert (s.OH, s.OW, s.pad_t, s.pad_l) == (8, 8, 1, 1)

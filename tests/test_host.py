@@ -1,0 +1,91 @@
+"""Host-side logic that needs no GPU: layer tables, parameter layout, CLI flags (repair R6), schedule helpers."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_layer_tables_match_the_oracle():
+    from action_conditioned_gans_b200 import engine as E
+    from oracle import np_ref
+    for spec, ospec in ((E.g_dna_spec(5), np_ref.g_dna_spec(5)), (E.g_dna_spec(6), np_ref.g_dna_spec(6)),
+                        (E.g_direct_spec(), np_ref.g_direct_spec()), (E.d_spec(), np_ref.d_spec())):
+        assert [(L.name, L.kind, L.k, L.cin, L.cout, L.bn, L.bias) for L in spec] == [tuple(o) for o in ospec]
+        ours = {n: s for n, s in E.variable_list(spec)}
+        theirs = {k: v.shape for k, v in np_ref.init_params(ospec, np.random.RandomState(0)).items()}
+        assert ours == theirs
+
+
+def test_xavier_init_is_the_oracles():
+    from action_conditioned_gans_b200 import engine as E
+    from oracle import np_ref
+    a = E.xavier_init(E.d_spec(), np.random.RandomState(7))
+    b = np_ref.init_params(np_ref.d_spec(), np.random.RandomState(7))
+    assert all(np.array_equal(a[k], b[k]) for k in b)
+    w = a["d/conv1/weights"]
+    assert abs(np.abs(w).max() - np.sqrt(6.0 / (25 * 6 + 25 * 64))) < 1e-3
+
+
+def test_param_store_layout_on_cpu():
+    from action_conditioned_gans_b200 import engine as E
+    st = E.ParamStore(E.d_spec(), torch.device("cpu"))
+    assert st.numel >= 4755137 and st.numel % 4 == 0
+    for name, (off, n, shape) in st.offsets.items():
+        assert off % 4 == 0 and st.views[name].shape == torch.Size(shape)
+    assert st.views["d/conv6/weights"].data_ptr() == st.flat.data_ptr() + 4 * st.offsets["d/conv6/weights"][0]
+
+
+def test_cli_flags_repair_r6():
+    from action_conditioned_gans_b200.train import build_parser
+    p = build_parser()
+    a = p.parse_args(["IN", "OUT"])
+    assert (a.adv, a.dna, a.loss, a.opt) == (True, True, "bce", "adam")          # README defaults
+    a = p.parse_args(["IN", "OUT", "--dna", "True", "--adv", "True", "--loss", "bce", "--opt", "adam"])
+    assert (a.adv, a.dna) == (True, True)                                       # BASELINE.json configs[0] spelling
+    a = p.parse_args(["IN", "OUT", "--dna", "False", "--adv", "--loss", "wass", "--opt", "rmsprop"])
+    assert (a.adv, a.dna, a.loss, a.opt) == (True, False, "wass", "rmsprop")
+    from action_conditioned_gans_b200.test import build_parser as tp
+    t = tp().parse_args(["M", "F.npy", "A.npy", "O", "--dna"])
+    assert t.dna is True and t.model_path == "M"
+
+
+def test_bad_flag_values_raise_like_the_reference():
+    from action_conditioned_gans_b200.trainer import Trainer
+    with pytest.raises(ValueError, match="unexpected loss argument"):
+        Trainer(None, True, "hinge", "adam", True)
+    with pytest.raises(ValueError, match="unexpected opt argument"):
+        Trainer(None, True, "bce", "sgd", True)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from action_conditioned_gans_b200 import kernels as K
+    from action_conditioned_gans_b200.trainer import Trainer
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Trainer(None, True, "bce", "adam", True, batch_size=2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        K.dna_fwd(torch.zeros(1, 8, 8, 25), torch.zeros(1, 8, 8, 3), torch.zeros(1, 8, 8, 3), 5)
+
+
+def test_frame_pair_masks_and_schedule():
+    from action_conditioned_gans_b200.util import build_all_mask
+    m = build_all_mask(7)
+    assert m.shape == (6, 7) and m.sum() == 6 and not m[:, 6].any()           # t in [0,5], paired with t+1
+    end = np.roll(m, 1, axis=1)
+    assert (np.argmax(end, 1) == np.argmax(m, 1) + 1).all()
+
+
+def test_synthetic_data_shapes():
+    from action_conditioned_gans_b200.train import SyntheticPush
+    img, act = SyntheticPush(4, 0).get_batch()
+    assert img.shape == (4, 7, 64, 64, 3) and act.shape == (4, 7, 10)
+    assert img.min() >= -1 and img.max() <= 1 and img.dtype == np.float32
+
+
+def test_save_samples_layout(tmp_path):
+    from action_conditioned_gans_b200.util import save_samples
+    a = np.random.uniform(-1, 1, (2, 1, 64, 64, 3))
+    save_samples(str(tmp_path), a, a, a, 3)
+    assert (tmp_path / "sample3" / "vid1" / "generated0.png").exists()
+    assert (tmp_path / "sample3" / "vid0" / "ground_truth0.png").exists()
+    save_samples(str(tmp_path), np.repeat(a, 3, 1), np.repeat(a, 3, 1), np.array([0]), 4, gif=True)
+    assert (tmp_path / "sample4" / "vid0" / "generated.gif").exists()
