@@ -36,7 +36,8 @@ _FP = C.POINTER(TcArgs)
 # name -> argtypes; must list every function include/acg_b200.h declares (tests/test_abi.py checks this)
 SIGNATURES = {
     "acg_dna_fwd": [_P, _I, _P, _P, _I, _I, _I, _I, _I, _P],
-    "acg_dna_bwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P],
+    "acg_dna_bwd": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P],
+    "acg_bias_grad": [_P, _I, _F, _P, _P],
     "acg_conv_fprop_f32": [_SP, _P, _P, _P, _P],
     "acg_conv_dgrad_f32": [_SP, _P, _P, _P, _P],
     "acg_conv_wgrad_f32": [_SP, _P, _P, _P, _P],
@@ -56,8 +57,9 @@ SIGNATURES = {
     "acg_frame_losses": [_P, _P, _I, _I, _I, _P, _P, _F, _F, _P, _I, _I, _P],
     "acg_dlogit_loss": [_P, _I, _I, _F, _F, _P, _P, _P],
     "acg_state_loss": [_P, _P, _I, _F, _F, _P, _P, _P],
-    "acg_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _P],
-    "acg_rmsprop_step": [_P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P],
+    "acg_debug_umma_shift": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "acg_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _P, _P],
+    "acg_rmsprop_step": [_P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P],
 }
 # calls that return a plain value instead of a status
 PLAIN = {"acg_version": ([], C.c_int), "acg_last_error": ([], C.c_char_p),

@@ -29,6 +29,8 @@ constexpr int kThreads = kRows * kMaxW;  // one pixel per thread
 constexpr int kPadCols = 4;              // zero columns left and right (4*12 B keeps rows 16 B aligned)
 constexpr int kRowStride = (kMaxW + 2 * kPadCols) * 3;  // floats per staged image row
 
+constexpr int pad16(int v) { return (v + 15) / 16 * 16; }
+
 template <int K, typename LT, bool BWD> struct StageLayout {
     static constexpr int KK = K * K;
     static constexpr int NR = kRows + K - 1;  // band rows + halo
@@ -40,17 +42,22 @@ template <int K, typename LT, bool BWD> struct StageLayout {
     static constexpr int bytes = ((off_dy + dy_bytes + 127) / 128) * 128;
 };
 
-template <int K, typename LT, bool BWD, int STAGES>
+// PADOUT (backward only): dlogits are written as bf16 with the channel count padded to 16 (zeros in the pad) into
+// a separate double-buffered shared-memory tile -- the layout the tensor-core convolutions consume -- instead of
+// in place over the staged logits.
+template <int K, typename LT, bool BWD, int STAGES, bool PADOUT>
 __global__ void __launch_bounds__(kThreads)
 dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const float* __restrict__ dy,
-           float* __restrict__ out, LT* __restrict__ dlogits, int B, int H, int W) {
+           float* __restrict__ out, void* __restrict__ dlogits_v, int B, int H, int W) {
     using L = StageLayout<K, LT, BWD>;
     constexpr int KK = K * K;
+    constexpr int LDO = pad16(KK);
     constexpr int PB = (K - 1) / 2;  // TF SAME: pad_before = (K-1)/2, the odd element goes after
-    // forward keeps STAGES-1 bands in flight; backward one fewer so that the bulk store of the
+    // forward keeps STAGES-1 bands in flight; the in-place backward one fewer so that the bulk store of the
     // previous band may still be reading its stage while the next load is issued.
-    constexpr int PREFETCH = BWD ? STAGES - 2 : STAGES - 1;
+    constexpr int PREFETCH = (BWD && !PADOUT) ? STAGES - 2 : STAGES - 1;
     static_assert(PREFETCH >= 1, "need a deeper ring");
+    LT* dlogits = static_cast<LT*>(dlogits_v);
 
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -117,7 +124,7 @@ dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const f
         if (tid == 0) {
             int nb = band + PREFETCH * gridDim.x;
             if (nb < nbands) {
-                if (BWD) bulk_wait_read<1>();  // the store that last read this stage has drained
+                if (BWD && !PADOUT) bulk_wait_read<1>();  // the store that last read this stage has drained
                 issue(nb, (it + PREFETCH) % STAGES);
             }
         }
@@ -128,8 +135,8 @@ dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const f
         const float* tile = reinterpret_cast<const float*>(st + L::off_img);
         const int r0 = (band % bands_per_img) * kRows;
 
+        float e[KK];
         if (active) {
-            float e[KK];
             float m = -INFINITY;
 #pragma unroll
             for (int p = 0; p < KK; ++p) {
@@ -181,10 +188,38 @@ dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const f
                         dot = fmaf(e[a * K + c], gv, dot);
                     }
                 }
+                if (!PADOUT) {
 #pragma unroll
-                for (int p = 0; p < KK; ++p) st_from_float<LT>(lg, (size_t)tid * KK + p, e[p] * (g[p] - dot));
-                fence_proxy_async();  // make the in-place dlogits visible to the bulk-copy engine
+                    for (int p = 0; p < KK; ++p) st_from_float<LT>(lg, (size_t)tid * KK + p, e[p] * (g[p] - dot));
+                    fence_proxy_async();  // make the in-place dlogits visible to the bulk-copy engine
+                } else {
+#pragma unroll
+                    for (int p = 0; p < KK; ++p) e[p] *= (g[p] - dot);
+                }
             }
+        }
+        if (BWD && PADOUT) {
+            // the bulk store that read this out tile two bands ago must have drained before it is overwritten
+            if (tid == 0) bulk_wait_read<1>();
+            __syncthreads();
+            __nv_bfloat16* ot = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)STAGES * L::bytes) +
+                                (size_t)(it & 1) * kThreads * LDO;
+            if (active) {
+                __nv_bfloat16* row = ot + (size_t)tid * LDO;
+#pragma unroll
+                for (int p = 0; p < LDO; p += 2) {
+                    const float v0 = p < KK ? e[p < KK ? p : 0] : 0.f;
+                    const float v1 = p + 1 < KK ? e[p + 1 < KK ? p + 1 : 0] : 0.f;
+                    *reinterpret_cast<__nv_bfloat162*>(row + p) = __floats2bfloat162_rn(v0, v1);
+                }
+                fence_proxy_async();
+            }
+            __syncthreads();
+            if (tid == 0) {
+                bulk_s2g(static_cast<__nv_bfloat16*>(dlogits_v) + (size_t)band * npx * LDO, ot, (uint32_t)(npx * LDO * 2));
+                bulk_commit();
+            }
+            continue;
         }
         __syncthreads();  // every thread is done with this stage
         if (BWD && tid == 0) {
@@ -195,12 +230,12 @@ dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const f
     if (BWD && tid == 0) bulk_wait<0>();  // smem must stay alive until the last store has read it
 }
 
-template <int K, typename LT, bool BWD, int STAGES>
+template <int K, typename LT, bool BWD, int STAGES, bool PADOUT = false>
 int launch(const void* logits, const float* img, const float* dy, float* out, void* dlogits, int B, int H,
            int W, cudaStream_t stream) {
     using L = StageLayout<K, LT, BWD>;
-    auto kern = dna_kernel<K, LT, BWD, STAGES>;
-    const int smem = STAGES * L::bytes;
+    auto kern = dna_kernel<K, LT, BWD, STAGES, PADOUT>;
+    const int smem = STAGES * L::bytes + (PADOUT ? 2 * kThreads * pad16(K * K) * 2 : 0);
     static int occ = 0;  // per template instance
     if (occ == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
@@ -218,8 +253,7 @@ int launch(const void* logits, const float* img, const float* dy, float* out, vo
     const int nbands = B * (H / kRows);
     int grid = num_sms() * occ;
     if (grid > nbands) grid = nbands;
-    kern<<<grid, kThreads, smem, stream>>>(static_cast<const LT*>(logits), img, dy, out,
-                                           static_cast<LT*>(dlogits), B, H, W);
+    kern<<<grid, kThreads, smem, stream>>>(static_cast<const LT*>(logits), img, dy, out, dlogits, B, H, W);
     return check_launch(BWD ? "acg_dna_bwd" : "acg_dna_fwd");
 }
 
@@ -256,11 +290,22 @@ int acg_dna_fwd(const void* logits, int logits_dtype, const float* img, float* o
     return launch<6, __nv_bfloat16, false, 3>(logits, img, nullptr, out, nullptr, B, H, W, s);
 }
 
-int acg_dna_bwd(const void* logits, int logits_dtype, const float* img, const float* dy, void* dlogits, int B,
-                int H, int W, int C, int K, void* stream) {
+int acg_dna_bwd(const void* logits, int logits_dtype, const float* img, const float* dy, void* dlogits,
+                int dlogits_dtype, int ld_dlogits, int B, int H, int W, int C, int K, void* stream) {
     using namespace acg;
     int rc = validate(logits, img, B, H, W, C, K, logits_dtype);
     if (rc) return rc;
+    const bool dense = dlogits_dtype == logits_dtype && ld_dlogits == K * K;
+    const bool padded = logits_dtype == ACG_F32 && dlogits_dtype == ACG_BF16 && ld_dlogits == pad16(K * K);
+    ACG_REQUIRE(dense || padded, ACG_ERR_UNSUPPORTED,
+                "acg_dna_bwd: dlogits must be dense in the logits dtype, or bf16 with ld = K*K rounded up to 16");
+    if (padded) {
+        ACG_REQUIRE(dy && dlogits && ((uintptr_t)dy % 16) == 0 && ((uintptr_t)dlogits % 16) == 0, ACG_ERR_INVALID,
+                    "acg_dna_bwd: null or misaligned pointer");
+        cudaStream_t s2 = static_cast<cudaStream_t>(stream);
+        if (K == 5) return launch<5, float, true, 3, true>(logits, img, dy, nullptr, dlogits, B, H, W, s2);
+        return launch<6, float, true, 3, true>(logits, img, dy, nullptr, dlogits, B, H, W, s2);
+    }
     ACG_REQUIRE(dy && dlogits, ACG_ERR_INVALID, "acg_dna_bwd: null pointer");
     ACG_REQUIRE(((uintptr_t)dy % 16) == 0 && ((uintptr_t)dlogits % 16) == 0, ACG_ERR_INVALID,
                 "acg_dna_bwd: buffers must be 16-byte aligned");

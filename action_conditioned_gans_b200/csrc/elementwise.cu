@@ -174,6 +174,11 @@ tile_actions_kernel(const float* __restrict__ actions, int B, int hw, int A, voi
     }
 }
 
+__global__ void bias_grad_kernel(const double* __restrict__ red, int C, float scale, float* __restrict__ dbias) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < C) dbias[c] += scale * (float)red[c];
+}
+
 int ew_grid(long long total) {
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)num_sms() * 16;
@@ -265,33 +270,50 @@ vec_col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void
             if (rstd) rs = load8f(rstd + (size_t)g * C, c);
             if (shift) sh = load8f(shift + (size_t)g * C, c);
         }
+        constexpr int U = MODE == 0 ? 4 : 2;     // independent row vectors in flight per thread
+        const long long rstep = (long long)gridDim.y * by;
         int k = 0;
-        for (long long r = (long long)blockIdx.y * by + threadIdx.y; r < rows_per_group; r += (long long)gridDim.y * by) {
-            F8 zv;
-            if (z) zv = load8(z, z_dt, (size_t)(r_begin + r) * ld_z + c);
-            else {
+        for (long long r0 = (long long)blockIdx.y * by + threadIdx.y; r0 < rows_per_group; r0 += rstep * U) {
+            F8 zv[U], da[U];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) zv.v[i] = 0.f;
-            }
-            if (MODE == 0) {
+            for (int u = 0; u < U; ++u) {
+                const long long r = r0 + u * rstep;
+                const bool ok = r < rows_per_group;
+                if (z && ok) zv[u] = load8(z, z_dt, (size_t)(r_begin + r) * ld_z + c);
+                else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { s0[i] += zv.v[i]; s1[i] += zv.v[i] * zv.v[i]; }
-            } else {
-                F8 da = load8(dA, d_dt, (size_t)(r_begin + r) * ld_d + c);
-                if (dA2) {
-                    const F8 db = load8(dA2, d_dt, (size_t)(r_begin + r) * ld_d + c);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) da.v[i] += db.v[i];
+                    for (int i = 0; i < 8; ++i) zv[u].v[i] = 0.f;
                 }
+                if (MODE == 1) {
+                    if (ok) {
+                        da[u] = load8(dA, d_dt, (size_t)(r_begin + r) * ld_d + c);
+                        if (dA2) {
+                            const F8 db = load8(dA2, d_dt, (size_t)(r_begin + r) * ld_d + c);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float u = zv.v[i] * rs.v[i] + sh.v[i];
-                    const float dzh = da.v[i] * act_bwd(u, act);
-                    s0[i] += dzh;
-                    s1[i] += dzh * ((zv.v[i] - mu.v[i]) * rs.v[i]);
+                            for (int i = 0; i < 8; ++i) da[u].v[i] += db.v[i];
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) da[u].v[i] = 0.f;
+                    }
                 }
             }
-            if (++k == 32) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (MODE == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { s0[i] += zv[u].v[i]; s1[i] += zv[u].v[i] * zv[u].v[i]; }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float uu = zv[u].v[i] * rs.v[i] + sh.v[i];
+                        const float dzh = da[u].v[i] * act_bwd(uu, act);
+                        s0[i] += dzh;
+                        s1[i] += dzh * ((zv[u].v[i] - mu.v[i]) * rs.v[i]);
+                    }
+                }
+            }
+            if (++k == 16) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { d0[i] += s0[i]; d1[i] += s1[i]; s0[i] = s1[i] = 0.f; }
                 k = 0;
@@ -320,21 +342,33 @@ vec_bn_act_fwd_kernel(const void* __restrict__ z, int z_dt, long long rows, int 
                       int o_dt, int ld_out) {
     const int nv = C >> 3;
     const long long total = rows * nv;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long r = idx / nv;
-        const int c = (int)(idx - r * nv) * 8;
-        const size_t gc = (size_t)(r / rows_per_group) * C + c;
-        F8 u = load8(z, z_dt, (size_t)r * ld_in + c);
-        if (scale) { const F8 sc = load8f(scale, gc);
+    constexpr int U = 4;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += step * U) {
+        F8 u[U];
+        long long rr[U];
+        int cc[U];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) u.v[i] *= sc.v[i]; }
-        if (shift) { const F8 sh = load8f(shift, gc);
+        for (int q = 0; q < U; ++q) {
+            const long long idx = idx0 + q * step;
+            rr[q] = idx / nv;
+            cc[q] = (int)(idx - rr[q] * nv) * 8;
+            if (idx < total) u[q] = load8(z, z_dt, (size_t)rr[q] * ld_in + cc[q]);
+        }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) u.v[i] += sh.v[i]; }
+        for (int q = 0; q < U; ++q) {
+            if (idx0 + q * step >= total) break;
+            const size_t gc = (size_t)(rr[q] / rows_per_group) * C + cc[q];
+            if (scale) { const F8 sc = load8f(scale, gc);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) u.v[i] = act_fwd(u.v[i], act);
-        store8(out, o_dt, (size_t)r * ld_out + c, u);
+                for (int i = 0; i < 8; ++i) u[q].v[i] *= sc.v[i]; }
+            if (shift) { const F8 sh = load8f(shift, gc);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) u[q].v[i] += sh.v[i]; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[q].v[i] = act_fwd(u[q].v[i], act);
+            store8(out, o_dt, (size_t)rr[q] * ld_out + cc[q], u[q]);
+        }
     }
 }
 
@@ -348,42 +382,57 @@ vec_bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict_
     const int nv = C >> 3;
     const long long total = rows * nv;
     const float inv_r = 1.f / (float)norm_rows;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const long long r = idx / nv;
-        const int c = (int)(idx - r * nv) * 8;
-        const int g = (int)(r / rows_per_group);
-        const size_t gc = (size_t)g * C + c;
-        F8 mu, rs, sh;
+    constexpr int U = 2;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += step * U) {
+        F8 zv[U], d[U];
+        long long rr[U];
+        int cc[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { mu.v[i] = 0.f; rs.v[i] = 1.f; sh.v[i] = 0.f; }
-        if (mean) mu = load8f(mean, gc);
-        if (rstd) rs = load8f(rstd, gc);
-        if (shift) sh = load8f(shift, gc);
-        F8 zv;
-        if (z) zv = load8(z, z_dt, (size_t)r * ld_z + c);
-        else {
+        for (int q = 0; q < U; ++q) {
+            const long long idx = idx0 + q * step;
+            rr[q] = idx / nv;
+            cc[q] = (int)(idx - rr[q] * nv) * 8;
+            const bool ok = idx < total;
+            if (z && ok) zv[q] = load8(z, z_dt, (size_t)rr[q] * ld_z + cc[q]);
+            else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) zv.v[i] = 0.f;
-        }
-        F8 d = load8(dA, d_dt, (size_t)r * ld_d + c);
-        if (dA2) {
-            const F8 d2 = load8(dA2, d_dt, (size_t)r * ld_d + c);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) d.v[i] += d2.v[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float u = zv.v[i] * rs.v[i] + sh.v[i];
-            float dv = d.v[i] * act_bwd(u, act);
-            if (has_bn) {
-                const float m0 = (float)red[(size_t)g * 2 * C + c + i] * inv_r;
-                const float m1 = (float)red[(size_t)g * 2 * C + C + c + i] * inv_r;
-                dv = rs.v[i] * (dv - m0 - (zv.v[i] - mu.v[i]) * rs.v[i] * m1);
+                for (int i = 0; i < 8; ++i) zv[q].v[i] = 0.f;
             }
-            d.v[i] = dv;
+            if (ok) {
+                d[q] = load8(dA, d_dt, (size_t)rr[q] * ld_d + cc[q]);
+                if (dA2) {
+                    const F8 d2 = load8(dA2, d_dt, (size_t)rr[q] * ld_d + cc[q]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) d[q].v[i] += d2.v[i];
+                }
+            }
         }
-        store8(dz, dz_dt, (size_t)r * ld_dz + c, d);
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            if (idx0 + q * step >= total) break;
+            const int c = cc[q];
+            const int g = (int)(rr[q] / rows_per_group);
+            const size_t gc = (size_t)g * C + c;
+            F8 mu, rs, sh;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { mu.v[i] = 0.f; rs.v[i] = 1.f; sh.v[i] = 0.f; }
+            if (mean) mu = load8f(mean, gc);
+            if (rstd) rs = load8f(rstd, gc);
+            if (shift) sh = load8f(shift, gc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float u = zv[q].v[i] * rs.v[i] + sh.v[i];
+                float dv = d[q].v[i] * act_bwd(u, act);
+                if (has_bn) {
+                    const float m0 = (float)red[(size_t)g * 2 * C + c + i] * inv_r;
+                    const float m1 = (float)red[(size_t)g * 2 * C + C + c + i] * inv_r;
+                    dv = rs.v[i] * (dv - m0 - (zv[q].v[i] - mu.v[i]) * rs.v[i] * m1);
+                }
+                d[q].v[i] = dv;
+            }
+            store8(dz, dz_dt, (size_t)rr[q] * ld_dz + c, d[q]);
+        }
     }
     if (dbeta && blockIdx.x == 0) {
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -519,6 +568,13 @@ int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d,
         dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, rows, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
         dz, dz_dtype, ld_dz, dbeta, norm_rows > 0 ? norm_rows : rows / groups, dbeta_scale);
     return check_launch("acg_bn_act_bwd_apply");
+}
+
+int acg_bias_grad(const double* red, int C, float scale, float* dbias, void* stream) {
+    using namespace acg;
+    ACG_REQUIRE(red && dbias && C > 0, ACG_ERR_INVALID, "acg_bias_grad: bad argument");
+    bias_grad_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(red, C, scale, dbias);
+    return check_launch("acg_bias_grad");
 }
 
 int acg_copy_channels(const void* src, int src_dtype, int ld_src, int off_src, void* dst, int dst_dtype,

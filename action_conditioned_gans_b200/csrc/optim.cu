@@ -20,7 +20,9 @@ __device__ __forceinline__ float clipf(float p, float lo, float hi, bool do_clip
 
 __global__ void __launch_bounds__(kThreads)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-            long long n, float lr_t, float b1, float b2, float eps, float lo, float hi, float gs) {
+            long long n, float lr_t, float b1, float b2, float eps, float lo, float hi, float gs,
+            const float* __restrict__ lr_dev) {
+    if (lr_dev) lr_t = *lr_dev;   // CUDA-graph replays: the bias-corrected rate changes every step
     const bool do_clip = lo <= hi;
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -54,7 +56,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 
 __global__ void __launch_bounds__(kThreads)
 rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ ms, long long n, float lr,
-               float decay, float eps, float lo, float hi, float gs) {
+               float decay, float eps, float lo, float hi, float gs, const float* __restrict__ lr_dev) {
+    if (lr_dev) lr = *lr_dev;
     const bool do_clip = lo <= hi;
     const long long n4 = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -94,26 +97,26 @@ int grid_for(long long n) {
 extern "C" {
 
 int acg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2,
-                  float eps, float clip_lo, float clip_hi, float grad_scale, void* stream) {
+                  float eps, float clip_lo, float clip_hi, float grad_scale, const float* lr_t_dev, void* stream) {
     using namespace acg;
     ACG_REQUIRE(p && g && m && v, ACG_ERR_INVALID, "acg_adam_step: null pointer");
     ACG_REQUIRE(n > 0, ACG_ERR_INVALID, "acg_adam_step: n=%lld", n);
     ACG_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0, ACG_ERR_INVALID,
                 "acg_adam_step: buffers must be 16-byte aligned");
     adam_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr_t, b1, b2, eps,
-                                                                                clip_lo, clip_hi, grad_scale);
+                                                                                clip_lo, clip_hi, grad_scale, lr_t_dev);
     return check_launch("acg_adam_step");
 }
 
 int acg_rmsprop_step(float* p, const float* g, float* ms, long long n, float lr, float decay, float eps,
-                     float clip_lo, float clip_hi, float grad_scale, void* stream) {
+                     float clip_lo, float clip_hi, float grad_scale, const float* lr_dev, void* stream) {
     using namespace acg;
     ACG_REQUIRE(p && g && ms, ACG_ERR_INVALID, "acg_rmsprop_step: null pointer");
     ACG_REQUIRE(n > 0, ACG_ERR_INVALID, "acg_rmsprop_step: n=%lld", n);
     ACG_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)ms) % 16) == 0, ACG_ERR_INVALID,
                 "acg_rmsprop_step: buffers must be 16-byte aligned");
     rmsprop_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, g, ms, n, lr, decay, eps,
-                                                                                   clip_lo, clip_hi, grad_scale);
+                                                                                   clip_lo, clip_hi, grad_scale, lr_dev);
     return check_launch("acg_rmsprop_step");
 }
 

@@ -165,15 +165,16 @@ class NetRun:
         self.bf16 = precision == "bf16"
         self.adt = torch.bfloat16 if self.bf16 else torch.float32
         self.layers = {}
-        n_stat = sum(4 * L.cout for L in store.spec)
+        n_stat = sum(4 * ru16(L.cout) for L in store.spec)
         self.f64 = torch.zeros(n_stat, dtype=torch.float64, device=device)   # [stats | red] per layer
         soff = 0
         for L in store.spec:
             st = _LayerState()
             st.spec = L
-            st.stats = self.f64[soff:soff + 2 * L.cout]
-            st.red = self.f64[soff + 2 * L.cout:soff + 4 * L.cout]
-            soff += 4 * L.cout
+            cp = ru16(L.cout)
+            st.stats = self.f64[soff:soff + 2 * cp]
+            st.red = self.f64[soff + 2 * cp:soff + 4 * cp]
+            soff += 4 * cp
             st.mean = torch.zeros(L.cout, device=device)
             st.rstd = torch.ones(L.cout, device=device)
             st.scale = torch.ones(L.cout, device=device)
@@ -188,7 +189,7 @@ class NetRun:
         """zero-initialised so that pad channels stay zero forever (kernels only write the real channels)"""
         return torch.zeros(self.B, h, w, self.ld(c), dtype=dtype or self.adt, device=self.device)
 
-    def plan(self, name, h, w, ld_in, fused_out=False):
+    def plan(self, name, h, w, ld_in, fused_out=False, dx=True, dx_dtype=None):
         """Fix the geometry of layer `name` for an input of h x w pixels with channel stride ld_in.
         fused_out: (bf16 only) a layer without batch-norm and activation whose bias is added in the conv epilogue,
         writing the caller's output buffer directly; no raw z is kept."""
@@ -209,7 +210,8 @@ class NetRun:
         st.fused = bool(fused_out and self.bf16 and not L.bn and L.act == "none")
         st.z = None if st.fused else torch.empty(B, oh, ow, st.ldz, dtype=self.adt, device=self.device)
         st.dz = torch.zeros(B, oh, ow, st.ldz, dtype=self.adt, device=self.device)
-        st.dx = None
+        # gradient w.r.t. the layer input (preallocated: nothing is allocated inside a step / a CUDA graph)
+        st.dx = torch.zeros(B, h, w, ld_in, dtype=dx_dtype or self.adt, device=self.device) if dx else None
         if self.bf16 and name not in self.store.packs:
             # forward / backward-data packs; conv2d_transpose swaps the roles (see include/acg_b200.h)
             fwd_which, bwd_which = (0, 1) if L.kind == "conv" else (1, 0)
@@ -262,18 +264,27 @@ class NetRun:
             mean, rstd, shift = st.mean, st.rstd, st.shift
         else:
             mean, rstd, shift = None, None, (self.store.views[name + "/biases"] if L.bias else None)
-        K.bn_act_bwd_reduce(dA, dA2, ld_d, st.z, st.ldz, st.rows, L.cout, 1, mean, rstd, shift, L.act, st.red)
-        world = 1
-        if self.dp is not None:
-            world = self.dp.world
-            if L.bn:
-                self.dp.allreduce_sum(st.red)
-        dpar = None
-        if need_dw:
-            dpar = self.store.gviews[name + ("/BatchNorm/beta" if L.bn else "/biases")]
-        K.bn_act_bwd_apply(dA, dA2, ld_d, st.z, st.ldz, st.rows, L.cout, 1, mean, rstd, shift, L.act, L.bn,
-                           st.red, st.dz, dpar, norm_rows=st.rows * world,
-                           dbeta_scale=(1.0 / world if L.bn else 1.0), ld_dz=st.ldz)
+        if dA is st.dz:
+            # a fused (no batch-norm, no activation) layer whose producer already wrote dz in operand layout
+            # (acg_dna_bwd -> g/tconv4): only the bias gradient (column sums) is left to do
+            assert st.fused and dA2 is None
+            if need_dw and L.bias:
+                K.bn_act_bwd_reduce(st.dz, None, st.ldz, None, st.ldz, st.rows, st.ldz, 1, None, None, None, "none",
+                                    st.red)
+                K.bias_grad(st.red, L.cout, 1.0, self.store.gviews[name + "/biases"])
+        else:
+            K.bn_act_bwd_reduce(dA, dA2, ld_d, st.z, st.ldz, st.rows, L.cout, 1, mean, rstd, shift, L.act, st.red)
+            world = 1
+            if self.dp is not None:
+                world = self.dp.world
+                if L.bn:
+                    self.dp.allreduce_sum(st.red)
+            dpar = None
+            if need_dw:
+                dpar = self.store.gviews[name + ("/BatchNorm/beta" if L.bn else "/biases")]
+            K.bn_act_bwd_apply(dA, dA2, ld_d, st.z, st.ldz, st.rows, L.cout, 1, mean, rstd, shift, L.act, L.bn,
+                               st.red, st.dz, dpar, norm_rows=st.rows * world,
+                               dbeta_scale=(1.0 / world if L.bn else 1.0), ld_dz=st.ldz)
         if need_dw:
             dw = self.store.gviews[name + "/weights"]
             if self.bf16:
@@ -287,8 +298,7 @@ class NetRun:
                 K.conv_wgrad_f32(st.shape, st.dz, st.x, dw)
         if need_dx:
             if st.dx is None:
-                st.dx = torch.zeros(self.B, st.in_hw[0], st.in_hw[1], st.ld_in, dtype=dx_dtype or self.adt,
-                                    device=self.device)
+                raise RuntimeError("layer %s was planned without an input-gradient buffer" % name)
             if self.bf16:
                 pk = self.store.packs[name]
                 fn = K.conv_dgrad_tc if L.kind == "conv" else K.conv_fprop_tc
@@ -312,7 +322,7 @@ class GeneratorRun(NetRun):
         h = w = IMG
         ld = self.ld(3)
         for n in ["g/conv1", "g/conv2", "g/conv3", "g/conv4"]:
-            h, w = self.plan(n, h, w, ld)
+            h, w = self.plan(n, h, w, ld, dx=(n != "g/conv1"))
             ld = self.ld(Ls[n].spec.cout)
         c4 = Ls["g/conv4"].spec.cout
         self.cat_c = c4
@@ -338,7 +348,8 @@ class GeneratorRun(NetRun):
         if dna:
             kk = ksize * ksize
             self.logits = torch.empty(B, IMG, IMG, kk, device=dev)               # fp32, dense: what acg_dna_* reads
-            self.dlogits = torch.empty(B, IMG, IMG, kk, device=dev)
+            # bf16 path: acg_dna_bwd writes g/tconv4's dz (bf16, channels padded to 16) directly
+            self.dlogits = Ls["g/tconv4"].dz if self.bf16 else torch.empty(B, IMG, IMG, kk, device=dev)
             self.state = torch.empty(B, STATE_DIM, device=dev)
             self.dstate = torch.empty(B, STATE_DIM, device=dev)
         else:
@@ -382,7 +393,7 @@ class GeneratorRun(NetRun):
         Ls = self.layers
         if self.dna:
             K.dna_bwd(self.logits, self.img, self.dg_out, self.dlogits, self.ksize)
-            d = self.layer_bwd("g/tconv4", self.dlogits, self.ksize * self.ksize)
+            d = self.layer_bwd("g/tconv4", self.dlogits, self.dlogits.shape[3])
         else:
             d = self.layer_bwd("g/tconv4", self.dg_out, 3)
         d3 = self.layer_bwd("g/tconv3", d, d.shape[3])
@@ -408,7 +419,7 @@ class DiscriminatorRun(NetRun):
         Ls = self.layers
         self.d_in = self.act_buffer(IMG, IMG, 6)                                 # train.py:64,68
         h = w = IMG
-        h, w = self.plan("d/conv1", h, w, self.d_in.shape[3])
+        h, w = self.plan("d/conv1", h, w, self.d_in.shape[3], dx_dtype=torch.float32)
         h, w = self.plan("d/conv2", h, w, self.ld(64))
         self.cat = self.act_buffer(h, w, 128 + ACTION_DIM)                       # models.py:84 (R3: 16x16)
         ld = self.cat.shape[3]
@@ -459,6 +470,7 @@ class TFOptimizer:
         if kind not in ("adam", "rmsprop"):
             raise ValueError("unexpected opt argument")
         self.kind, self.store, self.t = kind, store, 0
+        self.lr_dev = torch.zeros(1, device=store.flat.device)
         if kind == "adam":
             self.lr = 1e-3                                                       # train.py:20
             self.m = torch.zeros_like(store.flat)
@@ -467,12 +479,23 @@ class TFOptimizer:
             self.lr = 5e-5                                                       # train.py:93
             self.ms = torch.ones_like(store.flat)                                # TF initialises ms to ONE
 
-    def step(self, clip=K.NO_CLIP, grad_scale=1.0):
+    def tick(self):
+        """Host side of a step: advance t and publish this step's (bias-corrected) rate to the device scalar the
+        kernel reads.  Kept apart from enqueue() so that the kernel launches can live inside a CUDA graph."""
         self.t += 1
-        s = self.store
+        lr_t = self.lr
         if self.kind == "adam":
             lr_t = self.lr * math.sqrt(1.0 - 0.999 ** self.t) / (1.0 - 0.9 ** self.t)
-            K.adam_step(s.flat, s.grad, self.m, self.v, lr_t, clip=clip, grad_scale=grad_scale)
+        self.lr_dev.fill_(lr_t)
+
+    def enqueue(self, clip=K.NO_CLIP, grad_scale=1.0):
+        s = self.store
+        if self.kind == "adam":
+            K.adam_step(s.flat, s.grad, self.m, self.v, 0.0, clip=clip, grad_scale=grad_scale, lr_dev=self.lr_dev)
         else:
-            K.rmsprop_step(s.flat, s.grad, self.ms, self.lr, clip=clip, grad_scale=grad_scale)
+            K.rmsprop_step(s.flat, s.grad, self.ms, 0.0, clip=clip, grad_scale=grad_scale, lr_dev=self.lr_dev)
         s.refresh_packs()
+
+    def step(self, clip=K.NO_CLIP, grad_scale=1.0):
+        self.tick()
+        self.enqueue(clip, grad_scale)

@@ -37,10 +37,14 @@ def dna_fwd(logits, img, out, K):
 
 
 def dna_bwd(logits, img, dy, dlogits, K):
+    """dlogits: dense [B,H,W,K*K] in the logits dtype, or bf16 [B,H,W,ru16(K*K)] (zero pad channels) for fp32 logits"""
     B, H, W, Cc = img.shape
-    if dlogits.dtype != logits.dtype:
-        raise RuntimeError("dlogits must have the dtype of logits")
-    call("acg_dna_bwd", ptr(logits), dtype_id(logits), ptr(img), ptr(dy), ptr(dlogits), B, H, W, Cc, K, stream())
+    call("acg_dna_bwd", ptr(logits), dtype_id(logits), ptr(img), ptr(dy), ptr(dlogits), dtype_id(dlogits),
+         dlogits.shape[3], B, H, W, Cc, K, stream())
+
+
+def bias_grad(red, Cc, scale, dbias):
+    call("acg_bias_grad", ptr(red), Cc, scale, ptr(dbias), stream())
 
 
 # ---- convolutions -----------------------------------------------------------------------------
@@ -150,11 +154,11 @@ def state_loss(s, t, n, inv_batch, grad_scale, loss_out, dstate=None):
 NO_CLIP = (1.0, -1.0)  # lo > hi disables the clip
 
 
-def adam_step(p, g, m, v, lr_t, b1=0.9, b2=0.999, eps=1e-8, clip=NO_CLIP, grad_scale=1.0):
+def adam_step(p, g, m, v, lr_t, b1=0.9, b2=0.999, eps=1e-8, clip=NO_CLIP, grad_scale=1.0, lr_dev=None):
     call("acg_adam_step", ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr_t, b1, b2, eps, clip[0], clip[1],
-         grad_scale, stream())
+         grad_scale, ptr(lr_dev), stream())
 
 
-def rmsprop_step(p, g, ms, lr, decay=0.9, eps=1e-10, clip=NO_CLIP, grad_scale=1.0):
+def rmsprop_step(p, g, ms, lr, decay=0.9, eps=1e-10, clip=NO_CLIP, grad_scale=1.0, lr_dev=None):
     call("acg_rmsprop_step", ptr(p), ptr(g), ptr(ms), p.numel(), lr, decay, eps, clip[0], clip[1], grad_scale,
-         stream())
+         ptr(lr_dev), stream())

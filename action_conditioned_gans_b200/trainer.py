@@ -40,7 +40,7 @@ class DataParallel:
 class Trainer:
     def __init__(self, sess=None, arg_adv=True, arg_loss="bce", arg_opt="adam", arg_transform=True,
                  batch_size=BATCH_SIZE, ksize=DNA_KSIZE, device=None, params=None, seed=7, dp=None,
-                 precision="bf16"):
+                 precision="bf16", use_graphs=True):
         if arg_loss not in ("bce", "wass"):
             raise ValueError("unexpected loss argument")          # ops.py:35,47
         if arg_opt not in ("adam", "rmsprop"):
@@ -79,24 +79,63 @@ class Trainer:
         self.sc = torch.zeros(4, dtype=torch.float32, device=dev)
         self.zero_state = torch.zeros(self.B, E.STATE_DIM, device=dev)
         self._have = set()
+        # static feed buffers + one captured CUDA graph per step kind (the step is ~300 small launches; replaying a
+        # graph removes the per-launch host cost and the idle gaps between tiny kernels)
+        self.use_graphs = bool(use_graphs)
+        self.in_img = torch.zeros(self.B, E.IMG, E.IMG, 3, device=dev)
+        self.in_next = torch.zeros(self.B, E.IMG, E.IMG, 3, device=dev)
+        self.in_act = torch.zeros(self.B, E.ACTION_DIM, device=dev)
+        self.in_state = torch.zeros(self.B, E.STATE_DIM, device=dev)
+        self._graphs, self._calls, self._graph_launches = {}, {}, {}
+        self.replayed_launches = 0      # kernels launched through graph replays (acg_launch_count sees eager ones)
+
+    def _stage(self, img, nxt, act, st):
+        """Copy the feeds into the static buffers the kernels (and the captured graphs) read."""
+        self.in_img.copy_(img.reshape(self.in_img.shape), non_blocking=True)
+        self.in_next.copy_(nxt.reshape(self.in_next.shape), non_blocking=True)
+        self.in_act.copy_(act.reshape(self.in_act.shape), non_blocking=True)
+        if st is not None:
+            self.in_state.copy_(st.reshape(self.in_state.shape), non_blocking=True)
+        else:
+            self.in_state.zero_()
+
+    def _run(self, key, fn):
+        """Eager on the first call (one-time kernel attribute setup), captured on the second, replayed after."""
+        if not self.use_graphs:
+            fn()
+            return
+        n = self._calls.get(key, 0)
+        self._calls[key] = n + 1
+        if n == 0:
+            fn()
+            return
+        if key not in self._graphs:
+            torch.cuda.synchronize()
+            from . import _lib
+            n0 = _lib.launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self._graphs[key] = g
+            self._graph_launches[key] = _lib.launch_count() - n0
+        self._graphs[key].replay()
+        self.replayed_launches += self._graph_launches[key]
 
     # ---- feeds -----------------------------------------------------------------------------------
-    def _dev(self, a, shape):
+    @staticmethod
+    def _as_tensor(a):
+        """numpy / torch (host or device) -> float32 torch tensor, no device copy yet"""
         if isinstance(a, torch.Tensor):
-            t = a.to(device=self.device, dtype=torch.float32, non_blocking=True)
-        else:
-            t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32))).to(self.device,
-                                                                                          non_blocking=True)
-        t = t.reshape(shape).contiguous()
-        return t
+            return a if a.dtype == torch.float32 else a.float()
+        return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32)))
+
+    def _dev(self, a, shape):
+        return self._as_tensor(a).to(self.device, non_blocking=True).reshape(shape).contiguous()
 
     def _feed(self, img, nxt, act, state=None):
-        B = self.B
-        img = self._dev(img, (B, E.IMG, E.IMG, 3))
-        nxt = self._dev(nxt, (B, E.IMG, E.IMG, 3))
-        act = self._dev(act, (B, E.ACTION_DIM))
-        st = self._dev(state, (B, E.STATE_DIM)) if state is not None else self.zero_state
-        return img, nxt, act, st
+        """Feeds stay where they are (host or device); _stage() copies them straight into the static buffers."""
+        return (self._as_tensor(img), self._as_tensor(nxt), self._as_tensor(act),
+                self._as_tensor(state) if state is not None else None)
 
     # ---- shared pieces -----------------------------------------------------------------------------
     def _g_losses(self, nxt, state_gt, want_grad, with_adv_grad):
@@ -119,6 +158,12 @@ class Trainer:
         if self.arg_transform:
             K.state_loss(g.state, state_gt, self.B * E.STATE_DIM, 1.0 / self.GB, 1.0, self.sc[3:4],
                          g.dstate if want_grad else None)
+            if self.dp is not None and want_grad:
+                # train.py:77 is a Frobenius norm over the GLOBAL batch: rescale the local-norm gradient
+                n2 = (self.sc[3:4] * self.GB) ** 2
+                tot = n2.clone()
+                self.dp.allreduce_sum(tot)
+                g.dstate.mul_(torch.sqrt(n2 / tot.clamp_min(1e-30)))
 
     def _scalars(self):
         """Host values of the loss scalars of the last step (synchronises; logging only)."""
@@ -168,13 +213,20 @@ class Trainer:
         return self._scalars()["g_loss"]
 
     def enqueue_pretrain_g(self, img, nxt, act, st):
+        self._stage(img, nxt, act, st)
+        self.g_pretrain_opt.tick()
+        self._run("pretrain_g", self._body_pretrain_g)
+
+    def _body_pretrain_g(self):
+        img, nxt, act, st = self.in_img, self.in_next, self.in_act, self.in_state
         self.g_store.grad.zero_()
         g_out, _ = self.g_run.forward(img, act)
-        self.d_gen.forward(img, g_out, act)          # self.g_loss is fetched -> D(gen) forward runs too
+        if self.arg_adv:
+            self.d_gen.forward(img, g_out, act)      # self.g_loss is fetched -> D(gen) forward runs too
         self._g_losses(nxt, st, want_grad=True, with_adv_grad=False)
         self.g_run.backward(with_state=self.arg_transform)
         self._sync_grads(self.g_store)
-        self.g_pretrain_opt.step()
+        self.g_pretrain_opt.enqueue()
 
     # ---- train.py:123-130 -------------------------------------------------------------------------------
     def train_g(self, input_images, next_frame, actions, state):
@@ -183,6 +235,12 @@ class Trainer:
         return self.g_run.g_out.cpu().numpy()
 
     def enqueue_train_g(self, img, nxt, act, st):
+        self._stage(img, nxt, act, st)
+        self.g_opt.tick()
+        self._run("train_g", self._body_train_g)
+
+    def _body_train_g(self):
+        img, nxt, act, st = self.in_img, self.in_next, self.in_act, self.in_state
         self.g_store.grad.zero_()
         g_out, _ = self.g_run.forward(img, act)
         if self.arg_adv:
@@ -190,7 +248,7 @@ class Trainer:
         self._g_losses(nxt, st, want_grad=True, with_adv_grad=self.arg_adv)
         self.g_run.backward(with_state=self.arg_transform)
         self._sync_grads(self.g_store)
-        self.g_opt.step()
+        self.g_opt.enqueue()
 
     # ---- train.py:132-144 -------------------------------------------------------------------------------
     def train_d(self, input_images, next_frame, actions, summarize=False):
@@ -198,12 +256,19 @@ class Trainer:
         self.enqueue_train_d(img, nxt, act)
         if summarize:
             # merged_summaries also holds the generator scalars (train.py:112,140)
-            self._g_losses(nxt, st, want_grad=False, with_adv_grad=False)
+            self._g_losses(self.in_next, self.in_state, want_grad=False, with_adv_grad=False)
             self._have = {"g", "d"}
             return self.summaries()
         return None
 
     def enqueue_train_d(self, img, nxt, act):
+        self._stage(img, nxt, act, None)
+        self.d_opt.tick()
+        self._run("train_d", self._body_train_d)
+        self._have = {"d"}
+
+    def _body_train_d(self):
+        img, nxt, act = self.in_img, self.in_next, self.in_act
         self.d_store.grad.zero_()
         g_out, _ = self.g_run.forward(img, act)
         self.d_gen.forward(img, g_out, act)
@@ -218,8 +283,7 @@ class Trainer:
         self.d_real.backward(need_dw=True, need_dinput=False)
         self.d_gen.backward(need_dw=True, need_dinput=False)
         self._sync_grads(self.d_store)
-        self.d_opt.step(clip=(-0.01, 0.01))                          # train.py:89, update then clip
-        self._have = {"d"}
+        self.d_opt.enqueue(clip=(-0.01, 0.01))                       # train.py:89, update then clip
 
     # ---- train.py:146-155 -------------------------------------------------------------------------------
     def test(self, input_images, next_frame, actions):
@@ -229,6 +293,13 @@ class Trainer:
         return g_out.cpu().numpy(), state, self.summaries()
 
     def enqueue_test(self, img, nxt, act, st):
+        self._stage(img, nxt, act, st)
+        self._run("test", self._body_test)
+        self._have = {"g", "d"}
+        return self.g_run.g_out, self.g_run.state
+
+    def _body_test(self):
+        img, nxt, act, st = self.in_img, self.in_next, self.in_act, self.in_state
         g_out, g_state = self.g_run.forward(img, act)
         self.d_gen.forward(img, g_out, act)
         self.d_real.forward(img, nxt, act)
@@ -239,8 +310,6 @@ class Trainer:
         else:
             K.dlogit_loss(self.d_real.logits, self.d_real.n_logits, "wass", 1.0, 1.0, self.sc[1:2], None)
             K.dlogit_loss(self.d_gen.logits, self.d_gen.n_logits, "wass", -1.0, 1.0, self.sc[2:3], None)
-        self._have = {"g", "d"}
-        return g_out, g_state
 
     # ---- train.py:157-176 -------------------------------------------------------------------------------
     def test_sequence(self, input_images, test_next_frame, test_actions):

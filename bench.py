@@ -224,6 +224,8 @@ def main_ours(args):
     dp = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's banner goes to stdout; the contract is ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
         dp = DataParallel()
     peaks = load_peaks()
@@ -251,7 +253,7 @@ def main_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.launch_count()
+    launches0 = _lib.launch_count() + trn.replayed_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -260,7 +262,7 @@ def main_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = _lib.launch_count() - launches0
+    launches = _lib.launch_count() + trn.replayed_launches - launches0
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if dp is not None:
@@ -289,13 +291,14 @@ def main_ours(args):
     h2d = sum(x.numel() * 4 for x in host[0][:3]) + sum(x.numel() * 4 for x in host[0])
     d2h = frames.nbytes
 
+    # ---- per-kernel breakdown of one iteration (instrumented pass, right after the timed region; every rank
+    # takes part because the step contains collectives) -----------------------------------------------------
+    breakdown = kernel_breakdown(trn, resident[0])
+    barrier()
     if rank != 0:
         if dp is not None:
             dp.dist.destroy_process_group()
         return
-
-    # ---- per-kernel breakdown of one iteration (instrumented pass, right after the timed region) ----------------
-    breakdown = kernel_breakdown(trn, resident[0])
     dna = dna_microbench(dev, peaks)
     flops = flops_per_iter(B, KSIZE)
     conv_ms = sum(v["ms"] for k, v in breakdown.items() if k.startswith("acg_conv"))
@@ -348,6 +351,7 @@ def kernel_breakdown(trn, feeds):
         records.append((name, e0, e1))
 
     Kn.call = timed_call
+    graphs, trn.use_graphs = trn.use_graphs, False        # the per-kernel view needs eager launches
     try:
         img, nxt, act, state = feeds
         trn.enqueue_train_d(img, nxt, act)
@@ -355,6 +359,7 @@ def kernel_breakdown(trn, feeds):
         torch.cuda.synchronize()
     finally:
         Kn.call = orig
+        trn.use_graphs = graphs
     out = {}
     for name, e0, e1 in records:
         d = out.setdefault(name, {"ms": 0.0, "n": 0})

@@ -60,10 +60,12 @@ long long acg_launch_count(void);
  * ------------------------------------------------------------------------------------------ */
 int acg_dna_fwd(const void* logits, int logits_dtype, const float* img, float* out,
                 int B, int H, int W, int C, int K, void* stream);
-/* dlogits (same dtype as logits) = s_p * (g_p - sum_q s_q g_q), g_p = sum_c dy_c * img_{p,c}.
+/* dlogits = s_p * (g_p - sum_q s_q g_q), g_p = sum_c dy_c * img_{p,c}; written either dense in the logits dtype
+ * (ld_dlogits == K*K) or, for fp32 logits, as bf16 rows of ld_dlogits == ru16(K*K) channels with zero pad channels
+ * (the operand layout of the tensor-core convolutions, i.e. directly the dz of g/tconv4).
  * img is a fed placeholder in the reference (train.py:31-34) so no image gradient is produced. */
 int acg_dna_bwd(const void* logits, int logits_dtype, const float* img, const float* dy,
-                void* dlogits, int B, int H, int W, int C, int K, void* stream);
+                void* dlogits, int dlogits_dtype, int ld_dlogits, int B, int H, int W, int C, int K, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Convolution family: replaces slim.conv2d (models.py:12-15,34-37,42-51,82-88),
@@ -152,6 +154,8 @@ int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d,
                          const float* shift, int act, int has_bn, const double* red, void* dz,
                          int dz_dtype, int ld_dz, float* dbeta, long long norm_rows, float dbeta_scale,
                          void* stream);
+/* dbias[c] += scale * red[c], c < C: bias gradient from the column sums acg_bn_act_bwd_reduce leaves in red[0:C] */
+int acg_bias_grad(const double* red, int C, float scale, float* dbias, void* stream);
 /* dst[r, off_dst:off_dst+n] = src[r, off_src:off_src+n]  (channel-slice copy with dtype conversion) */
 int acg_copy_channels(const void* src, int src_dtype, int ld_src, int off_src, void* dst, int dst_dtype,
                       int ld_dst, int off_dst, long long rows, int n, void* stream);
@@ -183,12 +187,20 @@ int acg_state_loss(const float* s, const float* t, int n, float inv_batch, float
  * (train.py:91-102) with the weight clip of train.py:89 fused (update, THEN clip).
  * Flat fp32 buffers of n elements; clip_lo > clip_hi disables the clip.
  * ------------------------------------------------------------------------------------------ */
-/* lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller (host scalar) */
+/* lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller: host scalar, or -- when lr_t_dev != NULL -- read from
+ * device memory at kernel time so that a captured CUDA graph can be replayed with a new rate every step */
 int acg_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1,
-                  float b2, float eps, float clip_lo, float clip_hi, float grad_scale, void* stream);
+                  float b2, float eps, float clip_lo, float clip_hi, float grad_scale, const float* lr_t_dev,
+                  void* stream);
 /* ms starts at ONE; p -= lr*g/sqrt(ms+eps) */
 int acg_rmsprop_step(float* p, const float* g, float* ms, long long n, float lr, float decay, float eps,
-                     float clip_lo, float clip_hi, float grad_scale, void* stream);
+                     float clip_lo, float clip_hi, float grad_scale, const float* lr_dev, void* stream);
+
+/* Probe (tests only): D[128][N] = A_window * B^T where A_window's logical row m is shared-memory row
+ * shift + (m/8)*pitch + (m%8) of a 128-byte-swizzled K-major [n_rows][64] bf16 tile (start not 1024 B aligned, 8-row
+ * groups spaced by `pitch` rows).  base_offset_mode 1 sets the descriptor's base-offset field to (addr>>7)&7. */
+int acg_debug_umma_shift(const void* a_rows, int n_rows, const void* b_rows, int N, int shift, int pitch,
+                         int base_offset_mode, float* out, void* stream);
 
 #ifdef __cplusplus
 }

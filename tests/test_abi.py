@@ -62,7 +62,7 @@ def test_argument_validation_without_a_device(built_lib):
     assert b"unexpected loss argument" in lib.acg_last_error()
     shape = _lib.ConvShape(1, 8, 8, 4, 4, 4, 4, 5, 5, 3, 1, 1)             # stride 3
     assert lib.acg_conv_fprop_f32(C.byref(shape), p, p, p, None) == -2
-    assert lib.acg_adam_step(None, p, p, p, 4, 1e-3, 0.9, 0.999, 1e-8, 1.0, -1.0, 1.0, None) == -1
+    assert lib.acg_adam_step(None, p, p, p, 4, 1e-3, 0.9, 0.999, 1e-8, 1.0, -1.0, 1.0, None, None) == -1
     with pytest.raises(RuntimeError, match="acg_dna_fwd failed"):
         _lib.call("acg_dna_fwd", None, 0, None, None, 1, 8, 8, 3, 5, None)
 

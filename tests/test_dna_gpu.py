@@ -122,3 +122,19 @@ def test_dna_rejects_bad_arguments(cuda):
         Kn.dna_fwd(lg, img, out, 4)                      # K must be 5 or 6
     with pytest.raises(RuntimeError):
         Kn.dna_fwd(lg.cpu(), img, out, 5)                # no CPU path
+
+
+@pytest.mark.parametrize("K", [5, 6])
+def test_dna_bwd_padded_bf16_output(cuda, K):
+    """dlogits written as bf16 rows of ru16(K*K) channels with zero pad channels (the dz operand of g/tconv4)."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    B, H, W = 3, 16, 64
+    logits, img, dy = _inputs(B, H, W, K, seed=21)
+    ref_b = np_ref.dna_backward(logits.astype(np.float64), img.astype(np.float64), dy.astype(np.float64), K)
+    tl, ti, td = (torch.from_numpy(a).to(cuda) for a in (logits, img, dy))
+    ld = (K * K + 15) // 16 * 16
+    dl = torch.full((B, H, W, ld), float("nan"), device=cuda, dtype=torch.bfloat16)
+    Kn.dna_bwd(tl, ti, td, dl, K)
+    got = dl.float().cpu().numpy()
+    assert np.abs(got[..., :K * K] - ref_b).max() <= 8e-3 * np.abs(ref_b).max()      # bf16 storage
+    assert np.abs(got[..., K * K:]).max() == 0.0
