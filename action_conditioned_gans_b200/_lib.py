@@ -26,7 +26,9 @@ class ConvShape(C.Structure):
 class TcArgs(C.Structure):
     """struct acg_tc_args"""
     _fields_ = [("ld_in", C.c_int), ("ld_out", C.c_int), ("bias", C.c_void_p), ("out_dtype", C.c_int),
-                ("out_act", C.c_int)]
+                ("out_act", C.c_int), ("stats", C.c_void_p), ("bn_counter", C.c_void_p), ("bn_beta", C.c_void_p),
+                ("bn_mean", C.c_void_p), ("bn_rstd", C.c_void_p), ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
+                ("bn_rows", C.c_longlong), ("bn_eps", C.c_float)]
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -57,6 +59,7 @@ SIGNATURES = {
     "acg_frame_losses": [_P, _P, _I, _I, _I, _P, _P, _F, _F, _P, _I, _I, _P],
     "acg_dlogit_loss": [_P, _I, _I, _F, _F, _P, _P, _P],
     "acg_state_loss": [_P, _P, _I, _F, _F, _P, _P, _P],
+    "acg_debug_phase_times": [_P],
     "acg_debug_umma_shift": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
     "acg_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _P, _P],
     "acg_rmsprop_step": [_P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P],

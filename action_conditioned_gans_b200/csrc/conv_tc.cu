@@ -17,6 +17,9 @@
 //   epilogue   tcgen05.ld 32 lanes x 16 columns per warp -> (+bias, tanh) -> bf16 / fp32 NHWC rows.
 // Two CTAs are resident per SM (3 stages x 32 KB, 128 TMEM columns each) so one CTA's epilogue overlaps the
 // other's main loop.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace acg {
@@ -40,10 +43,54 @@ struct Params {
     int n_store;     // output channels written per row: min(N, ldo)
     int out_dtype, out_act;
     long long w_class_off[4];   // ADJ: element offset of each parity class' [N][Kc] matrix inside w_pack
+    // fused batch-norm moments of THIS layer's output (optional)
+    double* stats;              // [2][n_bias] fp64 (sum | sum of squares), accumulated with atomics
+    unsigned int* counter;      // when non-NULL the last CTA to finish also finalises mean/rstd/scale/shift
+    unsigned int total_ctas;    // CTAs that reach the epilogue (smaller parity classes exit early)
+    const float* beta;
+    float* bn_mean; float* bn_rstd; float* bn_scale; float* bn_shift;
+    long long bn_rows;
+    float bn_eps;
+    int dbg_skip;               // profiling experiments (env ACG_DBG_SKIP): bit 3 = per-phase timing
 };
+
+// Column sums of a 32-lane x 16-column register tile: after the butterfly lane L holds the total of column L>>1.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+    float w[8], x[4], y[2], z;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = h16 ? v[i] : v[i + 8];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+        w[i] = (h16 ? v[i + 8] : v[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h8 ? w[i] : w[i + 4];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+        x[i] = (h8 ? w[i + 4] : w[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h4 ? x[i] : x[i + 2];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        y[i] = (h4 ? x[i + 2] : x[i]) + recv;
+    }
+    {
+        const float send = h2 ? y[0] : y[1];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+        z = (h2 ? y[1] : y[0]) + recv;
+    }
+    z += __shfl_xor_sync(0xffffffffu, z, 1);
+    return z;
+}
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -62,6 +109,29 @@ __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
         : "memory");
 }
+// Same instruction with the two shared-memory descriptors passed as (lo, hi) 32-bit halves.  Only the low word
+// (start address >> 4 | LBO << 16) changes from MMA to MMA; the issuing thread adds a constant to it instead of
+// rebuilding a 64-bit descriptor with shifts and masks (the single issuing thread is latency bound: ~40 dependent
+// instructions per MMA made descriptor arithmetic, not the tensor pipe, the limiter of the first version).
+__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                        uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// descriptor halves for 128-byte swizzle: lo = start>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -92,7 +162,97 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_m
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One 32-row x 16-column accumulator chunk: (+bias) (tanh) -> moments -> store.  All mode tests are kernel-uniform
+// and sit OUTSIDE the unrolled element loops so that they compile to branches, not to predicated instruction bloat
+// (a first version that tested bias / tanh per element spent ~800 issue slots per chunk on predicated-off code).
+__device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&v)[16], int ncol, bool row_ok,
+                                               size_t row_off, int lane, float* sm_sum, float* sm_sq) {
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+    if (p.bias) {
+        if (ncol + 16 <= p.n_bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + ncol);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 b = b4[i];
+                f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (ncol + i < p.n_bias) f[i] += p.bias[ncol + i];
+        }
+    }
+    if (p.out_act == ACG_ACT_TANH) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = tanh_fast(f[i]);
+    }
+    const bool bf16_out = p.out_dtype == ACG_BF16;
+    uint32_t w[8];
+    if (bf16_out) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+    if (p.stats) {
+        // batch-norm moments of exactly what is stored (bf16-rounded when the output is bf16)
+        float q[16], q2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float t = f[i];
+            if (bf16_out) t = __uint_as_float((i & 1) ? (w[i >> 1] & 0xffff0000u) : (w[i >> 1] << 16));
+            t = row_ok ? t : 0.f;
+            q[i] = t;
+            q2[i] = t * t;
+        }
+        const float cs = warp_colsum16(q, lane), cs2 = warp_colsum16(q2, lane);
+        if ((lane & 1) == 0) {
+            atomicAdd(sm_sum + (lane >> 1), cs);
+            atomicAdd(sm_sq + (lane >> 1), cs2);
+        }
+    }
+    if (!row_ok) return;
+    const bool full = ncol + 16 <= p.n_store;
+    if (bf16_out) {
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + row_off + ncol;
+        if (full && (p.ldo & 7) == 0) {
+            reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+            for (int i = 0; i < 16; ++i)
+                if (ncol + i < p.n_store) o[i] = __float2bfloat16_rn(f[i]);
+        }
+    } else {
+        float* o = static_cast<float*>(p.out) + row_off + ncol;
+        if (full && (p.ldo & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        } else {
+            for (int i = 0; i < 16; ++i)
+                if (ncol + i < p.n_store) o[i] = f[i];
+        }
+    }
+}
+
 enum { CONV = 0, ADJ = 1 };
+
+// timing experiments (ACG_DBG_SKIP bit 3): per-phase nanoseconds summed over CTAs
+__device__ unsigned long long g_phase_ns[8];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
@@ -100,10 +260,16 @@ conv_tc_kernel(const Params p) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
     __shared__ uint32_t tmem_base_sh;
+    __shared__ float sm_stats[2][BN];
+    __shared__ int last_cta_sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smemA = smem_base, smemB = smem_base + STAGES * kStageA;
+    if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
+    const bool timing = (p.dbg_skip & 8) && tid == 0;
+    unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    if (timing) t0 = gtime();
 
     // ---- geometry of this CTA ---------------------------------------------------------------------------
     const int s = p.stride;
@@ -144,6 +310,7 @@ conv_tc_kernel(const Params p) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_sh;
+    if (timing) t1 = gtime();
 
     if (warp < 4) {
         // ================================ producers ================================
@@ -207,15 +374,16 @@ conv_tc_kernel(const Params p) {
     } else if (lane == 0) {
         // ================================ MMA issuer ================================
         const uint32_t idesc = make_idesc(n_cta, 0, 0);
+        const uint32_t hi = desc_hi(1024);
+        const uint32_t alo0 = desc_lo(smemA, 16), blo0 = desc_lo(smemB, 16);
         for (int kb = 0; kb < nkb; ++kb) {
             const int stage = kb % STAGES;
             mbar_wait(&full_bar[stage], (uint32_t)((kb / STAGES) & 1));
             tc_fence_after();
-            const uint32_t aaddr = smemA + stage * kStageA, baddr = smemB + stage * kStageB;
+            const uint32_t alo = alo0 + stage * (kStageA >> 4), blo = blo0 + stage * (kStageB >> 4);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-                tc_mma(tmem_base, kmajor_sw128_desc(aaddr + k * 32), kmajor_sw128_desc(baddr + k * 32), idesc,
-                       (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the swizzle atom
+                tc_mma2(tmem_base, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
             tc_commit(&empty_bar[stage]);   // arrives when the MMAs above have finished reading this stage
         }
         tc_commit(&acc_bar);
@@ -227,6 +395,7 @@ conv_tc_kernel(const Params p) {
             mbar_wait(&acc_bar, 0);
             tc_fence_after();
         }
+        if (timing) t2 = gtime();
         const int m = tile_m + warp * 32 + lane;
         size_t row_off = 0;
         if (m < M) {
@@ -244,45 +413,7 @@ conv_tc_kernel(const Params p) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0u;
             }
-            if (m < M) {
-                float f[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    f[i] = __uint_as_float(v[i]);
-                    const int n = n0 + cb + i;
-                    if (p.bias && n < p.n_bias) f[i] += p.bias[n];
-                    if (p.out_act == ACG_ACT_TANH) f[i] = tanhf(f[i]);
-                }
-                const bool full = n0 + cb + 16 <= p.n_store;
-                if (p.out_dtype == ACG_BF16) {
-                    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + row_off + n0 + cb;
-                    if (full && (p.ldo & 7) == 0) {
-                        uint32_t w[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-                            w[i] = *reinterpret_cast<uint32_t*>(&h);
-                        }
-                        reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                        reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (n0 + cb + i < p.n_store) o[i] = __float2bfloat16_rn(f[i]);
-                    }
-                } else {
-                    float* o = static_cast<float*>(p.out) + row_off + n0 + cb;
-                    if (full && (p.ldo & 3) == 0) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (n0 + cb + i < p.n_store) o[i] = f[i];
-                    }
-                }
-            }
+            epilogue_chunk(p, v, n0 + cb, m < M, row_off, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
         }
     }
     tc_fence_before();
@@ -291,8 +422,345 @@ conv_tc_kernel(const Params p) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
     }
+    if (timing) {
+        t3 = gtime();
+        atomicAdd(&g_phase_ns[0], t1 - t0);
+        atomicAdd(&g_phase_ns[1], t2 - t1);
+        atomicAdd(&g_phase_ns[2], t3 - t2);
+        atomicAdd(&g_phase_ns[3], 1ull);
+        atomicAdd(&g_phase_ns[4], (unsigned long long)nkb);
+    }
+    if (p.stats) {
+        if (tid < n_cta && n0 + tid < p.n_bias) {
+            atomicAdd(&p.stats[n0 + tid], (double)sm_stats[0][tid]);
+            atomicAdd(&p.stats[p.n_bias + n0 + tid], (double)sm_stats[1][tid]);
+        }
+        if (p.counter) {
+            // last CTA of the launch turns the moments into mean / rstd / scale / shift (slim.batch_norm, eps 1e-3)
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) last_cta_sh = (atomicAdd(p.counter, 1u) == p.total_ctas - 1u);
+            __syncthreads();
+            if (last_cta_sh) {
+                __threadfence();
+                const double inv = 1.0 / (double)p.bn_rows;
+                for (int c = tid; c < p.n_bias; c += kThreads) {
+                    const double mu = __ldcg(&p.stats[c]) * inv;
+                    double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
+                    if (var < 0.0) var = 0.0;
+                    const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+                    const float b = p.beta ? p.beta[c] : 0.f;
+                    p.bn_mean[c] = (float)mu;
+                    p.bn_rstd[c] = rs;
+                    p.bn_scale[c] = rs;
+                    p.bn_shift[c] = b - (float)mu * rs;
+                }
+                if (tid == 0) *p.counter = 0u;   // ready for the next launch
+            }
+        }
+    }
 }
 
+
+// ---- ADJ gather, halo-tile variant ---------------------------------------------------------------------------------
+// For a stride-2 transposed convolution every tap of an output-parity class is a pure 2-D shift of the (small-grid)
+// input: out_class[b][y][x] = sum_{ta,tc,k} in[b][y + ea - ta][x + ec - tc][k] * W[class][n][(ta,tc)][k].
+// The generic kernel above re-gathers the shifted 128-row A slice from L2 for every tap and re-reads the 16 KB
+// weight slice for every 128 output rows; it sits on the L2->SM bandwidth (~4.8 TB/s), not on the tensor pipe.
+// Here one CTA owns 4 accumulators = 512 output pixels (16 rows x 32 columns of one image, or 16 x 16 of two):
+//   * per 64-channel block the (16+na-1) x (W+nc-1) input halo patch of each image is staged ONCE (<= 83 KB, two
+//     buffers) in the 128-byte-swizzled K-major layout with swizzle phase = absolute row index;
+//   * each tap's A operand is then just a descriptor into that patch: start row = shift(tap) + 8*column-group, 8-row
+//     groups spaced by the halo width (SBO = WH*128 B) -- tcgen05.mma applies the swizzle on absolute smem address
+//     bits, so a start that is not 1024-B aligned is fine (verified on hardware by acg_debug_umma_shift);
+//   * every streamed weight slice (tap x 64 channels, N x 128 B) feeds 16 MMAs (4 accumulators x K=64) instead of 4.
+// L2->SM traffic per output tile drops ~5x (A: taps x 16 KB -> 1/4 of a shared 83 KB halo; B: 16 KB -> 4 KB).
+constexpr int HALO_ACC = 4;
+constexpr int HALO_H = 18;    // staged halo rows per image: 16 output rows + (na-1) <= 2
+
+struct alignas(64) HaloParams {
+    Params p;
+    CUtensorMap map_a;        // bf16 [B][OH][OW][lda], box {64 ch, OW+2, 18, TB}, 128B swizzle, zero OOB fill
+    CUtensorMap map_b[4];     // per parity class: bf16 [N][Kc], box {64, N}, 128B swizzle
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+constexpr int kHaloBuf = 648 * 128;                       // 18 x 34 (one image) or 2 x 18 x 18 rows of 128 B
+constexpr int kHaloBStage = BN * BK * 2;
+constexpr int kHaloBStages = 3;
+constexpr int kHaloSmem = 2 * kHaloBuf + kHaloBStages * kHaloBStage + 1024;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
+    const Params& p = hp.p;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t halo_full[2], halo_empty[2], b_full[kHaloBStages], b_empty[kHaloBStages], acc_bar;
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ float sm_stats[2][BN];
+    __shared__ int last_cta_sh;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smemH = smem_base, smemB = smem_base + 2 * kHaloBuf;
+    if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
+    const bool timing = (p.dbg_skip & 8) && tid == 0;
+    const bool mtiming = (p.dbg_skip & 8) && tid == 128;
+    unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, w_halo = 0, w_b = 0;
+    if (timing) t0 = gtime();
+
+    // ---- geometry (stride 2) -----------------------------------------------------------------------------
+    const int ph = blockIdx.z >> 1, pw = blockIdx.z & 1;
+    const int Hs = p.H >> 1, Ws = p.W >> 1;                 // class grid == conv-output grid (OH x OW)
+    const int a0 = (ph + p.pad_t) & 1, c0 = (pw + p.pad_l) & 1;
+    const int na = (p.KH - a0 + 1) >> 1, nc = (p.KW - c0 + 1) >> 1;
+    const int ea = (ph + p.pad_t - a0) >> 1, ec = (pw + p.pad_l - c0) >> 1;
+    const int ntaps = na * nc;
+    const int XG = Ws >> 3, TB = HALO_ACC / XG;             // column groups of 8 per image row, images per CTA
+    const int WH = Ws + 2, HR = HALO_H * WH;                // staged halo: 18 rows x (Ws+2) pixels per image
+    const int tiles_y = Hs >> 4;
+    const int b0 = (blockIdx.x / tiles_y) * TB, y0 = (blockIdx.x % tiles_y) << 4;
+    const int N = p.N;                                      // <= 128, multiple of 16
+    const int nkc = p.lda >> 6;                             // 64-channel blocks
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(HALO_ACC * N)) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); }
+        for (int i = 0; i < kHaloBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(&acc_bar, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&hp.map_a);
+        tma_prefetch_desc(&hp.map_b[blockIdx.z]);
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+    if (timing) t1 = gtime();
+
+    if (tid == 0) {
+        // ================================ producer: one thread, TMA only ================================
+        // The whole halo patch of a 64-channel block is ONE 4-D tensor copy (hardware zero fill outside the image,
+        // hardware 128B swizzle); every (tap, channel block) weight slice is ONE 2-D tensor copy.
+        const uint32_t a_bytes = (uint32_t)(TB * HR) * 128u, b_bytes = (uint32_t)N * 128u;
+        const int oh0 = y0 + ea - (na - 1), ow0 = ec - (nc - 1);
+        auto load_halo = [&](int kc) {
+            mbar_expect_tx(&halo_full[kc & 1], a_bytes);
+            tma_load_4d(smemH + (kc & 1) * kHaloBuf, &hp.map_a, kc * 64, ow0, oh0, b0, &halo_full[kc & 1]);
+        };
+        load_halo(0);
+        if (nkc > 1) load_halo(1);
+        int bcount = 0;
+        for (int kc = 0; kc < nkc; ++kc) {
+            for (int tap = 0; tap < ntaps; ++tap, ++bcount) {
+                const int st = bcount % kHaloBStages;
+                if (bcount >= kHaloBStages) mbar_wait(&b_empty[st], (uint32_t)(((bcount / kHaloBStages) - 1) & 1));
+                mbar_expect_tx(&b_full[st], b_bytes);
+                tma_load_2d(smemB + st * kHaloBStage, &hp.map_b[blockIdx.z], tap * p.lda + kc * 64, 0, &b_full[st]);
+            }
+            if (kc + 2 < nkc) {   // the buffer of block kc is reused by block kc+2 once its MMAs have drained
+                mbar_wait(&halo_empty[kc & 1], (uint32_t)((kc >> 1) & 1));
+                load_halo(kc + 2);
+            }
+        }
+    } else if (warp == 4 && lane == 0) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc = make_idesc(N, 0, 0);
+        const uint32_t ahi = desc_hi((uint32_t)WH * 128u), bhi = desc_hi(1024);
+        const uint32_t blo0 = desc_lo(smemB, 16);
+        uint32_t acc_row8[HALO_ACC];           // first halo row of accumulator q, in 16-byte units (x8 per row)
+#pragma unroll
+        for (int q = 0; q < HALO_ACC; ++q) {
+            const int tb = q / XG, xg = q - tb * XG;
+            acc_row8[q] = (uint32_t)(tb * HR + xg * 8) * 8u;
+        }
+        int bcount = 0;
+        for (int kc = 0; kc < nkc; ++kc) {
+            unsigned long long ta0 = 0;
+            if (mtiming) ta0 = gtime();
+            mbar_wait(&halo_full[kc & 1], (uint32_t)((kc >> 1) & 1));
+            if (mtiming) w_halo += gtime() - ta0;
+            const uint32_t hbase = smemH + (kc & 1) * kHaloBuf;
+            for (int tap = 0; tap < ntaps; ++tap, ++bcount) {
+                const int st = bcount % kHaloBStages;
+                if (mtiming) ta0 = gtime();
+                mbar_wait(&b_full[st], (uint32_t)((bcount / kHaloBStages) & 1));
+                if (mtiming) w_b += gtime() - ta0;
+                tc_fence_after();
+                const int ta = tap / nc, tcc = tap - ta * nc;
+                const int shift = (na - 1 - ta) * WH + (nc - 1 - tcc);
+                const uint32_t blo = blo0 + st * (kHaloBStage >> 4);
+                const uint32_t alo_t = desc_lo(hbase, 16) + (uint32_t)shift * 8u;   // 128 B per halo row
+#pragma unroll
+                for (int q = 0; q < HALO_ACC; ++q) {
+                    const uint32_t alo = alo_t + acc_row8[q];
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc_mma2(tmem_base + q * N, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc,
+                                (kc | tap | k) != 0 ? 1u : 0u);
+                }
+                tc_commit(&b_empty[st]);
+            }
+            tc_commit(&halo_empty[kc & 1]);
+        }
+        tc_commit(&acc_bar);
+        if (mtiming) { atomicAdd(&g_phase_ns[6], w_halo + w_b); }
+    }
+
+    // ================================ epilogue (warps 0-3): 4 accumulators ================================
+    if (warp < 4) {
+        mbar_wait(&acc_bar, 0);
+        tc_fence_after();
+        if (timing) t2 = gtime();
+        const int ml = warp * 32 + lane, yy = ml >> 3, xi = ml & 7;
+        for (int q = 0; q < HALO_ACC; ++q) {
+            const int tb = q / XG, xg = q - tb * XG;
+            const int ih = ((y0 + yy) << 1) + ph, iw = ((xg * 8 + xi) << 1) + pw;
+            const size_t row_off = ((size_t)((b0 + tb) * p.H + ih) * p.W + iw) * p.ldo;
+            for (int cb = 0; cb < N; cb += 16) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + q * N + cb, v);
+                epilogue_chunk(p, v, cb, true, row_off, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
+            }
+        }
+    }
+    unsigned long long tb4 = 0;
+    if ((p.dbg_skip & 8) && lane == 0) tb4 = gtime();
+    tc_fence_before();
+    __syncthreads();
+    if ((p.dbg_skip & 8) && lane == 0 && warp == 1) atomicAdd(&g_phase_ns[7], gtime() - tb4);   // warp 1's barrier wait
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+    if (timing) {
+        t3 = gtime();
+        atomicAdd(&g_phase_ns[5], tb4 - t2);   // thread 0: epilogue loop only (overwrites the halo-wait slot semantics)
+        atomicAdd(&g_phase_ns[0], t1 - t0);
+        atomicAdd(&g_phase_ns[1], t2 - t1);
+        atomicAdd(&g_phase_ns[2], t3 - t2);
+        atomicAdd(&g_phase_ns[3], 1ull);
+        atomicAdd(&g_phase_ns[4], (unsigned long long)(nkc * ntaps));
+    }
+    if (p.stats) {
+        if (tid < N && tid < p.n_bias) {
+            atomicAdd(&p.stats[tid], (double)sm_stats[0][tid]);
+            atomicAdd(&p.stats[p.n_bias + tid], (double)sm_stats[1][tid]);
+        }
+        if (p.counter) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) last_cta_sh = (atomicAdd(p.counter, 1u) == p.total_ctas - 1u);
+            __syncthreads();
+            if (last_cta_sh) {
+                __threadfence();
+                const double inv = 1.0 / (double)p.bn_rows;
+                for (int c = tid; c < p.n_bias; c += kThreads) {
+                    const double mu = __ldcg(&p.stats[c]) * inv;
+                    double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
+                    if (var < 0.0) var = 0.0;
+                    const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+                    const float b = p.beta ? p.beta[c] : 0.f;
+                    p.bn_mean[c] = (float)mu;
+                    p.bn_rstd[c] = rs;
+                    p.bn_scale[c] = rs;
+                    p.bn_shift[c] = b - (float)mu * rs;
+                }
+                if (tid == 0) *p.counter = 0u;
+            }
+        }
+    }
+}
+
+int ru(int v, int m) { return (v + m - 1) / m * m; }
+
+void class_taps(const acg_conv_shape* s, int cls, int* na, int* nc) {
+    const int ph = cls / s->stride, pw = cls % s->stride;
+    const int a0 = (ph + s->pad_t) % s->stride, c0 = (pw + s->pad_l) % s->stride;
+    *na = a0 < s->KH ? (s->KH - a0 + s->stride - 1) / s->stride : 0;
+    *nc = c0 < s->KW ? (s->KW - c0 + s->stride - 1) / s->stride : 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+int encode_halo_maps(HaloParams* hp, const acg_conv_shape* s, const acg_tc_args* t, int N, int TB, const void* dy,
+                     const void* w_pack) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    ACG_REQUIRE(enc, ACG_ERR_CUDA, "acg_conv_dgrad_tc: cuTensorMapEncodeTiled is not available");
+    const cuuint64_t lda = (cuuint64_t)t->ld_in;
+    {   // activations: [B][OH][OW][lda] bf16, innermost first
+        cuuint64_t dims[4] = {lda, (cuuint64_t)s->OW, (cuuint64_t)s->OH, (cuuint64_t)s->B};
+        cuuint64_t strides[3] = {lda * 2, (cuuint64_t)s->OW * lda * 2, (cuuint64_t)s->OH * s->OW * lda * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(s->OW + 2), (cuuint32_t)HALO_H, (cuuint32_t)TB};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&hp->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(dy), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        ACG_REQUIRE(r == CUDA_SUCCESS, ACG_ERR_CUDA, "acg_conv_dgrad_tc: activation tensor map failed (%d)", (int)r);
+    }
+    for (int cls = 0; cls < 4; ++cls) {   // weights of each parity class: [N][Kc] bf16
+        int na, nc;
+        class_taps(s, cls, &na, &nc);
+        const cuuint64_t Kc = (cuuint64_t)na * nc * lda;
+        cuuint64_t dims[2] = {Kc, (cuuint64_t)N};
+        cuuint64_t strides[1] = {Kc * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)N};
+        cuuint32_t estr[2] = {1, 1};
+        void* base = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(w_pack) + hp->p.w_class_off[cls]);
+        CUresult r = enc(&hp->map_b[cls], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        ACG_REQUIRE(r == CUDA_SUCCESS, ACG_ERR_CUDA, "acg_conv_dgrad_tc: weight tensor map %d failed (%d)", cls, (int)r);
+    }
+    return ACG_OK;
+}
+
+// the halo variant covers stride-2 layers whose class grid is 16k rows x 16 or 32 columns, N <= 128, 64-channel K blocks
+bool halo_ok(const acg_conv_shape* s, const acg_tc_args* t, int N) {
+    if (getenv("ACG_NO_HALO")) return false;
+    if (s->stride != 2 || s->KH > 6 || s->KW > 6 || s->KH < 2 || s->KW < 2) return false;
+    if (s->H % 32 != 0 || (s->W != 32 && s->W != 64)) return false;
+    if (s->OH != s->H / 2 || s->OW != s->W / 2) return false;
+    if (N > BN || t->ld_in % 64 != 0) return false;
+    const int TB = HALO_ACC / (s->W / 16);
+    if (s->B % TB != 0) return false;
+    return true;
+}
 
 // ---- wgrad ---------------------------------------------------------------------------------------------------
 // dW[tap][ci][co] += sum_pix x[pix @ tap][ci] * dy[pix][co]   as   D[m = co][n = (tap, ci)] = sum_k A[m][k] B[n][k]
@@ -384,15 +852,16 @@ conv_wgrad_tc_kernel(const WgradParams p) {
         }
     } else if (lane == 0) {
         const uint32_t idesc = make_idesc(n_cta, 1, 1);
+        const uint32_t hi = desc_hi(1024);
+        const uint32_t alo0 = desc_lo(smemA, BK * 128), blo0 = desc_lo(smemB, BK * 128);
         for (int kb = 0; kb < nkb; ++kb) {
             const int stage = kb % STAGES;
             mbar_wait(&full_bar[stage], (uint32_t)((kb / STAGES) & 1));
             tc_fence_after();
-            const uint32_t aaddr = smemA + stage * kStageA, baddr = smemB + stage * kStageB;
+            const uint32_t alo = alo0 + stage * (kStageA >> 4), blo = blo0 + stage * (kStageB >> 4);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)   // 16 pixels = two 8-row groups further down each atom
-                tc_mma(tmem_base, sw128_desc(aaddr + k * 2048, BK * 128, 1024), sw128_desc(baddr + k * 2048, BK * 128, 1024),
-                       idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k)   // 16 pixels = two 8-row groups (2048 B) further down each atom
+                tc_mma2(tmem_base, alo + 128 * k, hi, blo + 128 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
             tc_commit(&empty_bar[stage]);
         }
         tc_commit(&acc_bar);
@@ -471,15 +940,6 @@ pack_adj_kernel(const float* __restrict__ w, int KH, int KW, int Cin, int Cout, 
     }
 }
 
-int ru(int v, int m) { return (v + m - 1) / m * m; }
-
-void class_taps(const acg_conv_shape* s, int cls, int* na, int* nc) {
-    const int ph = cls / s->stride, pw = cls % s->stride;
-    const int a0 = (ph + s->pad_t) % s->stride, c0 = (pw + s->pad_l) % s->stride;
-    *na = a0 < s->KH ? (s->KH - a0 + s->stride - 1) / s->stride : 0;
-    *nc = c0 < s->KW ? (s->KW - c0 + s->stride - 1) / s->stride : 0;
-}
-
 int check(const acg_conv_shape* s, const acg_tc_args* t, const char* who) {
     ACG_REQUIRE(s && t, ACG_ERR_INVALID, "%s: null shape/args", who);
     ACG_REQUIRE(s->stride == 1 || s->stride == 2, ACG_ERR_UNSUPPORTED, "%s: stride %d", who, s->stride);
@@ -491,6 +951,26 @@ int check(const acg_conv_shape* s, const acg_tc_args* t, const char* who) {
                     (long long)s->B * s->OH * s->OW * (long long)t->ld_in < (1ll << 31) &&
                     (long long)s->B * s->H * s->W * (long long)t->ld_out < (1ll << 40),
                 ACG_ERR_UNSUPPORTED, "%s: tensor too large", who);
+    return ACG_OK;
+}
+
+int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char* who) {
+    {
+        const char* e = getenv("ACG_DBG_SKIP");
+        p->dbg_skip = e ? atoi(e) : 0;
+    }
+    p->stats = t->stats;
+    p->counter = nullptr;
+    p->total_ctas = total_ctas;
+    if (t->stats && t->bn_counter) {
+        ACG_REQUIRE(t->bn_mean && t->bn_rstd && t->bn_scale && t->bn_shift && t->bn_rows > 0, ACG_ERR_INVALID,
+                    "%s: in-kernel batch-norm finalize needs mean/rstd/scale/shift buffers and the row count", who);
+        p->counter = t->bn_counter;
+        p->beta = t->bn_beta;
+        p->bn_mean = t->bn_mean; p->bn_rstd = t->bn_rstd; p->bn_scale = t->bn_scale; p->bn_shift = t->bn_shift;
+        p->bn_rows = t->bn_rows;
+        p->bn_eps = t->bn_eps;
+    }
     return ACG_OK;
 }
 
@@ -507,6 +987,15 @@ int set_smem(const void* kern) {
 }  // namespace acg
 
 extern "C" {
+
+/* timing experiments: returns {setup ns, main loop ns, epilogue ns, CTAs, K blocks} summed since the last call */
+int acg_debug_phase_times(unsigned long long* out5 /* 8 entries */) {
+    using namespace acg::tc;
+    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (cudaMemcpyFromSymbol(out5, g_phase_ns, sizeof(zero)) != cudaSuccess) return ACG_ERR_CUDA;
+    if (cudaMemcpyToSymbol(g_phase_ns, zero, sizeof(zero)) != cudaSuccess) return ACG_ERR_CUDA;
+    return ACG_OK;
+}
 
 long long acg_pack_size(const acg_conv_shape* s, int which, int ld_k) {
     using namespace acg::tc;
@@ -570,6 +1059,8 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     p.lda = t->ld_in; p.ldo = t->ld_out; p.N = N; p.n_bias = s->Cout; p.n_store = N < t->ld_out ? N : t->ld_out; p.out_dtype = t->out_dtype; p.out_act = t->out_act;
     const long long M = (long long)s->B * s->OH * s->OW;
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, 1);
+    rc = fill_bn(&p, t, grid.x * grid.y, "acg_conv_fprop_tc");
+    if (rc) return rc;
     conv_tc_kernel<CONV><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
     return check_launch("acg_conv_fprop_tc");
 }
@@ -594,15 +1085,44 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     p.lda = t->ld_in; p.ldo = t->ld_out; p.N = N; p.n_bias = s->Cin; p.n_store = N < t->ld_out ? N : t->ld_out; p.out_dtype = t->out_dtype; p.out_act = t->out_act;
     long long off = 0;
     const int ncls = s->stride * s->stride;
+    unsigned int active = 0;
     for (int cls = 0; cls < ncls; ++cls) {
         int na, nc;
         class_taps(s, cls, &na, &nc);
         p.w_class_off[cls] = off;
         off += (long long)N * na * nc * t->ld_in;
+        const int ph = cls / s->stride, pw = cls % s->stride;
+        const long long Mc = (long long)s->B * ((s->H - ph + s->stride - 1) / s->stride) *
+                             ((s->W - pw + s->stride - 1) / s->stride);
+        active += (unsigned int)((Mc + BM - 1) / BM) * (unsigned int)((N + BN - 1) / BN);
     }
     const int Hp = (s->H + s->stride - 1) / s->stride, Wp = (s->W + s->stride - 1) / s->stride;
     const long long M = (long long)s->B * Hp * Wp;
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, ncls);
+    if (halo_ok(s, t, N)) {
+        static bool halo_ready = false;
+        if (!halo_ready) {
+            if (cudaFuncSetAttribute(conv_adj_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem) !=
+                cudaSuccess) {
+                cudaError_t e = cudaGetLastError();
+                set_error("acg_conv_dgrad_tc: cannot set %d B dynamic smem: %s", kHaloSmem, cudaGetErrorString(e));
+                return ACG_ERR_CUDA;
+            }
+            halo_ready = true;
+        }
+        const int TB = HALO_ACC / (s->W / 16);
+        dim3 hgrid((unsigned)((s->B / TB) * (s->H / 32)), 1, 4);
+        rc = fill_bn(&p, t, hgrid.x * 4u, "acg_conv_dgrad_tc");
+        if (rc) return rc;
+        HaloParams hp;
+        hp.p = p;
+        rc = encode_halo_maps(&hp, s, t, N, TB, dy_bf16, w_pack);
+        if (rc) return rc;
+        conv_adj_halo_kernel<<<hgrid, kThreads, kHaloSmem, static_cast<cudaStream_t>(stream)>>>(hp);
+        return check_launch("acg_conv_dgrad_tc(halo)");
+    }
+    rc = fill_bn(&p, t, active, "acg_conv_dgrad_tc");
+    if (rc) return rc;
     conv_tc_kernel<ADJ><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
     return check_launch("acg_conv_dgrad_tc");
 }

@@ -167,6 +167,7 @@ class NetRun:
         self.layers = {}
         n_stat = sum(4 * ru16(L.cout) for L in store.spec)
         self.f64 = torch.zeros(n_stat, dtype=torch.float64, device=device)   # [stats | red] per layer
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)      # "last CTA" ticket of the conv kernels
         soff = 0
         for L in store.spec:
             st = _LayerState()
@@ -224,12 +225,12 @@ class NetRun:
         self.f64.zero_()
 
     # -- convolution dispatch ------------------------------------------------------------------------------
-    def _conv_fwd(self, st, x, out, ld_out, bias=None):
+    def _conv_fwd(self, st, x, out, ld_out, bias=None, stats=None, bn=None):
         L = st.spec
         if self.bf16:
             pk = self.store.packs[L.name]
             fn = K.conv_fprop_tc if L.kind == "conv" else K.conv_dgrad_tc
-            fn(st.shape, x, pk[3], out, st.ld_in, ld_out, bias=bias)
+            fn(st.shape, x, pk[3], out, st.ld_in, ld_out, bias=bias, stats=stats, bn=bn)
         else:
             w = self.store.views[L.name + "/weights"]
             (K.conv_fprop_f32 if L.kind == "conv" else K.conv_dgrad_f32)(st.shape, x, w, out)
@@ -241,6 +242,19 @@ class NetRun:
         st.x = x
         if st.fused:
             self._conv_fwd(st, x, out, ld_out, bias=self.store.views[name + "/biases"] if L.bias else None)
+            return
+        if L.bn and self.bf16:
+            # moments in the conv epilogue; on one GPU the last CTA also finalises mean / rstd / scale / shift
+            beta = self.store.views[name + "/BatchNorm/beta"]
+            if self.dp is None:
+                self._conv_fwd(st, x, st.z, st.ldz, stats=st.stats,
+                               bn=(self.counter, beta, st.mean, st.rstd, st.scale, st.shift, st.rows, BN_EPS))
+            else:
+                self._conv_fwd(st, x, st.z, st.ldz, stats=st.stats)
+                self.dp.allreduce_sum(st.stats)        # SyncBN: statistics over the GLOBAL batch
+                K.bn_finalize(st.stats, beta, st.rows * self.dp.world, L.cout, 1, st.mean, st.rstd, st.scale,
+                              st.shift, BN_EPS)
+            K.bn_act_fwd(st.z, st.rows, L.cout, st.ldz, 1, st.scale, st.shift, L.act, out, ld_out)
             return
         self._conv_fwd(st, x, st.z, st.ldz)
         if L.bn:

@@ -64,17 +64,24 @@ def tc_supported(shape, which):
     return bool(_lib.load().acg_conv_tc_supported(C.byref(shape), which))
 
 
-def _tc_args(ld_in, ld_out, bias, out, out_act):
-    return TcArgs(ld_in, ld_out, ptr(bias), dtype_id(out), ACT_IDS[out_act])
+def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None):
+    """bn = (counter, beta, mean, rstd, scale, shift, rows, eps): finalise the moments in-kernel (single GPU)"""
+    t = TcArgs(ld_in, ld_out, ptr(bias), dtype_id(out), ACT_IDS[out_act], ptr(stats))
+    if bn is not None:
+        counter, beta, mean, rstd, scale, shift, rows, eps = bn
+        t.bn_counter, t.bn_beta = ptr(counter), ptr(beta)
+        t.bn_mean, t.bn_rstd, t.bn_scale, t.bn_shift = ptr(mean), ptr(rstd), ptr(scale), ptr(shift)
+        t.bn_rows, t.bn_eps = rows, eps
+    return t
 
 
-def conv_fprop_tc(shape, x, w_pack, y, ld_in, ld_out, bias=None, out_act=None):
-    t = _tc_args(ld_in, ld_out, bias, y, out_act)
+def conv_fprop_tc(shape, x, w_pack, y, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None):
+    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn)
     call("acg_conv_fprop_tc", C.byref(shape), ptr(x), ptr(w_pack), ptr(y), C.byref(t), stream())
 
 
-def conv_dgrad_tc(shape, dy, w_pack, dx, ld_in, ld_out, bias=None, out_act=None):
-    t = _tc_args(ld_in, ld_out, bias, dx, out_act)
+def conv_dgrad_tc(shape, dy, w_pack, dx, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None):
+    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn)
     call("acg_conv_dgrad_tc", C.byref(shape), ptr(dy), ptr(w_pack), ptr(dx), C.byref(t), stream())
 
 

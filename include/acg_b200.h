@@ -102,6 +102,17 @@ typedef struct acg_tc_args {
     const float* bias;  /* [output channels] or NULL */
     int out_dtype;      /* ACG_F32 | ACG_BF16 */
     int out_act;        /* ACG_ACT_NONE | ACG_ACT_TANH */
+    /* optional: batch-norm moments of THIS layer fused into the epilogue (slim.batch_norm of models.py:11,32,81).
+     * stats [2][C] fp64 (sum | sum of squares over all rows, of the values as stored) is accumulated with atomics
+     * (caller zeroes).  If bn_counter (a zeroed uint32 in device memory) is also given, the last CTA to finish
+     * writes mean / rstd / scale = rstd / shift = beta - mean*rstd (bn_rows rows, epsilon bn_eps) and resets the
+     * counter, so no separate acg_bn_stats / acg_bn_finalize launch is needed on a single GPU. */
+    double* stats;
+    unsigned int* bn_counter;
+    const float* bn_beta;   /* [C] or NULL */
+    float* bn_mean; float* bn_rstd; float* bn_scale; float* bn_shift;
+    long long bn_rows;
+    float bn_eps;
 } acg_tc_args;
 
 /* y = conv(x): x [B,H,W,ld_in] -> y [B,OH,OW,ld_out]; w_pack = acg_pack_weights(which=0, ld_k=ld_in) */
@@ -199,6 +210,10 @@ int acg_rmsprop_step(float* p, const float* g, float* ms, long long n, float lr,
 /* Probe (tests only): D[128][N] = A_window * B^T where A_window's logical row m is shared-memory row
  * shift + (m/8)*pitch + (m%8) of a 128-byte-swizzled K-major [n_rows][64] bf16 tile (start not 1024 B aligned, 8-row
  * groups spaced by `pitch` rows).  base_offset_mode 1 sets the descriptor's base-offset field to (addr>>7)&7. */
+/* Probe (profiling experiments, ACG_DBG_SKIP=8): out[8] = {setup ns, main-loop ns, epilogue ns, CTAs, K blocks,
+ * MMA-thread wait for halo ns, MMA-thread wait for weights ns, 0} of the conv_tc kernels summed over CTAs since the
+ * previous call (synchronises the device). */
+int acg_debug_phase_times(unsigned long long* out8);
 int acg_debug_umma_shift(const void* a_rows, int n_rows, const void* b_rows, int N, int shift, int pitch,
                          int base_offset_mode, float* out, void* stream);
 

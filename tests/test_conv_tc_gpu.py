@@ -37,6 +37,10 @@ CASES = [
     (3, 8, 8, 272, 128, 5, 2, "SAME"),     # adjoint of g/tconv1 with the action concat (266 -> 272)
     (2, 16, 16, 128, 32, 3, 2, "SAME"),    # g/sconv3
     (1, 7, 9, 24, 40, 5, 2, "SAME"),       # odd extents, ragged N
+    (4, 32, 32, 32, 64, 5, 2, "SAME"),     # g/conv2: its dgrad takes the halo-tile kernel (16x16 class grid, 2 images per CTA)
+    (3, 64, 64, 6, 64, 5, 2, "SAME"),      # d/conv1: halo dgrad with N=16, one 64-channel block
+    (2, 32, 32, 128, 128, 3, 2, "SAME"),   # 3x3 stride 2 (pad 0/1): 2x2 / 2x1 / 1x2 / 1x1 taps per class in the halo kernel
+    (2, 64, 64, 128, 192, 5, 2, "SAME"),   # three 64-channel blocks: the halo double buffer is recycled
 ]
 
 
