@@ -244,7 +244,7 @@ __device__ __forceinline__ F8 load8f(const float* p, int c) {   // per-channel p
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 vec_col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void* __restrict__ dA,
                       const void* __restrict__ dA2, int d_dt, int ld_d, long long rows_per_group, int C,
                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ shift,
@@ -256,10 +256,10 @@ vec_col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void
     const int cv = blockIdx.x * bx + threadIdx.x;
     const int g = blockIdx.z;
     const long long r_begin = (long long)g * rows_per_group;
+    // per-thread partial sums stay fp32 (a thread sees ~50 rows); everything across threads / blocks is fp64
     float s0[8], s1[8];
-    double d0[8], d1[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s0[i] = s1[i] = 0.f; d0[i] = d1[i] = 0.0; }
+    for (int i = 0; i < 8; ++i) { s0[i] = s1[i] = 0.f; }
     if (cv < nv) {
         const int c = cv * 8;
         F8 mu, rs, sh;
@@ -272,7 +272,6 @@ vec_col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void
         }
         constexpr int U = MODE == 0 ? 4 : 2;     // independent row vectors in flight per thread
         const long long rstep = (long long)gridDim.y * by;
-        int k = 0;
         for (long long r0 = (long long)blockIdx.y * by + threadIdx.y; r0 < rows_per_group; r0 += rstep * U) {
             F8 zv[U], da[U];
 #pragma unroll
@@ -313,17 +312,10 @@ vec_col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void
                     }
                 }
             }
-            if (++k == 16) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { d0[i] += s0[i]; d1[i] += s1[i]; s0[i] = s1[i] = 0.f; }
-                k = 0;
-            }
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { d0[i] += s0[i]; d1[i] += s1[i]; }
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { sm[i][tid] = d0[i]; sm[8 + i][tid] = d1[i]; }
+    for (int i = 0; i < 8; ++i) { sm[i][tid] = (double)s0[i]; sm[8 + i][tid] = (double)s1[i]; }
     __syncthreads();
     // thread (x, y) finalises values y, y+by, ... (of 16) of vector column x
     if (cv < nv) {
@@ -336,111 +328,140 @@ vec_col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void
     }
 }
 
+// Streaming kernels use the same 2-D thread map as the reductions: thread (x, y) owns the 8-channel vector column
+// blockIdx.x*bx + x and walks rows blockIdx.y*by + y, + gridDim.y*by, ...  No index division in the loop, and the
+// per-channel parameters live in registers for the whole kernel.
 __global__ void __launch_bounds__(256)
-vec_bn_act_fwd_kernel(const void* __restrict__ z, int z_dt, long long rows, int C, int ld_in, long long rows_per_group,
+vec_bn_act_fwd_kernel(const void* __restrict__ z, int z_dt, int C, int ld_in, long long rows_per_group,
                       const float* __restrict__ scale, const float* __restrict__ shift, int act, void* __restrict__ out,
                       int o_dt, int ld_out) {
-    const int nv = C >> 3;
-    const long long total = rows * nv;
+    const int bx = blockDim.x, by = blockDim.y;
+    const int cv = blockIdx.x * bx + threadIdx.x;
+    if (cv >= (C >> 3)) return;
+    const int c = cv * 8, g = blockIdx.z;
+    F8 sc, sh;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc.v[i] = 1.f; sh.v[i] = 0.f; }
+    if (scale) sc = load8f(scale + (size_t)g * C, c);
+    if (shift) sh = load8f(shift + (size_t)g * C, c);
+    const long long r_begin = (long long)g * rows_per_group;
     constexpr int U = 4;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += step * U) {
+    const long long rstep = (long long)gridDim.y * by;
+    for (long long r0 = (long long)blockIdx.y * by + threadIdx.y; r0 < rows_per_group; r0 += rstep * U) {
         F8 u[U];
-        long long rr[U];
-        int cc[U];
 #pragma unroll
         for (int q = 0; q < U; ++q) {
-            const long long idx = idx0 + q * step;
-            rr[q] = idx / nv;
-            cc[q] = (int)(idx - rr[q] * nv) * 8;
-            if (idx < total) u[q] = load8(z, z_dt, (size_t)rr[q] * ld_in + cc[q]);
+            const long long r = r0 + q * rstep;
+            if (r < rows_per_group) u[q] = load8(z, z_dt, (size_t)(r_begin + r) * ld_in + c);
         }
 #pragma unroll
         for (int q = 0; q < U; ++q) {
-            if (idx0 + q * step >= total) break;
-            const size_t gc = (size_t)(rr[q] / rows_per_group) * C + cc[q];
-            if (scale) { const F8 sc = load8f(scale, gc);
+            const long long r = r0 + q * rstep;
+            if (r >= rows_per_group) break;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) u[q].v[i] *= sc.v[i]; }
-            if (shift) { const F8 sh = load8f(shift, gc);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) u[q].v[i] += sh.v[i]; }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) u[q].v[i] = act_fwd(u[q].v[i], act);
-            store8(out, o_dt, (size_t)rr[q] * ld_out + cc[q], u[q]);
+            for (int i = 0; i < 8; ++i) u[q].v[i] = act_fwd(fmaf(u[q].v[i], sc.v[i], sh.v[i]), act);
+            store8(out, o_dt, (size_t)(r_begin + r) * ld_out + c, u[q]);
         }
     }
 }
 
-__global__ void __launch_bounds__(256)
+// dz = rs*dzh - rs*m0 - rs^2*m1*(z - mu) = rs*dzh + k1*z + k0 with per-channel k1 = -rs^2*m1, k0 = rs^2*m1*mu - rs*m0:
+// the fp64 reduction results are folded into fp32 coefficients once per thread, the streaming loop is 3 FMAs/element.
+__global__ void __launch_bounds__(256, 4)
 vec_bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict__ dA2, int d_dt, int ld_d,
-                            const void* __restrict__ z, int z_dt, int ld_z, long long rows, int C, int groups,
+                            const void* __restrict__ z, int z_dt, int ld_z, int C, int groups,
                             long long rows_per_group, const float* __restrict__ mean, const float* __restrict__ rstd,
                             const float* __restrict__ shift, int act, int has_bn, const double* __restrict__ red,
                             void* __restrict__ dz, int dz_dt, int ld_dz, float* __restrict__ dbeta, long long norm_rows,
                             float dbeta_scale) {
-    const int nv = C >> 3;
-    const long long total = rows * nv;
-    const float inv_r = 1.f / (float)norm_rows;
+    __shared__ float4 coef[256];               // this block's <= 32 vector columns x 8 channels: rs, sh, k1, k0
+    const int bx = blockDim.x, by = blockDim.y;
+    const int tid = threadIdx.y * bx + threadIdx.x;
+    const int cv = blockIdx.x * bx + threadIdx.x;
+    const int g = blockIdx.z;
+    if (dbeta && blockIdx.x == 0 && blockIdx.y == 0 && g == 0) {
+        for (int c = tid; c < C; c += bx * by) {
+            double t = 0.0;
+            for (int gg = 0; gg < groups; ++gg) t += red[(size_t)gg * 2 * C + c];
+            dbeta[c] += dbeta_scale * (float)t;
+        }
+    }
+    if (tid < bx * 8) {
+        const int c = blockIdx.x * bx * 8 + tid;
+        float4 k = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (c < C) {
+            const size_t gc = (size_t)g * C + c;
+            const float r = rstd ? rstd[gc] : 1.f, mu = mean ? mean[gc] : 0.f;
+            k.x = r;
+            k.y = shift ? shift[gc] : 0.f;
+            if (has_bn) {
+                const double inv_r = 1.0 / (double)norm_rows;
+                const double m0 = red[(size_t)g * 2 * C + c] * inv_r, m1 = red[(size_t)g * 2 * C + C + c] * inv_r;
+                k.z = (float)(-(double)r * r * m1);
+                k.w = (float)((double)r * r * m1 * mu - (double)r * m0);
+            }
+        }
+        coef[tid] = k;
+    }
+    __syncthreads();
+    if (cv >= (C >> 3)) return;
+    const int c = cv * 8;
+    const float4* cf = coef + threadIdx.x * 8;
+    const long long r_begin = (long long)g * rows_per_group;
     constexpr int U = 2;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long idx0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx0 < total; idx0 += step * U) {
+    const long long rstep = (long long)gridDim.y * by;
+    for (long long r0 = (long long)blockIdx.y * by + threadIdx.y; r0 < rows_per_group; r0 += rstep * U) {
         F8 zv[U], d[U];
-        long long rr[U];
-        int cc[U];
 #pragma unroll
         for (int q = 0; q < U; ++q) {
-            const long long idx = idx0 + q * step;
-            rr[q] = idx / nv;
-            cc[q] = (int)(idx - rr[q] * nv) * 8;
-            const bool ok = idx < total;
-            if (z && ok) zv[q] = load8(z, z_dt, (size_t)rr[q] * ld_z + cc[q]);
+            const long long r = r0 + q * rstep;
+            const bool ok = r < rows_per_group;
+            if (z && ok) zv[q] = load8(z, z_dt, (size_t)(r_begin + r) * ld_z + c);
             else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) zv[q].v[i] = 0.f;
             }
             if (ok) {
-                d[q] = load8(dA, d_dt, (size_t)rr[q] * ld_d + cc[q]);
+                d[q] = load8(dA, d_dt, (size_t)(r_begin + r) * ld_d + c);
                 if (dA2) {
-                    const F8 d2 = load8(dA2, d_dt, (size_t)rr[q] * ld_d + cc[q]);
+                    const F8 d2 = load8(dA2, d_dt, (size_t)(r_begin + r) * ld_d + c);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) d[q].v[i] += d2.v[i];
                 }
             }
         }
 #pragma unroll
-        for (int q = 0; q < U; ++q) {
-            if (idx0 + q * step >= total) break;
-            const int c = cc[q];
-            const int g = (int)(rr[q] / rows_per_group);
-            const size_t gc = (size_t)g * C + c;
-            F8 mu, rs, sh;
+        for (int i = 0; i < 8; ++i) {
+            const float4 k = cf[i];                       // rs, sh, k1, k0
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { mu.v[i] = 0.f; rs.v[i] = 1.f; sh.v[i] = 0.f; }
-            if (mean) mu = load8f(mean, gc);
-            if (rstd) rs = load8f(rstd, gc);
-            if (shift) sh = load8f(shift, gc);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float u = zv[q].v[i] * rs.v[i] + sh.v[i];
-                float dv = d[q].v[i] * act_bwd(u, act);
-                if (has_bn) {
-                    const float m0 = (float)red[(size_t)g * 2 * C + c + i] * inv_r;
-                    const float m1 = (float)red[(size_t)g * 2 * C + C + c + i] * inv_r;
-                    dv = rs.v[i] * (dv - m0 - (zv[q].v[i] - mu.v[i]) * rs.v[i] * m1);
-                }
-                d[q].v[i] = dv;
+            for (int q = 0; q < U; ++q) {
+                const float zz = zv[q].v[i];
+                const float dzh = d[q].v[i] * act_bwd(fmaf(zz, k.x, k.y), act);
+                d[q].v[i] = has_bn ? fmaf(k.x, dzh, fmaf(k.z, zz, k.w)) : dzh;
             }
-            store8(dz, dz_dt, (size_t)rr[q] * ld_dz + c, d[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            const long long r = r0 + q * rstep;
+            if (r < rows_per_group) store8(dz, dz_dt, (size_t)(r_begin + r) * ld_dz + c, d[q]);
         }
     }
-    if (dbeta && blockIdx.x == 0) {
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            double t = 0.0;
-            for (int g = 0; g < groups; ++g) t += red[(size_t)g * 2 * C + c];
-            dbeta[c] += dbeta_scale * (float)t;
-        }
-    }
+}
+
+// 2-D launch shape shared by the streaming kernels: `waves` resident blocks per SM
+void vec_stream_launch_dims(long long rows_per_group, int C, int groups, int blocks_per_sm, dim3* grid, dim3* block) {
+    const int nv = C >> 3;
+    int bx = 1;
+    while (bx < nv && bx < 32) bx <<= 1;
+    const int by = 256 / bx;
+    const int gx = (nv + bx - 1) / bx;
+    long long gy = (rows_per_group + (long long)by * 8 - 1) / ((long long)by * 8);
+    long long cap = ((long long)num_sms() * blocks_per_sm) / ((long long)gx * groups);
+    if (cap < 1) cap = 1;
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    *grid = dim3(gx, (unsigned)gy, groups);
+    *block = dim3(bx, by);
 }
 
 bool al16(const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; }
@@ -451,8 +472,10 @@ void vec_reduce_launch_dims(long long rows_per_group, int C, int groups, dim3* g
     while (bx < nv && bx < 32) bx <<= 1;
     const int by = 256 / bx;
     const int gx = (nv + bx - 1) / bx;
-    long long gy = (rows_per_group + (long long)by * 4 - 1) / ((long long)by * 4);   // >= 4 rows per thread
-    long long cap = ((long long)num_sms() * 8) / ((long long)gx * groups);
+    long long gy = (rows_per_group + (long long)by * 16 - 1) / ((long long)by * 16);   // >= 16 rows per thread
+    // two resident 256-thread blocks per SM (register limited): one wave, so the per-block tree reduction and the
+    // fp64 atomics are amortised over ~50 rows per thread instead of ~14
+    long long cap = ((long long)num_sms() * 3) / ((long long)gx * groups);
     if (cap < 1) cap = 1;
     if (gy > cap) gy = cap;
     if (gy < 1) gy = 1;
@@ -512,8 +535,10 @@ int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in,
                 ACG_ERR_INVALID, "acg_bn_act_fwd: bad size");
     ACG_REQUIRE(dt_ok(z_dtype) && dt_ok(out_dtype), ACG_ERR_UNSUPPORTED, "acg_bn_act_fwd: dtype");
     if (C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && al16(z) && al16(out) && al16(scale) && al16(shift)) {
-        vec_bn_act_fwd_kernel<<<vec_ew_grid(rows * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            z, z_dtype, rows, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
+        dim3 grid, block;
+        vec_stream_launch_dims(rows / groups, C, groups, 8, &grid, &block);
+        vec_bn_act_fwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+            z, z_dtype, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
         return check_launch("acg_bn_act_fwd");
     }
     bn_act_fwd_kernel<<<ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -559,8 +584,10 @@ int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d,
                 "acg_bn_act_bwd_apply: dtype");
     if (C % 8 == 0 && ld_d % 8 == 0 && (!z || ld_z % 8 == 0) && ld_dz % 8 == 0 && al16(z) && al16(dA) && al16(dA2) &&
         al16(dz) && al16(mean) && al16(rstd) && al16(shift)) {
-        vec_bn_act_bwd_apply_kernel<<<vec_ew_grid(rows * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, rows, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
+        dim3 grid, block;
+        vec_stream_launch_dims(rows / groups, C, groups, 8, &grid, &block);   // 4 resident blocks/SM, 2 waves
+        vec_bn_act_bwd_apply_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+            dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
             dz, dz_dtype, ld_dz, dbeta, norm_rows > 0 ? norm_rows : rows / groups, dbeta_scale);
         return check_launch("acg_bn_act_bwd_apply");
     }
