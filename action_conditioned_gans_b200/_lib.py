@@ -31,6 +31,13 @@ class TcArgs(C.Structure):
                 ("bn_rows", C.c_longlong), ("bn_eps", C.c_float)]
 
 
+class PackJob(C.Structure):
+    """struct acg_pack_job"""
+    _fields_ = [("w", C.c_void_p), ("pack", C.c_void_p), ("first", C.c_longlong), ("which", C.c_int),
+                ("ld_k", C.c_int), ("KH", C.c_int), ("KW", C.c_int), ("Cin", C.c_int), ("Cout", C.c_int),
+                ("stride", C.c_int), ("pad_t", C.c_int), ("pad_l", C.c_int), ("N", C.c_int)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _SP = C.POINTER(ConvShape)
 _FP = C.POINTER(TcArgs)
@@ -47,6 +54,7 @@ SIGNATURES = {
     "acg_conv_dgrad_tc": [_SP, _P, _P, _P, _FP, _P],
     "acg_conv_wgrad_tc": [_SP, _P, _P, _P, _FP, _P],
     "acg_pack_weights": [_SP, _P, _I, _I, _P, _P],
+    "acg_pack_weights_batched": [_P, _I, _L, _P],
     "acg_conv_tc_supported": [_SP, _I],
     "acg_bn_stats": [_P, _I, _L, _I, _I, _I, _P, _P],
     "acg_bn_finalize": [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _P],

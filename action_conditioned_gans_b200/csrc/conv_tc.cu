@@ -29,6 +29,7 @@ constexpr int BM = 128, BK = 64, BN = 128, STAGES = 3;
 constexpr int kProducers = 128, kThreads = 160;
 constexpr int kStageA = BM * BK * 2, kStageB = BN * BK * 2;
 constexpr int kSmemBytes = STAGES * (kStageA + kStageB) + 1024;  // + alignment slack
+constexpr int kSmemBytes6 = 6 * (kStageA + kStageB) + 1024;
 
 struct Params {
     const __nv_bfloat16* a_src;
@@ -244,6 +245,42 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
     }
 }
 
+constexpr int HALO_ACC = 4;
+constexpr int HALO_H = 18;    // staged halo rows per image: 16 output rows + (na-1) <= 2
+
+struct alignas(64) HaloParams {
+    Params p;
+    CUtensorMap map_a;        // bf16 [B][OH][OW][lda], box {64 ch, OW+2, 18, TB}, 128B swizzle, zero OOB fill
+    CUtensorMap map_b[4];     // per parity class: bf16 [N][Kc], box {64, N}, 128B swizzle
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+constexpr int kHaloBuf = 648 * 128;                       // 18 x 34 (one image) or 2 x 18 x 18 rows of 128 B
+constexpr int kHaloBStage = BN * BK * 2;
+constexpr int kHaloBStages = 3;
+constexpr int kHaloSmem = 2 * kHaloBuf + kHaloBStages * kHaloBStage + 1024;
+
+
+struct alignas(64) ConvParams {
+    Params p;
+    CUtensorMap map_b[4];     // weights: CONV [N][Ktot] (entry 0) / ADJ per parity class [N][Kc]; box {64, 128}, 128B swizzle
+};
+
 enum { CONV = 0, ADJ = 1 };
 
 // timing experiments (ACG_DBG_SKIP bit 3): per-phase nanoseconds summed over CTAs
@@ -254,9 +291,14 @@ __device__ __forceinline__ unsigned long long gtime() {
     return t;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2)
-conv_tc_kernel(const Params p) {
+// NST = pipeline depth.  3 stages (96 KB) keep two CTAs per SM so that one CTA's epilogue overlaps the other's main loop;
+// launches with fewer CTAs than SMs (the 4x4 / 8x8 layers: few tiles, K up to 6400) are latency bound per K slice and
+// take the 6-stage variant (192 KB, one CTA per SM) instead.
+template <int MODE, int NST>
+__global__ void __launch_bounds__(kThreads, NST == 3 ? 2 : 1)
+conv_tc_kernel(const __grid_constant__ ConvParams cp) {
+    const Params& p = cp.p;
+    constexpr int STAGES = NST;
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
     __shared__ uint32_t tmem_base_sh;
@@ -297,9 +339,10 @@ conv_tc_kernel(const Params p) {
     const int nkb = (Ktot + BK - 1) / BK;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], kProducers); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], kProducers + 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(&acc_bar, 1);
         fence_mbar_init();
+        tma_prefetch_desc(&cp.map_b[MODE == ADJ ? blockIdx.z : 0]);
     }
     if (warp == 4) {   // tensor-memory allocation is warp-collective; this warp also owns the dealloc
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
@@ -314,58 +357,66 @@ conv_tc_kernel(const Params p) {
 
     if (warp < 4) {
         // ================================ producers ================================
+        // A (activations): cp.async 16 B gathers.  Everything that does not change along K is hoisted: per row an
+        // element offset of its tap-(0,0) source pixel and a bit mask of the taps that fall inside the image, so a
+        // K slice costs ~6 instructions per row (mask test, 64-bit add, LDGSTS) instead of the full index math.
+        // B (weights): ONE 2-D TMA copy per K slice issued by thread 0 (hardware swizzle, zero fill past N / Ktot).
         const int j = tid & 7, rslot = tid >> 3;
-        int row_b[8], row_y[8], row_x[8];
+        long long row_off[8];
+        uint32_t row_mask[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int m = tile_m + rslot + 16 * i;
+            row_off[i] = 0;
+            row_mask[i] = 0;
             if (m < M) {
                 if (MODE == CONV) {
                     const int b = m / (p.OH * p.OW), r = m - b * p.OH * p.OW;
                     const int oh = r / p.OW, ow = r - oh * p.OW;
-                    row_b[i] = b * p.H * p.W; row_y[i] = oh * s - p.pad_t; row_x[i] = ow * s - p.pad_l;
+                    const int y0 = oh * s - p.pad_t, x0 = ow * s - p.pad_l;
+                    row_off[i] = ((long long)(b * p.H + y0) * p.W + x0) * p.lda;
+                    // taps a in [a_lo, a_hi) x c in [c_lo, c_hi) fall inside the image
+                    const int a_lo = max(0, -y0), a_hi = min(p.KH, p.H - y0);
+                    const int c_lo = max(0, -x0), c_hi = min(p.KW, p.W - x0);
+                    if (c_hi > c_lo) {
+                        const uint32_t cm = ((1u << c_hi) - 1u) & ~((1u << c_lo) - 1u);
+                        for (int a = a_lo; a < a_hi; ++a) row_mask[i] |= cm << (a * p.KW);
+                    }
                 } else {
                     const int b = m / (Hp * Wp), r = m - b * Hp * Wp;
                     const int ih = (r / Wp) * s + ph, iw = (r % Wp) * s + pw;
-                    row_b[i] = b * p.OH * p.OW; row_y[i] = ih + p.pad_t; row_x[i] = iw + p.pad_l;
+                    const int ohb = (ih + p.pad_t - a0) / s, owb = (iw + p.pad_l - c0) / s;   // tap (0,0) of the class
+                    row_off[i] = ((long long)(b * p.OH + ohb) * p.OW + owb) * p.lda;
+                    // class taps ta in [a_lo, a_hi) x tc in [c_lo, c_hi): 0 <= ohb - ta < OH, 0 <= owb - tc < OW
+                    const int a_lo = max(0, ohb - p.OH + 1), a_hi = min(ntaps / nc, ohb + 1);
+                    const int c_lo = max(0, owb - p.OW + 1), c_hi = min(nc, owb + 1);
+                    if (c_hi > c_lo) {
+                        const uint32_t cm = ((1u << c_hi) - 1u) & ~((1u << c_lo) - 1u);
+                        for (int ta = a_lo; ta < a_hi; ++ta) row_mask[i] |= cm << (ta * nc);
+                    }
                 }
-            } else {
-                row_b[i] = 0; row_y[i] = -(1 << 28); row_x[i] = -(1 << 28);   // always out of range -> zero fill
             }
         }
+        const CUtensorMap* bmap = &cp.map_b[MODE == ADJ ? blockIdx.z : 0];
         int tap = (j * 8) / p.lda, ci = (j * 8) % p.lda;
         for (int kb = 0; kb < nkb; ++kb) {
             const int stage = kb % STAGES;
             if (kb >= STAGES) mbar_wait(&empty_bar[stage], (uint32_t)(((kb / STAGES) - 1) & 1));
-            const bool kvalid = tap < ntaps;
-            int a, c;
-            if (MODE == CONV) { a = tap / p.KW; c = tap - a * p.KW; }
-            else { const int ta = tap / nc, tcc = tap - ta * nc; a = a0 + s * ta; c = c0 + s * tcc; }
-            const uint32_t dstA = smemA + stage * kStageA;
+            if (tid == 0) {
+                mbar_expect_tx(&full_bar[stage], (uint32_t)min(p.N, BN) * 128u);
+                tma_load_2d(smemB + stage * kStageB, bmap, kb * BK, n0, &full_bar[stage]);
+            }
+            const uint32_t tbit = tap < ntaps ? (1u << tap) : 0u;
+            long long koff;
+            if (MODE == CONV) { const int a = tap / p.KW, c = tap - a * p.KW; koff = (long long)(a * p.W + c) * p.lda + ci; }
+            else { const int ta = tap / nc, tcc = tap - ta * nc; koff = ci - (long long)(ta * p.OW + tcc) * p.lda; }
+            const uint32_t dstA = smemA + stage * kStageA + (rslot * 128) + (j << 4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int r = rslot + 16 * i;
-                bool ok;
-                long long off;
-                if (MODE == CONV) {
-                    const int ih = row_y[i] + a, iw = row_x[i] + c;
-                    ok = kvalid && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
-                    off = ((long long)(row_b[i] + ih * p.W + iw)) * p.lda + ci;
-                } else {
-                    const int ny = row_y[i] - a, nx = row_x[i] - c;   // multiples of the stride inside a class
-                    const int oh = ny / s, ow = nx / s;
-                    ok = kvalid && ny >= 0 && nx >= 0 && oh < p.OH && ow < p.OW;
-                    off = ((long long)(row_b[i] + oh * p.OW + ow)) * p.lda + ci;
-                }
-                cp_async16(dstA + r * 128 + ((j ^ (r & 7)) << 4), ok ? (const void*)(p.a_src + off) : (const void*)p.a_src,
-                           ok ? 16u : 0u);
-            }
-            const uint32_t dstB = smemB + stage * kStageB;
-            const long long kk = (long long)kb * BK + j * 8;
-            for (int r = rslot; r < n_cta; r += 16) {
-                const bool ok = kk < Ktot;
-                cp_async16(dstB + r * 128 + ((j ^ (r & 7)) << 4),
-                           ok ? (const void*)(wmat + (long long)(n0 + r) * Ktot + kk) : (const void*)wmat, ok ? 16u : 0u);
+                // row r = rslot + 16 i: r & 7 == rslot & 7, so the swizzle term is the same for all 8 rows
+                const bool ok = (row_mask[i] & tbit) != 0;
+                cp_async16((dstA ^ ((uint32_t)(rslot & 7) << 4)) + i * 2048,
+                           ok ? (const void*)(p.a_src + row_off[i] + koff) : (const void*)p.a_src, ok ? 16u : 0u);
             }
             cp_async_arrive_noinc(&full_bar[stage]);
             ci += BK;
@@ -475,36 +526,6 @@ conv_tc_kernel(const Params p) {
 //     bits, so a start that is not 1024-B aligned is fine (verified on hardware by acg_debug_umma_shift);
 //   * every streamed weight slice (tap x 64 channels, N x 128 B) feeds 16 MMAs (4 accumulators x K=64) instead of 4.
 // L2->SM traffic per output tile drops ~5x (A: taps x 16 KB -> 1/4 of a shared 83 KB halo; B: 16 KB -> 4 KB).
-constexpr int HALO_ACC = 4;
-constexpr int HALO_H = 18;    // staged halo rows per image: 16 output rows + (na-1) <= 2
-
-struct alignas(64) HaloParams {
-    Params p;
-    CUtensorMap map_a;        // bf16 [B][OH][OW][lda], box {64 ch, OW+2, 18, TB}, 128B swizzle, zero OOB fill
-    CUtensorMap map_b[4];     // per parity class: bf16 [N][Kc], box {64, N}, 128B swizzle
-};
-
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-constexpr int kHaloBuf = 648 * 128;                       // 18 x 34 (one image) or 2 x 18 x 18 rows of 128 B
-constexpr int kHaloBStage = BN * BK * 2;
-constexpr int kHaloBStages = 3;
-constexpr int kHaloSmem = 2 * kHaloBuf + kHaloBStages * kHaloBStage + 1024;
-
 __global__ void __launch_bounds__(kThreads, 1)
 conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
     const Params& p = hp.p;
@@ -692,6 +713,52 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
     }
 }
 
+
+// ---- all packs of a parameter store in ONE launch ---------------------------------------------------------------
+// After every optimizer step ~22 weight tensors x 2 packs have to be refreshed; one launch per pack costs more in
+// launch latency than in work.  The job table lives in device memory (built once by the host).
+__global__ void __launch_bounds__(256)
+pack_batched_kernel(const acg_pack_job* __restrict__ jobs, int njobs, long long total) {
+    for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < total;
+         gidx += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = njobs - 1;          // last job whose first element is <= gidx
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].first <= gidx) lo = mid; else hi = mid - 1;
+        }
+        const acg_pack_job j = jobs[lo];
+        const long long idx = gidx - j.first;
+        const float* w = static_cast<const float*>(j.w);
+        __nv_bfloat16* out = static_cast<__nv_bfloat16*>(j.pack);
+        const int ld = j.ld_k;
+        float v = 0.f;
+        if (j.which == 0) {                  // [N][tap][ld]
+            const int taps = j.KH * j.KW;
+            const int ci = (int)(idx % ld);
+            const long long r = idx / ld;
+            const int tap = (int)(r % taps), n = (int)(r / taps);
+            if (ci < j.Cin && n < j.Cout) v = w[((size_t)tap * j.Cin + ci) * j.Cout + n];
+        } else {                             // per parity class [N][class tap][ld], classes back to back
+            long long rem = idx;
+            int cls = 0, na = 0, nc = 0, a0 = 0, c0 = 0;
+            for (; cls < j.stride * j.stride; ++cls) {
+                a0 = (cls / j.stride + j.pad_t) % j.stride; c0 = (cls % j.stride + j.pad_l) % j.stride;
+                na = a0 < j.KH ? (j.KH - a0 + j.stride - 1) / j.stride : 0;
+                nc = c0 < j.KW ? (j.KW - c0 + j.stride - 1) / j.stride : 0;
+                const long long sz = (long long)j.N * na * nc * ld;
+                if (rem < sz) break;
+                rem -= sz;
+            }
+            const int co = (int)(rem % ld);
+            const long long r = rem / ld;
+            const int t = (int)(r % (na * nc)), n = (int)(r / (na * nc));
+            const int a = a0 + j.stride * (t / nc), c = c0 + j.stride * (t % nc);
+            if (co < j.Cout && n < j.Cin) v = w[((size_t)(a * j.KW + c) * j.Cin + n) * j.Cout + co];
+        }
+        out[idx] = __float2bfloat16_rn(v);
+    }
+}
+
 int ru(int v, int m) { return (v + m - 1) / m * m; }
 
 void class_taps(const acg_conv_shape* s, int cls, int* na, int* nc) {
@@ -716,6 +783,21 @@ EncodeTiledFn encode_tiled_fn() {
         fn = reinterpret_cast<EncodeTiledFn>(ptr);
     }
     return fn;
+}
+
+// bf16 [rows][K] row-major weight pack -> 2-D map with a {64 x 128} box (128B swizzle, zero fill out of bounds)
+int encode_weight_map(CUtensorMap* map, const void* base, long long K, int rows, const char* who) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    ACG_REQUIRE(enc, ACG_ERR_CUDA, "%s: cuTensorMapEncodeTiled is not available", who);
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(rows < BN ? rows : BN)};   // kernels expect min(N, 128) x 128 B per slice
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACG_REQUIRE(r == CUDA_SUCCESS, ACG_ERR_CUDA, "%s: weight tensor map failed (%d)", who, (int)r);
+    return ACG_OK;
 }
 
 int encode_halo_maps(HaloParams* hp, const acg_conv_shape* s, const acg_tc_args* t, int N, int TB, const void* dy,
@@ -943,6 +1025,7 @@ pack_adj_kernel(const float* __restrict__ w, int KH, int KW, int Cin, int Cout, 
 int check(const acg_conv_shape* s, const acg_tc_args* t, const char* who) {
     ACG_REQUIRE(s && t, ACG_ERR_INVALID, "%s: null shape/args", who);
     ACG_REQUIRE(s->stride == 1 || s->stride == 2, ACG_ERR_UNSUPPORTED, "%s: stride %d", who, s->stride);
+    ACG_REQUIRE(s->KH * s->KW <= 32, ACG_ERR_UNSUPPORTED, "%s: more than 32 filter taps", who);
     ACG_REQUIRE(t->ld_in % 8 == 0 && t->ld_in > 0, ACG_ERR_UNSUPPORTED, "%s: ld_in=%d must be a multiple of 8", who,
                 t->ld_in);
     ACG_REQUIRE(t->ld_out > 0, ACG_ERR_INVALID, "%s: ld_out=%d", who, t->ld_out);
@@ -974,8 +1057,8 @@ int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char
     return ACG_OK;
 }
 
-int set_smem(const void* kern) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) != cudaSuccess) {
+int set_smem(const void* kern, int bytes) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
         cudaError_t e = cudaGetLastError();
         set_error("conv_tc: cannot set dynamic smem: %s", cudaGetErrorString(e));
         return ACG_ERR_CUDA;
@@ -1033,6 +1116,16 @@ int acg_pack_weights(const acg_conv_shape* s, const float* w, int which, int ld_
     return check_launch("acg_pack_weights");
 }
 
+int acg_pack_weights_batched(const acg_pack_job* jobs_dev, int njobs, long long total, void* stream) {
+    using namespace acg;
+    using namespace acg::tc;
+    ACG_REQUIRE(jobs_dev && njobs > 0 && total > 0, ACG_ERR_INVALID, "acg_pack_weights_batched: bad argument");
+    long long blocks = (total + 255) / 256;
+    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+    pack_batched_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_dev, njobs, total);
+    return check_launch("acg_pack_weights_batched");
+}
+
 int acg_conv_tc_supported(const acg_conv_shape* s, int which) {
     if (!s) return 0;
     if (s->stride != 1 && s->stride != 2) return 0;
@@ -1050,7 +1143,12 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     const int N = ru(s->Cout, 16);
     ACG_REQUIRE(t->ld_out >= s->Cout, ACG_ERR_INVALID, "acg_conv_fprop_tc: ld_out=%d < Cout=%d", t->ld_out, s->Cout);
     static bool ready = false;
-    if (!ready) { rc = set_smem((const void*)conv_tc_kernel<CONV>); if (rc) return rc; ready = true; }
+    if (!ready) {
+        rc = set_smem((const void*)conv_tc_kernel<CONV, 3>, kSmemBytes);
+        if (!rc) rc = set_smem((const void*)conv_tc_kernel<CONV, 6>, kSmemBytes6);
+        if (rc) return rc;
+        ready = true;
+    }
     Params p{};
     p.a_src = static_cast<const __nv_bfloat16*>(x_bf16); p.w_pack = static_cast<const __nv_bfloat16*>(w_pack);
     p.out = y; p.bias = t->bias;
@@ -1061,7 +1159,14 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, 1);
     rc = fill_bn(&p, t, grid.x * grid.y, "acg_conv_fprop_tc");
     if (rc) return rc;
-    conv_tc_kernel<CONV><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+    ConvParams cp;
+    cp.p = p;
+    rc = encode_weight_map(&cp.map_b[0], w_pack, (long long)s->KH * s->KW * t->ld_in, N, "acg_conv_fprop_tc");
+    if (rc) return rc;
+    if ((long long)grid.x * grid.y <= num_sms())
+        conv_tc_kernel<CONV, 6><<<grid, kThreads, kSmemBytes6, static_cast<cudaStream_t>(stream)>>>(cp);
+    else
+        conv_tc_kernel<CONV, 3><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(cp);
     return check_launch("acg_conv_fprop_tc");
 }
 
@@ -1076,7 +1181,12 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     const int N = ru(s->Cin, 16);
     ACG_REQUIRE(t->ld_out >= s->Cin, ACG_ERR_INVALID, "acg_conv_dgrad_tc: ld_out=%d < Cin=%d", t->ld_out, s->Cin);
     static bool ready = false;
-    if (!ready) { rc = set_smem((const void*)conv_tc_kernel<ADJ>); if (rc) return rc; ready = true; }
+    if (!ready) {
+        rc = set_smem((const void*)conv_tc_kernel<ADJ, 3>, kSmemBytes);
+        if (!rc) rc = set_smem((const void*)conv_tc_kernel<ADJ, 6>, kSmemBytes6);
+        if (rc) return rc;
+        ready = true;
+    }
     Params p{};
     p.a_src = static_cast<const __nv_bfloat16*>(dy_bf16); p.w_pack = static_cast<const __nv_bfloat16*>(w_pack);
     p.out = dx; p.bias = t->bias;
@@ -1123,7 +1233,20 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     }
     rc = fill_bn(&p, t, active, "acg_conv_dgrad_tc");
     if (rc) return rc;
-    conv_tc_kernel<ADJ><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+    ConvParams cp;
+    cp.p = p;
+    for (int cls = 0; cls < ncls; ++cls) {
+        int na, nc;
+        class_taps(s, cls, &na, &nc);
+        if (na * nc == 0) { cp.map_b[cls] = cp.map_b[0]; continue; }
+        rc = encode_weight_map(&cp.map_b[cls], static_cast<const __nv_bfloat16*>(w_pack) + p.w_class_off[cls],
+                               (long long)na * nc * t->ld_in, N, "acg_conv_dgrad_tc");
+        if (rc) return rc;
+    }
+    if ((long long)active <= num_sms())
+        conv_tc_kernel<ADJ, 6><<<grid, kThreads, kSmemBytes6, static_cast<cudaStream_t>(stream)>>>(cp);
+    else
+        conv_tc_kernel<ADJ, 3><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(cp);
     return check_launch("acg_conv_dgrad_tc");
 }
 
@@ -1141,7 +1264,7 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
                     (long long)s->B * s->OH * s->OW < (1ll << 31),
                 ACG_ERR_UNSUPPORTED, "acg_conv_wgrad_tc: tensor too large");
     static bool ready = false;
-    if (!ready) { int rc = set_smem((const void*)conv_wgrad_tc_kernel); if (rc) return rc; ready = true; }
+    if (!ready) { int rc = set_smem((const void*)conv_wgrad_tc_kernel, kSmemBytes); if (rc) return rc; ready = true; }
     WgradParams p{};
     p.x = static_cast<const __nv_bfloat16*>(x_bf16); p.dy = static_cast<const __nv_bfloat16*>(dy_bf16); p.dw = dw;
     p.B = s->B; p.H = s->H; p.W = s->W; p.OH = s->OH; p.OW = s->OW; p.KH = s->KH; p.KW = s->KW;

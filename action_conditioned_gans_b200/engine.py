@@ -118,16 +118,25 @@ class ParamStore:
         self.grad = torch.zeros(off, dtype=torch.float32, device=device)
         self.views = {n: self.flat[o:o + k].view(shape) for n, (o, k, shape) in self.offsets.items()}
         self.gviews = {n: self.grad[o:o + k].view(shape) for n, (o, k, shape) in self.offsets.items()}
+        self._pack_table = None
         self.packs = {}      # layer name -> (shape, fwd_which, fwd_ld, fwd_pack, bwd_which, bwd_ld, bwd_pack)
         if init is not None:
             self.load(init)
 
     def refresh_packs(self):
-        """bf16 GEMM-ready copies of the fp32 master weights (after init / load and after every optimizer step)."""
-        for name, (shape, fw, fld, pf, bw, bld, pb) in self.packs.items():
-            w = self.views[name + "/weights"]
-            K.pack_weights(shape, w, fw, fld, pf)
-            K.pack_weights(shape, w, bw, bld, pb)
+        """bf16 GEMM-ready copies of the fp32 master weights (after init / load and after every optimizer step):
+        every pack of the store in ONE launch through a device-side job table."""
+        if not self.packs:
+            return
+        if self._pack_table is None or self._pack_table[3] != len(self.packs):
+            entries = []
+            for name, (shape, fw, fld, pf, bw, bld, pb) in self.packs.items():
+                w = self.views[name + "/weights"]
+                entries.append((shape, w, fw, fld, pf))
+                entries.append((shape, w, bw, bld, pb))
+            table, njobs, total = K.make_pack_jobs(entries, self.device)
+            self._pack_table = (table, njobs, total, len(self.packs))
+        K.pack_weights_batched(*self._pack_table[:3])
 
     def load(self, arrays):
         for name, (o, k, shape) in self.offsets.items():

@@ -97,6 +97,24 @@ def pack_size(shape, which, ld_k):
     return n
 
 
+def make_pack_jobs(entries, device):
+    """entries: [(shape, w, which, ld_k, pack)] -> (device uint8 tensor holding acg_pack_job[], njobs, total)"""
+    jobs = (_lib.PackJob * len(entries))()
+    first = 0
+    for i, (shape, w, which, ld_k, pack) in enumerate(entries):
+        n_rows = (shape.Cout + 15) // 16 * 16 if which == 0 else (shape.Cin + 15) // 16 * 16
+        jobs[i] = _lib.PackJob(ptr(w), ptr(pack), first, which, ld_k, shape.KH, shape.KW, shape.Cin, shape.Cout,
+                               shape.stride, shape.pad_t, shape.pad_l, n_rows)
+        first += pack_size(shape, which, ld_k)
+    raw = bytes(jobs)
+    table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+    return table, len(entries), first
+
+
+def pack_weights_batched(table, njobs, total):
+    call("acg_pack_weights_batched", ptr(table), njobs, total, stream())
+
+
 def pack_weights(shape, w, which, ld_k, pack):
     call("acg_pack_weights", C.byref(shape), ptr(w), which, ld_k, ptr(pack), stream())
 

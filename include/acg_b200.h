@@ -128,6 +128,18 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
  * [ru16(Cin)][class taps][ld_k>=Cout] matrix per output-parity class.  acg_pack_size gives the element count. */
 long long acg_pack_size(const acg_conv_shape* s, int which, int ld_k);
 int acg_pack_weights(const acg_conv_shape* s, const float* w, int which, int ld_k, void* pack, void* stream);
+/* All packs of a parameter store in one launch.  jobs_dev is a DEVICE array sorted by `first` (the running element
+ * count: job i produces elements [first_i, first_i + acg_pack_size_i) of a virtual concatenation), total = sum of
+ * the pack sizes.  Each job is what one acg_pack_weights call would do. */
+typedef struct acg_pack_job {
+    const void* w;       /* fp32 HWIO weights */
+    void* pack;          /* bf16 output */
+    long long first;
+    int which, ld_k;     /* as in acg_pack_weights */
+    int KH, KW, Cin, Cout, stride, pad_t, pad_l;
+    int N;               /* rows of the pack: ru16(Cout) for which=0, ru16(Cin) for which=1 */
+} acg_pack_job;
+int acg_pack_weights_batched(const acg_pack_job* jobs_dev, int njobs, long long total, void* stream);
 /* 1 when the tcgen05 kernels accept the shape, 0 otherwise (which: 0 fprop, 1 dgrad, 2 wgrad) */
 int acg_conv_tc_supported(const acg_conv_shape* s, int which);
 
