@@ -905,30 +905,30 @@ conv_wgrad_tc_kernel(const WgradParams p) {
         const bool b_ch_ok = c16 * 8 < n_cta;
         const int tap = nn / p.ldx, ci = nn - tap * p.ldx;
         const int ta = tap / p.KW, tcc = tap - ta * p.KW;
+        // running decode of this thread's pixel (it advances by 8 per step, 64 per K slice): no divisions in the loop
+        int pix = k_begin + pslot;
+        int pb = pix / (p.OH * p.OW), pr = pix - pb * p.OH * p.OW;
+        int poh = pr / p.OW, pow_ = pr - poh * p.OW;
+        const int soff0 = pslot * 128 + ((jc ^ pslot) << 4);       // k & 7 == pslot for every k = pslot + 8 i
         for (int kb = 0; kb < nkb; ++kb) {
             const int stage = kb % STAGES;
             if (kb >= STAGES) mbar_wait(&empty_bar[stage], (uint32_t)(((kb / STAGES) - 1) & 1));
-            const uint32_t dstA = smemA + stage * kStageA + atom * (BK * 128);
-            const uint32_t dstB = smemB + stage * kStageB + atom * (BK * 128);
+            const uint32_t dstA = smemA + stage * kStageA + atom * (BK * 128) + soff0;
+            const uint32_t dstB = smemB + stage * kStageB + atom * (BK * 128) + soff0;
 #pragma unroll
             for (int i = 0; i < BK / 8; ++i) {
-                const int k = pslot + 8 * i;
-                const int pix = k_begin + kb * BK + k;
                 const bool pv = pix < k_end;
-                const uint32_t soff = k * 128 + ((jc ^ (k & 7)) << 4);
                 const bool aok = pv && a_ch_ok;
-                cp_async16(dstA + soff, aok ? (const void*)(p.dy + (long long)pix * p.ldy + a_ch) : (const void*)p.dy,
+                cp_async16(dstA + i * 1024, aok ? (const void*)(p.dy + (long long)pix * p.ldy + a_ch) : (const void*)p.dy,
                            aok ? 16u : 0u);
-                bool bok = false;
-                long long boff = 0;
-                if (pv && b_ch_ok) {
-                    const int b = pix / (p.OH * p.OW), r = pix - b * p.OH * p.OW;
-                    const int oh = r / p.OW, ow = r - oh * p.OW;
-                    const int ih = oh * p.stride + ta - p.pad_t, iw = ow * p.stride + tcc - p.pad_l;
-                    bok = (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
-                    boff = ((long long)(b * p.H + ih) * p.W + iw) * p.ldx + ci;
-                }
-                cp_async16(dstB + soff, bok ? (const void*)(p.x + boff) : (const void*)p.x, bok ? 16u : 0u);
+                const int ih = poh * p.stride + ta - p.pad_t, iw = pow_ * p.stride + tcc - p.pad_l;
+                const bool bok = pv && b_ch_ok && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+                const long long boff = ((long long)(pb * p.H + ih) * p.W + iw) * p.ldx + ci;
+                cp_async16(dstB + i * 1024, bok ? (const void*)(p.x + boff) : (const void*)p.x, bok ? 16u : 0u);
+                pix += 8;
+                pow_ += 8;
+                while (pow_ >= p.OW) { pow_ -= p.OW; ++poh; }
+                while (poh >= p.OH) { poh -= p.OH; ++pb; }
             }
             cp_async_arrive_noinc(&full_bar[stage]);
         }
