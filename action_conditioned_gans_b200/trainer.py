@@ -86,18 +86,51 @@ class Trainer:
         self.in_next = torch.zeros(self.B, E.IMG, E.IMG, 3, device=dev)
         self.in_act = torch.zeros(self.B, E.ACTION_DIM, device=dev)
         self.in_state = torch.zeros(self.B, E.STATE_DIM, device=dev)
+        self._copy_stream = None
+        self._staging = None
+        self._frames_host = None
+        self._pending_fetch = None
         self._graphs, self._calls, self._graph_launches = {}, {}, {}
         self.replayed_launches = 0      # kernels launched through graph replays (acg_launch_count sees eager ones)
 
     def _stage(self, img, nxt, act, st):
-        """Copy the feeds into the static buffers the kernels (and the captured graphs) read."""
-        self.in_img.copy_(img.reshape(self.in_img.shape), non_blocking=True)
-        self.in_next.copy_(nxt.reshape(self.in_next.shape), non_blocking=True)
-        self.in_act.copy_(act.reshape(self.in_act.shape), non_blocking=True)
+        """Copy the feeds into the static buffers the kernels (and the captured graphs) read.
+
+        Host feeds go through a COPY STREAM into one of two device staging sets, so the host->device transfer of this
+        call overlaps the device work of the previous call (train_d's graph is still running when train_g's feeds
+        arrive); the compute stream then only does a device->device copy into the static buffers."""
+        if self._pending_fetch is not None:
+            torch.cuda.current_stream().wait_event(self._pending_fetch)
+            self._pending_fetch = None
+        feeds = [(self.in_img, img), (self.in_next, nxt), (self.in_act, act)]
         if st is not None:
-            self.in_state.copy_(st.reshape(self.in_state.shape), non_blocking=True)
+            feeds.append((self.in_state, st))
         else:
             self.in_state.zero_()
+        if all(t.is_cuda for _, t in feeds):
+            for dst, t in feeds:
+                dst.copy_(t.reshape(dst.shape), non_blocking=True)
+            return
+        if self._staging is None:
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._staging = [[torch.empty_like(b) for b in (self.in_img, self.in_next, self.in_act, self.in_state)]
+                             for _ in range(2)]
+            self._staging_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._staging_idx = 0
+        k = self._staging_idx
+        self._staging_idx ^= 1
+        main, cs = torch.cuda.current_stream(), self._copy_stream
+        cs.wait_event(self._staging_free[k])          # the compute stream is done with this set (two calls ago)
+        ready = torch.cuda.Event()
+        with torch.cuda.stream(cs):
+            for i, (dst, t) in enumerate(feeds):
+                self._staging[k][i].copy_(t.reshape(dst.shape), non_blocking=True)
+            ready.record(cs)
+        main.wait_event(ready)
+        for i, (dst, t) in enumerate(feeds):
+            dst.copy_(self._staging[k][i], non_blocking=True)
+        self._staging_free[k].record(main)
 
     def _run(self, key, fn):
         """Eager on the first call (one-time kernel attribute setup), captured on the second, replayed after."""
@@ -230,19 +263,47 @@ class Trainer:
 
     # ---- train.py:123-130 -------------------------------------------------------------------------------
     def train_g(self, input_images, next_frame, actions, state):
+        """Returns the generated frames of this step (train.py:124,130) as a NumPy array.  The array is a view of a
+        pinned host buffer from a ring of 4: it stays valid until the fourth following train_g call."""
         img, nxt, act, st = self._feed(input_images, next_frame, actions, state)
-        self.enqueue_train_g(img, nxt, act, st)
-        return self.g_run.g_out.cpu().numpy()
+        done = self.enqueue_train_g(img, nxt, act, st, fetch=True)
+        done.synchronize()          # only the device->host copy of the frames; the backward pass keeps running
+        return self._frames_host[self._frames_idx].numpy()
 
-    def enqueue_train_g(self, img, nxt, act, st):
+    def enqueue_train_g(self, img, nxt, act, st, fetch=False):
+        """The step is two captured graphs: (a) generator forward, (b) everything else.  With fetch=True the frames
+        leave for the host on the copy stream as soon as (a) is done, overlapping (b)."""
         self._stage(img, nxt, act, st)
         self.g_opt.tick()
-        self._run("train_g", self._body_train_g)
+        self._run("train_g_a", self._body_train_g_a)
+        done = None
+        if fetch:
+            if self._frames_host is None:
+                self._frames_host = [torch.empty(self.g_run.g_out.shape, dtype=torch.float32).pin_memory()
+                                     for _ in range(4)]
+                self._frames_idx = 0
+                if self._copy_stream is None:
+                    self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._frames_idx = (self._frames_idx + 1) % 4
+            main, cs = torch.cuda.current_stream(), self._copy_stream
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(main)
+            cs.wait_event(fwd_done)
+            done = torch.cuda.Event()
+            with torch.cuda.stream(cs):
+                self._frames_host[self._frames_idx].copy_(self.g_run.g_out, non_blocking=True)
+                done.record(cs)
+            self._pending_fetch = done     # the NEXT step's forward overwrites g_out: it waits for this copy
+        self._run("train_g_b", self._body_train_g_b)
+        return done
 
-    def _body_train_g(self):
-        img, nxt, act, st = self.in_img, self.in_next, self.in_act, self.in_state
+    def _body_train_g_a(self):
         self.g_store.grad.zero_()
-        g_out, _ = self.g_run.forward(img, act)
+        self.g_run.forward(self.in_img, self.in_act)
+
+    def _body_train_g_b(self):
+        img, nxt, act, st = self.in_img, self.in_next, self.in_act, self.in_state
+        g_out = self.g_run.g_out
         if self.arg_adv:
             self.d_gen.forward(img, g_out, act)
         self._g_losses(nxt, st, want_grad=True, with_adv_grad=self.arg_adv)
