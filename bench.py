@@ -224,9 +224,19 @@ def main_ours(args):
     dp = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's banner goes to stdout; the contract is ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on STDOUT when the communicator is created; the contract is ONE JSON line
+        # there, so stdout points at stderr while the communicator comes up (init + first collective).
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
         dp = DataParallel()
     peaks = load_peaks()
     B = args.batch
