@@ -71,10 +71,18 @@ SIGNATURES = {
     "acg_debug_umma_shift": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
     "acg_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _P, _P],
     "acg_rmsprop_step": [_P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P],
+    "acg_peer_alloc": [_L, C.POINTER(C.c_void_p)],
+    "acg_peer_free": [_P],
+    "acg_peer_export": [_P, _P],
+    "acg_peer_open": [_P, C.POINTER(C.c_void_p)],
+    "acg_peer_close": [_P],
+    "acg_peer_allreduce_f64": [_P, _I, _I, _L, _I, _I, C.POINTER(C.c_void_p), _P, _F, _I, _P, _L, _F, _P, _P, _P, _P,
+                               _P],
 }
 # calls that return a plain value instead of a status
 PLAIN = {"acg_version": ([], C.c_int), "acg_last_error": ([], C.c_char_p),
-         "acg_launch_count": ([], C.c_longlong), "acg_pack_size": ([_SP, _I, _I], C.c_longlong)}
+         "acg_launch_count": ([], C.c_longlong), "acg_pack_size": ([_SP, _I, _I], C.c_longlong),
+         "acg_peer_slot_bytes": ([_I, _I], C.c_longlong)}
 
 _lib = None
 

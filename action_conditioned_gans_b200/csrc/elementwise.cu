@@ -144,7 +144,7 @@ bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict__ dA
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             double t = 0.0;
             for (int g = 0; g < groups; ++g) t += red[(size_t)g * 2 * C + c];
-            dbeta[c] += dbeta_scale * (float)t;
+            atomicAdd(dbeta + c, dbeta_scale * (float)t);   // D(real) and D(generated) chains run concurrently
         }
     }
 }
@@ -176,7 +176,7 @@ tile_actions_kernel(const float* __restrict__ actions, int B, int hw, int A, voi
 
 __global__ void bias_grad_kernel(const double* __restrict__ red, int C, float scale, float* __restrict__ dbias) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < C) dbias[c] += scale * (float)red[c];
+    if (c < C) atomicAdd(dbias + c, scale * (float)red[c]);
 }
 
 int ew_grid(long long total) {
@@ -383,7 +383,7 @@ vec_bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict_
         for (int c = tid; c < C; c += bx * by) {
             double t = 0.0;
             for (int gg = 0; gg < groups; ++gg) t += red[(size_t)gg * 2 * C + c];
-            dbeta[c] += dbeta_scale * (float)t;
+            atomicAdd(dbeta + c, dbeta_scale * (float)t);   // D(real) and D(generated) chains run concurrently
         }
     }
     if (tid < bx * 8) {

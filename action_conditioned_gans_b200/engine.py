@@ -155,6 +155,53 @@ class _LayerState:
     pass
 
 
+class Branch:
+    """A side stream for an independent chain of kernels of a step (`with branch: ...` forks from the current stream,
+    `branch.join()` makes the current stream wait for it).  Inside a captured CUDA graph this becomes a parallel
+    branch of the graph: most layers of this model launch fewer CTAs than the 148 SMs x 2 hold or are latency bound
+    (4x4 / 8x8 feature maps), so independent chains -- D(real) beside G and D(generated), every weight gradient beside
+    the data-gradient chain, the state head beside the frame head -- fill each other's idle SMs."""
+
+    enabled = True      # class-wide switch: False runs every chain on the caller's stream (per-kernel timing passes)
+
+    def __init__(self, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self._ctx = None
+        self.dirty = False
+
+    def __enter__(self):
+        if not Branch.enabled:
+            return self
+        self.stream.wait_stream(torch.cuda.current_stream())
+        self._ctx = torch.cuda.stream(self.stream)
+        self._ctx.__enter__()
+        self.dirty = True
+        return self
+
+    def __exit__(self, *exc):
+        ctx, self._ctx = self._ctx, None
+        return ctx.__exit__(*exc) if ctx is not None else False
+
+    def join(self):
+        if self.dirty:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.dirty = False
+
+
+class _NoBranch:
+    """Same interface, no fork (used when a chain holds an NCCL collective: one communicator, one stream order)."""
+    dirty = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def join(self):
+        pass
+
+
 def ru16(v):
     return (v + 15) // 16 * 16
 
@@ -169,18 +216,28 @@ class NetRun:
       GEMM-ready packs refreshed from the fp32 master copy after every optimizer step.
     precision 'fp32': fp32 SIMT kernels end to end (the tight-tolerance parity mode)."""
 
-    def __init__(self, store, batch, device, dp=None, precision="bf16"):
+    def __init__(self, store, batch, device, dp=None, precision="bf16", branches=True):
         self.store, self.B, self.device, self.dp = store, batch, device, dp
         self.bf16 = precision == "bf16"
         self.adt = torch.bfloat16 if self.bf16 else torch.float32
         self.layers = {}
         n_stat = sum(4 * ru16(L.cout) for L in store.spec)
         self.f64 = torch.zeros(n_stat, dtype=torch.float64, device=device)   # [stats | red] per layer
-        self.counter = torch.zeros(1, dtype=torch.int32, device=device)      # "last CTA" ticket of the conv kernels
+        # "last CTA" tickets of the conv kernels, one per layer (layers of one network may run concurrently)
+        self.counters = torch.zeros(len(store.spec), dtype=torch.int32, device=device)
+        # side streams: weight gradients (no collective inside -> also with data parallelism) and a second chain
+        self.branches = bool(branches)
+        self.wgrad_branch = Branch(device) if self.branches else _NoBranch()
+        self.side_branch = Branch(device) if self.branches and not self._chain_has_nccl() else _NoBranch()
         soff = 0
-        for L in store.spec:
+        for li, L in enumerate(store.spec):
             st = _LayerState()
             st.spec = L
+            st.counter = self.counters[li:li + 1]
+            if dp is not None and getattr(dp, "peer_sync", False) and L.bn:
+                # exchange slots of this layer's forward moments / backward reduction terms (same order on every rank)
+                st.slot_f = dp.mailbox.new_slot(2 * L.cout)
+                st.slot_b = dp.mailbox.new_slot(2 * L.cout)
             cp = ru16(L.cout)
             st.stats = self.f64[soff:soff + 2 * cp]
             st.red = self.f64[soff + 2 * cp:soff + 4 * cp]
@@ -190,6 +247,16 @@ class NetRun:
             st.scale = torch.ones(L.cout, device=device)
             st.shift = torch.zeros(L.cout, device=device)
             self.layers[L.name] = st
+
+    def _chain_has_nccl(self):
+        """True when the batch-norm statistics of this network are all-reduced through NCCL (one communicator: its
+        collectives must stay on one stream, in one order); the peer-memory exchange has no such restriction."""
+        return self.dp is not None and not getattr(self.dp, "peer_sync", False)
+
+    def join(self):
+        """Make the current stream wait for every side chain of this network."""
+        self.wgrad_branch.join()
+        self.side_branch.join()
 
     def ld(self, c):
         """channel stride of a buffer holding c channels"""
@@ -244,6 +311,16 @@ class NetRun:
             w = self.store.views[L.name + "/weights"]
             (K.conv_fprop_f32 if L.kind == "conv" else K.conv_dgrad_f32)(st.shape, x, w, out)
 
+    def _sync_moments(self, st, beta):
+        """Sum the [2C] moments over the ranks and finalise mean / rstd / scale / shift over the global batch."""
+        L, dp = st.spec, self.dp
+        if dp.peer_sync:       # one launch: push to the peers' mailboxes, wait, sum in rank order, finalise
+            dp.mailbox.allreduce_f64(st.stats, 2 * L.cout, st.slot_f,
+                                     bn=(L.cout, beta, st.rows * dp.world, BN_EPS, st.mean, st.rstd, st.scale, st.shift))
+        else:
+            dp.allreduce_sum(st.stats)
+            K.bn_finalize(st.stats, beta, st.rows * dp.world, L.cout, 1, st.mean, st.rstd, st.scale, st.shift, BN_EPS)
+
     # -- one layer forward: conv -> (bias | batch-norm) -> activation --------------------------------------
     def layer_fwd(self, name, x, out, ld_out):
         st = self.layers[name]
@@ -257,23 +334,20 @@ class NetRun:
             beta = self.store.views[name + "/BatchNorm/beta"]
             if self.dp is None:
                 self._conv_fwd(st, x, st.z, st.ldz, stats=st.stats,
-                               bn=(self.counter, beta, st.mean, st.rstd, st.scale, st.shift, st.rows, BN_EPS))
+                               bn=(st.counter, beta, st.mean, st.rstd, st.scale, st.shift, st.rows, BN_EPS))
             else:
                 self._conv_fwd(st, x, st.z, st.ldz, stats=st.stats)
-                self.dp.allreduce_sum(st.stats)        # SyncBN: statistics over the GLOBAL batch
-                K.bn_finalize(st.stats, beta, st.rows * self.dp.world, L.cout, 1, st.mean, st.rstd, st.scale,
-                              st.shift, BN_EPS)
+                self._sync_moments(st, beta)           # SyncBN: statistics over the GLOBAL batch
             K.bn_act_fwd(st.z, st.rows, L.cout, st.ldz, 1, st.scale, st.shift, L.act, out, ld_out)
             return
         self._conv_fwd(st, x, st.z, st.ldz)
         if L.bn:
             K.bn_stats(st.z, st.rows, L.cout, st.ldz, 1, st.stats)
-            world = 1
+            beta = self.store.views[name + "/BatchNorm/beta"]
             if self.dp is not None:
-                world = self.dp.world
-                self.dp.allreduce_sum(st.stats)        # SyncBN: statistics over the GLOBAL batch
-            K.bn_finalize(st.stats, self.store.views[name + "/BatchNorm/beta"], st.rows * world, L.cout, 1,
-                          st.mean, st.rstd, st.scale, st.shift, BN_EPS)
+                self._sync_moments(st, beta)           # SyncBN: statistics over the GLOBAL batch
+            else:
+                K.bn_finalize(st.stats, beta, st.rows, L.cout, 1, st.mean, st.rstd, st.scale, st.shift, BN_EPS)
             K.bn_act_fwd(st.z, st.rows, L.cout, st.ldz, 1, st.scale, st.shift, L.act, out, ld_out)
         else:
             bias = self.store.views[name + "/biases"] if L.bias else None
@@ -300,7 +374,9 @@ class NetRun:
             world = 1
             if self.dp is not None:
                 world = self.dp.world
-                if L.bn:
+                if L.bn and self.dp.peer_sync:
+                    self.dp.mailbox.allreduce_f64(st.red, 2 * L.cout, st.slot_b)
+                elif L.bn:
                     self.dp.allreduce_sum(st.red)
             dpar = None
             if need_dw:
@@ -309,16 +385,19 @@ class NetRun:
                                st.red, st.dz, dpar, norm_rows=st.rows * world,
                                dbeta_scale=(1.0 / world if L.bn else 1.0), ld_dz=st.ldz)
         if need_dw:
+            # the weight gradient only feeds the optimizer: it runs beside the data-gradient chain (join() before
+            # the gradient all-reduce / optimizer step)
             dw = self.store.gviews[name + "/weights"]
-            if self.bf16:
-                if L.kind == "conv":
-                    K.conv_wgrad_tc(st.shape, st.x, st.dz, dw, st.ld_in, st.ldz)
+            with self.wgrad_branch:
+                if self.bf16:
+                    if L.kind == "conv":
+                        K.conv_wgrad_tc(st.shape, st.x, st.dz, dw, st.ld_in, st.ldz)
+                    else:
+                        K.conv_wgrad_tc(st.shape, st.dz, st.x, dw, st.ldz, st.ld_in)
+                elif L.kind == "conv":
+                    K.conv_wgrad_f32(st.shape, st.x, st.dz, dw)
                 else:
-                    K.conv_wgrad_tc(st.shape, st.dz, st.x, dw, st.ldz, st.ld_in)
-            elif L.kind == "conv":
-                K.conv_wgrad_f32(st.shape, st.x, st.dz, dw)
-            else:
-                K.conv_wgrad_f32(st.shape, st.dz, st.x, dw)
+                    K.conv_wgrad_f32(st.shape, st.dz, st.x, dw)
         if need_dx:
             if st.dx is None:
                 raise RuntimeError("layer %s was planned without an input-gradient buffer" % name)
@@ -335,8 +414,8 @@ class NetRun:
 class GeneratorRun(NetRun):
     """One application of the generator (DNA: models.py:24-74, direct: models.py:8-22)."""
 
-    def __init__(self, store, batch, device, dna, ksize, dp=None, precision="bf16"):
-        super().__init__(store, batch, device, dp, precision)
+    def __init__(self, store, batch, device, dna, ksize, dp=None, precision="bf16", branches=True):
+        super().__init__(store, batch, device, dp, precision, branches)
         self.dna, self.ksize = dna, ksize
         B = batch
         dev = device
@@ -378,7 +457,8 @@ class GeneratorRun(NetRun):
         else:
             self.state = None
 
-    def forward(self, img, actions):
+    def forward(self, img, actions, need_state=True):
+        """need_state=False skips the state head (sconv3-5): train_d only fetches the frame (train.py:132-144)."""
         self.zero_reductions()
         self.img = img
         Ls = self.layers
@@ -398,10 +478,11 @@ class GeneratorRun(NetRun):
         self.layer_fwd("g/tconv1", self.cat, Ls["g/tconv1"].a, Ls["g/tconv1"].a.shape[3])
         self.layer_fwd("g/tconv2", Ls["g/tconv1"].a, Ls["g/tconv2"].a, Ls["g/tconv2"].a.shape[3])
         t2 = Ls["g/tconv2"].a
-        if self.dna:
-            self.layer_fwd("g/sconv3", t2, Ls["g/sconv3"].a, Ls["g/sconv3"].a.shape[3])
-            self.layer_fwd("g/sconv4", Ls["g/sconv3"].a, Ls["g/sconv4"].a, Ls["g/sconv4"].a.shape[3])
-            self.layer_fwd("g/sconv5", Ls["g/sconv4"].a, self.state, STATE_DIM)
+        if self.dna and need_state:
+            with self.side_branch:      # the state head runs beside tconv3 / tconv4 / DNA
+                self.layer_fwd("g/sconv3", t2, Ls["g/sconv3"].a, Ls["g/sconv3"].a.shape[3])
+                self.layer_fwd("g/sconv4", Ls["g/sconv3"].a, Ls["g/sconv4"].a, Ls["g/sconv4"].a.shape[3])
+                self.layer_fwd("g/sconv5", Ls["g/sconv4"].a, self.state, STATE_DIM)
         self.layer_fwd("g/tconv3", t2, Ls["g/tconv3"].a, Ls["g/tconv3"].a.shape[3])
         if self.dna:
             kk = self.ksize * self.ksize
@@ -409,35 +490,39 @@ class GeneratorRun(NetRun):
             K.dna_fwd(self.logits, img, self.g_out, self.ksize)                  # models.py:60-72
         else:
             self.layer_fwd("g/tconv4", Ls["g/tconv3"].a, self.g_out, 3)          # tanh image
+        self.side_branch.join()
         return self.g_out, self.state
 
     def backward(self, with_state):
         """dg_out (and dstate when with_state) must be filled; accumulates into store.grad."""
         Ls = self.layers
+        d2b = None
+        if self.dna and with_state:
+            with self.side_branch:      # state head beside the frame head
+                ds = self.layer_bwd("g/sconv5", self.dstate, STATE_DIM)
+                ds = self.layer_bwd("g/sconv4", ds, ds.shape[3])
+                d2b = self.layer_bwd("g/sconv3", ds, ds.shape[3])
         if self.dna:
             K.dna_bwd(self.logits, self.img, self.dg_out, self.dlogits, self.ksize)
             d = self.layer_bwd("g/tconv4", self.dlogits, self.dlogits.shape[3])
         else:
             d = self.layer_bwd("g/tconv4", self.dg_out, 3)
         d3 = self.layer_bwd("g/tconv3", d, d.shape[3])
-        d2b = None
-        if self.dna and with_state:
-            ds = self.layer_bwd("g/sconv5", self.dstate, STATE_DIM)
-            ds = self.layer_bwd("g/sconv4", ds, ds.shape[3])
-            d2b = self.layer_bwd("g/sconv3", ds, ds.shape[3])
+        self.side_branch.join()
         d = self.layer_bwd("g/tconv2", d3, d3.shape[3], dA2=d2b)
         d = self.layer_bwd("g/tconv1", d, d.shape[3])                           # [B,4,4,ld(c4+10)]
         d = self.layer_bwd("g/conv4", d, d.shape[3])                            # first c4 channels
         d = self.layer_bwd("g/conv3", d, d.shape[3])
         d = self.layer_bwd("g/conv2", d, d.shape[3])
         self.layer_bwd("g/conv1", d, d.shape[3], need_dx=False)
+        self.join()
 
 
 class DiscriminatorRun(NetRun):
     """One application of build_discriminator (models.py:76-88) to concat([img, frame], 3)."""
 
-    def __init__(self, store, batch, device, dp=None, precision="bf16"):
-        super().__init__(store, batch, device, dp, precision)
+    def __init__(self, store, batch, device, dp=None, precision="bf16", branches=True):
+        super().__init__(store, batch, device, dp, precision, branches)
         B = batch
         Ls = self.layers
         self.d_in = self.act_buffer(IMG, IMG, 6)                                 # train.py:64,68
@@ -482,8 +567,9 @@ class DiscriminatorRun(NetRun):
         d = self.layer_bwd("d/conv4", d, d.shape[3], need_dw=need_dw)
         d = self.layer_bwd("d/conv3", d, d.shape[3], need_dw=need_dw)           # [B,16,16,ld(138)]
         d = self.layer_bwd("d/conv2", d, d.shape[3], need_dw=need_dw)
-        return self.layer_bwd("d/conv1", d, d.shape[3], need_dw=need_dw, need_dx=need_dinput,
-                              dx_dtype=torch.float32)
+        d = self.layer_bwd("d/conv1", d, d.shape[3], need_dw=need_dw, need_dx=need_dinput, dx_dtype=torch.float32)
+        self.join()
+        return d
 
 
 class TFOptimizer:

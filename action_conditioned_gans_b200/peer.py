@@ -1,0 +1,81 @@
+"""Host side of the NVLink peer-memory exchange (csrc/peer.cu, include/acg_b200.h "Data parallelism").
+
+One `Mailbox` per process: a device segment every peer maps through a cudaIpc handle.  `new_slot()` hands out exchange
+slots; every rank creates its slots in the same order, so a slot has the same byte offset in every mailbox."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+MAX_PEERS = 8
+SEGMENT_BYTES = 32 << 20
+MAX_SLOTS = 1024
+
+
+def slot_bytes(cap, world):
+    n = int(_lib.load().acg_peer_slot_bytes(int(cap), int(world)))
+    if n < 0:
+        raise RuntimeError("acg_peer_slot_bytes: invalid arguments (cap %d, world %d)" % (cap, world))
+    return n
+
+
+class SlotPlan:
+    """Byte offsets of the slots of one mailbox (pure host logic: same sequence of requests -> same offsets)."""
+
+    def __init__(self, world, segment_bytes=SEGMENT_BYTES, slot_bytes_fn=slot_bytes):
+        self.world, self.segment_bytes, self.next_off, self.count = world, segment_bytes, 0, 0
+        self._slot_bytes = slot_bytes_fn
+
+    def take(self, cap):
+        off, idx = self.next_off, self.count
+        self.next_off += self._slot_bytes(cap, self.world)
+        self.count += 1
+        if self.next_off > self.segment_bytes or self.count > MAX_SLOTS:
+            raise RuntimeError("peer mailbox exhausted (%d bytes, %d slots)" % (self.next_off, self.count))
+        return off, idx
+
+
+class Mailbox:
+    def __init__(self, dist, group, device, timeout_s=30.0):
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > MAX_PEERS:
+            raise RuntimeError("peer exchange supports at most %d ranks (one NVSwitch domain)" % MAX_PEERS)
+        self.device = torch.device(device)
+        self.timeout_s = float(timeout_s)
+        own = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.call("acg_peer_alloc", SEGMENT_BYTES, C.byref(own))
+            handle = C.create_string_buffer(64)
+            _lib.call("acg_peer_export", own, handle)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            self.ptrs = (C.c_void_p * self.world)()
+            for r in range(self.world):
+                if r == self.rank:
+                    self.ptrs[r] = own.value
+                else:
+                    p = C.c_void_p()
+                    _lib.call("acg_peer_open", C.create_string_buffer(handles[r], 64), C.byref(p))
+                    self.ptrs[r] = p.value
+        self.plan = SlotPlan(self.world)
+        self.epochs = torch.zeros(MAX_SLOTS, dtype=torch.int64, device=self.device)
+        dist.barrier(group=group)       # every segment is mapped everywhere before the first push
+
+    def new_slot(self, cap):
+        off, idx = self.plan.take(cap)
+        return (off, int(cap), self.epochs[idx:idx + 1])
+
+    def allreduce_f64(self, vec, n, slot, bn=None):
+        """vec[0:n] <- sum over ranks.  bn = (C, beta, global_rows, eps, mean, rstd, scale, shift) also finalises the
+        batch-norm coefficients in the same launch."""
+        off, cap, epoch = slot
+        if vec.dtype != torch.float64:
+            raise RuntimeError("peer exchange vectors are fp64")
+        if bn is None:
+            args = (0, None, 0, 0.0, None, None, None, None)
+        else:
+            Cc, beta, rows, eps, mean, rstd, scale, shift = bn
+            args = (Cc, _lib.ptr(beta), rows, eps, _lib.ptr(mean), _lib.ptr(rstd), _lib.ptr(scale), _lib.ptr(shift))
+        _lib.call("acg_peer_allreduce_f64", _lib.ptr(vec), n, cap, off, self.rank, self.world, self.ptrs,
+                  _lib.ptr(epoch), self.timeout_s, *args, _lib.stream())

@@ -26,12 +26,24 @@ class DataParallel:
     Collectives on the path: the flat gradient bucket of the network being updated, the per-layer batch-norm
     moment vectors (SyncBN: the reference normalises over the WHOLE batch) and the loss sums."""
 
-    def __init__(self, group=None):
+    def __init__(self, group=None, device=None, peer_sync=None):
+        """peer_sync: exchange the batch-norm vectors through NVLink peer memory (csrc/peer.cu) instead of NCCL.
+        Default: on for CUDA runs (ACG_DP_SYNC=nccl switches it off), off for the CPU/gloo host-logic tests."""
+        import os
         import torch.distributed as dist
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        if peer_sync is None:
+            peer_sync = (dist.get_backend(group) == "nccl" and torch.cuda.is_available()
+                         and os.environ.get("ACG_DP_SYNC", "peer") != "nccl")
+        self.peer_sync = bool(peer_sync)
+        self.mailbox = None
+        if self.peer_sync:
+            from .peer import Mailbox
+            dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+            self.mailbox = Mailbox(dist, group, dev)
 
     def allreduce_sum(self, t):
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
@@ -40,7 +52,7 @@ class DataParallel:
 class Trainer:
     def __init__(self, sess=None, arg_adv=True, arg_loss="bce", arg_opt="adam", arg_transform=True,
                  batch_size=BATCH_SIZE, ksize=DNA_KSIZE, device=None, params=None, seed=7, dp=None,
-                 precision="bf16", use_graphs=True):
+                 precision="bf16", use_graphs=True, branches=True):
         if arg_loss not in ("bce", "wass"):
             raise ValueError("unexpected loss argument")          # ops.py:35,47
         if arg_opt not in ("adam", "rmsprop"):
@@ -66,9 +78,12 @@ class Trainer:
         dev = self.device
         self.g_store = E.ParamStore(g_spec, dev, params)
         self.d_store = E.ParamStore(d_spec, dev, params)
-        self.g_run = E.GeneratorRun(self.g_store, self.B, dev, arg_transform, ksize, dp, precision)
-        self.d_gen = E.DiscriminatorRun(self.d_store, self.B, dev, dp, precision)
-        self.d_real = E.DiscriminatorRun(self.d_store, self.B, dev, dp, precision)
+        self.g_run = E.GeneratorRun(self.g_store, self.B, dev, arg_transform, ksize, dp, precision, branches)
+        self.d_gen = E.DiscriminatorRun(self.d_store, self.B, dev, dp, precision, branches)
+        self.d_real = E.DiscriminatorRun(self.d_store, self.B, dev, dp, precision, branches)
+        # D(real) is independent of G and D(generated) until the optimizer step: it gets its own chain of the step
+        nccl_bn = dp is not None and not getattr(dp, "peer_sync", False)
+        self.real_branch = E.Branch(dev) if branches and not nccl_bn else E._NoBranch()
         self.g_store.refresh_packs()
         self.d_store.refresh_packs()
         self.g_opt = E.TFOptimizer(self.g_store, arg_opt)            # train.py:100
@@ -314,7 +329,7 @@ class Trainer:
     # ---- train.py:132-144 -------------------------------------------------------------------------------
     def train_d(self, input_images, next_frame, actions, summarize=False):
         img, nxt, act, st = self._feed(input_images, next_frame, actions, None)
-        self.enqueue_train_d(img, nxt, act)
+        self.enqueue_train_d(img, nxt, act, need_state=summarize)
         if summarize:
             # merged_summaries also holds the generator scalars (train.py:112,140)
             self._g_losses(self.in_next, self.in_state, want_grad=False, with_adv_grad=False)
@@ -322,18 +337,24 @@ class Trainer:
             return self.summaries()
         return None
 
-    def enqueue_train_d(self, img, nxt, act):
+    def enqueue_train_d(self, img, nxt, act, need_state=False):
+        """need_state: also run the generator's state head (only the summaries of train.py:140 read it)."""
         self._stage(img, nxt, act, None)
         self.d_opt.tick()
-        self._run("train_d", self._body_train_d)
+        if need_state:
+            self._run("train_d_state", lambda: self._body_train_d(True))
+        else:
+            self._run("train_d", lambda: self._body_train_d(False))
         self._have = {"d"}
 
-    def _body_train_d(self):
+    def _body_train_d(self, need_state=False):
         img, nxt, act = self.in_img, self.in_next, self.in_act
         self.d_store.grad.zero_()
-        g_out, _ = self.g_run.forward(img, act)
+        with self.real_branch:
+            self.d_real.forward(img, nxt, act)
+        g_out, _ = self.g_run.forward(img, act, need_state=need_state)
         self.d_gen.forward(img, g_out, act)
-        self.d_real.forward(img, nxt, act)
+        self.real_branch.join()
         gs = 1.0 / self.world
         if self.arg_loss == "bce":                                   # ops.py:38-42
             K.dlogit_loss(self.d_real.logits, self.d_real.n_logits, "bce", 0.9, gs, self.sc[1:2], self.d_real.dlogits)
@@ -341,8 +362,10 @@ class Trainer:
         else:                                                        # ops.py:43-45
             K.dlogit_loss(self.d_real.logits, self.d_real.n_logits, "wass", 1.0, gs, self.sc[1:2], self.d_real.dlogits)
             K.dlogit_loss(self.d_gen.logits, self.d_gen.n_logits, "wass", -1.0, gs, self.sc[2:3], self.d_gen.dlogits)
-        self.d_real.backward(need_dw=True, need_dinput=False)
+        with self.real_branch:
+            self.d_real.backward(need_dw=True, need_dinput=False)
         self.d_gen.backward(need_dw=True, need_dinput=False)
+        self.real_branch.join()
         self._sync_grads(self.d_store)
         self.d_opt.enqueue(clip=(-0.01, 0.01))                       # train.py:89, update then clip
 
@@ -361,9 +384,11 @@ class Trainer:
 
     def _body_test(self):
         img, nxt, act, st = self.in_img, self.in_next, self.in_act, self.in_state
+        with self.real_branch:
+            self.d_real.forward(img, nxt, act)
         g_out, g_state = self.g_run.forward(img, act)
         self.d_gen.forward(img, g_out, act)
-        self.d_real.forward(img, nxt, act)
+        self.real_branch.join()
         self._g_losses(nxt, st, want_grad=False, with_adv_grad=False)
         if self.arg_loss == "bce":
             K.dlogit_loss(self.d_real.logits, self.d_real.n_logits, "bce", 0.9, 1.0, self.sc[1:2], None)

@@ -240,7 +240,8 @@ def main_ours(args):
         dp = DataParallel()
     peaks = load_peaks()
     B = args.batch
-    trn = Trainer(None, True, "bce", "adam", True, batch_size=B, ksize=KSIZE, device=dev, seed=7, dp=dp)
+    trn = Trainer(None, True, "bce", "adam", True, batch_size=B, ksize=KSIZE, device=dev, seed=7, dp=dp,
+                  branches=not args.no_branches)
 
     # feeds: a few distinct host batches (pinned), rotated; device copies for the HBM-resident measurement
     nfeeds = 2
@@ -370,6 +371,8 @@ def kernel_breakdown(trn, feeds):
 
     Kn.call = timed_call
     graphs, trn.use_graphs = trn.use_graphs, False        # the per-kernel view needs eager launches
+    from action_conditioned_gans_b200 import engine as En
+    En.Branch.enabled = False                             # ... on ONE stream (no overlapping kernels)
     try:
         img, nxt, act, state = feeds
         trn.enqueue_train_d(img, nxt, act)
@@ -378,6 +381,7 @@ def kernel_breakdown(trn, feeds):
     finally:
         Kn.call = orig
         trn.use_graphs = graphs
+        En.Branch.enabled = True
     out = {}
     for name, e0, e1 in records:
         d = out.setdefault(name, {"ms": 0.0, "n": 0})
@@ -392,6 +396,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-branches", action="store_true", help="every chain of a step on one stream (A/B switch)")
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     a = ap.parse_args()
     if a.impl == "reference":

@@ -219,6 +219,37 @@ int acg_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
 int acg_rmsprop_step(float* p, const float* g, float* ms, long long n, float lr, float decay, float eps,
                      float clip_lo, float clip_hi, float grad_scale, const float* lr_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Data parallelism over NVLink peer memory.  The reference is single-GPU and normalises
+ * over the whole batch (slim.batch_norm, models.py:11,32,81); with the batch sharded over one process per GPU the
+ * [2C] fp64 moment / reduction vectors of every batch-norm layer are summed over the ranks by ONE single-CTA kernel
+ * that pushes its vector into every peer's mailbox, waits on flags in its own mailbox, sums in rank order (identical
+ * bits on every rank) and optionally finalises mean / rstd / scale / shift.  The flat gradient buckets stay on NCCL.
+ *
+ * Mailboxes are the one exception to "the caller owns all buffers": a segment that peers can map must come from
+ * cudaMalloc directly, so the library allocates it.  Handles are cudaIpcMemHandle_t (64 bytes, HOST memory); the host
+ * side all-gathers them (torch.distributed) and opens the peers' segments once.
+ * ------------------------------------------------------------------------------------------ */
+#define ACG_MAX_PEERS 8
+#define ACG_PEER_HANDLE_BYTES 64
+int acg_peer_alloc(long long bytes, void** out_ptr);                 /* zero-filled device segment */
+int acg_peer_free(void* ptr);
+int acg_peer_export(void* ptr, void* host_handle64);                  /* ptr from acg_peer_alloc */
+int acg_peer_open(const void* host_handle64, void** out_ptr);         /* another process's segment */
+int acg_peer_close(void* ptr);
+/* bytes one exchange slot for vectors of up to `cap` doubles takes in a mailbox (256-byte multiple); -1 if invalid */
+long long acg_peer_slot_bytes(int cap, int world);
+/* vec[0:n] (fp64, this rank's partial sums) <- sum over ranks, through the slot at byte offset slot_off (same offset
+ * on every rank) of the mailboxes host_mailboxes[0..world) (HOST array of DEVICE pointers, [rank] = own segment).
+ * epoch: device uint64 owned by this slot on this rank, starts at 0, advanced by the kernel (graph-replay safe).
+ * Every rank must enqueue the same sequence of exchanges per slot.  A peer that does not show up within timeout_s
+ * (<= 0: 30 s) traps the kernel instead of hanging the GPU.  bn_C > 0 (then n == 2*bn_C): also write
+ * mean / rstd / scale = rstd / shift = beta - mean*rstd [bn_C] from the summed moments over bn_rows GLOBAL rows. */
+int acg_peer_allreduce_f64(double* vec, int n, int cap, long long slot_off, int rank, int world,
+                           void* const* host_mailboxes, unsigned long long* epoch, float timeout_s, int bn_C,
+                           const float* beta, long long bn_rows, float eps, float* mean, float* rstd, float* scale,
+                           float* shift, void* stream);
+
 /* Probe (tests only): D[128][N] = A_window * B^T where A_window's logical row m is shared-memory row
  * shift + (m/8)*pitch + (m%8) of a 128-byte-swizzled K-major [n_rows][64] bf16 tile (start not 1024 B aligned, 8-row
  * groups spaced by `pitch` rows).  base_offset_mode 1 sets the descriptor's base-offset field to (addr>>7)&7. */

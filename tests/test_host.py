@@ -89,3 +89,23 @@ def test_save_samples_layout(tmp_path):
     assert (tmp_path / "sample3" / "vid0" / "ground_truth0.png").exists()
     save_samples(str(tmp_path), np.repeat(a, 3, 1), np.repeat(a, 3, 1), np.array([0]), 4, gif=True)
     assert (tmp_path / "sample4" / "vid0" / "generated.gif").exists()
+
+
+def test_peer_slot_plan_is_symmetric(built_lib):
+    """Every rank requests its exchange slots in the same order -> same byte offsets in every mailbox (host logic of
+    action_conditioned_gans_b200/peer.py; acg_peer_slot_bytes needs no device)."""
+    from action_conditioned_gans_b200 import peer
+    caps = [64, 128, 256, 512, 1024, 2, 64]
+    plans = [peer.SlotPlan(8) for _ in range(2)]
+    offs = [[p.take(c) for c in caps] for p in plans]
+    assert offs[0] == offs[1]
+    prev_end = 0
+    for (off, idx), c in zip(offs[0], caps):
+        assert off % 256 == 0 and off >= prev_end
+        prev_end = off + peer.slot_bytes(c, 8)
+        assert peer.slot_bytes(c, 8) >= 128 + 2 * 8 * c * 8
+    assert built_lib.acg_peer_slot_bytes(16, 9) == -1          # more than ACG_MAX_PEERS ranks
+    small = peer.SlotPlan(2, segment_bytes=4096)
+    small.take(64)
+    with pytest.raises(RuntimeError, match="exhausted"):
+        small.take(1024)

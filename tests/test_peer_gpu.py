@@ -1,0 +1,161 @@
+"""NVLink peer-memory exchange (csrc/peer.cu) through the C-ABI.
+
+On ONE device two ranks are simulated by two mailbox segments and two streams: each rank's single-CTA kernel pushes
+into both mailboxes and waits for the other, so the kernels must really run concurrently and exchange through memory.
+With >= 2 devices the same exchange runs across processes through cudaIpc handles (torch.multiprocessing, NCCL for
+the handle all-gather)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _alloc(lib_call, nbytes):
+    p = C.c_void_p()
+    lib_call("acg_peer_alloc", nbytes, C.byref(p))
+    return p
+
+
+def test_two_simulated_ranks_on_one_device(cuda):
+    from action_conditioned_gans_b200 import _lib
+    from action_conditioned_gans_b200.peer import slot_bytes
+    world, Cc, rows = 2, 24, 96
+    cap = 2 * Cc
+    nslot = slot_bytes(cap, world)
+    assert nslot % 256 == 0 and nslot >= 128 + 2 * world * cap * 8
+    seg = [_alloc(_lib.call, 4 * nslot) for _ in range(world)]
+    ptrs = (C.c_void_p * world)(*[s.value for s in seg])
+    handle = C.create_string_buffer(64)
+    _lib.call("acg_peer_export", seg[0], handle)
+    assert any(b != 0 for b in handle.raw)
+    rng = np.random.RandomState(0)
+    streams = [torch.cuda.Stream(device=cuda) for _ in range(world)]
+    epochs = [torch.zeros(1, dtype=torch.int64, device=cuda) for _ in range(world)]
+    beta = torch.from_numpy(rng.randn(Cc).astype(np.float32)).to(cuda)
+    outs = [[torch.empty(Cc, device=cuda) for _ in range(4)] for _ in range(world)]
+    slot_off = nslot            # second slot of the segment
+    for it in range(5):         # several epochs through the same slot (parity double-buffering, monotonic flags)
+        z = [rng.randn(rows, Cc) * (1 + r) + it for r in range(world)]
+        part = [np.concatenate([a.sum(0), (a * a).sum(0)]) for a in z]
+        vecs = [torch.from_numpy(p.copy()).to(cuda) for p in part]
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                m, rs, sc, sh = outs[r]
+                _lib.call("acg_peer_allreduce_f64", _lib.ptr(vecs[r]), 2 * Cc, cap, slot_off, r, world, ptrs,
+                          _lib.ptr(epochs[r]), 10.0, Cc, _lib.ptr(beta), world * rows, 1e-3, _lib.ptr(m), _lib.ptr(rs),
+                          _lib.ptr(sc), _lib.ptr(sh), _lib.stream())
+        torch.cuda.synchronize()
+        tot = part[0] + part[1]
+        mu = tot[:Cc] / (world * rows)
+        var = tot[Cc:] / (world * rows) - mu * mu
+        rstd = 1.0 / np.sqrt(var + 1e-3)
+        for r in range(world):
+            got = vecs[r].cpu().numpy()
+            assert np.array_equal(got, vecs[0].cpu().numpy())          # identical bits on every rank
+            np.testing.assert_allclose(got, tot, rtol=1e-14)
+            m, rs, sc, sh = [t.cpu().numpy() for t in outs[r]]
+            np.testing.assert_allclose(m, mu, rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(rs, rstd, rtol=1e-6)
+            np.testing.assert_allclose(sc, rstd, rtol=1e-6)
+            np.testing.assert_allclose(sh, beta.cpu().numpy() - mu * rstd, rtol=1e-5, atol=1e-6)
+            assert int(epochs[r].item()) == it + 1
+    # plain sum (no batch-norm finalisation), world 1 degenerates to a copy through the own mailbox
+    v = torch.arange(7, dtype=torch.float64, device=cuda)
+    one = (C.c_void_p * 1)(seg[0].value)
+    ep = torch.zeros(1, dtype=torch.int64, device=cuda)
+    _lib.call("acg_peer_allreduce_f64", _lib.ptr(v), 7, cap, 0, 0, 1, one, _lib.ptr(ep), 1.0, 0, None, 0, 0.0, None,
+              None, None, None, _lib.stream())
+    torch.cuda.synchronize()
+    assert v.cpu().tolist() == list(range(7))
+    for s in seg:
+        _lib.call("acg_peer_free", s)
+
+
+def test_argument_checks(cuda):
+    from action_conditioned_gans_b200 import _lib
+    v = torch.zeros(8, dtype=torch.float64, device=cuda)
+    ep = torch.zeros(1, dtype=torch.int64, device=cuda)
+    one = (C.c_void_p * 1)(v.data_ptr())
+    with pytest.raises(RuntimeError, match="rank"):
+        _lib.call("acg_peer_allreduce_f64", _lib.ptr(v), 8, 8, 0, 3, 2, one, _lib.ptr(ep), 1.0, 0, None, 0, 0.0, None,
+                  None, None, None, None)
+    with pytest.raises(RuntimeError, match="slot offset"):
+        _lib.call("acg_peer_allreduce_f64", _lib.ptr(v), 8, 8, 100, 0, 1, one, _lib.ptr(ep), 1.0, 0, None, 0, 0.0,
+                  None, None, None, None, None)
+
+
+def _dp_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    from action_conditioned_gans_b200.trainer import DataParallel, Trainer
+    dp = DataParallel(device=dev)
+    assert dp.peer_sync and dp.mailbox is not None
+    B = 4
+    rng = np.random.RandomState(5)
+    img = rng.uniform(-1, 1, (world * B, 64, 64, 3)).astype(np.float32)
+    nxt = np.clip(img + 0.1 * rng.randn(*img.shape), -1, 1).astype(np.float32)
+    act = rng.randn(world * B, 10).astype(np.float32)
+    st = rng.randn(world * B, 5).astype(np.float32)
+    sl = slice(rank * B, (rank + 1) * B)
+    trn = Trainer(None, True, "bce", "adam", True, batch_size=B, device=dev, seed=7, dp=dp)
+    for _ in range(3):          # eager, capture, replay
+        trn.train_d(img[sl], nxt[sl], act[sl])
+        trn.train_g(img[sl], nxt[sl], act[sl], st[sl])
+    s = trn.train_d(img[sl], nxt[sl], act[sl], summarize=True)
+    w = trn.d_store.flat.clone()
+    ws = [torch.empty_like(w) for _ in range(world)]
+    dist.all_gather(ws, w)
+    same = all(torch.equal(ws[0], t) for t in ws)
+    res = [rank, bool(same), s["discriminator_loss"], s["g_loss"], trn.g_store.flat.double().sum().item()]
+    torch.cuda.synchronize()
+    with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as fh:
+        json.dump(res, fh)
+        fh.flush()
+        os.fsync(fh.fileno())
+    os._exit(0)     # NCCL collectives captured in CUDA graphs: skip the communicator teardown (see bench.py)
+
+
+def test_data_parallel_step_two_gpus(cuda, tmp_path):
+    """Two processes, two GPUs, peer-memory SyncBN + NCCL gradient bucket: replicas stay bit-identical and agree with
+    a single-GPU run over the global batch (bf16 tolerance)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    port = 29600 + os.getpid() % 1000
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        if p.is_alive():
+            p.kill()
+            pytest.fail("data-parallel worker did not finish")
+        assert p.exitcode == 0
+    res = [json.load(open(os.path.join(str(tmp_path), "rank%d.json" % r))) for r in range(2)]
+    assert all(r[1] for r in res), "replica weights diverged"
+    assert res[0][2] == pytest.approx(res[1][2], rel=1e-6) and res[0][4] == res[1][4]
+    # single process over the global batch
+    from action_conditioned_gans_b200.trainer import Trainer
+    B, world = 4, 2
+    rng = np.random.RandomState(5)
+    img = rng.uniform(-1, 1, (world * B, 64, 64, 3)).astype(np.float32)
+    nxt = np.clip(img + 0.1 * rng.randn(*img.shape), -1, 1).astype(np.float32)
+    act = rng.randn(world * B, 10).astype(np.float32)
+    st = rng.randn(world * B, 5).astype(np.float32)
+    trn = Trainer(None, True, "bce", "adam", True, batch_size=world * B, device=cuda, seed=7)
+    for _ in range(3):
+        trn.train_d(img, nxt, act)
+        trn.train_g(img, nxt, act, st)
+    s = trn.train_d(img, nxt, act, summarize=True)
+    assert res[0][2] == pytest.approx(s["discriminator_loss"], rel=5e-2)
+    assert res[0][3] == pytest.approx(s["g_loss"], rel=5e-2)
