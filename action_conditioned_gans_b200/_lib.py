@@ -28,7 +28,9 @@ class TcArgs(C.Structure):
     _fields_ = [("ld_in", C.c_int), ("ld_out", C.c_int), ("bias", C.c_void_p), ("out_dtype", C.c_int),
                 ("out_act", C.c_int), ("stats", C.c_void_p), ("bn_counter", C.c_void_p), ("bn_beta", C.c_void_p),
                 ("bn_mean", C.c_void_p), ("bn_rstd", C.c_void_p), ("bn_scale", C.c_void_p), ("bn_shift", C.c_void_p),
-                ("bn_rows", C.c_longlong), ("bn_eps", C.c_float)]
+                ("bn_rows", C.c_longlong), ("bn_eps", C.c_float),
+                ("red_z", C.c_void_p), ("red_ldz", C.c_int), ("red_C", C.c_int), ("red_act", C.c_int),
+                ("red_mean", C.c_void_p), ("red_rstd", C.c_void_p), ("red_shift", C.c_void_p)]
 
 
 class PackJob(C.Structure):
@@ -54,7 +56,7 @@ SIGNATURES = {
     "acg_conv_dgrad_tc": [_SP, _P, _P, _P, _FP, _P],
     "acg_conv_wgrad_tc": [_SP, _P, _P, _P, _FP, _P],
     "acg_pack_weights": [_SP, _P, _I, _I, _P, _P],
-    "acg_pack_weights_batched": [_P, _I, _L, _P],
+    "acg_pack_weights_batched": [_P, _I, _P, _I, _P],
     "acg_conv_tc_supported": [_SP, _I],
     "acg_bn_stats": [_P, _I, _L, _I, _I, _I, _P, _P],
     "acg_bn_finalize": [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _P],
@@ -63,6 +65,7 @@ SIGNATURES = {
     "acg_bn_act_bwd_apply": [_P, _P, _I, _I, _P, _I, _I, _L, _I, _I, _P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _L, _F,
                              _P],
     "acg_copy_channels": [_P, _I, _I, _I, _P, _I, _I, _I, _L, _I, _P],
+    "acg_pack_frames": [_P, _P, _I, _P, _I, _L, _P],
     "acg_tile_actions": [_P, _I, _I, _I, _P, _I, _I, _I, _P],
     "acg_frame_losses": [_P, _P, _I, _I, _I, _P, _P, _F, _F, _P, _I, _I, _P],
     "acg_dlogit_loss": [_P, _I, _I, _F, _F, _P, _P, _P],
@@ -82,7 +85,8 @@ SIGNATURES = {
 # calls that return a plain value instead of a status
 PLAIN = {"acg_version": ([], C.c_int), "acg_last_error": ([], C.c_char_p),
          "acg_launch_count": ([], C.c_longlong), "acg_pack_size": ([_SP, _I, _I], C.c_longlong),
-         "acg_peer_slot_bytes": ([_I, _I], C.c_longlong)}
+         "acg_peer_slot_bytes": ([_I, _I], C.c_longlong),
+         "acg_pack_plan": ([_P, _I, _P, _L], C.c_longlong)}
 
 _lib = None
 

@@ -52,6 +52,13 @@ struct Params {
     float* bn_mean; float* bn_rstd; float* bn_scale; float* bn_shift;
     long long bn_rows;
     float bn_eps;
+    // fused batch-norm BACKWARD reduction (optional; then `stats` is the consumer layer's `red` buffer): this launch
+    // computes dA = d loss / d activation of a layer with pre-activation rz [rows][rz_ld] (bf16), and the epilogue adds
+    // sum_r dzh and sum_r dzh*xhat (dzh = dA*act'(rz*rstd + shift), xhat = (rz - mean)*rstd) of its tile to stats[2][n_stat]
+    const __nv_bfloat16* rz;
+    int rz_ld, r_act;
+    const float* r_mean; const float* r_rstd; const float* r_shift;
+    int n_stat;                 // columns of stats (== n_bias for forward moments, the consumer's C for the reduction)
     int dbg_skip;               // profiling experiments (env ACG_DBG_SKIP): bit 3 = per-phase timing
 };
 
@@ -173,7 +180,7 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // and sit OUTSIDE the unrolled element loops so that they compile to branches, not to predicated instruction bloat
 // (a first version that tested bias / tanh per element spent ~800 issue slots per chunk on predicated-off code).
 __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&v)[16], int ncol, bool row_ok,
-                                               size_t row_off, int lane, float* sm_sum, float* sm_sq) {
+                                               size_t row_off, uint32_t z_smem, int lane, float* sm_sum, float* sm_sq) {
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
@@ -204,7 +211,7 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
             w[i] = *reinterpret_cast<uint32_t*>(&h);
         }
     }
-    if (p.stats) {
+    if (p.stats && ncol < p.n_stat) {      // n_stat % 16 == 0 in the reduction mode (host check)
         // batch-norm moments of exactly what is stored (bf16-rounded when the output is bf16)
         float q[16], q2[16];
 #pragma unroll
@@ -213,7 +220,62 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
             if (bf16_out) t = __uint_as_float((i & 1) ? (w[i >> 1] & 0xffff0000u) : (w[i >> 1] << 16));
             t = row_ok ? t : 0.f;
             q[i] = t;
-            q2[i] = t * t;
+        }
+        if (p.rz) {
+            // backward reduction terms of the layer that consumes this gradient (same arithmetic as
+            // vec_col_reduce_kernel<1>): q = dA*act'(u), q2 = q*xhat
+            // z_smem: this row's 16 pre-activations, staged in shared memory by stage_z_row (zero filled for rows
+            // outside the tensor, whose q is zero anyway)
+            float zf[16];
+            {
+                uint32_t zw[8];
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(zw[0]), "=r"(zw[1]), "=r"(zw[2]), "=r"(zw[3]) : "r"(z_smem));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(zw[4]), "=r"(zw[5]), "=r"(zw[6]), "=r"(zw[7]) : "r"(z_smem + 16u));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    zf[2 * i] = __uint_as_float(zw[i] << 16);
+                    zf[2 * i + 1] = __uint_as_float(zw[i] & 0xffff0000u);
+                }
+            }
+            const float4* mu4 = reinterpret_cast<const float4*>(p.r_mean + ncol);
+            const float4* rs4 = reinterpret_cast<const float4*>(p.r_rstd + ncol);
+            const float4* sh4 = reinterpret_cast<const float4*>(p.r_shift + ncol);
+            if (p.r_act == ACG_ACT_RELU) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 mu = mu4[g], rs = rs4[g], sh = sh4[g];
+                    const float m_[4] = {mu.x, mu.y, mu.z, mu.w}, r_[4] = {rs.x, rs.y, rs.z, rs.w},
+                                s_[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = 4 * g + k;
+                        const float u = zf[i] * r_[k] + s_[k];
+                        const float d = u > 0.f ? q[i] : 0.f;
+                        q[i] = d;
+                        q2[i] = d * ((zf[i] - m_[k]) * r_[k]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 mu = mu4[g], rs = rs4[g], sh = sh4[g];
+                    const float m_[4] = {mu.x, mu.y, mu.z, mu.w}, r_[4] = {rs.x, rs.y, rs.z, rs.w},
+                                s_[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = 4 * g + k;
+                        const float u = zf[i] * r_[k] + s_[k];
+                        const float d = q[i] * act_bwd(u, p.r_act);
+                        q[i] = d;
+                        q2[i] = d * ((zf[i] - m_[k]) * r_[k]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) q2[i] = q[i] * q[i];
         }
         const float cs = warp_colsum16(q, lane), cs2 = warp_colsum16(q2, lane);
         if ((lane & 1) == 0) {
@@ -243,6 +305,17 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
                 if (ncol + i < p.n_store) o[i] = f[i];
         }
     }
+}
+
+// Fused backward reduction: the consumer's pre-activation rows of a tile are staged in the (by then idle) pipeline
+// shared memory with cp.async right after the accumulator barrier -- one exposed L2 latency per tile instead of one
+// global-load latency per 16-column chunk; the rows were pulled into L2 by a prefetch at kernel start.
+constexpr int kZRowBytes = BN * 2 + 16;     // +16 B: 16-byte row accesses of a quarter warp hit distinct banks
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void stage_z_row(uint32_t dst, const __nv_bfloat16* src, int ncols, bool ok) {
+    for (int c = 0; c < ncols; c += 8) cp_async16(dst + 2 * c, ok ? (const void*)(src + c) : (const void*)src, ok ? 16u : 0u);
 }
 
 constexpr int HALO_ACC = 4;
@@ -355,6 +428,26 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
     const uint32_t tmem_base = tmem_base_sh;
     if (timing) t1 = gtime();
 
+    // epilogue row of this thread (warps 0-3): output offset and, for the fused backward reduction, the offset of
+    // the consumer's pre-activation row, prefetched into L2 now so that the epilogue finds it there
+    size_t ep_row_off = 0, ep_rz_off = 0;
+    const int ep_m = tile_m + warp * 32 + lane;
+    const int nz = p.rz ? max(0, min(n_cta, p.n_stat - n0)) : 0;      // staged z columns of this CTA
+    if (warp < 4 && ep_m < M) {
+        if (MODE == CONV) { ep_row_off = (size_t)ep_m * p.ldo; ep_rz_off = (size_t)ep_m * p.rz_ld; }
+        else {
+            const int b = ep_m / (Hp * Wp), r = ep_m - b * Hp * Wp;
+            const int ih = (r / Wp) * s + ph, iw = (r % Wp) * s + pw;
+            const size_t pix = (size_t)(b * p.H + ih) * p.W + iw;
+            ep_row_off = pix * p.ldo;
+            ep_rz_off = pix * p.rz_ld;
+        }
+        if (nz > 0) {
+            prefetch_l2(p.rz + ep_rz_off + n0);
+            if (nz > 64) prefetch_l2(p.rz + ep_rz_off + n0 + 64);
+        }
+    }
+
     if (warp < 4) {
         // ================================ producers ================================
         // A (activations): cp.async 16 B gathers.  Everything that does not change along K is hoisted: per row an
@@ -447,15 +540,13 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
             tc_fence_after();
         }
         if (timing) t2 = gtime();
-        const int m = tile_m + warp * 32 + lane;
-        size_t row_off = 0;
-        if (m < M) {
-            if (MODE == CONV) row_off = (size_t)m * p.ldo;
-            else {
-                const int b = m / (Hp * Wp), r = m - b * Hp * Wp;
-                const int ih = (r / Wp) * s + ph, iw = (r % Wp) * s + pw;
-                row_off = ((size_t)(b * p.H + ih) * p.W + iw) * p.ldo;
-            }
+        const int m = ep_m;
+        const size_t row_off = ep_row_off;
+        const uint32_t zrow = smem_base + (uint32_t)(warp * 32 + lane) * kZRowBytes;
+        if (nz > 0) {       // every MMA has completed: the pipeline stages are free
+            stage_z_row(zrow, p.rz + ep_rz_off + n0, nz, m < M);
+            cp_async_commit();
+            cp_async_wait<0>();
         }
         for (int cb = 0; cb < n_cta; cb += 16) {
             uint32_t v[16];
@@ -464,7 +555,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0u;
             }
-            epilogue_chunk(p, v, n0 + cb, m < M, row_off, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
+            epilogue_chunk(p, v, n0 + cb, m < M, row_off, zrow + 2 * cb, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
         }
     }
     tc_fence_before();
@@ -482,9 +573,9 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
         atomicAdd(&g_phase_ns[4], (unsigned long long)nkb);
     }
     if (p.stats) {
-        if (tid < n_cta && n0 + tid < p.n_bias) {
+        if (tid < n_cta && n0 + tid < p.n_stat) {
             atomicAdd(&p.stats[n0 + tid], (double)sm_stats[0][tid]);
-            atomicAdd(&p.stats[p.n_bias + n0 + tid], (double)sm_stats[1][tid]);
+            atomicAdd(&p.stats[p.n_stat + n0 + tid], (double)sm_stats[1][tid]);
         }
         if (p.counter) {
             // last CTA of the launch turns the moments into mean / rstd / scale / shift (slim.batch_norm, eps 1e-3)
@@ -579,6 +670,18 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
     const uint32_t tmem_base = tmem_base_sh;
     if (timing) t1 = gtime();
 
+    if (p.rz && warp < 4) {   // fused backward reduction: pull this thread's 4 pre-activation rows into L2 now
+        const int ml = warp * 32 + lane, yy = ml >> 3, xi = ml & 7;
+        const int nz = min(N, p.n_stat);
+        for (int q = 0; q < HALO_ACC; ++q) {
+            const int tb = q / XG, xg = q - tb * XG;
+            const int ih = ((y0 + yy) << 1) + ph, iw = ((xg * 8 + xi) << 1) + pw;
+            const __nv_bfloat16* zr = p.rz + ((size_t)((b0 + tb) * p.H + ih) * p.W + iw) * p.rz_ld;
+            prefetch_l2(zr);
+            if (nz > 64) prefetch_l2(zr + 64);
+        }
+    }
+
     if (tid == 0) {
         // ================================ producer: one thread, TMA only ================================
         // The whole halo patch of a 64-channel block is ONE 4-D tensor copy (hardware zero fill outside the image,
@@ -654,14 +757,28 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
         tc_fence_after();
         if (timing) t2 = gtime();
         const int ml = warp * 32 + lane, yy = ml >> 3, xi = ml & 7;
+        const int nz = p.rz ? min(N, p.n_stat) : 0;
+        const uint32_t zrow0 = smem_base + (uint32_t)ml * kZRowBytes;     // + q * 128 rows; the halo buffers are idle now
+        if (nz > 0) {
+            for (int q = 0; q < HALO_ACC; ++q) {
+                const int tb = q / XG, xg = q - tb * XG;
+                const int ih = ((y0 + yy) << 1) + ph, iw = ((xg * 8 + xi) << 1) + pw;
+                const size_t pix = (size_t)((b0 + tb) * p.H + ih) * p.W + iw;
+                stage_z_row(zrow0 + (uint32_t)q * (BM * kZRowBytes), p.rz + pix * p.rz_ld, nz, true);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+        }
         for (int q = 0; q < HALO_ACC; ++q) {
             const int tb = q / XG, xg = q - tb * XG;
             const int ih = ((y0 + yy) << 1) + ph, iw = ((xg * 8 + xi) << 1) + pw;
-            const size_t row_off = ((size_t)((b0 + tb) * p.H + ih) * p.W + iw) * p.ldo;
+            const size_t pix = (size_t)((b0 + tb) * p.H + ih) * p.W + iw;
+            const size_t row_off = pix * p.ldo;
+            const uint32_t zrow = zrow0 + (uint32_t)q * (BM * kZRowBytes);
             for (int cb = 0; cb < N; cb += 16) {
                 uint32_t v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + q * N + cb, v);
-                epilogue_chunk(p, v, cb, true, row_off, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
+                epilogue_chunk(p, v, cb, true, row_off, zrow + 2 * cb, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
             }
         }
     }
@@ -684,9 +801,9 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
         atomicAdd(&g_phase_ns[4], (unsigned long long)(nkc * ntaps));
     }
     if (p.stats) {
-        if (tid < N && tid < p.n_bias) {
+        if (tid < N && tid < p.n_stat) {
             atomicAdd(&p.stats[tid], (double)sm_stats[0][tid]);
-            atomicAdd(&p.stats[p.n_bias + tid], (double)sm_stats[1][tid]);
+            atomicAdd(&p.stats[p.n_stat + tid], (double)sm_stats[1][tid]);
         }
         if (p.counter) {
             __threadfence();
@@ -716,46 +833,46 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
 
 // ---- all packs of a parameter store in ONE launch ---------------------------------------------------------------
 // After every optimizer step ~22 weight tensors x 2 packs have to be refreshed; one launch per pack costs more in
-// launch latency than in work.  The job table lives in device memory (built once by the host).
+// launch latency than in work.  The job table and a TILE table live in device memory (built once by the host,
+// acg_pack_plan): a tile is 32 pack rows x 32 pack columns of one tap.  The CONV pack is a per-tap transpose of the
+// HWIO matrix ([ci][n] -> [n][ci]), done through shared memory so that both the fp32 reads (128 B per warp row) and
+// the bf16 writes (64 B per warp row) are coalesced; the ADJ pack keeps the channel order and only re-groups taps.
 __global__ void __launch_bounds__(256)
-pack_batched_kernel(const acg_pack_job* __restrict__ jobs, int njobs, long long total) {
-    for (long long gidx = (long long)blockIdx.x * blockDim.x + threadIdx.x; gidx < total;
-         gidx += (long long)gridDim.x * blockDim.x) {
-        int lo = 0, hi = njobs - 1;          // last job whose first element is <= gidx
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (jobs[mid].first <= gidx) lo = mid; else hi = mid - 1;
-        }
-        const acg_pack_job j = jobs[lo];
-        const long long idx = gidx - j.first;
-        const float* w = static_cast<const float*>(j.w);
-        __nv_bfloat16* out = static_cast<__nv_bfloat16*>(j.pack);
+pack_tiles_kernel(const acg_pack_job* __restrict__ jobs, const int4* __restrict__ tiles, int ntiles) {
+    __shared__ float sm[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int4 T = tiles[tile];
+        const acg_pack_job j = jobs[T.x];
+        const int tap = T.y & 255, t = (T.y >> 8) & 255, nt = (T.y >> 16) & 255;
+        const int n0 = T.z & 0xffff, c0 = (int)((unsigned)T.z >> 16);
+        const float* __restrict__ w = static_cast<const float*>(j.w);
+        __nv_bfloat16* __restrict__ out = static_cast<__nv_bfloat16*>(j.pack) + T.w;
         const int ld = j.ld_k;
-        float v = 0.f;
-        if (j.which == 0) {                  // [N][tap][ld]
+        if (j.which == 0) {                  // out[(n*taps + tap)*ld + ci] = w[(tap*Cin + ci)*Cout + n]
             const int taps = j.KH * j.KW;
-            const int ci = (int)(idx % ld);
-            const long long r = idx / ld;
-            const int tap = (int)(r % taps), n = (int)(r / taps);
-            if (ci < j.Cin && n < j.Cout) v = w[((size_t)tap * j.Cin + ci) * j.Cout + n];
-        } else {                             // per parity class [N][class tap][ld], classes back to back
-            long long rem = idx;
-            int cls = 0, na = 0, nc = 0, a0 = 0, c0 = 0;
-            for (; cls < j.stride * j.stride; ++cls) {
-                a0 = (cls / j.stride + j.pad_t) % j.stride; c0 = (cls % j.stride + j.pad_l) % j.stride;
-                na = a0 < j.KH ? (j.KH - a0 + j.stride - 1) / j.stride : 0;
-                nc = c0 < j.KW ? (j.KW - c0 + j.stride - 1) / j.stride : 0;
-                const long long sz = (long long)j.N * na * nc * ld;
-                if (rem < sz) break;
-                rem -= sz;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int ci = c0 + ty + 8 * k, n = n0 + tx;
+                sm[ty + 8 * k][tx] = (ci < j.Cin && n < j.Cout) ? w[((size_t)tap * j.Cin + ci) * j.Cout + n] : 0.f;
             }
-            const int co = (int)(rem % ld);
-            const long long r = rem / ld;
-            const int t = (int)(r % (na * nc)), n = (int)(r / (na * nc));
-            const int a = a0 + j.stride * (t / nc), c = c0 + j.stride * (t % nc);
-            if (co < j.Cout && n < j.Cin) v = w[((size_t)(a * j.KW + c) * j.Cin + n) * j.Cout + co];
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int n = n0 + ty + 8 * k, ci = c0 + tx;
+                if (n < j.N && ci < ld) out[((size_t)n * taps + tap) * ld + ci] = __float2bfloat16_rn(sm[tx][ty + 8 * k]);
+            }
+            __syncthreads();
+        } else {                             // out[class offset + (n*nt + t)*ld + co] = w[(tap*Cin + n)*Cout + co]
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int n = n0 + ty + 8 * k, co = c0 + tx;
+                if (n < j.N && co < ld) {
+                    const float v = (co < j.Cout && n < j.Cin) ? w[((size_t)tap * j.Cin + n) * j.Cout + co] : 0.f;
+                    out[((size_t)n * nt + t) * ld + co] = __float2bfloat16_rn(v);
+                }
+            }
         }
-        out[idx] = __float2bfloat16_rn(v);
     }
 }
 
@@ -870,7 +987,8 @@ conv_wgrad_tc_kernel(const WgradParams p) {
 
     const int Ntot = p.KH * p.KW * p.ldx;
     const int n0 = blockIdx.x * BN;
-    const int n_cta = min(BN, Ntot - n0);
+    const int n_valid = min(BN, Ntot - n0);          // multiple of 8 (ldx % 8 == 0)
+    const int n_cta = (n_valid + 15) & ~15;          // MMA N: multiple of 16, columns past n_valid are zero filled
     const int co0 = blockIdx.y * BM;
     const int Kd = p.B * p.OH * p.OW;
     const int k_begin = blockIdx.z * p.k_chunk;
@@ -902,7 +1020,7 @@ conv_wgrad_tc_kernel(const WgradParams p) {
         const bool a_ch_ok = a_ch + 8 <= p.ldy;
         // B: n = n0 + c16*8 -> (tap, ci) fixed for the whole kernel
         const int nn = n0 + c16 * 8;
-        const bool b_ch_ok = c16 * 8 < n_cta;
+        const bool b_ch_ok = c16 * 8 < n_valid;
         const int tap = nn / p.ldx, ci = nn - tap * p.ldx;
         const int ta = tap / p.KW, tcc = tap - ta * p.KW;
         // running decode of this thread's pixel (it advances by 8 per step, 64 per K slice): no divisions in the loop
@@ -957,12 +1075,17 @@ conv_wgrad_tc_kernel(const WgradParams p) {
             uint32_t v[16];
             tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + cb, v);
             if (co < p.Cout) {
-                const int nn = n0 + cb;
-                const int tap = nn / p.ldx, ci0 = nn - tap * p.ldx;   // 16-column groups never straddle a tap (ldx % 16 == 0)
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int ci = ci0 + i;
-                    if (ci < p.Cin) atomicAdd(p.dw + ((size_t)tap * p.Cin + ci) * p.Cout + co, __uint_as_float(v[i]));
+                for (int h = 0; h < 2; ++h) {       // 8-column groups never straddle a tap (ldx % 8 == 0)
+                    const int nn = n0 + cb + 8 * h;
+                    if (nn >= Ntot) break;
+                    const int tap = nn / p.ldx, ci0 = nn - tap * p.ldx;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int ci = ci0 + i;
+                        if (ci < p.Cin)
+                            atomicAdd(p.dw + ((size_t)tap * p.Cin + ci) * p.Cout + co, __uint_as_float(v[8 * h + i]));
+                    }
                 }
             }
         }
@@ -1045,6 +1168,26 @@ int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char
     p->stats = t->stats;
     p->counter = nullptr;
     p->total_ctas = total_ctas;
+    p->n_stat = p->n_bias;
+    p->rz = nullptr;
+    if (t->red_z) {
+        ACG_REQUIRE(t->stats && !t->bn_counter, ACG_ERR_INVALID,
+                    "%s: the fused backward reduction accumulates into `stats` and excludes the forward finalize", who);
+        ACG_REQUIRE(t->red_mean && t->red_rstd && t->red_shift, ACG_ERR_INVALID,
+                    "%s: the fused backward reduction needs mean / rstd / shift of the consumer layer", who);
+        ACG_REQUIRE(t->red_C > 0 && t->red_C % 16 == 0 && t->red_C <= p->n_bias && t->red_ldz % 8 == 0 &&
+                        t->red_ldz >= t->red_C && t->out_dtype == ACG_BF16,
+                    ACG_ERR_UNSUPPORTED, "%s: fused backward reduction: C=%d (multiple of 16, <= output channels), ldz=%d",
+                    who, t->red_C, t->red_ldz);
+        ACG_REQUIRE(((uintptr_t)t->red_z & 15) == 0 && ((uintptr_t)t->red_mean & 15) == 0 &&
+                        ((uintptr_t)t->red_rstd & 15) == 0 && ((uintptr_t)t->red_shift & 15) == 0,
+                    ACG_ERR_UNSUPPORTED, "%s: fused backward reduction needs 16-byte aligned buffers", who);
+        p->rz = static_cast<const __nv_bfloat16*>(t->red_z);
+        p->rz_ld = t->red_ldz;
+        p->r_act = t->red_act;
+        p->r_mean = t->red_mean; p->r_rstd = t->red_rstd; p->r_shift = t->red_shift;
+        p->n_stat = t->red_C;
+    }
     if (t->stats && t->bn_counter) {
         ACG_REQUIRE(t->bn_mean && t->bn_rstd && t->bn_scale && t->bn_shift && t->bn_rows > 0, ACG_ERR_INVALID,
                     "%s: in-kernel batch-norm finalize needs mean/rstd/scale/shift buffers and the row count", who);
@@ -1116,14 +1259,54 @@ int acg_pack_weights(const acg_conv_shape* s, const float* w, int which, int ld_
     return check_launch("acg_pack_weights");
 }
 
-int acg_pack_weights_batched(const acg_pack_job* jobs_dev, int njobs, long long total, void* stream) {
+int acg_pack_weights_batched(const acg_pack_job* jobs_dev, int njobs, const void* tiles_dev, int ntiles, void* stream) {
     using namespace acg;
     using namespace acg::tc;
-    ACG_REQUIRE(jobs_dev && njobs > 0 && total > 0, ACG_ERR_INVALID, "acg_pack_weights_batched: bad argument");
-    long long blocks = (total + 255) / 256;
-    if (blocks > num_sms() * 16) blocks = num_sms() * 16;
-    pack_batched_kernel<<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_dev, njobs, total);
+    ACG_REQUIRE(jobs_dev && tiles_dev && njobs > 0 && ntiles > 0, ACG_ERR_INVALID,
+                "acg_pack_weights_batched: bad argument");
+    int blocks = ntiles < num_sms() * 8 ? ntiles : num_sms() * 8;
+    pack_tiles_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        jobs_dev, static_cast<const int4*>(tiles_dev), ntiles);
     return check_launch("acg_pack_weights_batched");
+}
+
+long long acg_pack_plan(const acg_pack_job* host_jobs, int njobs, int* host_tiles, long long capacity) {
+    using namespace acg;
+    using namespace acg::tc;
+    if (!host_jobs || njobs <= 0) return -1;
+    long long n = 0;
+    auto emit = [&](int job, int a, int n0, int c0, long long off) {
+        if (host_tiles && n < capacity) {
+            int* t = host_tiles + 4 * n;
+            t[0] = job; t[1] = a; t[2] = n0 | (c0 << 16); t[3] = (int)off;
+        }
+        ++n;
+    };
+    for (int ji = 0; ji < njobs; ++ji) {
+        const acg_pack_job& j = host_jobs[ji];
+        if (j.KH * j.KW > 255 || j.N > 0xffff || j.ld_k > 0xffff || j.N <= 0 || j.ld_k <= 0) return -1;
+        if (j.which == 0) {
+            for (int tap = 0; tap < j.KH * j.KW; ++tap)
+                for (int n0 = 0; n0 < j.N; n0 += 32)
+                    for (int c0 = 0; c0 < j.ld_k; c0 += 32) emit(ji, tap, n0, c0, 0);
+        } else {
+            long long off = 0;
+            for (int cls = 0; cls < j.stride * j.stride; ++cls) {
+                const int a0 = (cls / j.stride + j.pad_t) % j.stride, c0s = (cls % j.stride + j.pad_l) % j.stride;
+                const int na = a0 < j.KH ? (j.KH - a0 + j.stride - 1) / j.stride : 0;
+                const int nc = c0s < j.KW ? (j.KW - c0s + j.stride - 1) / j.stride : 0;
+                const int nt = na * nc;
+                for (int t = 0; t < nt; ++t) {
+                    const int tap = (a0 + j.stride * (t / nc)) * j.KW + c0s + j.stride * (t % nc);
+                    for (int n0 = 0; n0 < j.N; n0 += 32)
+                        for (int c0 = 0; c0 < j.ld_k; c0 += 32) emit(ji, tap | (t << 8) | (nt << 16), n0, c0, off);
+                }
+                off += (long long)j.N * nt * j.ld_k;
+                if (off > 0x7fffffffll) return -1;
+            }
+        }
+    }
+    return n;
 }
 
 int acg_conv_tc_supported(const acg_conv_shape* s, int which) {
@@ -1256,8 +1439,8 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
     using namespace acg::tc;
     ACG_REQUIRE(s && t && x_bf16 && dy_bf16 && dw, ACG_ERR_INVALID, "acg_conv_wgrad_tc: null pointer");
     ACG_REQUIRE(s->stride == 1 || s->stride == 2, ACG_ERR_UNSUPPORTED, "acg_conv_wgrad_tc: stride %d", s->stride);
-    ACG_REQUIRE(t->ld_in % 16 == 0 && t->ld_in >= s->Cin, ACG_ERR_UNSUPPORTED,
-                "acg_conv_wgrad_tc: ld_x=%d must be a multiple of 16 and >= Cin", t->ld_in);
+    ACG_REQUIRE(t->ld_in % 8 == 0 && t->ld_in >= s->Cin, ACG_ERR_UNSUPPORTED,
+                "acg_conv_wgrad_tc: ld_x=%d must be a multiple of 8 and >= Cin", t->ld_in);
     ACG_REQUIRE(t->ld_out % 8 == 0 && t->ld_out >= s->Cout, ACG_ERR_UNSUPPORTED,
                 "acg_conv_wgrad_tc: ld_dy=%d must be a multiple of 8 and >= Cout", t->ld_out);
     ACG_REQUIRE((long long)s->B * s->H * s->W * (long long)t->ld_in < (1ll << 40) &&

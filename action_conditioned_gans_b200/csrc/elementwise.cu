@@ -161,6 +161,36 @@ copy_channels_kernel(const void* __restrict__ src, int s_dt, int ld_src, int off
     }
 }
 
+// One thread per pixel: dense fp32 frames a (and b) -> one bf16 row [a | b | zeros] of LD = 8 or 16 channels (one or
+// two 16-byte stores; a warp writes 512 B / 1 KB contiguous); replaces two strided channel-slice copies per
+// discriminator input.  LD = 8 keeps the first layers' implicit-GEMM K at 25 x 8 instead of 25 x 16.
+template <int C, int LD>
+__global__ void __launch_bounds__(256)
+pack_frames_kernel(const float* __restrict__ a, const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
+                   long long rows) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
+         r += (long long)gridDim.x * blockDim.x) {
+        float v[LD];
+#pragma unroll
+        for (int i = 0; i < LD; ++i) v[i] = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = a[r * C + c];
+        if (b) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[C + c] = b[r * C + c];
+        }
+        uint32_t w[LD / 2];
+#pragma unroll
+        for (int i = 0; i < LD / 2; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint4* o = reinterpret_cast<uint4*>(out + r * LD);
+#pragma unroll
+        for (int i = 0; i < LD / 8; ++i) o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 tile_actions_kernel(const float* __restrict__ actions, int B, int hw, int A, void* __restrict__ dst, int d_dt,
                     int ld_dst, int off) {
@@ -614,6 +644,22 @@ int acg_copy_channels(const void* src, int src_dtype, int ld_src, int off_src, v
     copy_channels_kernel<<<ew_grid(rows * n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, src_dtype, ld_src, off_src, dst, dst_dtype, ld_dst, off_dst, rows, n);
     return check_launch("acg_copy_channels");
+}
+
+int acg_pack_frames(const float* a, const float* b, int C, void* out_bf16, int ld_out, long long rows, void* stream) {
+    using namespace acg;
+    ACG_REQUIRE(a && out_bf16 && rows > 0, ACG_ERR_INVALID, "acg_pack_frames: bad argument");
+    ACG_REQUIRE(C == 3 && (ld_out == 8 || ld_out == 16) && al16(out_bf16), ACG_ERR_UNSUPPORTED,
+                "acg_pack_frames: built for RGB frames into 8- or 16-channel rows (C=%d, ld_out=%d)", C, ld_out);
+    long long blocks = (rows + 255) / 256;
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    if (ld_out == 8)
+        pack_frames_kernel<3, 8><<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            a, b, static_cast<__nv_bfloat16*>(out_bf16), rows);
+    else
+        pack_frames_kernel<3, 16><<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            a, b, static_cast<__nv_bfloat16*>(out_bf16), rows);
+    return check_launch("acg_pack_frames");
 }
 
 int acg_tile_actions(const float* actions, int B, int hw, int A, void* dst, int dst_dtype, int ld_dst, int off,

@@ -8,6 +8,7 @@ device storage only.  Layer tables restate models.py:8-88 with the slim/TF-1.0 d
 eps 1e-3) -> activation; SAME padding puts the odd element after; conv2d_transpose is the exact adjoint.
 """
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -19,6 +20,12 @@ IMG = 64            # train.py:17-18
 ACTION_DIM = 10     # train.py:39-42 (5-D action ++ 5-D state)
 STATE_DIM = 5       # train.py:43-46
 BN_EPS = 1e-3       # slim.batch_norm default
+# batch-norm backward sums in the epilogue of the producing data-gradient kernel (bf16 path) instead of the separate
+# acg_bn_act_bwd_reduce pass.  Measured on B200 at B=256 (scripts/step_time.py): 5.91 ms fused vs 5.89 ms separate --
+# the ~1 us the epilogue gains per tile costs what the 28 removed launches saved, because the epilogue warps are also
+# the gather producers of the generic kernel.  Kept (parity-tested) for a kernel with dedicated epilogue warps; off by
+# default (ACG_FUSE_BWD_REDUCE=1 switches it on).
+FUSE_BWD_REDUCE = os.environ.get("ACG_FUSE_BWD_REDUCE", "0") != "0"
 
 
 @dataclass(frozen=True)
@@ -128,15 +135,14 @@ class ParamStore:
         every pack of the store in ONE launch through a device-side job table."""
         if not self.packs:
             return
-        if self._pack_table is None or self._pack_table[3] != len(self.packs):
+        if self._pack_table is None or self._pack_table[4] != len(self.packs):
             entries = []
             for name, (shape, fw, fld, pf, bw, bld, pb) in self.packs.items():
                 w = self.views[name + "/weights"]
                 entries.append((shape, w, fw, fld, pf))
                 entries.append((shape, w, bw, bld, pb))
-            table, njobs, total = K.make_pack_jobs(entries, self.device)
-            self._pack_table = (table, njobs, total, len(self.packs))
-        K.pack_weights_batched(*self._pack_table[:3])
+            self._pack_table = K.make_pack_jobs(entries, self.device) + (len(self.packs),)
+        K.pack_weights_batched(*self._pack_table[:4])
 
     def load(self, arrays):
         for name, (o, k, shape) in self.offsets.items():
@@ -204,6 +210,9 @@ class _NoBranch:
 
 def ru16(v):
     return (v + 15) // 16 * 16
+
+
+FRAME_LD = 8        # channel stride of the bf16 frame operands (3 / 6 real channels): K of the first layers = 25 x 8
 
 
 class NetRun:
@@ -354,7 +363,21 @@ class NetRun:
             K.bn_act_fwd(st.z, st.rows, L.cout, st.ldz, 1, None, bias, L.act, out, ld_out)
 
     # -- one layer backward ----------------------------------------------------------------------------
-    def layer_bwd(self, name, dA, ld_d, dA2=None, need_dx=True, need_dw=True, dx_dtype=None):
+    def _fused_red(self, consumer):
+        """Arguments of the batch-norm backward reduction of layer `consumer` for the epilogue of the data-gradient
+        kernel that produces its dA (None when the separate acg_bn_act_bwd_reduce pass has to run)."""
+        if consumer is None or not self.bf16 or not FUSE_BWD_REDUCE:
+            return None
+        sc = self.layers[consumer]
+        Lc = sc.spec
+        if not Lc.bn or Lc.cout % 16 != 0 or sc.z is None:
+            return None
+        sc.red_ready = True
+        return (sc.red, sc.z, sc.ldz, Lc.cout, Lc.act, sc.mean, sc.rstd, sc.shift)
+
+    def layer_bwd(self, name, dA, ld_d, dA2=None, need_dx=True, need_dw=True, dx_dtype=None, consumer=None):
+        """consumer: the layer whose activation gradient this layer's dx is (its batch-norm backward sums are then
+        accumulated in the epilogue of the data-gradient kernel, and its own layer_bwd skips the reduction pass)."""
         st = self.layers[name]
         L = st.spec
         if L.bn:
@@ -370,7 +393,10 @@ class NetRun:
                                     st.red)
                 K.bias_grad(st.red, L.cout, 1.0, self.store.gviews[name + "/biases"])
         else:
-            K.bn_act_bwd_reduce(dA, dA2, ld_d, st.z, st.ldz, st.rows, L.cout, 1, mean, rstd, shift, L.act, st.red)
+            if getattr(st, "red_ready", False):
+                st.red_ready = False        # the producer(s) of dA already accumulated st.red
+            else:
+                K.bn_act_bwd_reduce(dA, dA2, ld_d, st.z, st.ldz, st.rows, L.cout, 1, mean, rstd, shift, L.act, st.red)
             world = 1
             if self.dp is not None:
                 world = self.dp.world
@@ -404,7 +430,7 @@ class NetRun:
             if self.bf16:
                 pk = self.store.packs[name]
                 fn = K.conv_dgrad_tc if L.kind == "conv" else K.conv_fprop_tc
-                fn(st.shape, st.dz, pk[6], st.dx, st.ldz, st.ld_in)
+                fn(st.shape, st.dz, pk[6], st.dx, st.ldz, st.ld_in, red=self._fused_red(consumer))
             else:
                 w = self.store.views[name + "/weights"]
                 (K.conv_dgrad_f32 if L.kind == "conv" else K.conv_fprop_f32)(st.shape, st.dz, w, st.dx)
@@ -420,9 +446,10 @@ class GeneratorRun(NetRun):
         B = batch
         dev = device
         Ls = self.layers
-        self.img_in = self.act_buffer(IMG, IMG, 3) if self.bf16 else None       # bf16 copy, 3 -> 16 channels
+        # bf16 copy of the frame, 3 -> 8 channels (zero pad)
+        self.img_in = torch.zeros(B, IMG, IMG, FRAME_LD, dtype=self.adt, device=dev) if self.bf16 else None
         h = w = IMG
-        ld = self.ld(3)
+        ld = FRAME_LD if self.bf16 else 3
         for n in ["g/conv1", "g/conv2", "g/conv3", "g/conv4"]:
             h, w = self.plan(n, h, w, ld, dx=(n != "g/conv1"))
             ld = self.ld(Ls[n].spec.cout)
@@ -464,7 +491,7 @@ class GeneratorRun(NetRun):
         Ls = self.layers
         rows = self.B * IMG * IMG
         if self.bf16:
-            K.copy_channels(img, 3, 0, self.img_in, self.img_in.shape[3], 0, rows, 3)
+            K.pack_frames(img, None, self.img_in, rows)
             x = self.img_in
         else:
             x = img
@@ -499,21 +526,21 @@ class GeneratorRun(NetRun):
         d2b = None
         if self.dna and with_state:
             with self.side_branch:      # state head beside the frame head
-                ds = self.layer_bwd("g/sconv5", self.dstate, STATE_DIM)
-                ds = self.layer_bwd("g/sconv4", ds, ds.shape[3])
-                d2b = self.layer_bwd("g/sconv3", ds, ds.shape[3])
+                ds = self.layer_bwd("g/sconv5", self.dstate, STATE_DIM, consumer="g/sconv4")
+                ds = self.layer_bwd("g/sconv4", ds, ds.shape[3], consumer="g/sconv3")
+                d2b = self.layer_bwd("g/sconv3", ds, ds.shape[3], consumer="g/tconv2")
         if self.dna:
             K.dna_bwd(self.logits, self.img, self.dg_out, self.dlogits, self.ksize)
-            d = self.layer_bwd("g/tconv4", self.dlogits, self.dlogits.shape[3])
+            d = self.layer_bwd("g/tconv4", self.dlogits, self.dlogits.shape[3], consumer="g/tconv3")
         else:
-            d = self.layer_bwd("g/tconv4", self.dg_out, 3)
-        d3 = self.layer_bwd("g/tconv3", d, d.shape[3])
+            d = self.layer_bwd("g/tconv4", self.dg_out, 3, consumer="g/tconv3")
+        d3 = self.layer_bwd("g/tconv3", d, d.shape[3], consumer="g/tconv2")
         self.side_branch.join()
-        d = self.layer_bwd("g/tconv2", d3, d3.shape[3], dA2=d2b)
-        d = self.layer_bwd("g/tconv1", d, d.shape[3])                           # [B,4,4,ld(c4+10)]
-        d = self.layer_bwd("g/conv4", d, d.shape[3])                            # first c4 channels
-        d = self.layer_bwd("g/conv3", d, d.shape[3])
-        d = self.layer_bwd("g/conv2", d, d.shape[3])
+        d = self.layer_bwd("g/tconv2", d3, d3.shape[3], dA2=d2b, consumer="g/tconv1")
+        d = self.layer_bwd("g/tconv1", d, d.shape[3], consumer="g/conv4")       # [B,4,4,ld(c4+10)]
+        d = self.layer_bwd("g/conv4", d, d.shape[3], consumer="g/conv3")        # first c4 channels
+        d = self.layer_bwd("g/conv3", d, d.shape[3], consumer="g/conv2")
+        d = self.layer_bwd("g/conv2", d, d.shape[3], consumer="g/conv1")
         self.layer_bwd("g/conv1", d, d.shape[3], need_dx=False)
         self.join()
 
@@ -525,7 +552,10 @@ class DiscriminatorRun(NetRun):
         super().__init__(store, batch, device, dp, precision, branches)
         B = batch
         Ls = self.layers
-        self.d_in = self.act_buffer(IMG, IMG, 6)                                 # train.py:64,68
+        if self.bf16:                                                            # train.py:64,68; 6 -> 8 channels
+            self.d_in = torch.zeros(B, IMG, IMG, FRAME_LD, dtype=self.adt, device=device)
+        else:
+            self.d_in = self.act_buffer(IMG, IMG, 6)
         h = w = IMG
         h, w = self.plan("d/conv1", h, w, self.d_in.shape[3], dx_dtype=torch.float32)
         h, w = self.plan("d/conv2", h, w, self.ld(64))
@@ -546,8 +576,11 @@ class DiscriminatorRun(NetRun):
         self.zero_reductions()
         rows = self.B * IMG * IMG
         ld_in = self.d_in.shape[3]
-        K.copy_channels(img, 3, 0, self.d_in, ld_in, 0, rows, 3)
-        K.copy_channels(frame, 3, 0, self.d_in, ld_in, 3, rows, 3)
+        if self.bf16:
+            K.pack_frames(img, frame, self.d_in, rows)                           # concat([img, frame], 3), one pass
+        else:
+            K.copy_channels(img, 3, 0, self.d_in, ld_in, 0, rows, 3)
+            K.copy_channels(frame, 3, 0, self.d_in, ld_in, 3, rows, 3)
         Ls = self.layers
         self.layer_fwd("d/conv1", self.d_in, Ls["d/conv1"].a, Ls["d/conv1"].a.shape[3])
         ld = self.cat.shape[3]
@@ -562,11 +595,11 @@ class DiscriminatorRun(NetRun):
 
     def backward(self, need_dw, need_dinput):
         """dlogits must be filled.  Returns d(d_in) [B,64,64,ld(6)] fp32 when need_dinput."""
-        d = self.layer_bwd("d/conv6", self.dlogits, 1, need_dw=need_dw)
-        d = self.layer_bwd("d/conv5", d, d.shape[3], need_dw=need_dw)
-        d = self.layer_bwd("d/conv4", d, d.shape[3], need_dw=need_dw)
-        d = self.layer_bwd("d/conv3", d, d.shape[3], need_dw=need_dw)           # [B,16,16,ld(138)]
-        d = self.layer_bwd("d/conv2", d, d.shape[3], need_dw=need_dw)
+        d = self.layer_bwd("d/conv6", self.dlogits, 1, need_dw=need_dw, consumer="d/conv5")
+        d = self.layer_bwd("d/conv5", d, d.shape[3], need_dw=need_dw, consumer="d/conv4")
+        d = self.layer_bwd("d/conv4", d, d.shape[3], need_dw=need_dw, consumer="d/conv3")
+        d = self.layer_bwd("d/conv3", d, d.shape[3], need_dw=need_dw, consumer="d/conv2")   # [B,16,16,ld(138)]
+        d = self.layer_bwd("d/conv2", d, d.shape[3], need_dw=need_dw, consumer="d/conv1")
         d = self.layer_bwd("d/conv1", d, d.shape[3], need_dw=need_dw, need_dx=need_dinput, dx_dtype=torch.float32)
         self.join()
         return d

@@ -64,9 +64,15 @@ def tc_supported(shape, which):
     return bool(_lib.load().acg_conv_tc_supported(C.byref(shape), which))
 
 
-def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None):
-    """bn = (counter, beta, mean, rstd, scale, shift, rows, eps): finalise the moments in-kernel (single GPU)"""
+def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None):
+    """bn = (counter, beta, mean, rstd, scale, shift, rows, eps): finalise the moments in-kernel (single GPU)
+    red = (red_buffer, z, ldz, C, act, mean, rstd, shift): fused batch-norm backward reduction of the consumer layer"""
     t = TcArgs(ld_in, ld_out, ptr(bias), dtype_id(out), ACT_IDS[out_act], ptr(stats))
+    if red is not None:
+        buf, z, ldz, Cc, act, mean, rstd, shift = red
+        t.stats = ptr(buf)
+        t.red_z, t.red_ldz, t.red_C, t.red_act = ptr(z), ldz, Cc, ACT_IDS[act]
+        t.red_mean, t.red_rstd, t.red_shift = ptr(mean), ptr(rstd), ptr(shift)
     if bn is not None:
         counter, beta, mean, rstd, scale, shift, rows, eps = bn
         t.bn_counter, t.bn_beta = ptr(counter), ptr(beta)
@@ -75,13 +81,13 @@ def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None):
     return t
 
 
-def conv_fprop_tc(shape, x, w_pack, y, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None):
-    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn)
+def conv_fprop_tc(shape, x, w_pack, y, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None):
+    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn, red)
     call("acg_conv_fprop_tc", C.byref(shape), ptr(x), ptr(w_pack), ptr(y), C.byref(t), stream())
 
 
-def conv_dgrad_tc(shape, dy, w_pack, dx, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None):
-    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn)
+def conv_dgrad_tc(shape, dy, w_pack, dx, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None):
+    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn, red)
     call("acg_conv_dgrad_tc", C.byref(shape), ptr(dy), ptr(w_pack), ptr(dx), C.byref(t), stream())
 
 
@@ -98,7 +104,7 @@ def pack_size(shape, which, ld_k):
 
 
 def make_pack_jobs(entries, device):
-    """entries: [(shape, w, which, ld_k, pack)] -> (device uint8 tensor holding acg_pack_job[], njobs, total)"""
+    """entries: [(shape, w, which, ld_k, pack)] -> (device job table, njobs, device tile table, ntiles)"""
     jobs = (_lib.PackJob * len(entries))()
     first = 0
     for i, (shape, w, which, ld_k, pack) in enumerate(entries):
@@ -106,13 +112,20 @@ def make_pack_jobs(entries, device):
         jobs[i] = _lib.PackJob(ptr(w), ptr(pack), first, which, ld_k, shape.KH, shape.KW, shape.Cin, shape.Cout,
                                shape.stride, shape.pad_t, shape.pad_l, n_rows)
         first += pack_size(shape, which, ld_k)
-    raw = bytes(jobs)
-    table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
-    return table, len(entries), first
+    lib = _lib.load()
+    ntiles = int(lib.acg_pack_plan(jobs, len(entries), None, 0))
+    if ntiles <= 0:
+        raise RuntimeError("acg_pack_plan: invalid pack jobs")
+    tiles = (C.c_int * (4 * ntiles))()
+    if int(lib.acg_pack_plan(jobs, len(entries), tiles, ntiles)) != ntiles:
+        raise RuntimeError("acg_pack_plan: tile count changed")
+    table = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(device)
+    tile_table = torch.frombuffer(bytearray(bytes(tiles)), dtype=torch.int32).to(device)
+    return table, len(entries), tile_table, ntiles
 
 
-def pack_weights_batched(table, njobs, total):
-    call("acg_pack_weights_batched", ptr(table), njobs, total, stream())
+def pack_weights_batched(table, njobs, tile_table, ntiles):
+    call("acg_pack_weights_batched", ptr(table), njobs, ptr(tile_table), ntiles, stream())
 
 
 def pack_weights(shape, w, which, ld_k, pack):
@@ -150,6 +163,11 @@ def bn_act_bwd_apply(dA, dA2, ld_d, z, ld_z, rows, Cc, groups, mean, rstd, shift
 def copy_channels(src, ld_src, off_src, dst, ld_dst, off_dst, rows, n):
     call("acg_copy_channels", ptr(src), dtype_id(src), ld_src, off_src, ptr(dst), dtype_id(dst), ld_dst, off_dst,
          rows, n, stream())
+
+
+def pack_frames(a, b, out, rows):
+    """out[r] (bf16, 16 channels) = [a[r] | b[r] | 0]; b may be None"""
+    call("acg_pack_frames", ptr(a), ptr(b), 3, ptr(out), out.shape[-1], rows, stream())
 
 
 def tile_actions(actions, B, hw, dst, ld_dst, off):

@@ -113,6 +113,15 @@ typedef struct acg_tc_args {
     float* bn_mean; float* bn_rstd; float* bn_scale; float* bn_shift;
     long long bn_rows;
     float bn_eps;
+    /* optional (data-gradient launches): fused batch-norm BACKWARD reduction.  This launch writes dA, the gradient
+     * w.r.t. the activation of a layer with pre-activation red_z [rows, red_C] (bf16, row stride red_ldz, same rows
+     * as the output) that was normalised with red_mean / red_rstd / red_shift and activation red_act; the epilogue
+     * adds sum_r dzh and sum_r dzh*xhat (dzh = dA*act'(z*rstd + shift), xhat = (z - mean)*rstd, dA as stored) of
+     * its tile to stats[2][red_C] -- exactly what acg_bn_act_bwd_reduce computes, without re-reading dA.
+     * red_C % 16 == 0, red_C <= output channels, bf16 output, bn_counter == NULL. */
+    const void* red_z;
+    int red_ldz, red_C, red_act;
+    const float* red_mean; const float* red_rstd; const float* red_shift;
 } acg_tc_args;
 
 /* y = conv(x): x [B,H,W,ld_in] -> y [B,OH,OW,ld_out]; w_pack = acg_pack_weights(which=0, ld_k=ld_in) */
@@ -128,9 +137,10 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
  * [ru16(Cin)][class taps][ld_k>=Cout] matrix per output-parity class.  acg_pack_size gives the element count. */
 long long acg_pack_size(const acg_conv_shape* s, int which, int ld_k);
 int acg_pack_weights(const acg_conv_shape* s, const float* w, int which, int ld_k, void* pack, void* stream);
-/* All packs of a parameter store in one launch.  jobs_dev is a DEVICE array sorted by `first` (the running element
- * count: job i produces elements [first_i, first_i + acg_pack_size_i) of a virtual concatenation), total = sum of
- * the pack sizes.  Each job is what one acg_pack_weights call would do. */
+/* All packs of a parameter store in one launch.  jobs_dev is a DEVICE copy of the job array (each job is what one
+ * acg_pack_weights call would do; `first` is the running element count and is informational), tiles_dev a DEVICE
+ * copy of the tile table acg_pack_plan wrote for the same jobs: int[4] per tile, one tile = 32 pack rows x 32 pack
+ * columns of one filter tap (the CONV pack is a per-tap transpose, done through shared memory). */
 typedef struct acg_pack_job {
     const void* w;       /* fp32 HWIO weights */
     void* pack;          /* bf16 output */
@@ -139,7 +149,11 @@ typedef struct acg_pack_job {
     int KH, KW, Cin, Cout, stride, pad_t, pad_l;
     int N;               /* rows of the pack: ru16(Cout) for which=0, ru16(Cin) for which=1 */
 } acg_pack_job;
-int acg_pack_weights_batched(const acg_pack_job* jobs_dev, int njobs, long long total, void* stream);
+int acg_pack_weights_batched(const acg_pack_job* jobs_dev, int njobs, const void* tiles_dev, int ntiles,
+                             void* stream);
+/* HOST: number of tiles of the jobs (host_jobs is a HOST array); when host_tiles != NULL also writes up to
+ * `capacity` tiles (4 ints each).  -1 on invalid jobs. */
+long long acg_pack_plan(const acg_pack_job* host_jobs, int njobs, int* host_tiles, long long capacity);
 /* 1 when the tcgen05 kernels accept the shape, 0 otherwise (which: 0 fprop, 1 dgrad, 2 wgrad) */
 int acg_conv_tc_supported(const acg_conv_shape* s, int which);
 
@@ -182,6 +196,10 @@ int acg_bias_grad(const double* red, int C, float scale, float* dbias, void* str
 /* dst[r, off_dst:off_dst+n] = src[r, off_src:off_src+n]  (channel-slice copy with dtype conversion) */
 int acg_copy_channels(const void* src, int src_dtype, int ld_src, int off_src, void* dst, int dst_dtype,
                       int ld_dst, int off_dst, long long rows, int n, void* stream);
+/* out[r, 0:ld_out] (bf16) = [a[r,0:C] | b[r,0:C] | 0...]: the conv-operand form of a frame (g/conv1 input, b == NULL)
+ * or of concat([img, frame], 3) (d/conv1 input, train.py:64,68) in one pass.  C == 3, ld_out == 8 or 16. */
+int acg_pack_frames(const float* a, const float* b, int C, void* out_bf16, int ld_out, long long rows,
+                    void* stream);
 /* dst[(b*hw + p), off:off+A] = actions[b, 0:A]  (tf.tile of the [B,1,1,A] action map) */
 int acg_tile_actions(const float* actions, int B, int hw, int A, void* dst, int dst_dtype, int ld_dst,
                      int off, void* stream);

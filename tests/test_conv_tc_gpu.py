@@ -135,3 +135,126 @@ def test_conv_wgrad_tc(cuda, case):
     # accumulate semantics: a second call doubles the result
     Kn.conv_wgrad_tc(shape, _pad_channels(x, ld_x, cuda), _pad_channels(dy, ld_dy, cuda), dw, ld_x, ld_dy)
     assert np.abs(dw.cpu().numpy() - 2 * dw_ref).max() <= 4e-3 * max(1.0, np.abs(dw_ref).max())
+
+
+def test_batched_tile_pack_equals_single_packs(cuda):
+    """acg_pack_weights_batched (one launch, tile table from acg_pack_plan, shared-memory transpose) writes exactly
+    what one acg_pack_weights call per pack writes -- every layer geometry of models.py, ragged channel counts."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    rng = np.random.RandomState(11)
+    geos = [(64, 64, 3, 32, 5, 2, "SAME", 16, 32), (16, 16, 138, 70, 5, 2, "SAME", 144, 80),
+            (16, 16, 128, 32, 3, 2, "SAME", 128, 32), (4, 4, 16, 5, 4, 1, "VALID", 16, 16),
+            (2, 2, 512, 1, 2, 1, "SAME", 512, 16), (64, 64, 36, 128, 5, 2, "SAME", 48, 128),
+            (8, 8, 266, 128, 5, 2, "SAME", 272, 128)]
+    entries, singles = [], []
+    for (H, W, Cin, Cout, k, s, pad, ld_ci, ld_co) in geos:
+        shape = Kn.conv_shape(2, H, W, Cin, Cout, k, s, pad)
+        w = torch.from_numpy(rng.randn(k, k, Cin, Cout).astype(np.float32)).to(cuda)
+        for which, ld in ((0, ld_ci), (1, ld_co)):
+            n = Kn.pack_size(shape, which, ld)
+            batched = torch.full((n,), 7.0, dtype=torch.bfloat16, device=cuda)
+            single = torch.full((n,), -7.0, dtype=torch.bfloat16, device=cuda)
+            Kn.pack_weights(shape, w, which, ld, single)
+            entries.append((shape, w, which, ld, batched))
+            singles.append(single)
+    table, njobs, tiles, ntiles = Kn.make_pack_jobs(entries, cuda)
+    assert njobs == len(entries) and ntiles > njobs
+    Kn.pack_weights_batched(table, njobs, tiles, ntiles)
+    torch.cuda.synchronize()
+    for (shape, w, which, ld, batched), single in zip(entries, singles):
+        assert torch.equal(batched.view(torch.int16), single.view(torch.int16)), (shape.Cin, shape.Cout, which)
+
+
+# (which data-gradient kernel, B, H, W, Cin, Cout, C of the consumer's batch-norm, activation)
+RED_CASES = [
+    ("dgrad", 3, 16, 16, 32, 64, 32, "relu"),        # generic ADJ kernel (small grid -> 6-stage variant)
+    ("dgrad", 5, 8, 8, 138, 128, 128, "lrelu"),      # d/conv3 -> d/conv2: concat gradient, only 128 of 138 channels
+    ("dgrad", 4, 32, 32, 128, 128, 128, "relu"),     # TMA halo-tile kernel (H=W=32, Cout=128)
+    ("dgrad", 2, 64, 64, 64, 128, 64, "lrelu"),      # halo-tile kernel, 64-wide rows
+    ("fprop", 3, 16, 16, 48, 128, 128, "relu"),      # data gradient of a conv2d_transpose = forward conv form
+    ("fprop", 2, 8, 8, 272, 128, 128, "relu"),
+]
+
+
+@pytest.mark.parametrize("case", RED_CASES)
+def test_fused_bwd_reduction_equals_separate_pass(cuda, case):
+    """The batch-norm backward sums accumulated in the epilogue of the data-gradient kernels (acg_tc_args.red_*) equal
+    what acg_bn_act_bwd_reduce computes from the stored gradient (fp32 partial sums in a different order)."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    which, B, H, W, Cin, Cout, Cc, act = case
+    g = torch.Generator(device=cuda).manual_seed(3)
+    shape = Kn.conv_shape(B, H, W, Cin, Cout, 5, 2, "SAME")
+    w = torch.randn(5, 5, Cin, Cout, device=cuda, generator=g) / 30
+    if which == "dgrad":        # out = gradient w.r.t. the conv input [B,H,W,Cin]
+        ld_in, ld_out, rows, n_out = ru(Cout, 16), ru(Cin, 16), B * H * W, Cin
+        src = torch.randn(B, shape.OH, shape.OW, ld_in, device=cuda, generator=g).to(torch.bfloat16)
+        pack = torch.empty(Kn.pack_size(shape, 1, ld_in), dtype=torch.bfloat16, device=cuda)
+        Kn.pack_weights(shape, w, 1, ld_in, pack)
+        fn = Kn.conv_dgrad_tc
+    else:                       # out = forward conv output [B,OH,OW,Cout]
+        ld_in, ld_out, rows, n_out = ru(Cin, 16), ru(Cout, 16), B * shape.OH * shape.OW, Cout
+        src = torch.randn(B, H, W, ld_in, device=cuda, generator=g).to(torch.bfloat16)
+        src[..., Cin:] = 0
+        pack = torch.empty(Kn.pack_size(shape, 0, ld_in), dtype=torch.bfloat16, device=cuda)
+        Kn.pack_weights(shape, w, 0, ld_in, pack)
+        fn = Kn.conv_fprop_tc
+    assert Cc <= n_out
+    ldz = Cc
+    z = torch.randn(rows, ldz, device=cuda, generator=g).to(torch.bfloat16)
+    mean = torch.randn(Cc, device=cuda, generator=g) * 0.3
+    rstd = torch.rand(Cc, device=cuda, generator=g) + 0.5
+    shift = torch.randn(Cc, device=cuda, generator=g) * 0.3
+    red_fused = torch.zeros(2 * Cc, dtype=torch.float64, device=cuda)
+    red_sep = torch.zeros(2 * Cc, dtype=torch.float64, device=cuda)
+    out = torch.zeros(rows, ld_out, dtype=torch.bfloat16, device=cuda)
+    out_plain = torch.zeros(rows, ld_out, dtype=torch.bfloat16, device=cuda)
+    fn(shape, src, pack, out, ld_in, ld_out, red=(red_fused, z, ldz, Cc, act, mean, rstd, shift))
+    fn(shape, src, pack, out_plain, ld_in, ld_out)
+    assert torch.equal(out, out_plain)                        # the output itself is untouched by the fusion
+    Kn.bn_act_bwd_reduce(out, None, ld_out, z, ldz, rows, Cc, 1, mean, rstd, shift, act, red_sep)
+    torch.cuda.synchronize()
+    a, b = red_fused.cpu().numpy(), red_sep.cpu().numpy()
+    scale = np.abs(b).max()
+    assert scale > 0
+    assert np.abs(a - b).max() <= 2e-5 * scale + 1e-3
+
+
+@pytest.mark.parametrize("Cin,Cout", [(3, 32), (6, 64)])
+def test_first_layers_with_8_channel_frames(cuda, Cin, Cout):
+    """g/conv1 / d/conv1 as the engine runs them: frame operands padded to 8 channels only (K = 25 x 8 = 200: K blocks
+    straddle taps and the last one is partial), forward, weight gradient (N tile of 72 -> 80 columns) and data
+    gradient into an 8-channel fp32 buffer."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    B, H, W, k, s = 3, 64, 64, 5, 2
+    rng = np.random.RandomState(Cin)
+    shape = Kn.conv_shape(B, H, W, Cin, Cout, k, s, "SAME")
+    x = _bf16_round(rng.randn(B, H, W, Cin))
+    w = rng.randn(k, k, Cin, Cout) / np.sqrt(k * k * Cin)
+    wt = torch.from_numpy(w.astype(np.float32)).to(cuda)
+    xt = torch.tensor(x, requires_grad=True)
+    wr = torch.tensor(_bf16_round(w), requires_grad=True)
+    yt = torch_ref.conv2d(xt, wr, s, "SAME")
+    dy = _bf16_round(rng.randn(*yt.shape))
+    dx_ref, dw_ref = torch.autograd.grad(yt, [xt, wr], torch.tensor(dy))
+    ld = 8
+    x8 = _pad_channels(x, ld, cuda)
+    # forward
+    pack = torch.empty(Kn.pack_size(shape, 0, ld), dtype=torch.bfloat16, device=cuda)
+    Kn.pack_weights(shape, wt, 0, ld, pack)
+    y = torch.zeros(B, shape.OH, shape.OW, Cout, device=cuda)
+    Kn.conv_fprop_tc(shape, x8, pack, y, ld, Cout)
+    assert np.abs(y.cpu().numpy() - yt.detach().numpy()).max() <= 2e-3 * max(1.0, float(yt.abs().max()))
+    # weight gradient
+    dyp = _pad_channels(dy, Cout, cuda)
+    dw = torch.zeros(k, k, Cin, Cout, device=cuda)
+    Kn.conv_wgrad_tc(shape, x8, dyp, dw, ld, Cout)
+    assert np.abs(dw.cpu().numpy() - dw_ref.numpy()).max() <= 2e-3 * max(1.0, float(dw_ref.abs().max()))
+    # data gradient, 8-channel fp32 output (what frame_losses reads for the adversarial term)
+    packb = torch.empty(Kn.pack_size(shape, 1, Cout), dtype=torch.bfloat16, device=cuda)
+    Kn.pack_weights(shape, wt, 1, Cout, packb)
+    dx = torch.full((B, H, W, ld), float("nan"), device=cuda)
+    Kn.conv_dgrad_tc(shape, dyp, packb, dx, Cout, ld)
+    got = dx.cpu().numpy()
+    assert np.isfinite(got).all()
+    assert np.abs(got[..., :Cin] - dx_ref.numpy()).max() <= 2e-3 * max(1.0, float(dx_ref.abs().max()))
+    assert np.abs(got[..., Cin:]).max() == 0.0

@@ -238,3 +238,21 @@ def test_optimizers(cuda, n):
         Kn.rmsprop_step(pc, gc, msc, 5e-5, clip=(-0.01, 0.01))
         assert np.abs(pc.cpu().numpy() - p).max() < 1e-6
         assert float(pc.abs().max()) <= 0.01
+
+
+def test_pack_frames(cuda):
+    """acg_pack_frames == concat([img, frame], 3) rounded to bf16, zero pad channels (train.py:64,68 / g/conv1 input)."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    rng = np.random.RandomState(4)
+    a = torch.from_numpy(rng.uniform(-1, 1, (3, 64, 64, 3)).astype(np.float32)).to(cuda)
+    b = torch.from_numpy(rng.uniform(-1, 1, (3, 64, 64, 3)).astype(np.float32)).to(cuda)
+    rows = 3 * 64 * 64
+    for second in (b, None):
+        for ld in (8, 16):
+            out = torch.full((3, 64, 64, ld), 5.0, dtype=torch.bfloat16, device=cuda)
+            Kn.pack_frames(a, second, out, rows)
+            ref = torch.zeros(3, 64, 64, ld, device=cuda)
+            ref[..., 0:3] = a
+            if second is not None:
+                ref[..., 3:6] = second
+            assert torch.equal(out, ref.to(torch.bfloat16))
