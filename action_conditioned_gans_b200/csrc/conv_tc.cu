@@ -831,6 +831,220 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
 }
 
 
+// ---- ADJ gather, PERSISTENT halo-tile variant ---------------------------------------------------------------------
+// Same tile, operand staging and MMA schedule as conv_adj_halo_kernel, but one CTA per SM walks a list of tiles and the
+// three phases of a tile (halo + weight copies, MMAs, epilogue) belong to different warps, so they overlap ACROSS tiles:
+//   warp 5 (one lane): halo TMA producer      warp 6 (one lane): weight-slice TMA producer
+//   warp 4 (one lane): tcgen05.mma issuer     warps 0-3: epilogue (tcgen05.ld -> bias/moments -> global stores)
+// The producers run ahead into the next tile as soon as a halo buffer / weight stage has drained, i.e. while the
+// epilogue of the current tile is still storing; with N <= 64 (g/tconv4: 4 accumulators x 48 columns) the accumulators
+// are double buffered in tensor memory as well, so the MMAs of tile i+1 run under the epilogue of tile i.  The
+// non-persistent kernel serialises copy -> MMA -> epilogue within its single CTA per SM (ncu: tensor pipe idle during
+// 33 % epilogue + the halo wait).  Tiles are ordered class-major (9-tap classes first), CTA b takes tiles b, b+grid, ...
+constexpr int kHaloPThreads = 224;
+
+struct HaloTile {
+    int ph, pw, na, nc, ea, ec, ntaps, b0, y0, cls;
+};
+__device__ __forceinline__ HaloTile halo_tile(const Params& p, int t, int n_sp, int tiles_y, int TB) {
+    HaloTile h;
+    const int ord = t / n_sp;                 // class-major, highest class first: with TF SAME padding of a 5x5
+    const int sp = t - ord * n_sp;            // stride-2 filter class 3 has 9 taps, 1/2 have 6, 0 has 4 (long tiles first)
+    h.cls = 3 - ord;
+    h.ph = h.cls >> 1; h.pw = h.cls & 1;
+    const int a0 = (h.ph + p.pad_t) & 1, c0 = (h.pw + p.pad_l) & 1;
+    h.na = (p.KH - a0 + 1) >> 1; h.nc = (p.KW - c0 + 1) >> 1;
+    h.ea = (h.ph + p.pad_t - a0) >> 1; h.ec = (h.pw + p.pad_l - c0) >> 1;
+    h.ntaps = h.na * h.nc;
+    h.b0 = (sp / tiles_y) * TB; h.y0 = (sp % tiles_y) << 4;
+    return h;
+}
+
+__global__ void __launch_bounds__(kHaloPThreads, 1)
+conv_adj_halo_persistent_kernel(const __grid_constant__ HaloParams hp, int ntiles) {
+    const Params& p = hp.p;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t halo_full[2], halo_empty[2], b_full[kHaloBStages], b_empty[kHaloBStages];
+    __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ float sm_stats[2][BN];
+    __shared__ int last_cta_sh;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smemH = smem_base, smemB = smem_base + 2 * kHaloBuf;
+    if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
+
+    const int Hs = p.H >> 1, Ws = p.W >> 1;
+    const int XG = Ws >> 3, TB = HALO_ACC / XG;
+    const int WH = Ws + 2, HR = HALO_H * WH;
+    const int tiles_y = Hs >> 4;
+    const int n_sp = (p.B / TB) * tiles_y;                  // tiles per parity class
+    const int N = p.N;
+    const int nkc = p.lda >> 6;
+    const int NB = (2 * HALO_ACC * N <= 512) ? 2 : 1;       // accumulator buffers in tensor memory
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(NB * HALO_ACC * N)) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
+        }
+        for (int i = 0; i < kHaloBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        fence_mbar_init();
+        tma_prefetch_desc(&hp.map_a);
+        for (int c = 0; c < 4; ++c) tma_prefetch_desc(&hp.map_b[c]);
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp == 5 && lane == 0) {
+        // ================================ halo producer ================================
+        const uint32_t a_bytes = (uint32_t)(TB * HR) * 128u;
+        int hcount = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const HaloTile h = halo_tile(p, t, n_sp, tiles_y, TB);
+            const int oh0 = h.y0 + h.ea - (h.na - 1), ow0 = h.ec - (h.nc - 1);
+            for (int kc = 0; kc < nkc; ++kc, ++hcount) {
+                const int buf = hcount & 1, use = hcount >> 1;
+                if (use >= 1) mbar_wait(&halo_empty[buf], (uint32_t)((use - 1) & 1));
+                mbar_expect_tx(&halo_full[buf], a_bytes);
+                tma_load_4d(smemH + buf * kHaloBuf, &hp.map_a, kc * 64, ow0, oh0, h.b0, &halo_full[buf]);
+            }
+        }
+    } else if (warp == 6 && lane == 0) {
+        // ================================ weight producer ================================
+        const uint32_t b_bytes = (uint32_t)N * 128u;
+        int bcount = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const HaloTile h = halo_tile(p, t, n_sp, tiles_y, TB);
+            for (int kc = 0; kc < nkc; ++kc) {
+                for (int tap = 0; tap < h.ntaps; ++tap, ++bcount) {
+                    const int st = bcount % kHaloBStages, use = bcount / kHaloBStages;
+                    if (use >= 1) mbar_wait(&b_empty[st], (uint32_t)((use - 1) & 1));
+                    mbar_expect_tx(&b_full[st], b_bytes);
+                    tma_load_2d(smemB + st * kHaloBStage, &hp.map_b[h.cls], tap * p.lda + kc * 64, 0, &b_full[st]);
+                }
+            }
+        }
+    } else if (warp == 4 && lane == 0) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc = make_idesc(N, 0, 0);
+        const uint32_t ahi = desc_hi((uint32_t)WH * 128u), bhi = desc_hi(1024);
+        const uint32_t blo0 = desc_lo(smemB, 16);
+        uint32_t acc_row8[HALO_ACC];
+#pragma unroll
+        for (int q = 0; q < HALO_ACC; ++q) {
+            const int tb = q / XG, xg = q - tb * XG;
+            acc_row8[q] = (uint32_t)(tb * HR + xg * 8) * 8u;
+        }
+        int hcount = 0, bcount = 0, tcount = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
+            const HaloTile h = halo_tile(p, t, n_sp, tiles_y, TB);
+            const int abuf = tcount % NB, ause = tcount / NB;
+            if (ause >= 1) {      // the epilogue has drained this accumulator buffer
+                mbar_wait(&acc_empty[abuf], (uint32_t)((ause - 1) & 1));
+                tc_fence_after();
+            }
+            const uint32_t tacc = tmem_base + (uint32_t)(abuf * HALO_ACC * N);
+            for (int kc = 0; kc < nkc; ++kc, ++hcount) {
+                const int buf = hcount & 1;
+                mbar_wait(&halo_full[buf], (uint32_t)((hcount >> 1) & 1));
+                const uint32_t hbase = smemH + buf * kHaloBuf;
+                for (int tap = 0; tap < h.ntaps; ++tap, ++bcount) {
+                    const int st = bcount % kHaloBStages;
+                    mbar_wait(&b_full[st], (uint32_t)((bcount / kHaloBStages) & 1));
+                    tc_fence_after();
+                    const int ta = tap / h.nc, tcc = tap - ta * h.nc;
+                    const int shift = (h.na - 1 - ta) * WH + (h.nc - 1 - tcc);
+                    const uint32_t blo = blo0 + st * (kHaloBStage >> 4);
+                    const uint32_t alo_t = desc_lo(hbase, 16) + (uint32_t)shift * 8u;
+#pragma unroll
+                    for (int q = 0; q < HALO_ACC; ++q) {
+                        const uint32_t alo = alo_t + acc_row8[q];
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            tc_mma2(tacc + q * N, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(&b_empty[st]);
+                }
+                tc_commit(&halo_empty[buf]);
+            }
+            tc_commit(&acc_full[abuf]);
+        }
+    } else if (warp < 4) {
+        // ================================ epilogue ================================
+        const int ml = warp * 32 + lane, yy = ml >> 3, xi = ml & 7;
+        int tcount = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
+            const HaloTile h = halo_tile(p, t, n_sp, tiles_y, TB);
+            const int abuf = tcount % NB, ause = tcount / NB;
+            mbar_wait(&acc_full[abuf], (uint32_t)(ause & 1));
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(abuf * HALO_ACC * N);
+            for (int q = 0; q < HALO_ACC; ++q) {
+                const int tb = q / XG, xg = q - tb * XG;
+                const int ih = ((h.y0 + yy) << 1) + h.ph, iw = ((xg * 8 + xi) << 1) + h.pw;
+                const size_t row_off = ((size_t)((h.b0 + tb) * p.H + ih) * p.W + iw) * p.ldo;
+                for (int cb = 0; cb < N; cb += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(tacc + q * N + cb, v);
+                    epilogue_chunk(p, v, cb, true, row_off, 0u, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
+                }
+            }
+            // this accumulator buffer may be overwritten by the MMAs of the tile after next
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[abuf]);
+            if (p.stats) {   // per-tile flush of the fp32 column sums into the fp64 accumulators (epilogue warps only)
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (tid < N && tid < p.n_stat) {
+                    atomicAdd(&p.stats[tid], (double)sm_stats[0][tid]);
+                    atomicAdd(&p.stats[p.n_stat + tid], (double)sm_stats[1][tid]);
+                }
+                if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+    if (p.stats && p.counter) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last_cta_sh = (atomicAdd(p.counter, 1u) == p.total_ctas - 1u);
+        __syncthreads();
+        if (last_cta_sh) {
+            __threadfence();
+            const double inv = 1.0 / (double)p.bn_rows;
+            for (int c = tid; c < p.n_bias; c += kHaloPThreads) {
+                const double mu = __ldcg(&p.stats[c]) * inv;
+                double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
+                if (var < 0.0) var = 0.0;
+                const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+                const float b = p.beta ? p.beta[c] : 0.f;
+                p.bn_mean[c] = (float)mu;
+                p.bn_rstd[c] = rs;
+                p.bn_scale[c] = rs;
+                p.bn_shift[c] = b - (float)mu * rs;
+            }
+            if (tid == 0) *p.counter = 0u;
+        }
+    }
+}
+
 // ---- all packs of a parameter store in ONE launch ---------------------------------------------------------------
 // After every optimizer step ~22 weight tensors x 2 packs have to be refreshed; one launch per pack costs more in
 // launch latency than in work.  The job table and a TILE table live in device memory (built once by the host,
@@ -1405,6 +1619,30 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
         }
         const int TB = HALO_ACC / (s->W / 16);
         dim3 hgrid((unsigned)((s->B / TB) * (s->H / 32)), 1, 4);
+        static const bool persistent = []() { const char* e = getenv("ACG_HALO_PERSISTENT"); return !e || atoi(e) != 0; }();
+        if (persistent && !t->red_z) {
+            // one CTA per SM walks the tile list: copies, MMAs and epilogue of consecutive tiles overlap
+            static bool pready = false;
+            if (!pready) {
+                if (cudaFuncSetAttribute(conv_adj_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kHaloSmem) != cudaSuccess) {
+                    cudaError_t e = cudaGetLastError();
+                    set_error("acg_conv_dgrad_tc: cannot set %d B dynamic smem: %s", kHaloSmem, cudaGetErrorString(e));
+                    return ACG_ERR_CUDA;
+                }
+                pready = true;
+            }
+            const int ntiles = (int)hgrid.x * 4;
+            const int ctas = ntiles < num_sms() ? ntiles : num_sms();
+            rc = fill_bn(&p, t, (unsigned int)ctas, "acg_conv_dgrad_tc");
+            if (rc) return rc;
+            HaloParams hp;
+            hp.p = p;
+            rc = encode_halo_maps(&hp, s, t, N, TB, dy_bf16, w_pack);
+            if (rc) return rc;
+            conv_adj_halo_persistent_kernel<<<ctas, kHaloPThreads, kHaloSmem, static_cast<cudaStream_t>(stream)>>>(hp, ntiles);
+            return check_launch("acg_conv_dgrad_tc(halo, persistent)");
+        }
         rc = fill_bn(&p, t, hgrid.x * 4u, "acg_conv_dgrad_tc");
         if (rc) return rc;
         HaloParams hp;
