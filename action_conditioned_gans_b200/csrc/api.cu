@@ -18,6 +18,11 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+    static const bool on = []() { const char* e = getenv("ACG_PDL"); return !e || atoi(e) != 0; }();
+    return on;
+}
+
 int num_sms() {
     static int sms = 0;
     if (sms == 0) {

@@ -4,6 +4,8 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <utility>
 
 #include "../../include/acg_b200.h"
 
@@ -63,6 +65,38 @@ __device__ __forceinline__ float act_bwd(float u, int act) {
         case ACG_ACT_TANH: { float t = tanhf(u); return 1.f - t * t; }
         default: return 1.f;
     }
+}
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// A training iteration is ~200 dependent launches inside a CUDA graph; with a plain kernel -> kernel edge the next grid
+// is only scheduled once the previous one has fully drained.  Every kernel here is launched with the programmatic
+// stream-serialization attribute and (a) allows its dependents to be scheduled as soon as all of its own CTAs are
+// resident (griddepcontrol.launch_dependents at the top), (b) executes griddepcontrol.wait -- which returns only when
+// the prerequisite grid has COMPLETED and its memory is visible -- before its first global-memory access.  So launch
+// latency, CTA rasterisation and the per-CTA prologue (barrier init, TMEM allocation, descriptor prefetch) of kernel
+// N+1 hide under the tail of kernel N, with unchanged memory semantics.  ACG_PDL=0 launches without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+    pdl_launch_dependents();
+    pdl_wait();
+}
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---- mbarrier / bulk-copy (TMA) PTX wrappers ---------------------------------------------

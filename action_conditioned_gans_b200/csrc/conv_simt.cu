@@ -27,6 +27,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads)
 conv_simt_kernel(const float* __restrict__ A_src, const float* __restrict__ B_src, float* __restrict__ C_dst,
                  const acg_conv_shape s) {
+    pdl_prologue();
     __shared__ __align__(16) float As[TK][TM + 4];
     __shared__ __align__(16) float Bs[TK][TN + 4];
 
@@ -187,7 +188,7 @@ int acg_conv_fprop_f32(const acg_conv_shape* s, const float* x, const float* w, 
     ACG_REQUIRE(x && w && y, ACG_ERR_INVALID, "acg_conv_fprop_f32: null pointer");
     const int M = s->B * s->OH * s->OW;
     dim3 grid((M + TM - 1) / TM, (s->Cout + TN - 1) / TN, 1);
-    conv_simt_kernel<FPROP><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, w, y, *s);
+    launch_pdl(conv_simt_kernel<FPROP>, grid, kThreads, 0, static_cast<cudaStream_t>(stream), x, w, y, *s);
     return check_launch("acg_conv_fprop_f32");
 }
 
@@ -199,7 +200,7 @@ int acg_conv_dgrad_f32(const acg_conv_shape* s, const float* dy, const float* w,
     const int Hp = (s->H + s->stride - 1) / s->stride, Wp = (s->W + s->stride - 1) / s->stride;
     const int M = s->B * Hp * Wp;  // largest parity class
     dim3 grid((M + TM - 1) / TM, (s->Cin + TN - 1) / TN, s->stride * s->stride);
-    conv_simt_kernel<DGRAD><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(dy, w, dx, *s);
+    launch_pdl(conv_simt_kernel<DGRAD>, grid, kThreads, 0, static_cast<cudaStream_t>(stream), dy, w, dx, *s);
     return check_launch("acg_conv_dgrad_f32");
 }
 
@@ -218,7 +219,7 @@ int acg_conv_wgrad_f32(const acg_conv_shape* s, const float* x, const float* dy,
     if (gz < 1) gz = 1;
     if (gz > 65535) gz = 65535;
     dim3 grid(gx, gy, (unsigned)gz);
-    conv_simt_kernel<WGRAD><<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, dy, dw, *s);
+    launch_pdl(conv_simt_kernel<WGRAD>, grid, kThreads, 0, static_cast<cudaStream_t>(stream), x, dy, dw, *s);
     return check_launch("acg_conv_wgrad_f32");
 }
 

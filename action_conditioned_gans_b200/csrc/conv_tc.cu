@@ -425,6 +425,9 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // PDL: dependents may be scheduled now that this CTA owns its tensor memory; nothing above touched global memory
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t tmem_base = tmem_base_sh;
     if (timing) t1 = gtime();
 
@@ -667,6 +670,9 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // PDL: dependents may be scheduled now that this CTA owns its tensor memory; nothing above touched global memory
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t tmem_base = tmem_base_sh;
     if (timing) t1 = gtime();
 
@@ -904,6 +910,9 @@ conv_adj_halo_persistent_kernel(const __grid_constant__ HaloParams hp, int ntile
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // PDL: dependents may be scheduled now that this CTA owns its tensor memory; nothing above touched global memory
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t tmem_base = tmem_base_sh;
 
     if (warp == 5 && lane == 0) {
@@ -1053,6 +1062,7 @@ conv_adj_halo_persistent_kernel(const __grid_constant__ HaloParams hp, int ntile
 // the bf16 writes (64 B per warp row) are coalesced; the ADJ pack keeps the channel order and only re-groups taps.
 __global__ void __launch_bounds__(256)
 pack_tiles_kernel(const acg_pack_job* __restrict__ jobs, const int4* __restrict__ tiles, int ntiles) {
+    pdl_prologue();
     __shared__ float sm[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -1223,6 +1233,9 @@ conv_wgrad_tc_kernel(const WgradParams p) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // PDL: dependents may be scheduled now that this CTA owns its tensor memory; nothing above touched global memory
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t tmem_base = tmem_base_sh;
 
     if (warp < 4) {
@@ -1316,6 +1329,7 @@ conv_wgrad_tc_kernel(const WgradParams p) {
 // HWIO fp32 w[a][c][ci][co] -> CONV pack bf16 Wf[n = co (N rows, zero padded)][tap][cis (zero padded)]
 __global__ void __launch_bounds__(256)
 pack_conv_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int Cis, int N, __nv_bfloat16* __restrict__ out) {
+    pdl_prologue();
     const long long total = (long long)N * taps * Cis;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -1332,6 +1346,7 @@ pack_conv_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int C
 __global__ void __launch_bounds__(256)
 pack_adj_kernel(const float* __restrict__ w, int KH, int KW, int Cin, int Cout, int Cos, int N, int stride, int pad_t,
                 int pad_l, __nv_bfloat16* __restrict__ out) {
+    pdl_prologue();
     const int cls = blockIdx.y;
     const int ph = cls / stride, pw = cls % stride;
     const int a0 = (ph + pad_t) % stride, c0 = (pw + pad_l) % stride;
@@ -1462,12 +1477,12 @@ int acg_pack_weights(const acg_conv_shape* s, const float* w, int which, int ld_
         const long long total = (long long)N * s->KH * s->KW * ld_k;
         long long blocks = (total + 255) / 256;
         if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-        pack_conv_kernel<<<(int)blocks, 256, 0, st>>>(w, s->KH * s->KW, s->Cin, s->Cout, ld_k, N,
+        launch_pdl(pack_conv_kernel, (int)blocks, 256, 0, st, w, s->KH * s->KW, s->Cin, s->Cout, ld_k, N,
                                                      static_cast<__nv_bfloat16*>(pack));
     } else {
         const int N = ru(s->Cin, 16);
         dim3 grid(num_sms(), s->stride * s->stride);
-        pack_adj_kernel<<<grid, 256, 0, st>>>(w, s->KH, s->KW, s->Cin, s->Cout, ld_k, N, s->stride, s->pad_t, s->pad_l,
+        launch_pdl(pack_adj_kernel, grid, 256, 0, st, w, s->KH, s->KW, s->Cin, s->Cout, ld_k, N, s->stride, s->pad_t, s->pad_l,
                                              static_cast<__nv_bfloat16*>(pack));
     }
     return check_launch("acg_pack_weights");
@@ -1479,8 +1494,7 @@ int acg_pack_weights_batched(const acg_pack_job* jobs_dev, int njobs, const void
     ACG_REQUIRE(jobs_dev && tiles_dev && njobs > 0 && ntiles > 0, ACG_ERR_INVALID,
                 "acg_pack_weights_batched: bad argument");
     int blocks = ntiles < num_sms() * 8 ? ntiles : num_sms() * 8;
-    pack_tiles_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        jobs_dev, static_cast<const int4*>(tiles_dev), ntiles);
+    launch_pdl(pack_tiles_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), jobs_dev, static_cast<const int4*>(tiles_dev), ntiles);
     return check_launch("acg_pack_weights_batched");
 }
 
@@ -1561,9 +1575,9 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     rc = encode_weight_map(&cp.map_b[0], w_pack, (long long)s->KH * s->KW * t->ld_in, N, "acg_conv_fprop_tc");
     if (rc) return rc;
     if ((long long)grid.x * grid.y <= num_sms())
-        conv_tc_kernel<CONV, 6><<<grid, kThreads, kSmemBytes6, static_cast<cudaStream_t>(stream)>>>(cp);
+        launch_pdl(conv_tc_kernel<CONV, 6>, grid, kThreads, kSmemBytes6, static_cast<cudaStream_t>(stream), cp);
     else
-        conv_tc_kernel<CONV, 3><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(cp);
+        launch_pdl(conv_tc_kernel<CONV, 3>, grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream), cp);
     return check_launch("acg_conv_fprop_tc");
 }
 
@@ -1640,7 +1654,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
             hp.p = p;
             rc = encode_halo_maps(&hp, s, t, N, TB, dy_bf16, w_pack);
             if (rc) return rc;
-            conv_adj_halo_persistent_kernel<<<ctas, kHaloPThreads, kHaloSmem, static_cast<cudaStream_t>(stream)>>>(hp, ntiles);
+            launch_pdl(conv_adj_halo_persistent_kernel, ctas, kHaloPThreads, kHaloSmem, static_cast<cudaStream_t>(stream), hp, ntiles);
             return check_launch("acg_conv_dgrad_tc(halo, persistent)");
         }
         rc = fill_bn(&p, t, hgrid.x * 4u, "acg_conv_dgrad_tc");
@@ -1649,7 +1663,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
         hp.p = p;
         rc = encode_halo_maps(&hp, s, t, N, TB, dy_bf16, w_pack);
         if (rc) return rc;
-        conv_adj_halo_kernel<<<hgrid, kThreads, kHaloSmem, static_cast<cudaStream_t>(stream)>>>(hp);
+        launch_pdl(conv_adj_halo_kernel, hgrid, kThreads, kHaloSmem, static_cast<cudaStream_t>(stream), hp);
         return check_launch("acg_conv_dgrad_tc(halo)");
     }
     rc = fill_bn(&p, t, active, "acg_conv_dgrad_tc");
@@ -1665,9 +1679,9 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
         if (rc) return rc;
     }
     if ((long long)active <= num_sms())
-        conv_tc_kernel<ADJ, 6><<<grid, kThreads, kSmemBytes6, static_cast<cudaStream_t>(stream)>>>(cp);
+        launch_pdl(conv_tc_kernel<ADJ, 6>, grid, kThreads, kSmemBytes6, static_cast<cudaStream_t>(stream), cp);
     else
-        conv_tc_kernel<ADJ, 3><<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(cp);
+        launch_pdl(conv_tc_kernel<ADJ, 3>, grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream), cp);
     return check_launch("acg_conv_dgrad_tc");
 }
 
@@ -1704,7 +1718,7 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
     splits = (Kd + chunk - 1) / chunk;
     p.k_chunk = (int)chunk;
     dim3 grid(gx, gy, (unsigned)splits);
-    conv_wgrad_tc_kernel<<<grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream)>>>(p);
+    launch_pdl(conv_wgrad_tc_kernel, grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream), p);
     return check_launch("acg_conv_wgrad_tc");
 }
 

@@ -9,6 +9,7 @@ namespace {
 __global__ void __launch_bounds__(128)
 umma_shift_probe(const __nv_bfloat16* __restrict__ a_rows, int n_rows, const __nv_bfloat16* __restrict__ b_rows, int N,
                  int shift, int pitch, int base_offset_mode, float* __restrict__ out) {
+    pdl_prologue();
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_sh;
@@ -96,8 +97,7 @@ extern "C" int acg_debug_umma_shift(const void* a_rows, int n_rows, const void* 
         }
         ready = true;
     }
-    umma_shift_probe<<<1, 128, 66560, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(a_rows), n_rows, static_cast<const __nv_bfloat16*>(b_rows), N, shift, pitch,
+    launch_pdl(umma_shift_probe, 1, 128, 66560, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(a_rows), n_rows, static_cast<const __nv_bfloat16*>(b_rows), N, shift, pitch,
         base_offset_mode, out);
     return check_launch("acg_debug_umma_shift");
 }

@@ -49,6 +49,7 @@ template <int K, typename LT, bool BWD, int STAGES, bool PADOUT>
 __global__ void __launch_bounds__(kThreads)
 dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const float* __restrict__ dy,
            float* __restrict__ out, void* __restrict__ dlogits_v, int B, int H, int W) {
+    pdl_prologue();
     using L = StageLayout<K, LT, BWD>;
     constexpr int KK = K * K;
     constexpr int LDO = pad16(KK);
@@ -253,7 +254,7 @@ int launch(const void* logits, const float* img, const float* dy, float* out, vo
     const int nbands = B * (H / kRows);
     int grid = num_sms() * occ;
     if (grid > nbands) grid = nbands;
-    kern<<<grid, kThreads, smem, stream>>>(static_cast<const LT*>(logits), img, dy, out, dlogits, B, H, W);
+    launch_pdl(kern, grid, kThreads, smem, stream, static_cast<const LT*>(logits), img, dy, out, dlogits, B, H, W);
     return check_launch(BWD ? "acg_dna_bwd" : "acg_dna_fwd");
 }
 

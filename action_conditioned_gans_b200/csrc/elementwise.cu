@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(kTX* kTY)
 col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void* __restrict__ dA,
                   const void* __restrict__ dA2, int d_dt, int ld_d, long long rows_per_group, int C, const float* __restrict__ mean, const float* __restrict__ rstd,
                   const float* __restrict__ shift, int act, double* __restrict__ out) {
+    pdl_prologue();
     const int c = blockIdx.x * kTX + threadIdx.x;
     const int g = blockIdx.z;
     const long long r_begin = (long long)g * rows_per_group;
@@ -78,6 +79,7 @@ col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void* __
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ beta,
                                    long long rows_per_group, int C, int groups, float eps, float* __restrict__ mean,
                                    float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift) {
+    pdl_prologue();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= groups * C) return;
     const int g = i / C, c = i % C;
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const void* __restrict__ z, int z_dt, long long rows, int C, int ld_in, long long rows_per_group,
                   const float* __restrict__ scale, const float* __restrict__ shift, int act, void* __restrict__ out,
                   int o_dt, int ld_out) {
+    pdl_prologue();
     const long long total = rows * C;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -117,6 +120,7 @@ bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict__ dA
                         const float* __restrict__ shift, int act, int has_bn, const double* __restrict__ red,
                         void* __restrict__ dz, int dz_dt, int ld_dz, float* __restrict__ dbeta, long long norm_rows,
                         float dbeta_scale) {
+    pdl_prologue();
     const long long total = rows * C;
     const float inv_r = 1.f / (float)norm_rows;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -152,6 +156,7 @@ bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict__ dA
 __global__ void __launch_bounds__(256)
 copy_channels_kernel(const void* __restrict__ src, int s_dt, int ld_src, int off_src, void* __restrict__ dst,
                      int d_dt, int ld_dst, int off_dst, long long rows, int n) {
+    pdl_prologue();
     const long long total = rows * n;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -168,6 +173,7 @@ template <int C, int LD>
 __global__ void __launch_bounds__(256)
 pack_frames_kernel(const float* __restrict__ a, const float* __restrict__ b, __nv_bfloat16* __restrict__ out,
                    long long rows) {
+    pdl_prologue();
     for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < rows;
          r += (long long)gridDim.x * blockDim.x) {
         float v[LD];
@@ -194,6 +200,7 @@ pack_frames_kernel(const float* __restrict__ a, const float* __restrict__ b, __n
 __global__ void __launch_bounds__(256)
 tile_actions_kernel(const float* __restrict__ actions, int B, int hw, int A, void* __restrict__ dst, int d_dt,
                     int ld_dst, int off) {
+    pdl_prologue();
     const long long total = (long long)B * hw * A;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -205,6 +212,7 @@ tile_actions_kernel(const float* __restrict__ actions, int B, int hw, int A, voi
 }
 
 __global__ void bias_grad_kernel(const double* __restrict__ red, int C, float scale, float* __restrict__ dbias) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c < C) atomicAdd(dbias + c, scale * (float)red[c]);
 }
@@ -279,6 +287,7 @@ vec_col_reduce_kernel(const void* __restrict__ z, int z_dt, int ld_z, const void
                       const void* __restrict__ dA2, int d_dt, int ld_d, long long rows_per_group, int C,
                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ shift,
                       int act, double* __restrict__ out) {
+    pdl_prologue();
     __shared__ double sm[16][256];
     const int bx = blockDim.x, by = blockDim.y;
     const int tid = threadIdx.y * bx + threadIdx.x;
@@ -365,6 +374,7 @@ __global__ void __launch_bounds__(256)
 vec_bn_act_fwd_kernel(const void* __restrict__ z, int z_dt, int C, int ld_in, long long rows_per_group,
                       const float* __restrict__ scale, const float* __restrict__ shift, int act, void* __restrict__ out,
                       int o_dt, int ld_out) {
+    pdl_prologue();
     const int bx = blockDim.x, by = blockDim.y;
     const int cv = blockIdx.x * bx + threadIdx.x;
     if (cv >= (C >> 3)) return;
@@ -404,6 +414,7 @@ vec_bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict_
                             const float* __restrict__ shift, int act, int has_bn, const double* __restrict__ red,
                             void* __restrict__ dz, int dz_dt, int ld_dz, float* __restrict__ dbeta, long long norm_rows,
                             float dbeta_scale) {
+    pdl_prologue();
     __shared__ float4 coef[256];               // this block's <= 32 vector columns x 8 channels: rs, sh, k1, k0
     const int bx = blockDim.x, by = blockDim.y;
     const int tid = threadIdx.y * bx + threadIdx.x;
@@ -537,12 +548,10 @@ int acg_bn_stats(const void* z, int dtype, long long rows, int C, int ld, int gr
     if (C % 8 == 0 && ld % 8 == 0 && al16(z)) {
         dim3 grid, block;
         vec_reduce_launch_dims(rpg, C, groups, &grid, &block);
-        vec_col_reduce_kernel<0><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-            z, dtype, ld, nullptr, nullptr, 0, 0, rpg, C, nullptr, nullptr, nullptr, 0, stats);
+        launch_pdl(vec_col_reduce_kernel<0>, grid, block, 0, static_cast<cudaStream_t>(stream), z, dtype, ld, nullptr, nullptr, 0, 0, rpg, C, nullptr, nullptr, nullptr, 0, stats);
         return check_launch("acg_bn_stats");
     }
-    col_reduce_kernel<0><<<reduce_grid(rpg, C, groups), dim3(kTX, kTY), 0, static_cast<cudaStream_t>(stream)>>>(
-        z, dtype, ld, nullptr, nullptr, 0, 0, rpg, C, nullptr, nullptr, nullptr, 0, stats);
+    launch_pdl(col_reduce_kernel<0>, reduce_grid(rpg, C, groups), dim3(kTX, kTY), 0, static_cast<cudaStream_t>(stream), z, dtype, ld, nullptr, nullptr, 0, 0, rpg, C, nullptr, nullptr, nullptr, 0, stats);
     return check_launch("acg_bn_stats");
 }
 
@@ -552,8 +561,7 @@ int acg_bn_finalize(const double* stats, const float* beta, long long rows_per_g
     ACG_REQUIRE(stats && mean && rstd && scale && shift, ACG_ERR_INVALID, "acg_bn_finalize: null pointer");
     ACG_REQUIRE(rows_per_group > 0 && C > 0 && groups > 0, ACG_ERR_INVALID, "acg_bn_finalize: bad size");
     const int n = C * groups;
-    bn_finalize_kernel<<<(n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        stats, beta, rows_per_group, C, groups, eps, mean, rstd, scale, shift);
+    launch_pdl(bn_finalize_kernel, (n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), stats, beta, rows_per_group, C, groups, eps, mean, rstd, scale, shift);
     return check_launch("acg_bn_finalize");
 }
 
@@ -567,12 +575,10 @@ int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in,
     if (C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && al16(z) && al16(out) && al16(scale) && al16(shift)) {
         dim3 grid, block;
         vec_stream_launch_dims(rows / groups, C, groups, 8, &grid, &block);
-        vec_bn_act_fwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-            z, z_dtype, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
+        launch_pdl(vec_bn_act_fwd_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), z, z_dtype, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
         return check_launch("acg_bn_act_fwd");
     }
-    bn_act_fwd_kernel<<<ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        z, z_dtype, rows, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
+    launch_pdl(bn_act_fwd_kernel, ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream), z, z_dtype, rows, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
     return check_launch("acg_bn_act_fwd");
 }
 
@@ -591,12 +597,10 @@ int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d
         al16(rstd) && al16(shift)) {
         dim3 grid, block;
         vec_reduce_launch_dims(rpg, C, groups, &grid, &block);
-        vec_col_reduce_kernel<1><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-            z, z_dtype, ld_z, dA, dA2, d_dtype, ld_d, rpg, C, mean, rstd, shift, act, red);
+        launch_pdl(vec_col_reduce_kernel<1>, grid, block, 0, static_cast<cudaStream_t>(stream), z, z_dtype, ld_z, dA, dA2, d_dtype, ld_d, rpg, C, mean, rstd, shift, act, red);
         return check_launch("acg_bn_act_bwd_reduce");
     }
-    col_reduce_kernel<1><<<reduce_grid(rpg, C, groups), dim3(kTX, kTY), 0, static_cast<cudaStream_t>(stream)>>>(
-        z, z_dtype, ld_z, dA, dA2, d_dtype, ld_d, rpg, C, mean, rstd, shift, act, red);
+    launch_pdl(col_reduce_kernel<1>, reduce_grid(rpg, C, groups), dim3(kTX, kTY), 0, static_cast<cudaStream_t>(stream), z, z_dtype, ld_z, dA, dA2, d_dtype, ld_d, rpg, C, mean, rstd, shift, act, red);
     return check_launch("acg_bn_act_bwd_reduce");
 }
 
@@ -616,13 +620,11 @@ int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d,
         al16(dz) && al16(mean) && al16(rstd) && al16(shift)) {
         dim3 grid, block;
         vec_stream_launch_dims(rows / groups, C, groups, 8, &grid, &block);   // 4 resident blocks/SM, 2 waves
-        vec_bn_act_bwd_apply_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-            dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
+        launch_pdl(vec_bn_act_bwd_apply_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
             dz, dz_dtype, ld_dz, dbeta, norm_rows > 0 ? norm_rows : rows / groups, dbeta_scale);
         return check_launch("acg_bn_act_bwd_apply");
     }
-    bn_act_bwd_apply_kernel<<<ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, rows, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
+    launch_pdl(bn_act_bwd_apply_kernel, ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream), dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, rows, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
         dz, dz_dtype, ld_dz, dbeta, norm_rows > 0 ? norm_rows : rows / groups, dbeta_scale);
     return check_launch("acg_bn_act_bwd_apply");
 }
@@ -630,7 +632,7 @@ int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d,
 int acg_bias_grad(const double* red, int C, float scale, float* dbias, void* stream) {
     using namespace acg;
     ACG_REQUIRE(red && dbias && C > 0, ACG_ERR_INVALID, "acg_bias_grad: bad argument");
-    bias_grad_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(red, C, scale, dbias);
+    launch_pdl(bias_grad_kernel, (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), red, C, scale, dbias);
     return check_launch("acg_bias_grad");
 }
 
@@ -641,8 +643,7 @@ int acg_copy_channels(const void* src, int src_dtype, int ld_src, int off_src, v
     ACG_REQUIRE(rows > 0 && n > 0 && off_src >= 0 && off_dst >= 0 && off_src + n <= ld_src && off_dst + n <= ld_dst,
                 ACG_ERR_INVALID, "acg_copy_channels: bad slice");
     ACG_REQUIRE(dt_ok(src_dtype) && dt_ok(dst_dtype), ACG_ERR_UNSUPPORTED, "acg_copy_channels: dtype");
-    copy_channels_kernel<<<ew_grid(rows * n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        src, src_dtype, ld_src, off_src, dst, dst_dtype, ld_dst, off_dst, rows, n);
+    launch_pdl(copy_channels_kernel, ew_grid(rows * n), 256, 0, static_cast<cudaStream_t>(stream), src, src_dtype, ld_src, off_src, dst, dst_dtype, ld_dst, off_dst, rows, n);
     return check_launch("acg_copy_channels");
 }
 
@@ -654,11 +655,9 @@ int acg_pack_frames(const float* a, const float* b, int C, void* out_bf16, int l
     long long blocks = (rows + 255) / 256;
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     if (ld_out == 8)
-        pack_frames_kernel<3, 8><<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            a, b, static_cast<__nv_bfloat16*>(out_bf16), rows);
+        launch_pdl(pack_frames_kernel<3, 8>, (int)blocks, 256, 0, static_cast<cudaStream_t>(stream), a, b, static_cast<__nv_bfloat16*>(out_bf16), rows);
     else
-        pack_frames_kernel<3, 16><<<(int)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-            a, b, static_cast<__nv_bfloat16*>(out_bf16), rows);
+        launch_pdl(pack_frames_kernel<3, 16>, (int)blocks, 256, 0, static_cast<cudaStream_t>(stream), a, b, static_cast<__nv_bfloat16*>(out_bf16), rows);
     return check_launch("acg_pack_frames");
 }
 
@@ -669,8 +668,7 @@ int acg_tile_actions(const float* actions, int B, int hw, int A, void* dst, int 
     ACG_REQUIRE(B > 0 && hw > 0 && A > 0 && off >= 0 && off + A <= ld_dst, ACG_ERR_INVALID,
                 "acg_tile_actions: bad size");
     ACG_REQUIRE(dt_ok(dst_dtype), ACG_ERR_UNSUPPORTED, "acg_tile_actions: dtype");
-    tile_actions_kernel<<<ew_grid((long long)B * hw * A), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        actions, B, hw, A, dst, dst_dtype, ld_dst, off);
+    launch_pdl(tile_actions_kernel, ew_grid((long long)B * hw * A), 256, 0, static_cast<cudaStream_t>(stream), actions, B, hw, A, dst, dst_dtype, ld_dst, off);
     return check_launch("acg_tile_actions");
 }
 

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(kThreads)
 frame_losses_kernel(const float* __restrict__ g, const float* __restrict__ n, int B, int H, int W,
                     double* __restrict__ sums, float* __restrict__ dg, float w_l1, float w_gdl,
                     const float* __restrict__ dadv, int ld_adv, int adv_off) {
+    pdl_prologue();
     const long long total = (long long)B * H * W * 3;
     const int rs = W * 3;  // row stride in floats
     float s_l1 = 0.f, s_sq = 0.f, s_gdl = 0.f;
@@ -68,6 +69,7 @@ frame_losses_kernel(const float* __restrict__ g, const float* __restrict__ n, in
 __global__ void __launch_bounds__(kThreads)
 dlogit_loss_kernel(const float* __restrict__ x, int n, int kind, float label_or_sign, float grad_scale,
                    float* __restrict__ loss_out, float* __restrict__ dlogits) {
+    pdl_prologue();
     double acc = 0.0;
     const float inv_n = 1.f / (float)n;
     for (int i = threadIdx.x; i < n; i += kThreads) {
@@ -98,6 +100,7 @@ dlogit_loss_kernel(const float* __restrict__ x, int n, int kind, float label_or_
 __global__ void __launch_bounds__(kThreads)
 state_loss_kernel(const float* __restrict__ s, const float* __restrict__ t, int n, float inv_batch,
                   float grad_scale, float* __restrict__ loss_out, float* __restrict__ ds) {
+    pdl_prologue();
     double acc = 0.0;
     for (int i = threadIdx.x; i < n; i += kThreads) {
         const double d = (double)s[i] - (double)t[i];
@@ -136,8 +139,7 @@ int acg_frame_losses(const float* g, const float* n, int B, int H, int W, double
     long long blocks = (total + kThreads - 1) / kThreads;
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    frame_losses_kernel<<<(int)blocks, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        g, n, B, H, W, sums, dg, w_l1, w_gdl, dadv, ld_adv, adv_off);
+    launch_pdl(frame_losses_kernel, (int)blocks, kThreads, 0, static_cast<cudaStream_t>(stream), g, n, B, H, W, sums, dg, w_l1, w_gdl, dadv, ld_adv, adv_off);
     return check_launch("acg_frame_losses");
 }
 
@@ -147,7 +149,7 @@ int acg_dlogit_loss(const float* x, int n, int kind, float label_or_sign, float 
     ACG_REQUIRE(x && loss_out, ACG_ERR_INVALID, "acg_dlogit_loss: null pointer");
     ACG_REQUIRE(n > 0, ACG_ERR_INVALID, "acg_dlogit_loss: n=%d", n);
     ACG_REQUIRE(kind == ACG_LOSS_BCE || kind == ACG_LOSS_WASS, ACG_ERR_INVALID, "unexpected loss argument");
-    dlogit_loss_kernel<<<1, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, n, kind, label_or_sign,
+    launch_pdl(dlogit_loss_kernel, 1, kThreads, 0, static_cast<cudaStream_t>(stream), x, n, kind, label_or_sign,
                                                                              grad_scale, loss_out, dlogits);
     return check_launch("acg_dlogit_loss");
 }
@@ -157,7 +159,7 @@ int acg_state_loss(const float* s, const float* t, int n, float inv_batch, float
     using namespace acg;
     ACG_REQUIRE(s && t && loss_out, ACG_ERR_INVALID, "acg_state_loss: null pointer");
     ACG_REQUIRE(n > 0, ACG_ERR_INVALID, "acg_state_loss: n=%d", n);
-    state_loss_kernel<<<1, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(s, t, n, inv_batch, grad_scale,
+    launch_pdl(state_loss_kernel, 1, kThreads, 0, static_cast<cudaStream_t>(stream), s, t, n, inv_batch, grad_scale,
                                                                             loss_out, dstate);
     return check_launch("acg_state_loss");
 }

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(kThreads)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             long long n, float lr_t, float b1, float b2, float eps, float lo, float hi, float gs,
             const float* __restrict__ lr_dev) {
+    pdl_prologue();
     if (lr_dev) lr_t = *lr_dev;   // CUDA-graph replays: the bias-corrected rate changes every step
     const bool do_clip = lo <= hi;
     const long long n4 = n >> 2;
@@ -57,6 +58,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 __global__ void __launch_bounds__(kThreads)
 rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ ms, long long n, float lr,
                float decay, float eps, float lo, float hi, float gs, const float* __restrict__ lr_dev) {
+    pdl_prologue();
     if (lr_dev) lr = *lr_dev;
     const bool do_clip = lo <= hi;
     const long long n4 = n >> 2;
@@ -103,7 +105,7 @@ int acg_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
     ACG_REQUIRE(n > 0, ACG_ERR_INVALID, "acg_adam_step: n=%lld", n);
     ACG_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) % 16) == 0, ACG_ERR_INVALID,
                 "acg_adam_step: buffers must be 16-byte aligned");
-    adam_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr_t, b1, b2, eps,
+    launch_pdl(adam_kernel, grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream), p, g, m, v, n, lr_t, b1, b2, eps,
                                                                                 clip_lo, clip_hi, grad_scale, lr_t_dev);
     return check_launch("acg_adam_step");
 }
@@ -115,7 +117,7 @@ int acg_rmsprop_step(float* p, const float* g, float* ms, long long n, float lr,
     ACG_REQUIRE(n > 0, ACG_ERR_INVALID, "acg_rmsprop_step: n=%lld", n);
     ACG_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)ms) % 16) == 0, ACG_ERR_INVALID,
                 "acg_rmsprop_step: buffers must be 16-byte aligned");
-    rmsprop_kernel<<<grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p, g, ms, n, lr, decay, eps,
+    launch_pdl(rmsprop_kernel, grid_for(n), kThreads, 0, static_cast<cudaStream_t>(stream), p, g, ms, n, lr, decay, eps,
                                                                                    clip_lo, clip_hi, grad_scale, lr_dev);
     return check_launch("acg_rmsprop_step");
 }

@@ -43,6 +43,7 @@ peer_allreduce_kernel(double* __restrict__ vec, int n, int cap, long long slot_o
                       // optional batch-norm finalisation of vec = [sum | sum of squares][C]
                       int bn_C, const float* __restrict__ beta, double inv_rows, float eps, float* __restrict__ mean,
                       float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift) {
+    pdl_prologue();
     const int tid = threadIdx.x;
     const unsigned long long epoch = *epoch_ptr + 1ull;
     const size_t data_off = (size_t)slot_off + 128 + (size_t)(epoch & 1ull) * world * cap * sizeof(double);
@@ -189,8 +190,7 @@ int acg_peer_allreduce_f64(double* vec, int n, int cap, long long slot_off, int 
         pp.p[i] = static_cast<unsigned char*>(host_mailboxes[i]);
     }
     const long long timeout_ns = (long long)((timeout_s > 0.f ? timeout_s : 30.f) * 1e9);
-    peer_allreduce_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        vec, n, cap, slot_off, rank, world, pp, epoch, timeout_ns, bn_C, beta, bn_C ? 1.0 / (double)bn_rows : 0.0, eps,
+    launch_pdl(peer_allreduce_kernel, 1, 256, 0, static_cast<cudaStream_t>(stream), vec, n, cap, slot_off, rank, world, pp, epoch, timeout_ns, bn_C, beta, bn_C ? 1.0 / (double)bn_rows : 0.0, eps,
         mean, rstd, scale, shift);
     return check_launch("acg_peer_allreduce_f64");
 }
