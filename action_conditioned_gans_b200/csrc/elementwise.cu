@@ -489,6 +489,250 @@ vec_bn_act_bwd_apply_kernel(const void* __restrict__ dA, const void* __restrict_
     }
 }
 
+// ---- bf16 fast path of the backward batch-norm kernels ------------------------------------------------------------
+// Every layer of the product path has bf16 z / dA / dz and relu, lrelu or no activation, so dtype and activation are
+// template parameters here (the runtime-dispatched kernels above kept their F8 arrays in local memory: 136 B stack,
+// 1.8-2.6 TB/s).  Loads are raw 16-byte vectors, FOUR rows in flight per thread before the first use, and the grid is
+// sized so that a thread of a small layer walks its rows in ONE pass (the old ">= 16 rows per thread" rule serialised
+// ~8 dependent memory latencies: 13 us for a 64 KB tensor).
+template <int ACT> __device__ __forceinline__ float act_bwd_t(float u) {
+    if (ACT == ACG_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+    if (ACT == ACG_ACT_LRELU) return 0.6f + 0.4f * (u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f));
+    return 1.f;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ uint4 ldg16(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+constexpr int kFastU = 4;
+
+template <int ACT, bool HAS_Z, bool HAS_D2>
+__global__ void __launch_bounds__(256)
+fast_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ z, int ld_z, const __nv_bfloat16* __restrict__ dA,
+                       const __nv_bfloat16* __restrict__ dA2, int ld_d, long long rows, int C,
+                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ shift,
+                       double* __restrict__ out) {
+    pdl_prologue();
+    __shared__ float sm[16][257];
+    const int bx = blockDim.x, by = blockDim.y;
+    const int tid = threadIdx.y * bx + threadIdx.x;
+    const int nv = C >> 3;
+    const int cv = blockIdx.x * bx + threadIdx.x;
+    float s0[8], s1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s0[i] = s1[i] = 0.f; }
+    if (cv < nv) {
+        const int c = cv * 8;
+        float mu[8], rs[8], sh[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { mu[i] = 0.f; rs[i] = 1.f; sh[i] = 0.f; }
+        if (HAS_Z) {
+            if (mean) { const F8 t = load8f(mean, c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mu[i] = t.v[i]; }
+            if (rstd) { const F8 t = load8f(rstd, c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) rs[i] = t.v[i]; }
+            if (shift) { const F8 t = load8f(shift, c);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) sh[i] = t.v[i]; }
+        }
+        const long long rstep = (long long)gridDim.y * by;
+        for (long long r0 = (long long)blockIdx.y * by + threadIdx.y; r0 < rows; r0 += rstep * kFastU) {
+            uint4 zr[kFastU], dr[kFastU], d2r[kFastU];
+#pragma unroll
+            for (int u = 0; u < kFastU; ++u) {
+                const long long r = r0 + u * rstep;
+                const bool ok = r < rows;
+                zr[u] = make_uint4(0u, 0u, 0u, 0u); dr[u] = zr[u]; d2r[u] = zr[u];
+                if (ok) {
+                    if (HAS_Z) zr[u] = ldg16(z + (size_t)r * ld_z + c);
+                    dr[u] = ldg16(dA + (size_t)r * ld_d + c);
+                    if (HAS_D2) d2r[u] = ldg16(dA2 + (size_t)r * ld_d + c);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kFastU; ++u) {
+                float zf[8], df[8];
+                unpack8(dr[u], df);
+                if (HAS_D2) {
+                    float d2[8];
+                    unpack8(d2r[u], d2);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) df[i] += d2[i];
+                }
+                if (HAS_Z) {
+                    unpack8(zr[u], zf);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float uu = fmaf(zf[i], rs[i], sh[i]);
+                        const float dzh = df[i] * act_bwd_t<ACT>(uu);
+                        s0[i] += dzh;
+                        s1[i] += dzh * ((zf[i] - mu[i]) * rs[i]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s0[i] += df[i];
+                }
+            }
+        }
+    }
+    // block reduction over the by row slots (fp32: <= 128 partials of <= ~50 rows each), then fp64 across blocks
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sm[i][tid] = s0[i]; sm[8 + i][tid] = s1[i]; }
+    __syncthreads();
+    if (cv < nv) {
+        for (int i = threadIdx.y; i < 16; i += by) {
+            float t = 0.f;
+            for (int y = 0; y < by; ++y) t += sm[i][y * bx + threadIdx.x];
+            const int c = cv * 8 + (i & 7);
+            atomicAdd(&out[(i < 8 ? 0 : C) + c], (double)t);
+        }
+    }
+}
+
+template <int ACT, bool HAS_BN, bool HAS_D2>
+__global__ void __launch_bounds__(256)
+fast_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16* __restrict__ dA2, int ld_d,
+                      const __nv_bfloat16* __restrict__ z, int ld_z, int C, long long rows,
+                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ shift,
+                      const double* __restrict__ red, __nv_bfloat16* __restrict__ dz, int ld_dz,
+                      float* __restrict__ dbeta, long long norm_rows, float dbeta_scale) {
+    pdl_prologue();
+    __shared__ float4 coef[256];               // this block's <= 32 vector columns x 8 channels: rs, sh, k1, k0
+    const int bx = blockDim.x, by = blockDim.y;
+    const int tid = threadIdx.y * bx + threadIdx.x;
+    const int cv = blockIdx.x * bx + threadIdx.x;
+    if (dbeta && blockIdx.x == 0 && blockIdx.y == 0) {
+        for (int c = tid; c < C; c += bx * by) atomicAdd(dbeta + c, dbeta_scale * (float)red[c]);
+    }
+    if (tid < bx * 8) {
+        const int c = blockIdx.x * bx * 8 + tid;
+        float4 k = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (c < C) {
+            const float r = rstd ? rstd[c] : 1.f, mu = mean ? mean[c] : 0.f;
+            k.x = r;
+            k.y = shift ? shift[c] : 0.f;
+            if (HAS_BN) {
+                const double inv_r = 1.0 / (double)norm_rows;
+                const double m0 = red[c] * inv_r, m1 = red[C + c] * inv_r;
+                k.z = (float)(-(double)r * r * m1);
+                k.w = (float)((double)r * r * m1 * mu - (double)r * m0);
+            }
+        }
+        coef[tid] = k;
+    }
+    __syncthreads();
+    if (cv >= (C >> 3)) return;
+    const int c = cv * 8;
+    float4 cf[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cf[i] = coef[threadIdx.x * 8 + i];
+    const long long rstep = (long long)gridDim.y * by;
+    for (long long r0 = (long long)blockIdx.y * by + threadIdx.y; r0 < rows; r0 += rstep * kFastU) {
+        uint4 zr[kFastU], dr[kFastU], d2r[kFastU];
+#pragma unroll
+        for (int u = 0; u < kFastU; ++u) {
+            const long long r = r0 + u * rstep;
+            zr[u] = make_uint4(0u, 0u, 0u, 0u); dr[u] = zr[u]; d2r[u] = zr[u];
+            if (r < rows) {
+                zr[u] = ldg16(z + (size_t)r * ld_z + c);
+                dr[u] = ldg16(dA + (size_t)r * ld_d + c);
+                if (HAS_D2) d2r[u] = ldg16(dA2 + (size_t)r * ld_d + c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kFastU; ++u) {
+            const long long r = r0 + u * rstep;
+            if (r >= rows) break;
+            float zf[8], df[8];
+            unpack8(zr[u], zf);
+            unpack8(dr[u], df);
+            if (HAS_D2) {
+                float d2[8];
+                unpack8(d2r[u], d2);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) df[i] += d2[i];
+            }
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                float o[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float4 k = cf[i + j];
+                    const float zz = zf[i + j];
+                    const float dzh = df[i + j] * act_bwd_t<ACT>(fmaf(zz, k.x, k.y));
+                    o[j] = HAS_BN ? fmaf(k.x, dzh, fmaf(k.z, zz, k.w)) : dzh;
+                }
+                __nv_bfloat162 h = __floats2bfloat162_rn(o[0], o[1]);
+                w[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(dz + (size_t)r * ld_dz + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+// grid for the fast kernels: thread (x, y) = (8-channel vector column, row slot); at most `blocks_per_sm` resident
+// blocks per SM in ONE wave, and never more blocks than one pass of kFastU rows per thread needs.  The reduction
+// additionally pays 16*bx fp64 atomics per block (measured ~13 G atomics/s on the 2C hot addresses), so for it the
+// row-block count minimises  passes x ~0.8 us (one dependent memory round trip each)  +  atomics / 13e3 us.
+void fast_launch_dims(long long rows, int C, int blocks_per_sm, bool atomics, dim3* grid, dim3* block) {
+    const int nv = C >> 3;
+    int bx = 1;
+    while (bx < nv && bx < 32) bx <<= 1;
+    const int by = 256 / bx;
+    const int gx = (nv + bx - 1) / bx;
+    const long long per_pass = (long long)by * kFastU;
+    long long gy = (rows + per_pass - 1) / per_pass;
+    long long cap = ((long long)num_sms() * blocks_per_sm) / gx;
+    if (cap < 1) cap = 1;
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    if (atomics) {
+        double best = 1e30;
+        long long best_gy = gy;
+        for (long long g = gy; g >= 1; g = (g + 1) / 2) {
+            const double passes = (double)((rows + g * per_pass - 1) / (g * per_pass));
+            const double t = passes * 0.8 + (double)(g * gx) * 16.0 * bx / 13000.0;
+            if (t < best) { best = t; best_gy = g; }
+            if (g == 1) break;
+        }
+        gy = best_gy;
+    }
+    *grid = dim3(gx, (unsigned)gy, 1);
+    *block = dim3(bx, by);
+}
+
+template <int ACT, bool HAS_Z>
+void launch_fast_reduce(dim3 grid, dim3 block, cudaStream_t st, const void* z, int ld_z, const void* dA, const void* dA2,
+                        int ld_d, long long rows, int C, const float* mean, const float* rstd, const float* shift,
+                        double* red) {
+    const __nv_bfloat16* zz = static_cast<const __nv_bfloat16*>(z);
+    const __nv_bfloat16* d1 = static_cast<const __nv_bfloat16*>(dA);
+    const __nv_bfloat16* d2 = static_cast<const __nv_bfloat16*>(dA2);
+    if (dA2) launch_pdl(fast_bwd_reduce_kernel<ACT, HAS_Z, true>, grid, block, 0, st, zz, ld_z, d1, d2, ld_d, rows, C, mean, rstd, shift, red);
+    else launch_pdl(fast_bwd_reduce_kernel<ACT, HAS_Z, false>, grid, block, 0, st, zz, ld_z, d1, d2, ld_d, rows, C, mean, rstd, shift, red);
+}
+
+template <int ACT, bool HAS_BN>
+void launch_fast_apply(dim3 grid, dim3 block, cudaStream_t st, const void* dA, const void* dA2, int ld_d, const void* z,
+                       int ld_z, int C, long long rows, const float* mean, const float* rstd, const float* shift,
+                       const double* red, void* dz, int ld_dz, float* dbeta, long long norm_rows, float dbeta_scale) {
+    const __nv_bfloat16* zz = static_cast<const __nv_bfloat16*>(z);
+    const __nv_bfloat16* d1 = static_cast<const __nv_bfloat16*>(dA);
+    const __nv_bfloat16* d2 = static_cast<const __nv_bfloat16*>(dA2);
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(dz);
+    if (dA2) launch_pdl(fast_bwd_apply_kernel<ACT, HAS_BN, true>, grid, block, 0, st, d1, d2, ld_d, zz, ld_z, C, rows, mean, rstd, shift, red, o, ld_dz, dbeta, norm_rows, dbeta_scale);
+    else launch_pdl(fast_bwd_apply_kernel<ACT, HAS_BN, false>, grid, block, 0, st, d1, d2, ld_d, zz, ld_z, C, rows, mean, rstd, shift, red, o, ld_dz, dbeta, norm_rows, dbeta_scale);
+}
+
 // 2-D launch shape shared by the streaming kernels: `waves` resident blocks per SM
 void vec_stream_launch_dims(long long rows_per_group, int C, int groups, int blocks_per_sm, dim3* grid, dim3* block) {
     const int nv = C >> 3;
@@ -596,6 +840,17 @@ int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d
     if (C % 8 == 0 && ld_d % 8 == 0 && (!z || ld_z % 8 == 0) && al16(z) && al16(dA) && al16(dA2) && al16(mean) &&
         al16(rstd) && al16(shift)) {
         dim3 grid, block;
+        const bool fast = groups == 1 && d_dtype == ACG_BF16 && (!z || z_dtype == ACG_BF16) &&
+                          (act == ACG_ACT_NONE || act == ACG_ACT_RELU || act == ACG_ACT_LRELU) && !getenv("ACG_NO_FAST_EW");
+        if (fast) {
+            cudaStream_t st = static_cast<cudaStream_t>(stream);
+            fast_launch_dims(rows, C, 2, true, &grid, &block);   // 100-128 registers: two resident blocks per SM
+            if (!z) launch_fast_reduce<ACG_ACT_NONE, false>(grid, block, st, z, ld_z, dA, dA2, ld_d, rows, C, mean, rstd, shift, red);
+            else if (act == ACG_ACT_RELU) launch_fast_reduce<ACG_ACT_RELU, true>(grid, block, st, z, ld_z, dA, dA2, ld_d, rows, C, mean, rstd, shift, red);
+            else if (act == ACG_ACT_LRELU) launch_fast_reduce<ACG_ACT_LRELU, true>(grid, block, st, z, ld_z, dA, dA2, ld_d, rows, C, mean, rstd, shift, red);
+            else launch_fast_reduce<ACG_ACT_NONE, true>(grid, block, st, z, ld_z, dA, dA2, ld_d, rows, C, mean, rstd, shift, red);
+            return check_launch("acg_bn_act_bwd_reduce");
+        }
         vec_reduce_launch_dims(rpg, C, groups, &grid, &block);
         launch_pdl(vec_col_reduce_kernel<1>, grid, block, 0, static_cast<cudaStream_t>(stream), z, z_dtype, ld_z, dA, dA2, d_dtype, ld_d, rpg, C, mean, rstd, shift, act, red);
         return check_launch("acg_bn_act_bwd_reduce");
@@ -619,6 +874,25 @@ int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d,
     if (C % 8 == 0 && ld_d % 8 == 0 && (!z || ld_z % 8 == 0) && ld_dz % 8 == 0 && al16(z) && al16(dA) && al16(dA2) &&
         al16(dz) && al16(mean) && al16(rstd) && al16(shift)) {
         dim3 grid, block;
+        const bool fast = groups == 1 && z && d_dtype == ACG_BF16 && z_dtype == ACG_BF16 && dz_dtype == ACG_BF16 &&
+                          (act == ACG_ACT_NONE || act == ACG_ACT_RELU || act == ACG_ACT_LRELU) && !getenv("ACG_NO_FAST_EW");
+        if (fast) {
+            cudaStream_t st = static_cast<cudaStream_t>(stream);
+            const long long nr = norm_rows > 0 ? norm_rows : rows;
+            fast_launch_dims(rows, C, 2, false, &grid, &block);   // 100-128 registers: two resident blocks per SM
+#define ACG_FAST_APPLY(A, BN) launch_fast_apply<A, BN>(grid, block, st, dA, dA2, ld_d, z, ld_z, C, rows, mean, rstd, shift, red, dz, ld_dz, dbeta, nr, dbeta_scale)
+            if (has_bn) {
+                if (act == ACG_ACT_RELU) ACG_FAST_APPLY(ACG_ACT_RELU, true);
+                else if (act == ACG_ACT_LRELU) ACG_FAST_APPLY(ACG_ACT_LRELU, true);
+                else ACG_FAST_APPLY(ACG_ACT_NONE, true);
+            } else {
+                if (act == ACG_ACT_RELU) ACG_FAST_APPLY(ACG_ACT_RELU, false);
+                else if (act == ACG_ACT_LRELU) ACG_FAST_APPLY(ACG_ACT_LRELU, false);
+                else ACG_FAST_APPLY(ACG_ACT_NONE, false);
+            }
+#undef ACG_FAST_APPLY
+            return check_launch("acg_bn_act_bwd_apply");
+        }
         vec_stream_launch_dims(rows / groups, C, groups, 8, &grid, &block);   // 4 resident blocks/SM, 2 waves
         launch_pdl(vec_bn_act_bwd_apply_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, C, groups, rows / groups, mean, rstd, shift, act, has_bn, red,
             dz, dz_dtype, ld_dz, dbeta, norm_rows > 0 ? norm_rows : rows / groups, dbeta_scale);
