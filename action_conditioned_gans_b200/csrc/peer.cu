@@ -43,7 +43,11 @@ peer_allreduce_kernel(double* __restrict__ vec, int n, int cap, long long slot_o
                       // optional batch-norm finalisation of vec = [sum | sum of squares][C]
                       int bn_C, const float* __restrict__ beta, double inv_rows, float eps, float* __restrict__ mean,
                       float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift) {
-    pdl_prologue();
+    // PDL: wait for the producer of `vec`, but do NOT let the dependents of this kernel be scheduled while it spins on
+    // its peers -- their CTAs would sit on the SMs (griddepcontrol.wait) and keep the kernels of the step's other
+    // branches, whose pushes the PEER is waiting for, from running: a cross-rank deadlock (seen at 2 GPUs).  The
+    // trigger comes after the flag wait instead.
+    pdl_wait();
     const int tid = threadIdx.x;
     const unsigned long long epoch = *epoch_ptr + 1ull;
     const size_t data_off = (size_t)slot_off + 128 + (size_t)(epoch & 1ull) * world * cap * sizeof(double);
@@ -72,6 +76,7 @@ peer_allreduce_kernel(double* __restrict__ vec, int n, int cap, long long slot_o
         }
     }
     __syncthreads();
+    pdl_launch_dependents();
     // 4. sum in rank order
     const double* mine = reinterpret_cast<const double*>(peers.p[rank] + data_off);
     for (int i = tid; i < n; i += blockDim.x) {

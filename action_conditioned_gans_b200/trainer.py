@@ -17,6 +17,10 @@ BATCH_SIZE = 64      # train.py:19
 L2_WEIGHT = 0.05     # train.py:22
 DNA_KSIZE = 6        # train.py:53-54 passes ksize=6
 
+# timing experiments only (scripts/dp_step_time.py): comma list of collectives to leave out -- results are then wrong
+import os as _os
+_DP_SKIP = set(filter(None, _os.environ.get("ACG_DP_SKIP", "").split(",")))
+
 SUMMARY_KEYS = ["discriminator_direct_loss", "discriminator_gen_loss", "discriminator_loss", "g_loss",
                 "g_l2_loss", "g_adv_loss", "g_psnr"]
 
@@ -251,7 +255,7 @@ class Trainer:
         return {k: s[k] for k in SUMMARY_KEYS if k in s}
 
     def _sync_grads(self, store):
-        if self.dp is not None:
+        if self.dp is not None and "grad" not in _DP_SKIP:
             self.dp.allreduce_sum(store.grad)
 
     # ---- train.py:114-121 -------------------------------------------------------------------------------
