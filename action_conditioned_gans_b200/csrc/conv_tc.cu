@@ -59,6 +59,13 @@ struct Params {
     int rz_ld, r_act;
     const float* r_mean; const float* r_rstd; const float* r_shift;
     int n_stat;                 // columns of stats (== n_bias for forward moments, the consumer's C for the reduction)
+    // split-K (generic kernel, launches with far fewer tiles than SMs: 4x4 / 2x2 feature maps, K up to 6400): grid.z
+    // carries `splits` K ranges of kb_per_split K blocks per tile; every CTA parks its fp32 accumulator tile in `ws`
+    // ([tile][split][16-column chunk][128 rows][16]) and takes a ticket; the LAST CTA of a tile adds the other
+    // partial tiles to its own accumulator and runs the normal epilogue (bias, moments, store).  No CTA ever waits.
+    int splits, kb_per_split;
+    float* ws;
+    unsigned int* tickets;
     int dbg_skip;               // profiling experiments (env ACG_DBG_SKIP): bit 3 = per-phase timing
 };
 
@@ -388,20 +395,22 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
 
     // ---- geometry of this CTA ---------------------------------------------------------------------------
     const int s = p.stride;
+    const int split = p.splits > 1 ? (int)(blockIdx.z % (unsigned)p.splits) : 0;
+    const int zcls = p.splits > 1 ? (int)(blockIdx.z / (unsigned)p.splits) : (int)blockIdx.z;
     int M, ntaps, nc = 1, a0 = 0, c0 = 0, ph = 0, pw = 0, Hp = 0, Wp = 0;
     const __nv_bfloat16* wmat = p.w_pack;
     if (MODE == CONV) {
         M = p.B * p.OH * p.OW;
         ntaps = p.KH * p.KW;
     } else {
-        ph = blockIdx.z / s; pw = blockIdx.z % s;
+        ph = zcls / s; pw = zcls % s;
         Hp = (p.H - ph + s - 1) / s; Wp = (p.W - pw + s - 1) / s;
         a0 = (ph + p.pad_t) % s; c0 = (pw + p.pad_l) % s;
         const int na = a0 < p.KH ? (p.KH - a0 + s - 1) / s : 0;
         nc = c0 < p.KW ? (p.KW - c0 + s - 1) / s : 0;
         ntaps = na * nc;
         M = p.B * Hp * Wp;
-        wmat += p.w_class_off[blockIdx.z];
+        wmat += p.w_class_off[zcls];
         if (nc == 0) nc = 1;
     }
     const int tile_m = blockIdx.x * BM;
@@ -409,13 +418,15 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
     const int n0 = blockIdx.y * BN;
     const int n_cta = min(BN, p.N - n0);
     const int Ktot = ntaps * p.lda;
-    const int nkb = (Ktot + BK - 1) / BK;
+    const int nkb_all = (Ktot + BK - 1) / BK;
+    const int kb0 = split * p.kb_per_split;                              // first K block of this CTA (0 without split-K)
+    const int nkb = p.splits > 1 ? max(0, min(nkb_all - kb0, p.kb_per_split)) : nkb_all;
 
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], kProducers + 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(&acc_bar, 1);
         fence_mbar_init();
-        tma_prefetch_desc(&cp.map_b[MODE == ADJ ? blockIdx.z : 0]);
+        tma_prefetch_desc(&cp.map_b[MODE == ADJ ? zcls : 0]);
     }
     if (warp == 4) {   // tensor-memory allocation is warp-collective; this warp also owns the dealloc
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
@@ -493,14 +504,14 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
                 }
             }
         }
-        const CUtensorMap* bmap = &cp.map_b[MODE == ADJ ? blockIdx.z : 0];
-        int tap = (j * 8) / p.lda, ci = (j * 8) % p.lda;
+        const CUtensorMap* bmap = &cp.map_b[MODE == ADJ ? zcls : 0];
+        int tap = (kb0 * BK + j * 8) / p.lda, ci = (kb0 * BK + j * 8) % p.lda;
         for (int kb = 0; kb < nkb; ++kb) {
             const int stage = kb % STAGES;
             if (kb >= STAGES) mbar_wait(&empty_bar[stage], (uint32_t)(((kb / STAGES) - 1) & 1));
             if (tid == 0) {
                 mbar_expect_tx(&full_bar[stage], (uint32_t)min(p.N, BN) * 128u);
-                tma_load_2d(smemB + stage * kStageB, bmap, kb * BK, n0, &full_bar[stage]);
+                tma_load_2d(smemB + stage * kStageB, bmap, (kb0 + kb) * BK, n0, &full_bar[stage]);
             }
             const uint32_t tbit = tap < ntaps ? (1u << tap) : 0u;
             long long koff;
@@ -543,6 +554,41 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
             tc_fence_after();
         }
         if (timing) t2 = gtime();
+    }
+    // ---- split-K: park the partial tile, take a ticket; only the last CTA of the tile goes on to the epilogue ----
+    bool final_cta = true;
+    float* ws_tile = nullptr;
+    if (p.splits > 1) {
+        const unsigned int tile_id = ((unsigned)zcls * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        ws_tile = p.ws + (size_t)tile_id * p.splits * (BM * BN);
+        if (warp < 4) {
+            float* mine = ws_tile + (size_t)split * (BM * BN) + (warp * 32 + lane) * 16;
+            for (int cb = 0; cb < n_cta; cb += 16) {
+                uint32_t v[16];
+                if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + cb, v);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0u;
+                }
+                float4* o = reinterpret_cast<float4*>(mine + (size_t)(cb >> 4) * (BM * 16));   // [chunk][row][16]
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                       __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int t = atomicAdd(&p.tickets[tile_id], 1u);
+            last_cta_sh = (t == (unsigned)p.splits - 1u);
+            if (last_cta_sh) p.tickets[tile_id] = 0u;       // ready for the next launch
+        }
+        __syncthreads();
+        final_cta = last_cta_sh != 0;
+        if (final_cta) __threadfence();
+    }
+    if (warp < 4 && final_cta) {
         const int m = ep_m;
         const size_t row_off = ep_row_off;
         const uint32_t zrow = smem_base + (uint32_t)(warp * 32 + lane) * kZRowBytes;
@@ -557,6 +603,21 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
             else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0u;
+            }
+            if (p.splits > 1) {     // add the other CTAs' partial tiles (L2-resident; bypass L1)
+                for (int sp = 0; sp < p.splits; ++sp) {
+                    if (sp == split) continue;
+                    const float4* o = reinterpret_cast<const float4*>(
+                        ws_tile + (size_t)sp * (BM * BN) + (size_t)(cb >> 4) * (BM * 16) + (warp * 32 + lane) * 16);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 t = __ldcg(o + i);
+                        v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + t.x);
+                        v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + t.y);
+                        v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + t.z);
+                        v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + t.w);
+                    }
+                }
             }
             epilogue_chunk(p, v, n0 + cb, m < M, row_off, zrow + 2 * cb, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
         }
@@ -575,7 +636,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
         atomicAdd(&g_phase_ns[3], 1ull);
         atomicAdd(&g_phase_ns[4], (unsigned long long)nkb);
     }
-    if (p.stats) {
+    if (p.stats && final_cta) {
         if (tid < n_cta && n0 + tid < p.n_stat) {
             atomicAdd(&p.stats[n0 + tid], (double)sm_stats[0][tid]);
             atomicAdd(&p.stats[p.n_stat + n0 + tid], (double)sm_stats[1][tid]);
@@ -1444,6 +1505,75 @@ int check(const acg_conv_shape* s, const acg_tc_args* t, const char* who) {
     return ACG_OK;
 }
 
+struct SplitPlan {
+    int splits, kb_per;
+    long long ws_bytes;
+    int tickets;
+};
+// Split-K only pays for launches that leave most SMs idle while each CTA walks a long K loop (the 4x4 / 2x2 layers).
+// tiles = CTAs that would reach the epilogue, tile_slots = tile ids the grid can produce (tickets / workspace index).
+SplitPlan plan_split(long long tiles, long long tile_slots, int max_nkb) {
+    SplitPlan r{1, max_nkb, 0, 0};
+    if (getenv("ACG_NO_SPLITK") || tiles <= 0 || tiles * 2 > num_sms() || max_nkb < 8) return r;
+    long long splits = num_sms() / tiles;
+    if (splits > max_nkb / 4) splits = max_nkb / 4;          // at least 4 K blocks per CTA
+    if (splits < 2) return r;
+    const int kb_per = (int)((max_nkb + splits - 1) / splits);
+    splits = (max_nkb + kb_per - 1) / kb_per;
+    if (splits < 2) return r;
+    r.splits = (int)splits;
+    r.kb_per = kb_per;
+    r.ws_bytes = tile_slots * splits * (long long)(BM * BN) * 4;
+    r.tickets = (int)tile_slots;
+    return r;
+}
+int max_class_taps(const acg_conv_shape* s) {
+    int mx = 0;
+    for (int cls = 0; cls < s->stride * s->stride; ++cls) {
+        int na, nc;
+        class_taps(s, cls, &na, &nc);
+        if (na * nc > mx) mx = na * nc;
+    }
+    return mx;
+}
+long long adj_active_tiles(const acg_conv_shape* s, int N) {
+    long long active = 0;
+    for (int cls = 0; cls < s->stride * s->stride; ++cls) {
+        const int ph = cls / s->stride, pw = cls % s->stride;
+        const long long Mc = (long long)s->B * ((s->H - ph + s->stride - 1) / s->stride) *
+                             ((s->W - pw + s->stride - 1) / s->stride);
+        active += ((Mc + BM - 1) / BM) * ((N + BN - 1) / BN);
+    }
+    return active;
+}
+SplitPlan plan_fprop(const acg_conv_shape* s, int ld_in) {
+    const int N = ru(s->Cout, 16);
+    const long long M = (long long)s->B * s->OH * s->OW;
+    const long long tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+    return plan_split(tiles, tiles, (s->KH * s->KW * ld_in + BK - 1) / BK);
+}
+SplitPlan plan_dgrad(const acg_conv_shape* s, int ld_in) {
+    const int N = ru(s->Cin, 16);
+    const int Hp = (s->H + s->stride - 1) / s->stride, Wp = (s->W + s->stride - 1) / s->stride;
+    const long long gx = ((long long)s->B * Hp * Wp + BM - 1) / BM, gy = (N + BN - 1) / BN;
+    return plan_split(adj_active_tiles(s, N), gx * gy * s->stride * s->stride, (max_class_taps(s) * ld_in + BK - 1) / BK);
+}
+// applies a plan to the launch when the caller passed a large enough workspace; returns the grid.z multiplier
+int apply_split(Params* p, const acg_tc_args* t, const SplitPlan& pl) {
+    p->splits = 1;
+    p->kb_per_split = 0;
+    p->ws = nullptr;
+    p->tickets = nullptr;
+    if (pl.splits > 1 && t->splitk_ws && t->splitk_tickets && t->splitk_ws_bytes >= pl.ws_bytes &&
+        t->splitk_n_tickets >= pl.tickets) {
+        p->splits = pl.splits;
+        p->kb_per_split = pl.kb_per;
+        p->ws = static_cast<float*>(t->splitk_ws);
+        p->tickets = t->splitk_tickets;
+    }
+    return p->splits;
+}
+
 int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char* who) {
     {
         const char* e = getenv("ACG_DBG_SKIP");
@@ -1592,6 +1722,18 @@ long long acg_pack_plan(const acg_pack_job* host_jobs, int njobs, int* host_tile
     return n;
 }
 
+int acg_conv_splitk_plan(const acg_conv_shape* s, int which, int ld_in, int* splits, long long* ws_bytes, int* n_tickets) {
+    using namespace acg;
+    using namespace acg::tc;
+    ACG_REQUIRE(s && splits && ws_bytes && n_tickets && ld_in > 0 && (which == 0 || which == 1), ACG_ERR_INVALID,
+                "acg_conv_splitk_plan: bad argument");
+    const SplitPlan pl = which == 0 ? plan_fprop(s, ld_in) : plan_dgrad(s, ld_in);
+    *splits = pl.splits;
+    *ws_bytes = pl.splits > 1 ? pl.ws_bytes : 0;
+    *n_tickets = pl.splits > 1 ? pl.tickets : 0;
+    return ACG_OK;
+}
+
 int acg_conv_tc_supported(const acg_conv_shape* s, int which) {
     if (!s) return 0;
     if (s->stride != 1 && s->stride != 2) return 0;
@@ -1625,6 +1767,7 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, 1);
     rc = fill_bn(&p, t, grid.x * grid.y, "acg_conv_fprop_tc");
     if (rc) return rc;
+    grid.z = (unsigned)apply_split(&p, t, plan_fprop(s, t->ld_in));
     ConvParams cp;
     cp.p = p;
     rc = encode_weight_map(&cp.map_b[0], w_pack, (long long)s->KH * s->KW * t->ld_in, N, "acg_conv_fprop_tc");
@@ -1723,6 +1866,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     }
     rc = fill_bn(&p, t, active, "acg_conv_dgrad_tc");
     if (rc) return rc;
+    grid.z = (unsigned)(ncls * apply_split(&p, t, plan_dgrad(s, t->ld_in)));
     ConvParams cp;
     cp.p = p;
     for (int cls = 0; cls < ncls; ++cls) {

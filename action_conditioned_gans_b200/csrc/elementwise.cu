@@ -679,6 +679,59 @@ fast_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16*
     }
 }
 
+template <int ACT> __device__ __forceinline__ float act_fwd_t(float u) {
+    if (ACT == ACG_ACT_RELU) return fmaxf(u, 0.f);
+    if (ACT == ACG_ACT_LRELU) return 0.6f * u + 0.4f * fabsf(u);
+    return u;
+}
+
+// a[r] = act(z[r]*scale + shift), bf16 -> bf16, same thread map / row pipelining as the backward kernels
+template <int ACT>
+__global__ void __launch_bounds__(256)
+fast_bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, int ld_in, int C, long long rows,
+                       const float* __restrict__ scale, const float* __restrict__ shift,
+                       __nv_bfloat16* __restrict__ out, int ld_out) {
+    pdl_prologue();
+    const int bx = blockDim.x, by = blockDim.y;
+    const int cv = blockIdx.x * bx + threadIdx.x;
+    if (cv >= (C >> 3)) return;
+    const int c = cv * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { sc[i] = 1.f; sh[i] = 0.f; }
+    if (scale) { const F8 t = load8f(scale, c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sc[i] = t.v[i]; }
+    if (shift) { const F8 t = load8f(shift, c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sh[i] = t.v[i]; }
+    const long long rstep = (long long)gridDim.y * by;
+    for (long long r0 = (long long)blockIdx.y * by + threadIdx.y; r0 < rows; r0 += rstep * kFastU) {
+        uint4 zr[kFastU];
+#pragma unroll
+        for (int u = 0; u < kFastU; ++u) {
+            const long long r = r0 + u * rstep;
+            zr[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (r < rows) zr[u] = ldg16(z + (size_t)r * ld_in + c);
+        }
+#pragma unroll
+        for (int u = 0; u < kFastU; ++u) {
+            const long long r = r0 + u * rstep;
+            if (r >= rows) break;
+            float zf[8];
+            unpack8(zr[u], zf);
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(act_fwd_t<ACT>(fmaf(zf[i], sc[i], sh[i])),
+                                                         act_fwd_t<ACT>(fmaf(zf[i + 1], sc[i + 1], sh[i + 1])));
+                w[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(out + (size_t)r * ld_out + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
 // grid for the fast kernels: thread (x, y) = (8-channel vector column, row slot); at most `blocks_per_sm` resident
 // blocks per SM in ONE wave, and never more blocks than one pass of kFastU rows per thread needs.  The reduction
 // additionally pays 16*bx fp64 atomics per block (measured ~13 G atomics/s on the 2C hot addresses), so for it the
@@ -818,6 +871,17 @@ int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in,
     ACG_REQUIRE(dt_ok(z_dtype) && dt_ok(out_dtype), ACG_ERR_UNSUPPORTED, "acg_bn_act_fwd: dtype");
     if (C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && al16(z) && al16(out) && al16(scale) && al16(shift)) {
         dim3 grid, block;
+        if (groups == 1 && z_dtype == ACG_BF16 && out_dtype == ACG_BF16 &&
+            (act == ACG_ACT_NONE || act == ACG_ACT_RELU || act == ACG_ACT_LRELU) && !getenv("ACG_NO_FAST_EW")) {
+            cudaStream_t st = static_cast<cudaStream_t>(stream);
+            const __nv_bfloat16* zz = static_cast<const __nv_bfloat16*>(z);
+            __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
+            fast_launch_dims(rows, C, 4, false, &grid, &block);
+            if (act == ACG_ACT_RELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_RELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out);
+            else if (act == ACG_ACT_LRELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_LRELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out);
+            else launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_NONE>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out);
+            return check_launch("acg_bn_act_fwd");
+        }
         vec_stream_launch_dims(rows / groups, C, groups, 8, &grid, &block);
         launch_pdl(vec_bn_act_fwd_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), z, z_dtype, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
         return check_launch("acg_bn_act_fwd");

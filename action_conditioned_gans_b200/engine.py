@@ -299,6 +299,12 @@ class NetRun:
         st.dz = torch.zeros(B, oh, ow, st.ldz, dtype=self.adt, device=self.device)
         # gradient w.r.t. the layer input (preallocated: nothing is allocated inside a step / a CUDA graph)
         st.dx = torch.zeros(B, h, w, ld_in, dtype=dx_dtype or self.adt, device=self.device) if dx else None
+        if self.bf16:
+            # split-K workspaces of the forward and the data-gradient launch (only the few-tile layers get one);
+            # per layer and per network application, because applications run concurrently on different streams
+            fwd_w, bwd_w = (0, 1) if L.kind == "conv" else (1, 0)
+            st.splitk_f = K.splitk_workspace(st.shape, fwd_w, ld_in, self.device)
+            st.splitk_b = K.splitk_workspace(st.shape, bwd_w, st.ldz, self.device) if dx else None
         if self.bf16 and name not in self.store.packs:
             # forward / backward-data packs; conv2d_transpose swaps the roles (see include/acg_b200.h)
             fwd_which, bwd_which = (0, 1) if L.kind == "conv" else (1, 0)
@@ -316,7 +322,7 @@ class NetRun:
         if self.bf16:
             pk = self.store.packs[L.name]
             fn = K.conv_fprop_tc if L.kind == "conv" else K.conv_dgrad_tc
-            fn(st.shape, x, pk[3], out, st.ld_in, ld_out, bias=bias, stats=stats, bn=bn)
+            fn(st.shape, x, pk[3], out, st.ld_in, ld_out, bias=bias, stats=stats, bn=bn, splitk=st.splitk_f)
         else:
             w = self.store.views[L.name + "/weights"]
             (K.conv_fprop_f32 if L.kind == "conv" else K.conv_dgrad_f32)(st.shape, x, w, out)
@@ -435,7 +441,7 @@ class NetRun:
             if self.bf16:
                 pk = self.store.packs[name]
                 fn = K.conv_dgrad_tc if L.kind == "conv" else K.conv_fprop_tc
-                fn(st.shape, st.dz, pk[6], st.dx, st.ldz, st.ld_in, red=self._fused_red(consumer))
+                fn(st.shape, st.dz, pk[6], st.dx, st.ldz, st.ld_in, red=self._fused_red(consumer), splitk=st.splitk_b)
             else:
                 w = self.store.views[name + "/weights"]
                 (K.conv_dgrad_f32 if L.kind == "conv" else K.conv_fprop_f32)(st.shape, st.dz, w, st.dx)

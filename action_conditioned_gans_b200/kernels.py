@@ -64,10 +64,25 @@ def tc_supported(shape, which):
     return bool(_lib.load().acg_conv_tc_supported(C.byref(shape), which))
 
 
-def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None):
+def splitk_workspace(shape, which, ld_in, device):
+    """(workspace, tickets) tensors a conv_fprop_tc (which=0) / conv_dgrad_tc (which=1) launch of this shape wants for
+    split-K, or None when it never splits (acg_conv_splitk_plan)."""
+    splits, nbytes, ntick = C.c_int(), C.c_longlong(), C.c_int()
+    call("acg_conv_splitk_plan", C.byref(shape), which, ld_in, C.byref(splits), C.byref(nbytes), C.byref(ntick))
+    if splits.value <= 1:
+        return None
+    return (torch.empty(nbytes.value // 4, dtype=torch.float32, device=device),
+            torch.zeros(ntick.value, dtype=torch.int32, device=device))
+
+
+def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, splitk=None):
     """bn = (counter, beta, mean, rstd, scale, shift, rows, eps): finalise the moments in-kernel (single GPU)
     red = (red_buffer, z, ldz, C, act, mean, rstd, shift): fused batch-norm backward reduction of the consumer layer"""
     t = TcArgs(ld_in, ld_out, ptr(bias), dtype_id(out), ACT_IDS[out_act], ptr(stats))
+    if splitk is not None:
+        ws, tickets = splitk
+        t.splitk_ws, t.splitk_ws_bytes = ptr(ws), ws.numel() * 4
+        t.splitk_tickets, t.splitk_n_tickets = ptr(tickets), tickets.numel()
     if red is not None:
         buf, z, ldz, Cc, act, mean, rstd, shift = red
         t.stats = ptr(buf)
@@ -81,13 +96,15 @@ def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None):
     return t
 
 
-def conv_fprop_tc(shape, x, w_pack, y, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None):
-    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn, red)
+def conv_fprop_tc(shape, x, w_pack, y, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None,
+                  splitk=None):
+    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn, red, splitk)
     call("acg_conv_fprop_tc", C.byref(shape), ptr(x), ptr(w_pack), ptr(y), C.byref(t), stream())
 
 
-def conv_dgrad_tc(shape, dy, w_pack, dx, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None):
-    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn, red)
+def conv_dgrad_tc(shape, dy, w_pack, dx, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None,
+                  splitk=None):
+    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn, red, splitk)
     call("acg_conv_dgrad_tc", C.byref(shape), ptr(dy), ptr(w_pack), ptr(dx), C.byref(t), stream())
 
 

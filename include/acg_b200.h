@@ -122,6 +122,14 @@ typedef struct acg_tc_args {
     const void* red_z;
     int red_ldz, red_C, red_act;
     const float* red_mean; const float* red_rstd; const float* red_shift;
+    /* optional: split-K workspace for launches with far fewer output tiles than SMs (acg_conv_splitk_plan says how
+     * many bytes / tickets a shape wants; tickets are uint32, zeroed once by the caller, and are left zeroed by every
+     * launch).  Without a workspace the launch runs unsplit.  One workspace must not be shared by launches that can
+     * run concurrently. */
+    void* splitk_ws;
+    long long splitk_ws_bytes;
+    unsigned int* splitk_tickets;
+    int splitk_n_tickets;
 } acg_tc_args;
 
 /* y = conv(x): x [B,H,W,ld_in] -> y [B,OH,OW,ld_out]; w_pack = acg_pack_weights(which=0, ld_k=ld_in) */
@@ -154,6 +162,9 @@ int acg_pack_weights_batched(const acg_pack_job* jobs_dev, int njobs, const void
 /* HOST: number of tiles of the jobs (host_jobs is a HOST array); when host_tiles != NULL also writes up to
  * `capacity` tiles (4 ints each).  -1 on invalid jobs. */
 long long acg_pack_plan(const acg_pack_job* host_jobs, int njobs, int* host_tiles, long long capacity);
+/* which = 0: acg_conv_fprop_tc, 1: acg_conv_dgrad_tc (ld_in as in acg_tc_args).  splits == 1: the launch never splits. */
+int acg_conv_splitk_plan(const acg_conv_shape* s, int which, int ld_in, int* splits, long long* ws_bytes,
+                         int* n_tickets);
 /* 1 when the tcgen05 kernels accept the shape, 0 otherwise (which: 0 fprop, 1 dgrad, 2 wgrad) */
 int acg_conv_tc_supported(const acg_conv_shape* s, int which);
 

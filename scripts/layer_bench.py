@@ -45,12 +45,12 @@ def main():
             dw = store.gviews[L.name + "/weights"]
             pk = store.packs[L.name]
             if L.kind == "conv":
-                t_f = timeit(lambda: K.conv_fprop_tc(s, x, pk[3], z, st.ld_in, st.ldz))
-                t_d = timeit(lambda: K.conv_dgrad_tc(s, dz, pk[6], dx, st.ldz, st.ld_in))
+                t_f = timeit(lambda: K.conv_fprop_tc(s, x, pk[3], z, st.ld_in, st.ldz, splitk=st.splitk_f))
+                t_d = timeit(lambda: K.conv_dgrad_tc(s, dz, pk[6], dx, st.ldz, st.ld_in, splitk=st.splitk_b))
                 t_w = timeit(lambda: K.conv_wgrad_tc(s, x, dz, dw, st.ld_in, st.ldz))
             else:
-                t_f = timeit(lambda: K.conv_dgrad_tc(s, x, pk[3], z, st.ld_in, st.ldz))
-                t_d = timeit(lambda: K.conv_fprop_tc(s, dz, pk[6], dx, st.ldz, st.ld_in))
+                t_f = timeit(lambda: K.conv_dgrad_tc(s, x, pk[3], z, st.ld_in, st.ldz, splitk=st.splitk_f))
+                t_d = timeit(lambda: K.conv_fprop_tc(s, dz, pk[6], dx, st.ldz, st.ld_in, splitk=st.splitk_b))
                 t_w = timeit(lambda: K.conv_wgrad_tc(s, dz, x, dw, st.ldz, st.ld_in))
             # stride-2 taps: a dgrad-form op only multiplies the taps that hit (1/4 of kh*kw*...) -> same FLOPs
             rows.append((L.name, L.kind, flops / 1e9, t_f, t_d, t_w))

@@ -17,7 +17,7 @@ for spec, kind in ((E.g_dna_spec(6), "g"), (E.d_spec(), "d")):
     run = E.GeneratorRun(store, B, dev, True, 6) if kind == "g" else E.DiscriminatorRun(store, B, dev)
     store.refresh_packs()
     for L in spec:
-        if L.name not in ("g/conv2", "g/tconv3", "g/tconv4", "d/conv1", "d/conv2"): continue
+        if L.name not in ("g/conv1", "g/conv2", "g/tconv4", "d/conv1", "d/conv2", "d/conv3", "d/conv5"): continue
         st = run.layers[L.name]; s = st.shape; pk = store.packs[L.name]
         x = torch.randn(B, st.in_hw[0], st.in_hw[1], st.ld_in, device=dev).to(torch.bfloat16)
         z = torch.empty(B, st.out_hw[0], st.out_hw[1], st.ldz, device=dev, dtype=torch.bfloat16)

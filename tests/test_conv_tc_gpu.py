@@ -258,3 +258,57 @@ def test_first_layers_with_8_channel_frames(cuda, Cin, Cout):
     assert np.isfinite(got).all()
     assert np.abs(got[..., :Cin] - dx_ref.numpy()).max() <= 2e-3 * max(1.0, float(dx_ref.abs().max()))
     assert np.abs(got[..., Cin:]).max() == 0.0
+
+
+@pytest.mark.parametrize("case", [(4, 4, 4, 256, 512, 5, 2), (64, 4, 4, 256, 512, 5, 2), (16, 8, 8, 128, 256, 5, 2),
+                                  (8, 2, 2, 512, 1, 2, 1)])
+def test_split_k_equals_unsplit(cuda, case):
+    """Few-tile layers (d/conv4, d/conv5, d/conv6 ...) split their K loop over grid.z; the last CTA of a tile adds the
+    parked partial tiles and runs the normal epilogue -- output, fused batch-norm moments and the in-kernel finalize
+    must equal the unsplit launch (fp32 sums in a different order)."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    B, H, W, Cin, Cout, k, s = case
+    g = torch.Generator(device=cuda).manual_seed(9)
+    shape = Kn.conv_shape(B, H, W, Cin, Cout, k, s, "SAME")
+    w = torch.randn(k, k, Cin, Cout, device=cuda, generator=g) / (k * Cin ** 0.5)
+    for which in (0, 1):
+        if which == 0:
+            ld_in, n_out, rows = ru(Cin, 16), Cout, B * shape.OH * shape.OW
+            src = torch.randn(B, H, W, ld_in, device=cuda, generator=g).to(torch.bfloat16)
+            fn = Kn.conv_fprop_tc
+        else:
+            ld_in, n_out, rows = ru(Cout, 16), Cin, B * H * W
+            src = torch.randn(B, shape.OH, shape.OW, ld_in, device=cuda, generator=g).to(torch.bfloat16)
+            if Cout < ld_in:
+                src[..., Cout:] = 0
+            fn = Kn.conv_dgrad_tc
+        ld_out = ru(n_out, 16)
+        pack = torch.empty(Kn.pack_size(shape, which, ld_in), dtype=torch.bfloat16, device=cuda)
+        Kn.pack_weights(shape, w, which, ld_in, pack)
+        wsp = Kn.splitk_workspace(shape, which, ld_in, cuda)
+        if which == 0:
+            assert wsp is not None, "the forward launch of this shape is expected to split"
+        if wsp is None:
+            continue
+        outs, stats_all, fin = [], [], []
+        for splitk in (None, wsp):
+            out = torch.zeros(rows, ld_out, dtype=torch.bfloat16, device=cuda)
+            stats = torch.zeros(2 * n_out, dtype=torch.float64, device=cuda)
+            counter = torch.zeros(1, dtype=torch.int32, device=cuda)
+            beta = torch.zeros(n_out, device=cuda)
+            mean, rstd, scale, shift = (torch.zeros(n_out, device=cuda) for _ in range(4))
+            for _ in range(2):          # twice: tickets and the finalize counter must be left ready for the next launch
+                stats.zero_()
+                fn(shape, src, pack, out, ld_in, ld_out, stats=stats,
+                   bn=(counter, beta, mean, rstd, scale, shift, rows, 1e-3), splitk=splitk)
+            torch.cuda.synchronize()
+            outs.append(out.float().cpu().numpy())
+            stats_all.append(stats.cpu().numpy())
+            fin.append(torch.stack([mean, rstd, shift]).cpu().numpy())
+            if splitk is not None:
+                assert int(splitk[1].abs().sum()) == 0 and int(counter.item()) == 0
+        sc = max(1.0, np.abs(outs[0]).max())
+        assert np.abs(outs[0] - outs[1]).max() <= 1e-2 * sc                # one bf16 ulp of the largest value
+        assert (outs[0] != outs[1]).mean() < 0.02                            # and only where a rounding flips
+        assert np.abs(stats_all[0] - stats_all[1]).max() <= 2e-2 * max(1.0, np.abs(stats_all[0]).max())
+        assert np.abs(fin[0] - fin[1]).max() <= 1e-2 * max(1.0, np.abs(fin[0]).max())
