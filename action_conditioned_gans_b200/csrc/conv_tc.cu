@@ -668,6 +668,261 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
 }
 
 
+// ---- CONV gather, persistent small-K variant (the first layers: K = 25 taps x 8 channels = 200) ---------------------
+// With 4 K slices per tile the generic kernel never reaches a steady state, and -- ncu source view -- its ~10 k warp
+// instructions per tile (row decode with divisions, per-chunk moment butterflies) run on 2 warps per scheduler at one
+// instruction per ~8 cycles: instruction ISSUE LATENCY, not memory or the tensor pipe, bounds it (66 / 74 us for
+// 1.3 / 5 GFLOP).  This kernel is specialised for what those layers are (32-wide output rows, N = 32 or 64):
+//   * one CTA per SM walks its tiles; the whole weight matrix is resident in shared memory (<= 4 TMA slices);
+//   * gather producers (warps 5-8), MMA issuer (warp 4) and epilogue (warps 0-3) are different warps; an 8-stage A
+//     ring keeps two tiles in flight and two accumulators in tensor memory decouple MMAs from the epilogue;
+//   * everything tile-invariant is computed once per kernel: per-slice tap offsets and tap bits, per-row column
+//     masks and offsets (a tile is 4 whole output rows); a tile costs the producer ~300 instructions instead of ~720;
+//   * the batch-norm moments are kept PER THREAD in registers across all tiles of the CTA (2 x N accumulators) and
+//     reduced over the 32 rows of a warp once at the end, instead of two 16-shuffle butterflies per 16-column chunk
+//     (epilogue ~75 instead of ~250 instructions per chunk).
+constexpr int kSmallKRing = 8;
+constexpr int kSmallKMaxKb = 4;
+constexpr int kSmallKSmem = kSmallKMaxKb * kStageB + kSmallKRing * kStageA + 1024;
+constexpr int kSmallKThreads = 288;      // warps 0-3 epilogue, warp 4 MMA issue + TMEM, warps 5-8 gather producers
+
+template <int NT>
+__global__ void __launch_bounds__(kSmallKThreads, 1)
+conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles) {
+    const Params& p = cp.p;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[kSmallKRing], empty_bar[kSmallKRing], b_full, acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ float sm_stats[2][BN];
+    __shared__ int last_cta_sh;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smemB = smem_base, smemA = smem_base + kSmallKMaxKb * kStageB;
+    if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
+
+    const int s = p.stride;
+    const int M = p.B * p.OH * p.OW;
+    const int ntaps = p.KH * p.KW;
+    const int nkb = (ntaps * p.lda + BK - 1) / BK;       // <= kSmallKMaxKb
+    constexpr uint32_t tmem_cols = 2 * NT < 32 ? 32 : 2 * NT;
+
+    if (tid == 0) {
+        for (int i = 0; i < kSmallKRing; ++i) { mbar_init(&full_bar[i], kProducers); mbar_init(&empty_bar[i], 1); }
+        mbar_init(&b_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+        fence_mbar_init();
+        tma_prefetch_desc(&cp.map_b[0]);
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp >= 5) {
+        // ================================ gather producers ================================
+        const int ptid = tid - 160;
+        if (ptid == 0) {     // resident weights: one TMA slice per K block, all on one barrier
+            mbar_expect_tx(&b_full, (uint32_t)(nkb * NT) * 128u);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smemB + kb * kStageB, &cp.map_b[0], kb * BK, 0, &b_full);
+        }
+        const int j = ptid & 7, rslot = ptid >> 3;
+        // per K slice (kernel constants): tap bit and source offset of this thread's 16-byte column
+        uint32_t tbit[kSmallKMaxKb];
+        int koff[kSmallKMaxKb];
+        {
+            int tap = (j * 8) / p.lda, ci = (j * 8) % p.lda;
+#pragma unroll
+            for (int kb = 0; kb < kSmallKMaxKb; ++kb) {
+                tbit[kb] = tap < ntaps ? (1u << tap) : 0u;
+                const int a = tap / p.KW, c = tap - a * p.KW;
+                koff[kb] = (a * p.W + c) * p.lda + ci;
+                ci += BK;
+                while (ci >= p.lda) { ci -= p.lda; ++tap; }
+            }
+        }
+        // per row slot (kernel constants; OW == 32: a tile is 4 whole output rows): row delta, column mask, offset
+        int doh[8], xoff[8];
+        uint32_t cmask[8];
+        uint32_t fullsel = 0;
+        for (int a = 0; a < p.KH; ++a) fullsel |= 1u << (a * p.KW);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int q = rslot + 16 * i;
+            doh[i] = q >> 5;
+            const int x0 = (q & 31) * s - p.pad_l;
+            const int c_lo = max(0, -x0), c_hi = min(p.KW, p.W - x0);
+            cmask[i] = c_hi > c_lo ? (((1u << c_hi) - 1u) & ~((1u << c_lo) - 1u)) : 0u;
+            xoff[i] = x0 * p.lda;
+        }
+        const int tiles_per_img = (p.OH * p.OW) >> 7;
+        int cnt = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const int b = tile / tiles_per_img, oh0 = (tile - b * tiles_per_img) << 2;
+            long long row_off[8];
+            uint32_t row_mask[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int y0 = (oh0 + doh[i]) * s - p.pad_t;
+                const int a_lo = max(0, -y0), a_hi = min(p.KH, p.H - y0);
+                const uint32_t rowsel = fullsel & ((1u << (a_hi * p.KW)) - 1u) & ~((1u << (a_lo * p.KW)) - 1u);
+                row_mask[i] = b < p.B ? cmask[i] * rowsel : 0u;       // cmask < 2^KW: the product has no carries
+                row_off[i] = (long long)(b * p.H + y0) * p.W * p.lda + xoff[i];
+            }
+#pragma unroll
+            for (int kb = 0; kb < kSmallKMaxKb; ++kb) {
+                if (kb < nkb) {
+                    const int stage = cnt % kSmallKRing, use = cnt / kSmallKRing;
+                    if (use >= 1) mbar_wait(&empty_bar[stage], (uint32_t)((use - 1) & 1));
+                    const uint32_t dstA = (smemA + stage * kStageA + (rslot * 128) + (j << 4)) ^ ((uint32_t)(rslot & 7) << 4);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool ok = (row_mask[i] & tbit[kb]) != 0;
+                        cp_async16(dstA + i * 2048, ok ? (const void*)(p.a_src + row_off[i] + koff[kb]) : (const void*)p.a_src,
+                                   ok ? 16u : 0u);
+                    }
+                    cp_async_arrive_noinc(&full_bar[stage]);
+                    ++cnt;
+                }
+            }
+        }
+    } else if (warp < 4) {
+        // ================================ epilogue ================================
+        float q1[NT], q2[NT];                 // per-thread batch-norm moments of this thread's row, over all tiles
+#pragma unroll
+        for (int i = 0; i < NT; ++i) { q1[i] = 0.f; q2[i] = 0.f; }
+        const bool bf16_out = p.out_dtype == ACG_BF16;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int abuf = it & 1;
+            mbar_wait(&acc_full[abuf], (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const int m = tile * BM + warp * 32 + lane;
+            const bool row_ok = m < M;
+            const size_t row_off = (size_t)m * p.ldo;
+            const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(abuf * NT);
+#pragma unroll
+            for (int cb = 0; cb < NT; cb += 16) {
+                uint32_t v[16];
+                tmem_ld16(tacc + cb, v);
+                if (bf16_out) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+                        w[i] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                    if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {     // moments of exactly what is stored
+                            const float lo = __uint_as_float(w[i] << 16), hi = __uint_as_float(w[i] & 0xffff0000u);
+                            q1[cb + 2 * i] += lo; q2[cb + 2 * i] = fmaf(lo, lo, q2[cb + 2 * i]);
+                            q1[cb + 2 * i + 1] += hi; q2[cb + 2 * i + 1] = fmaf(hi, hi, q2[cb + 2 * i + 1]);
+                        }
+                        uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + cb);
+                        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
+                } else if (row_ok) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float f = __uint_as_float(v[i]);
+                        q1[cb + i] += f; q2[cb + i] = fmaf(f, f, q2[cb + i]);
+                    }
+                    float4* o = reinterpret_cast<float4*>(static_cast<float*>(p.out) + row_off + cb);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        o[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                           __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[abuf]);
+        }
+        if (p.stats) {      // one reduction over the warp's 32 rows per 16-column chunk, for the whole kernel
+#pragma unroll
+            for (int cb = 0; cb < NT; cb += 16) {
+                float a16[16], b16[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { a16[i] = q1[cb + i]; b16[i] = q2[cb + i]; }
+                const float cs = warp_colsum16(a16, lane), cs2 = warp_colsum16(b16, lane);
+                if ((lane & 1) == 0) {
+                    atomicAdd(&sm_stats[0][cb + (lane >> 1)], cs);
+                    atomicAdd(&sm_stats[1][cb + (lane >> 1)], cs2);
+                }
+            }
+        }
+    } else if (warp == 4 && lane == 0) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc = make_idesc(NT, 0, 0);
+        const uint32_t hi = desc_hi(1024);
+        const uint32_t alo0 = desc_lo(smemA, 16), blo0 = desc_lo(smemB, 16);
+        mbar_wait(&b_full, 0);
+        int cnt = 0, it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int abuf = it & 1;
+            if (it >= 2) {
+                mbar_wait(&acc_empty[abuf], (uint32_t)(((it >> 1) - 1) & 1));
+                tc_fence_after();
+            }
+            const uint32_t tacc = tmem_base + (uint32_t)(abuf * NT);
+            for (int kb = 0; kb < nkb; ++kb, ++cnt) {
+                const int stage = cnt % kSmallKRing;
+                mbar_wait(&full_bar[stage], (uint32_t)((cnt / kSmallKRing) & 1));
+                tc_fence_after();
+                const uint32_t alo = alo0 + stage * (kStageA >> 4), blo = blo0 + kb * (kStageB >> 4);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                    tc_mma2(tacc, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                tc_commit(&empty_bar[stage]);
+            }
+            tc_commit(&acc_full[abuf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+    if (p.stats) {
+        if (tid < NT && tid < p.n_stat) {
+            atomicAdd(&p.stats[tid], (double)sm_stats[0][tid]);
+            atomicAdd(&p.stats[p.n_stat + tid], (double)sm_stats[1][tid]);
+        }
+        if (p.counter) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) last_cta_sh = (atomicAdd(p.counter, 1u) == p.total_ctas - 1u);
+            __syncthreads();
+            if (last_cta_sh) {
+                __threadfence();
+                const double inv = 1.0 / (double)p.bn_rows;
+                for (int c = tid; c < p.n_bias; c += kSmallKThreads) {
+                    const double mu = __ldcg(&p.stats[c]) * inv;
+                    double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
+                    if (var < 0.0) var = 0.0;
+                    const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+                    const float b = p.beta ? p.beta[c] : 0.f;
+                    p.bn_mean[c] = (float)mu;
+                    p.bn_rstd[c] = rs;
+                    p.bn_scale[c] = rs;
+                    p.bn_shift[c] = b - (float)mu * rs;
+                }
+                if (tid == 0) *p.counter = 0u;
+            }
+        }
+    }
+}
+
 // ---- ADJ gather, halo-tile variant ---------------------------------------------------------------------------------
 // For a stride-2 transposed convolution every tap of an output-parity class is a pure 2-D shift of the (small-grid)
 // input: out_class[b][y][x] = sum_{ta,tc,k} in[b][y + ea - ta][x + ec - tc][k] * W[class][n][(ta,tc)][k].
@@ -1767,6 +2022,36 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, 1);
     rc = fill_bn(&p, t, grid.x * grid.y, "acg_conv_fprop_tc");
     if (rc) return rc;
+    {   // first layers (tiny K, many tiles of 4 whole 32-pixel output rows, N = 32 / 64, plain bias-free epilogue)
+        const int nkb = (s->KH * s->KW * t->ld_in + BK - 1) / BK;
+        const long long tiles = (M + BM - 1) / BM;
+        const bool shape_ok = s->OW == 32 && (s->OH * s->OW) % BM == 0 && (N == 32 || N == 64) && s->Cout == N &&
+                              s->KH * s->KW < 32 && (long long)s->H * s->W * t->ld_in < (1ll << 30);
+        const bool epi_ok = !t->bias && t->out_act == ACG_ACT_NONE && !t->red_z && t->ld_out % 8 == 0 &&
+                            ((uintptr_t)y & 15) == 0;
+        if (nkb <= kSmallKMaxKb && shape_ok && epi_ok && tiles >= 2ll * num_sms() && !getenv("ACG_NO_SMALLK")) {
+            static bool sready = false;
+            if (!sready) {
+                rc = set_smem((const void*)conv_smallk_persistent_kernel<32>, kSmallKSmem);
+                if (!rc) rc = set_smem((const void*)conv_smallk_persistent_kernel<64>, kSmallKSmem);
+                if (rc) return rc;
+                sready = true;
+            }
+            p.splits = 1;
+            p.total_ctas = (unsigned int)num_sms();
+            ConvParams scp;
+            scp.p = p;
+            rc = encode_weight_map(&scp.map_b[0], w_pack, (long long)s->KH * s->KW * t->ld_in, N, "acg_conv_fprop_tc");
+            if (rc) return rc;
+            if (N == 32)
+                launch_pdl(conv_smallk_persistent_kernel<32>, num_sms(), kSmallKThreads, kSmallKSmem,
+                           static_cast<cudaStream_t>(stream), scp, (int)tiles);
+            else
+                launch_pdl(conv_smallk_persistent_kernel<64>, num_sms(), kSmallKThreads, kSmallKSmem,
+                           static_cast<cudaStream_t>(stream), scp, (int)tiles);
+            return check_launch("acg_conv_fprop_tc(small K, persistent)");
+        }
+    }
     grid.z = (unsigned)apply_split(&p, t, plan_fprop(s, t->ld_in));
     ConvParams cp;
     cp.p = p;

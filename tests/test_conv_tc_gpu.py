@@ -312,3 +312,55 @@ def test_split_k_equals_unsplit(cuda, case):
         assert (outs[0] != outs[1]).mean() < 0.02                            # and only where a rounding flips
         assert np.abs(stats_all[0] - stats_all[1]).max() <= 2e-2 * max(1.0, np.abs(stats_all[0]).max())
         assert np.abs(fin[0] - fin[1]).max() <= 1e-2 * max(1.0, np.abs(fin[0]).max())
+
+
+@pytest.mark.parametrize("Cin,Cout", [(3, 32), (6, 64)])
+def test_small_k_persistent_kernel_equals_generic(cuda, Cin, Cout, monkeypatch):
+    """The first layers at a batch that gives >= 2 tiles per SM take the persistent small-K kernel (resident weights,
+    register-resident moments); output must be bit-identical to the generic kernel (same MMA order), the fused
+    batch-norm moments / finalize equal to rounding, and both must match the fp32 SIMT convolution."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    B, ld = 40, 8
+    g = torch.Generator(device=cuda).manual_seed(Cin)
+    shape = Kn.conv_shape(B, 64, 64, Cin, Cout, 5, 2, "SAME")
+    x = torch.zeros(B, 64, 64, ld, dtype=torch.bfloat16, device=cuda)
+    x[..., :Cin] = (torch.rand(B, 64, 64, Cin, device=cuda, generator=g) * 2 - 1).to(torch.bfloat16)
+    w = (torch.randn(5, 5, Cin, Cout, device=cuda, generator=g) / (25 * Cin) ** 0.5).to(torch.bfloat16).float()
+    pack = torch.empty(Kn.pack_size(shape, 0, ld), dtype=torch.bfloat16, device=cuda)
+    Kn.pack_weights(shape, w, 0, ld, pack)
+    rows = B * 32 * 32
+    res = []
+    for generic in (False, True):
+        if generic:
+            monkeypatch.setenv("ACG_NO_SMALLK", "1")
+        else:
+            monkeypatch.delenv("ACG_NO_SMALLK", raising=False)
+        out = torch.zeros(rows, Cout, dtype=torch.bfloat16, device=cuda)
+        stats = torch.zeros(2 * Cout, dtype=torch.float64, device=cuda)
+        counter = torch.zeros(1, dtype=torch.int32, device=cuda)
+        beta = torch.randn(Cout, device=cuda, generator=g)
+        mean, rstd, scale, shift = (torch.zeros(Cout, device=cuda) for _ in range(4))
+        n0 = _launches()
+        for _ in range(2):
+            stats.zero_()
+            Kn.conv_fprop_tc(shape, x, pack, out, ld, Cout, stats=stats,
+                             bn=(counter, beta, mean, rstd, scale, shift, rows, 1e-3))
+        torch.cuda.synchronize()
+        assert int(counter.item()) == 0
+        res.append((out.clone(), stats.cpu().numpy(), torch.stack([mean, rstd, shift]).cpu().numpy()))
+    assert torch.equal(res[0][0], res[1][0])
+    assert np.abs(res[0][1] - res[1][1]).max() <= 1e-5 * np.abs(res[1][1]).max()
+    assert np.abs(res[0][2] - res[1][2]).max() <= 1e-5 * max(1.0, np.abs(res[1][2]).max())
+    ref = torch.empty(B, 32, 32, Cout, device=cuda)
+    Kn.conv_fprop_f32(shape, x[..., :Cin].float().contiguous(), w, ref)
+    assert (res[0][0].float().view_as(ref) - ref).abs().max() <= 1.2e-2 * max(1.0, float(ref.abs().max()))
+    # fp32 output variant (no bf16 rounding before the moments)
+    monkeypatch.delenv("ACG_NO_SMALLK", raising=False)
+    out32 = torch.zeros(rows, Cout, device=cuda)
+    Kn.conv_fprop_tc(shape, x, pack, out32, ld, Cout)
+    assert (out32.view_as(ref) - ref).abs().max() <= 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+def _launches():
+    from action_conditioned_gans_b200 import _lib
+    return _lib.launch_count()
