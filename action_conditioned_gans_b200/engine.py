@@ -398,9 +398,10 @@ class NetRun:
             # (acg_dna_bwd -> g/tconv4): only the bias gradient (column sums) is left to do
             assert st.fused and dA2 is None
             if need_dw and L.bias:
-                K.bn_act_bwd_reduce(st.dz, None, st.ldz, None, st.ldz, st.rows, st.ldz, 1, None, None, None, "none",
-                                    st.red)
-                K.bias_grad(st.red, L.cout, 1.0, self.store.gviews[name + "/biases"])
+                with self.wgrad_branch:     # feeds the optimizer only: off the data-gradient chain
+                    K.bn_act_bwd_reduce(st.dz, None, st.ldz, None, st.ldz, st.rows, st.ldz, 1, None, None, None,
+                                        "none", st.red)
+                    K.bias_grad(st.red, L.cout, 1.0, self.store.gviews[name + "/biases"])
         else:
             if getattr(st, "red_ready", False):
                 st.red_ready = False        # the producer(s) of dA already accumulated st.red
