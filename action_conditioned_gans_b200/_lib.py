@@ -32,7 +32,7 @@ class TcArgs(C.Structure):
                 ("red_z", C.c_void_p), ("red_ldz", C.c_int), ("red_C", C.c_int), ("red_act", C.c_int),
                 ("red_mean", C.c_void_p), ("red_rstd", C.c_void_p), ("red_shift", C.c_void_p),
                 ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_longlong), ("splitk_tickets", C.c_void_p),
-                ("splitk_n_tickets", C.c_int)]
+                ("splitk_n_tickets", C.c_int), ("n_limit", C.c_int)]
 
 
 class PackJob(C.Structure):

@@ -1446,12 +1446,13 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // bf16 [rows][K] row-major weight pack -> 2-D map with a {64 x 128} box (128B swizzle, zero fill out of bounds)
-int encode_weight_map(CUtensorMap* map, const void* base, long long K, int rows, const char* who) {
+int encode_weight_map(CUtensorMap* map, const void* base, long long K, int rows, const char* who, int n_used = 0) {
     EncodeTiledFn enc = encode_tiled_fn();
     ACG_REQUIRE(enc, ACG_ERR_CUDA, "%s: cuTensorMapEncodeTiled is not available", who);
+    if (n_used <= 0 || n_used > rows) n_used = rows;                 // rows of the matrix the launch actually reads
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)(rows < BN ? rows : BN)};   // kernels expect min(N, 128) x 128 B per slice
+    cuuint32_t box[2] = {64, (cuuint32_t)(n_used < BN ? n_used : BN)};   // kernels expect min(N, 128) x 128 B per slice
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -2006,7 +2007,8 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     if (rc) return rc;
     ACG_REQUIRE(x_bf16 && w_pack && y, ACG_ERR_INVALID, "acg_conv_fprop_tc: null pointer");
     ACG_REQUIRE(t->ld_in >= s->Cin, ACG_ERR_INVALID, "acg_conv_fprop_tc: ld_in < Cin");
-    const int N = ru(s->Cout, 16);
+    int N = ru(s->Cout, 16);
+    if (t->n_limit > 0 && ru(t->n_limit, 16) < N) N = ru(t->n_limit, 16);   // only the first n_limit output channels
     ACG_REQUIRE(t->ld_out >= s->Cout, ACG_ERR_INVALID, "acg_conv_fprop_tc: ld_out=%d < Cout=%d", t->ld_out, s->Cout);
     static bool ready = false;
     if (!ready) {
@@ -2020,7 +2022,7 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     p.out = y; p.bias = t->bias;
     p.B = s->B; p.H = s->H; p.W = s->W; p.OH = s->OH; p.OW = s->OW; p.KH = s->KH; p.KW = s->KW;
     p.stride = s->stride; p.pad_t = s->pad_t; p.pad_l = s->pad_l;
-    p.lda = t->ld_in; p.ldo = t->ld_out; p.N = N; p.n_bias = s->Cout; p.n_store = N < t->ld_out ? N : t->ld_out; p.out_dtype = t->out_dtype; p.out_act = t->out_act;
+    p.lda = t->ld_in; p.ldo = t->ld_out; p.N = N; p.n_bias = s->Cout < N ? s->Cout : N; p.n_store = N < t->ld_out ? N : t->ld_out; p.out_dtype = t->out_dtype; p.out_act = t->out_act;
     const long long M = (long long)s->B * s->OH * s->OW;
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, 1);
     rc = fill_bn(&p, t, grid.x * grid.y, "acg_conv_fprop_tc");
@@ -2075,7 +2077,9 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     if (rc) return rc;
     ACG_REQUIRE(dy_bf16 && w_pack && dx, ACG_ERR_INVALID, "acg_conv_dgrad_tc: null pointer");
     ACG_REQUIRE(t->ld_in >= s->Cout, ACG_ERR_INVALID, "acg_conv_dgrad_tc: ld_in < Cout");
-    const int N = ru(s->Cin, 16);
+    const int Npack = ru(s->Cin, 16);        // rows per parity class of the weight pack
+    int N = Npack;
+    if (t->n_limit > 0 && ru(t->n_limit, 16) < N) N = ru(t->n_limit, 16);   // only the first n_limit input channels
     ACG_REQUIRE(t->ld_out >= s->Cin, ACG_ERR_INVALID, "acg_conv_dgrad_tc: ld_out=%d < Cin=%d", t->ld_out, s->Cin);
     static bool ready = false;
     if (!ready) {
@@ -2089,7 +2093,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     p.out = dx; p.bias = t->bias;
     p.B = s->B; p.H = s->H; p.W = s->W; p.OH = s->OH; p.OW = s->OW; p.KH = s->KH; p.KW = s->KW;
     p.stride = s->stride; p.pad_t = s->pad_t; p.pad_l = s->pad_l;
-    p.lda = t->ld_in; p.ldo = t->ld_out; p.N = N; p.n_bias = s->Cin; p.n_store = N < t->ld_out ? N : t->ld_out; p.out_dtype = t->out_dtype; p.out_act = t->out_act;
+    p.lda = t->ld_in; p.ldo = t->ld_out; p.N = N; p.n_bias = s->Cin < N ? s->Cin : N; p.n_store = N < t->ld_out ? N : t->ld_out; p.out_dtype = t->out_dtype; p.out_act = t->out_act;
     long long off = 0;
     const int ncls = s->stride * s->stride;
     unsigned int active = 0;
@@ -2097,7 +2101,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
         int na, nc;
         class_taps(s, cls, &na, &nc);
         p.w_class_off[cls] = off;
-        off += (long long)N * na * nc * t->ld_in;
+        off += (long long)Npack * na * nc * t->ld_in;
         const int ph = cls / s->stride, pw = cls % s->stride;
         const long long Mc = (long long)s->B * ((s->H - ph + s->stride - 1) / s->stride) *
                              ((s->W - pw + s->stride - 1) / s->stride);
@@ -2106,7 +2110,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     const int Hp = (s->H + s->stride - 1) / s->stride, Wp = (s->W + s->stride - 1) / s->stride;
     const long long M = (long long)s->B * Hp * Wp;
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, ncls);
-    if (halo_ok(s, t, N)) {
+    if (N == Npack && halo_ok(s, t, N)) {
         static bool halo_ready = false;
         if (!halo_ready) {
             if (cudaFuncSetAttribute(conv_adj_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem) !=
@@ -2162,7 +2166,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
         class_taps(s, cls, &na, &nc);
         if (na * nc == 0) { cp.map_b[cls] = cp.map_b[0]; continue; }
         rc = encode_weight_map(&cp.map_b[cls], static_cast<const __nv_bfloat16*>(w_pack) + p.w_class_off[cls],
-                               (long long)na * nc * t->ld_in, N, "acg_conv_dgrad_tc");
+                               (long long)na * nc * t->ld_in, Npack, "acg_conv_dgrad_tc", N);
         if (rc) return rc;
     }
     if ((long long)active <= num_sms())

@@ -442,7 +442,9 @@ class NetRun:
             if self.bf16:
                 pk = self.store.packs[name]
                 fn = K.conv_dgrad_tc if L.kind == "conv" else K.conv_fprop_tc
-                fn(st.shape, st.dz, pk[6], st.dx, st.ldz, st.ld_in, red=self._fused_red(consumer), splitk=st.splitk_b)
+                # dx_channels: the input is a concat buffer whose tail (tiled actions) needs no gradient
+                fn(st.shape, st.dz, pk[6], st.dx, st.ldz, st.ld_in, red=self._fused_red(consumer), splitk=st.splitk_b,
+                   n_limit=getattr(st, "dx_channels", 0))
             else:
                 w = self.store.views[name + "/weights"]
                 (K.conv_dgrad_f32 if L.kind == "conv" else K.conv_fprop_f32)(st.shape, st.dz, w, st.dx)
@@ -470,6 +472,7 @@ class GeneratorRun(NetRun):
         self.cat = self.act_buffer(h, w, c4 + ACTION_DIM)                        # models.py:16,38
         cat_ld = self.cat.shape[3]
         h1, w1 = self.plan("g/tconv1", h, w, cat_ld)
+        Ls["g/tconv1"].dx_channels = c4
         h2, w2 = self.plan("g/tconv2", h1, w1, self.ld(Ls["g/tconv1"].spec.cout))
         ld2 = self.ld(Ls["g/tconv2"].spec.cout)
         if dna:
@@ -576,6 +579,7 @@ class DiscriminatorRun(NetRun):
         for n in ["d/conv3", "d/conv4", "d/conv5", "d/conv6"]:
             h, w = self.plan(n, h, w, ld)
             ld = self.ld(Ls[n].spec.cout)
+        Ls["d/conv3"].dx_channels = 128
         for n, st in Ls.items():
             if n in ("d/conv2", "d/conv6"):
                 continue

@@ -75,10 +75,11 @@ def splitk_workspace(shape, which, ld_in, device):
             torch.zeros(ntick.value, dtype=torch.int32, device=device))
 
 
-def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, splitk=None):
+def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, splitk=None, n_limit=0):
     """bn = (counter, beta, mean, rstd, scale, shift, rows, eps): finalise the moments in-kernel (single GPU)
     red = (red_buffer, z, ldz, C, act, mean, rstd, shift): fused batch-norm backward reduction of the consumer layer"""
     t = TcArgs(ld_in, ld_out, ptr(bias), dtype_id(out), ACT_IDS[out_act], ptr(stats))
+    t.n_limit = int(n_limit)
     if splitk is not None:
         ws, tickets = splitk
         t.splitk_ws, t.splitk_ws_bytes = ptr(ws), ws.numel() * 4
@@ -97,14 +98,14 @@ def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, s
 
 
 def conv_fprop_tc(shape, x, w_pack, y, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None,
-                  splitk=None):
-    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn, red, splitk)
+                  splitk=None, n_limit=0):
+    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn, red, splitk, n_limit)
     call("acg_conv_fprop_tc", C.byref(shape), ptr(x), ptr(w_pack), ptr(y), C.byref(t), stream())
 
 
 def conv_dgrad_tc(shape, dy, w_pack, dx, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None,
-                  splitk=None):
-    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn, red, splitk)
+                  splitk=None, n_limit=0):
+    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn, red, splitk, n_limit)
     call("acg_conv_dgrad_tc", C.byref(shape), ptr(dy), ptr(w_pack), ptr(dx), C.byref(t), stream())
 
 

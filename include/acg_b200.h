@@ -130,6 +130,9 @@ typedef struct acg_tc_args {
     long long splitk_ws_bytes;
     unsigned int* splitk_tickets;
     int splitk_n_tickets;
+    /* optional: compute only the first n_limit output channels (0 = all).  The data gradient w.r.t. a concat buffer
+     * whose tail is the tiled action map (models.py:16,38,84) is only needed for the feature channels. */
+    int n_limit;
 } acg_tc_args;
 
 /* y = conv(x): x [B,H,W,ld_in] -> y [B,OH,OW,ld_out]; w_pack = acg_pack_weights(which=0, ld_k=ld_in) */
