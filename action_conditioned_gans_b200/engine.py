@@ -151,9 +151,11 @@ class ParamStore:
         self.refresh_packs()
 
     def numpy(self):
+        torch.cuda.synchronize(self.device)      # optimizer steps may still be running on a side stream
         return {n: v.detach().cpu().numpy().copy() for n, v in self.views.items()}
 
     def grads_numpy(self):
+        torch.cuda.synchronize(self.device)
         return {n: v.detach().cpu().numpy().copy() for n, v in self.gviews.items()}
 
 

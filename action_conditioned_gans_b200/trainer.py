@@ -21,6 +21,9 @@ DNA_KSIZE = 6        # train.py:53-54 passes ksize=6
 import os as _os
 _DP_SKIP = set(filter(None, _os.environ.get("ACG_DP_SKIP", "").split(",")))
 
+# run train_d's optimizer part on a side stream under the next call's generator forward (ACG_OVERLAP_D_UPDATE=0: inline)
+OVERLAP_D_UPDATE = _os.environ.get("ACG_OVERLAP_D_UPDATE", "1") != "0"
+
 SUMMARY_KEYS = ["discriminator_direct_loss", "discriminator_gen_loss", "discriminator_loss", "g_loss",
                 "g_l2_loss", "g_adv_loss", "g_psnr"]
 
@@ -109,6 +112,10 @@ class Trainer:
         self._staging = None
         self._frames_host = None
         self._pending_fetch = None
+        # the discriminator update (gradient all-reduce, optimizer, weight packs) of train_d runs on its own stream so
+        # that the generator forward of the following train_g overlaps it; everything that reads D weights waits
+        self._d_update_stream = None
+        self._d_update_done = None
         self._graphs, self._calls, self._graph_launches = {}, {}, {}
         self.replayed_launches = 0      # kernels launched through graph replays (acg_launch_count sees eager ones)
 
@@ -150,6 +157,17 @@ class Trainer:
         for i, (dst, t) in enumerate(feeds):
             dst.copy_(self._staging[k][i], non_blocking=True)
         self._staging_free[k].record(main)
+
+    def synchronize(self):
+        """Block the host until every enqueued step (including a discriminator update on its side stream) is done."""
+        self._wait_d_update()
+        torch.cuda.synchronize(self.device)
+
+    def _wait_d_update(self):
+        """Make the current stream wait for a discriminator update that is still running on its side stream."""
+        if self._d_update_done is not None:
+            torch.cuda.current_stream().wait_event(self._d_update_done)
+            self._d_update_done = None
 
     def _run(self, key, fn):
         """Eager on the first call (one-time kernel attribute setup), captured on the second, replayed after."""
@@ -265,6 +283,7 @@ class Trainer:
         return self._scalars()["g_loss"]
 
     def enqueue_pretrain_g(self, img, nxt, act, st):
+        self._wait_d_update()
         self._stage(img, nxt, act, st)
         self.g_pretrain_opt.tick()
         self._run("pretrain_g", self._body_pretrain_g)
@@ -313,6 +332,7 @@ class Trainer:
                 self._frames_host[self._frames_idx].copy_(self.g_run.g_out, non_blocking=True)
                 done.record(cs)
             self._pending_fetch = done     # the NEXT step's forward overwrites g_out: it waits for this copy
+        self._wait_d_update()              # D(generated) reads the discriminator weights / packs
         self._run("train_g_b", self._body_train_g_b)
         return done
 
@@ -342,13 +362,28 @@ class Trainer:
         return None
 
     def enqueue_train_d(self, img, nxt, act, need_state=False):
-        """need_state: also run the generator's state head (only the summaries of train.py:140 read it)."""
+        """need_state: also run the generator's state head (only the summaries of train.py:140 read it).
+        Two graphs: (main) forward + backward of D on both pairs, (update) gradient all-reduce + optimizer + clip +
+        weight packs.  The update is replayed on a side stream: the next train_g's generator forward does not read D
+        weights and overlaps it (with data parallelism that hides the 19 MB gradient all-reduce)."""
+        self._wait_d_update()
         self._stage(img, nxt, act, None)
         self.d_opt.tick()
         if need_state:
             self._run("train_d_state", lambda: self._body_train_d(True))
         else:
             self._run("train_d", lambda: self._body_train_d(False))
+        if not self.use_graphs or not OVERLAP_D_UPDATE:
+            self._run("train_d_update", self._body_train_d_update)
+        else:
+            if self._d_update_stream is None:
+                self._d_update_stream = torch.cuda.Stream(device=self.device)
+            main, side = torch.cuda.current_stream(), self._d_update_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self._run("train_d_update", self._body_train_d_update)
+                self._d_update_done = torch.cuda.Event()
+                self._d_update_done.record(side)
         self._have = {"d"}
 
     def _body_train_d(self, need_state=False):
@@ -370,6 +405,8 @@ class Trainer:
             self.d_real.backward(need_dw=True, need_dinput=False)
         self.d_gen.backward(need_dw=True, need_dinput=False)
         self.real_branch.join()
+
+    def _body_train_d_update(self):
         self._sync_grads(self.d_store)
         self.d_opt.enqueue(clip=(-0.01, 0.01))                       # train.py:89, update then clip
 
@@ -381,6 +418,7 @@ class Trainer:
         return g_out.cpu().numpy(), state, self.summaries()
 
     def enqueue_test(self, img, nxt, act, st):
+        self._wait_d_update()
         self._stage(img, nxt, act, st)
         self._run("test", self._body_test)
         self._have = {"g", "d"}
@@ -425,6 +463,7 @@ class Trainer:
     # ---- checkpoints (replaces tf.train.Saver, train.py:215,274 / test.py:29-30) -------------------------------
     def state_dict(self):
         """All variables keyed by their TF names (HWIO layouts) + optimizer slots + step counters."""
+        self._wait_d_update()
         out = {}
         out.update(self.g_store.numpy())
         out.update(self.d_store.numpy())
@@ -436,6 +475,7 @@ class Trainer:
         return out
 
     def load_state_dict(self, sd):
+        self._wait_d_update()
         self.g_store.load(sd)
         self.d_store.load(sd)
         for oname, opt in (("g_opt", self.g_opt), ("g_pretrain_opt", self.g_pretrain_opt), ("d_opt", self.d_opt)):

@@ -111,6 +111,7 @@ def _dp_worker(rank, world, port, out_dir):
         trn.train_d(img[sl], nxt[sl], act[sl])
         trn.train_g(img[sl], nxt[sl], act[sl], st[sl])
     s = trn.train_d(img[sl], nxt[sl], act[sl], summarize=True)
+    trn.synchronize()
     w = trn.d_store.flat.clone()
     ws = [torch.empty_like(w) for _ in range(world)]
     dist.all_gather(ws, w)
