@@ -185,7 +185,7 @@ def dna_microbench(dev, peaks, B=256, K=KSIZE):
     larger than the 126 MB L2; B=64 rotates 8 buffer sets for the same reason."""
     from action_conditioned_gans_b200 import kernels as Kn
     out = {}
-    for (b, k, nset) in ((B, K, 2), (64, 5, 8)):
+    for (b, k, nset) in ((B, K, 4), (64, 5, 12)):
         sets = []
         for i in range(nset):
             g = torch.Generator(device=dev).manual_seed(i)
