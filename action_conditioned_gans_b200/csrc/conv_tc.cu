@@ -26,7 +26,7 @@ namespace acg {
 namespace tc {
 
 constexpr int BM = 128, BK = 64, BN = 128, STAGES = 3;
-constexpr int kProducers = 128, kThreads = 160;
+constexpr int kProducers = 128, kThreads = 160, kThreads6 = 288;
 constexpr int kStageA = BM * BK * 2, kStageB = BN * BK * 2;
 constexpr int kSmemBytes = STAGES * (kStageA + kStageB) + 1024;  // + alignment slack
 constexpr int kSmemBytes6 = 6 * (kStageA + kStageB) + 1024;
@@ -374,11 +374,19 @@ __device__ __forceinline__ unsigned long long gtime() {
 // NST = pipeline depth.  3 stages (96 KB) keep two CTAs per SM so that one CTA's epilogue overlaps the other's main loop;
 // launches with fewer CTAs than SMs (the 4x4 / 8x8 layers: few tiles, K up to 6400) are latency bound per K slice and
 // take the 6-stage variant (192 KB, one CTA per SM) instead.
+// The 6-stage variant runs ONE CTA per SM: with 4 producer warps that is one warp per scheduler, and the gather
+// (~70 dependent instructions per K slice per thread) issues at one instruction per ~8 cycles -- the phase probe showed
+// 0.57 us per K slice with the L2 -> SM path at 60 % and the tensor pipe at 20 %.  It therefore uses EIGHT producer
+// warps (4 rows per thread instead of 8); the MMA-issuing warp is the one after the producers.
 template <int MODE, int NST>
-__global__ void __launch_bounds__(kThreads, NST == 3 ? 2 : 1)
+__global__ void __launch_bounds__(NST == 3 ? kThreads : kThreads6, NST == 3 ? 2 : 1)
 conv_tc_kernel(const __grid_constant__ ConvParams cp) {
     const Params& p = cp.p;
     constexpr int STAGES = NST;
+    constexpr int PW = NST == 3 ? 4 : 8;            // producer warps
+    constexpr int NPROD = PW * 32;                  // producer threads
+    constexpr int RPT = BM / (NPROD / 8);           // A rows per producer thread (8 threads cover one 128-byte row)
+    constexpr int NTHREADS = NPROD + 32;
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
     __shared__ uint32_t tmem_base_sh;
@@ -423,12 +431,12 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
     const int nkb = p.splits > 1 ? max(0, min(nkb_all - kb0, p.kb_per_split)) : nkb_all;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], kProducers + 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], NPROD + 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(&acc_bar, 1);
         fence_mbar_init();
         tma_prefetch_desc(&cp.map_b[MODE == ADJ ? zcls : 0]);
     }
-    if (warp == 4) {   // tensor-memory allocation is warp-collective; this warp also owns the dealloc
+    if (warp == PW) {  // tensor-memory allocation is warp-collective; this warp also owns the dealloc
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
                      "r"((uint32_t)BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -462,18 +470,18 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
         }
     }
 
-    if (warp < 4) {
+    if (warp < PW) {
         // ================================ producers ================================
         // A (activations): cp.async 16 B gathers.  Everything that does not change along K is hoisted: per row an
         // element offset of its tap-(0,0) source pixel and a bit mask of the taps that fall inside the image, so a
         // K slice costs ~6 instructions per row (mask test, 64-bit add, LDGSTS) instead of the full index math.
         // B (weights): ONE 2-D TMA copy per K slice issued by thread 0 (hardware swizzle, zero fill past N / Ktot).
         const int j = tid & 7, rslot = tid >> 3;
-        long long row_off[8];
-        uint32_t row_mask[8];
+        long long row_off[RPT];
+        uint32_t row_mask[RPT];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int m = tile_m + rslot + 16 * i;
+        for (int i = 0; i < RPT; ++i) {
+            const int m = tile_m + rslot + (NPROD / 8) * i;
             row_off[i] = 0;
             row_mask[i] = 0;
             if (m < M) {
@@ -519,17 +527,17 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
             else { const int ta = tap / nc, tcc = tap - ta * nc; koff = ci - (long long)(ta * p.OW + tcc) * p.lda; }
             const uint32_t dstA = smemA + stage * kStageA + (rslot * 128) + (j << 4);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                // row r = rslot + 16 i: r & 7 == rslot & 7, so the swizzle term is the same for all 8 rows
+            for (int i = 0; i < RPT; ++i) {
+                // row r = rslot + (NPROD/8) i: r & 7 == rslot & 7, so the swizzle term is the same for all rows
                 const bool ok = (row_mask[i] & tbit) != 0;
-                cp_async16((dstA ^ ((uint32_t)(rslot & 7) << 4)) + i * 2048,
+                cp_async16((dstA ^ ((uint32_t)(rslot & 7) << 4)) + i * (NPROD / 8) * 128,
                            ok ? (const void*)(p.a_src + row_off[i] + koff) : (const void*)p.a_src, ok ? 16u : 0u);
             }
             cp_async_arrive_noinc(&full_bar[stage]);
             ci += BK;
             while (ci >= p.lda) { ci -= p.lda; ++tap; }
         }
-    } else if (lane == 0) {
+    } else if (warp == PW && lane == 0) {
         // ================================ MMA issuer ================================
         const uint32_t idesc = make_idesc(n_cta, 0, 0);
         const uint32_t hi = desc_hi(1024);
@@ -624,7 +632,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == PW) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
     }
@@ -650,7 +658,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
             if (last_cta_sh) {
                 __threadfence();
                 const double inv = 1.0 / (double)p.bn_rows;
-                for (int c = tid; c < p.n_bias; c += kThreads) {
+                for (int c = tid; c < p.n_bias; c += NTHREADS) {
                     const double mu = __ldcg(&p.stats[c]) * inv;
                     double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
                     if (var < 0.0) var = 0.0;
@@ -2063,7 +2071,7 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     rc = encode_weight_map(&cp.map_b[0], w_pack, (long long)s->KH * s->KW * t->ld_in, N, "acg_conv_fprop_tc");
     if (rc) return rc;
     if ((long long)grid.x * grid.y <= num_sms())
-        launch_pdl(conv_tc_kernel<CONV, 6>, grid, kThreads, kSmemBytes6, static_cast<cudaStream_t>(stream), cp);
+        launch_pdl(conv_tc_kernel<CONV, 6>, grid, kThreads6, kSmemBytes6, static_cast<cudaStream_t>(stream), cp);
     else
         launch_pdl(conv_tc_kernel<CONV, 3>, grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream), cp);
     return check_launch("acg_conv_fprop_tc");
@@ -2170,7 +2178,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
         if (rc) return rc;
     }
     if ((long long)active <= num_sms())
-        launch_pdl(conv_tc_kernel<ADJ, 6>, grid, kThreads, kSmemBytes6, static_cast<cudaStream_t>(stream), cp);
+        launch_pdl(conv_tc_kernel<ADJ, 6>, grid, kThreads6, kSmemBytes6, static_cast<cudaStream_t>(stream), cp);
     else
         launch_pdl(conv_tc_kernel<ADJ, 3>, grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream), cp);
     return check_launch("acg_conv_dgrad_tc");

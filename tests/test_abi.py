@@ -74,3 +74,36 @@ def test_pack_size_is_host_only(built_lib):
     # dgrad pack: 4 parity classes with 3x3 + 3x2 + 2x3 + 2x2 = 25 taps in total
     assert K.pack_size(s, 1, 128) == 64 * 25 * 128
     assert (s.OH, s.OW, s.pad_t, s.pad_l) == (8, 8, 1, 1)
+
+
+def test_host_side_planners_need_no_device(built_lib):
+    """acg_pack_plan and acg_conv_splitk_plan are host functions (tile table of the batched weight pack, split-K
+    decision); they must work on the CPU build box and give the documented answers for the model's layers."""
+    import ctypes as C
+    from action_conditioned_gans_b200 import _lib
+    from action_conditioned_gans_b200 import kernels as K
+    lib = built_lib
+    # d/conv5 at B=256: [B,4,4,256] -> [B,2,2,512]: 8 x 4 = 32 output tiles, 100 K blocks -> 4 splits of 25
+    s = K.conv_shape(256, 4, 4, 256, 512, 5, 2)
+    splits, nbytes, ntick = C.c_int(), C.c_longlong(), C.c_int()
+    assert lib.acg_conv_splitk_plan(C.byref(s), 0, 256, C.byref(splits), C.byref(nbytes), C.byref(ntick)) == 0
+    assert splits.value == 4 and ntick.value == 32 and nbytes.value == 32 * 4 * 128 * 128 * 4
+    # d/conv2 at B=256 has 512 tiles: never splits
+    s2 = K.conv_shape(256, 32, 32, 64, 128, 5, 2)
+    assert lib.acg_conv_splitk_plan(C.byref(s2), 0, 64, C.byref(splits), C.byref(nbytes), C.byref(ntick)) == 0
+    assert splits.value == 1 and nbytes.value == 0 and ntick.value == 0
+    assert lib.acg_conv_splitk_plan(None, 0, 64, C.byref(splits), C.byref(nbytes), C.byref(ntick)) == -1
+    # tile table of a CONV pack + an ADJ pack of one 5x5 layer (Cin 64 -> Cout 128, ld 64 / 128)
+    jobs = (_lib.PackJob * 2)()
+    jobs[0] = _lib.PackJob(None, None, 0, 0, 64, 5, 5, 64, 128, 2, 1, 1, 128)       # [128][25][64]
+    jobs[1] = _lib.PackJob(None, None, 0, 1, 128, 5, 5, 64, 128, 2, 1, 1, 64)       # 4 classes of [64][taps][128]
+    n = lib.acg_pack_plan(jobs, 2, None, 0)
+    assert n == 25 * 4 * 2 + 25 * 2 * 4          # taps x row tiles x column tiles, per job
+    tiles = (C.c_int * (4 * n))()
+    assert lib.acg_pack_plan(jobs, 2, tiles, n) == n
+    t = [tuple(tiles[4 * i:4 * i + 4]) for i in range(n)]
+    assert all(job in (0, 1) for job, _, _, _ in t) and sum(1 for x in t if x[0] == 0) == 200
+    # class offsets of the ADJ pack: 4 / 6 / 6 / 9 taps (TF SAME padding of a 5x5 stride-2 filter), 64 rows x 128 columns
+    offs = sorted(set(x[3] for x in t if x[0] == 1))
+    assert offs == [0, 4 * 64 * 128, 10 * 64 * 128, 16 * 64 * 128]
+    assert lib.acg_pack_plan(None, 2, None, 0) == -1
