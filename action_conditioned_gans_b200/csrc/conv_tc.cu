@@ -1526,10 +1526,16 @@ struct WgradParams {
     int Cin, Cout, ldx, ldy;
     int k_chunk;     // pixels per split (multiple of BK)
     int fast;        // 1: a 64-pixel K slice is whole rows of one image (OW | 64 | OH*OW) or whole images (OH*OW | 64)
+    int a_tma;       // 1: the dy operand (a plain [pixels][ldy] matrix) arrives by TMA: two 64 x 64 boxes per K slice
+};
+struct alignas(64) WgradTmaParams {
+    WgradParams p;
+    CUtensorMap map_a;        // dy as bf16 [Kd][ldy], box {64 channels, 64 pixels}, 128B swizzle, zero OOB fill
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
-conv_wgrad_tc_kernel(const WgradParams p) {
+conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
+    const WgradParams& p = wp.p;
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
     __shared__ uint32_t tmem_base_sh;
@@ -1550,7 +1556,8 @@ conv_wgrad_tc_kernel(const WgradParams p) {
     if (nkb == 0) return;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], kProducers); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], kProducers + (p.a_tma ? 1 : 0)); mbar_init(&empty_bar[i], 1); }
+        if (p.a_tma) tma_prefetch_desc(&wp.map_a);
         mbar_init(&acc_bar, 1);
         fence_mbar_init();
     }
@@ -1616,12 +1623,21 @@ conv_wgrad_tc_kernel(const WgradParams p) {
                 const uint32_t dstB = smemB + stage * kStageB + atom * (BK * 128) + soff0;
                 const __nv_bfloat16* xP = p.x + ((long long)(bP * p.H + ohP * p.stride) * p.W) * p.ldx + tap_off;
                 const int ihP = ohP * p.stride + ta - p.pad_t;
+                if (p.a_tma) {
+                    if (tid == 0) {     // dy slice: two 64-channel atoms x 64 pixels, hardware swizzle / zero fill
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)kStageA);
+                        tma_load_2d(smemA + stage * kStageA, &wp.map_a, co0, k_begin + kb * BK, &full_bar[stage]);
+                        tma_load_2d(smemA + stage * kStageA + BK * 128, &wp.map_a, co0 + 64, k_begin + kb * BK, &full_bar[stage]);
+                    }
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const bool pv = pslot + 8 * i < kleft;
-                    const bool aok = pv && a_ch_ok;
-                    cp_async16(dstA + i * 1024, aok ? (const void*)(dyP + (long long)(8 * i) * p.ldy) : (const void*)p.dy,
-                               aok ? 16u : 0u);
+                    if (!p.a_tma) {
+                        const bool aok = pv && a_ch_ok;
+                        cp_async16(dstA + i * 1024, aok ? (const void*)(dyP + (long long)(8 * i) * p.ldy) : (const void*)p.dy,
+                                   aok ? 16u : 0u);
+                    }
                     const bool bok = pv && b_ch_ok && ((iw_ok >> i) & 1u) && (unsigned)(ihP + dih[i]) < (unsigned)p.H;
                     cp_async16(dstB + i * 1024, bok ? (const void*)(xP + offB[i]) : (const void*)p.x, bok ? 16u : 0u);
                 }
@@ -1642,12 +1658,19 @@ conv_wgrad_tc_kernel(const WgradParams p) {
             if (kb >= STAGES) mbar_wait(&empty_bar[stage], (uint32_t)(((kb / STAGES) - 1) & 1));
             const uint32_t dstA = smemA + stage * kStageA + atom * (BK * 128) + soff0;
             const uint32_t dstB = smemB + stage * kStageB + atom * (BK * 128) + soff0;
+            if (p.a_tma && tid == 0) {
+                mbar_expect_tx(&full_bar[stage], (uint32_t)kStageA);
+                tma_load_2d(smemA + stage * kStageA, &wp.map_a, co0, k_begin + kb * BK, &full_bar[stage]);
+                tma_load_2d(smemA + stage * kStageA + BK * 128, &wp.map_a, co0 + 64, k_begin + kb * BK, &full_bar[stage]);
+            }
 #pragma unroll
             for (int i = 0; i < BK / 8; ++i) {
                 const bool pv = pix < k_end;
-                const bool aok = pv && a_ch_ok;
-                cp_async16(dstA + i * 1024, aok ? (const void*)(p.dy + (long long)pix * p.ldy + a_ch) : (const void*)p.dy,
-                           aok ? 16u : 0u);
+                if (!p.a_tma) {
+                    const bool aok = pv && a_ch_ok;
+                    cp_async16(dstA + i * 1024, aok ? (const void*)(p.dy + (long long)pix * p.ldy + a_ch) : (const void*)p.dy,
+                               aok ? 16u : 0u);
+                }
                 const int ih = poh * p.stride + ta - p.pad_t, iw = pow_ * p.stride + tcc - p.pad_l;
                 const bool bok = pv && b_ch_ok && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
                 const long long boff = ((long long)(pb * p.H + ih) * p.W + iw) * p.ldx + ci;
@@ -2070,7 +2093,7 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     cp.p = p;
     rc = encode_weight_map(&cp.map_b[0], w_pack, (long long)s->KH * s->KW * t->ld_in, N, "acg_conv_fprop_tc");
     if (rc) return rc;
-    if ((long long)grid.x * grid.y <= num_sms())
+    if ((long long)grid.x * grid.y <= num_sms() && !getenv("ACG_CONV_3STAGE"))
         launch_pdl(conv_tc_kernel<CONV, 6>, grid, kThreads6, kSmemBytes6, static_cast<cudaStream_t>(stream), cp);
     else
         launch_pdl(conv_tc_kernel<CONV, 3>, grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream), cp);
@@ -2177,7 +2200,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
                                (long long)na * nc * t->ld_in, Npack, "acg_conv_dgrad_tc", N);
         if (rc) return rc;
     }
-    if ((long long)active <= num_sms())
+    if ((long long)active <= num_sms() && !getenv("ACG_CONV_3STAGE"))
         launch_pdl(conv_tc_kernel<ADJ, 6>, grid, kThreads6, kSmemBytes6, static_cast<cudaStream_t>(stream), cp);
     else
         launch_pdl(conv_tc_kernel<ADJ, 3>, grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream), cp);
@@ -2224,7 +2247,24 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
         p.fast = (rows_ok || imgs_ok) && span < (1ll << 30) && !getenv("ACG_WGRAD_SLOW") ? 1 : 0;
     }
     dim3 grid(gx, gy, (unsigned)splits);
-    launch_pdl(conv_wgrad_tc_kernel, grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream), p);
+    WgradTmaParams wp;
+    wp.p = p;
+    wp.p.a_tma = 0;
+    if (!getenv("ACG_WGRAD_NO_TMA") && ((uintptr_t)dy_bf16 & 15) == 0) {
+        EncodeTiledFn enc = encode_tiled_fn();
+        if (enc) {
+            cuuint64_t dims[2] = {(cuuint64_t)t->ld_out, (cuuint64_t)Kd};
+            cuuint64_t strides[1] = {(cuuint64_t)t->ld_out * 2};
+            cuuint32_t box[2] = {64, (cuuint32_t)BK};
+            cuuint32_t estr[2] = {1, 1};
+            if (enc(&wp.map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(dy_bf16), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+                wp.p.a_tma = 1;
+        }
+    }
+    if (!wp.p.a_tma) memset(&wp.map_a, 0, sizeof(wp.map_a));
+    launch_pdl(conv_wgrad_tc_kernel, grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream), wp);
     return check_launch("acg_conv_wgrad_tc");
 }
 
