@@ -97,6 +97,20 @@ class ClockSampler:
                 pass
             time.sleep(0.005)
 
+    def sample_now(self):
+        """One sample taken from the calling thread (the polling thread can be starved of the GIL while the main thread
+        enqueues the timed iterations); called mid-way and at the end of the timed loop."""
+        if self.nvml is None:
+            return
+        try:
+            n = self.nvml
+            reasons_fn = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            self.bits |= int(reasons_fn(self.handle))
+        except Exception:
+            pass
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
@@ -324,6 +338,8 @@ def main_ours(args):
     e0.record()
     for i in range(args.steps):
         iteration_resident(i)
+        if rank == 0 and (i == args.steps // 2 or i == args.steps - 1):
+            sampler.sample_now()      # the device is busy with the queued iterations at this point
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
