@@ -14,6 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libacg_b200.so")
+# the same sources with -DACG_PROBES: profiling probes for scripts/ (never loaded by the product path)
+PROBE_LIB = os.path.join(HERE, "libacg_b200_probe.so")
 OBJ_DIR = os.path.join(CSRC, "build")
 
 NVCC_FLAGS = [
@@ -38,6 +40,7 @@ def _digest():
     h = hashlib.sha256()
     files = _sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
     files.append(os.path.join(ROOT, "include", "acg_b200.h"))
+    files.append(os.path.join(ROOT, "include", "acg_b200_probe.h"))
     for f in files:
         h.update(f.encode())
         with open(f, "rb") as fh:
@@ -46,18 +49,26 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
-    """Compile every .cu under csrc/ and link the shared library.  Returns the library path."""
+def build(force=False, verbose=False, probes=True):
+    """Compile every .cu under csrc/ and link the shared library (and, with probes=True, the probe variant of it).
+    Returns the product library path."""
+    _build_one(LIB, OBJ_DIR, [], force, verbose)
+    if probes:
+        _build_one(PROBE_LIB, OBJ_DIR + "_probe", ["-DACG_PROBES"], force, verbose)
+    return LIB
+
+
+def _build_one(LIB, OBJ_DIR, extra, force, verbose):
     os.makedirs(OBJ_DIR, exist_ok=True)
     stamp = os.path.join(OBJ_DIR, "stamp")
-    dig = _digest()
+    dig = _digest() + "|" + " ".join(extra)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, res.stdout, res.stderr))

@@ -72,9 +72,7 @@ SIGNATURES = {
     "acg_tile_actions": [_P, _I, _I, _I, _P, _I, _I, _I, _P],
     "acg_frame_losses": [_P, _P, _I, _I, _I, _P, _P, _F, _F, _P, _I, _I, _P],
     "acg_dlogit_loss": [_P, _I, _I, _F, _F, _P, _P, _P],
-    "acg_state_loss": [_P, _P, _I, _F, _F, _P, _P, _P],
-    "acg_debug_phase_times": [_P],
-    "acg_debug_umma_shift": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "acg_state_loss": [_P, _P, _I, _F, _F, _P, _P, _P, _P, _P],
     "acg_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _P, _P],
     "acg_rmsprop_step": [_P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P],
     "acg_peer_alloc": [_L, C.POINTER(C.c_void_p)],
@@ -91,7 +89,24 @@ PLAIN = {"acg_version": ([], C.c_int), "acg_last_error": ([], C.c_char_p),
          "acg_peer_slot_bytes": ([_I, _I], C.c_longlong),
          "acg_pack_plan": ([_P, _I, _P, _L], C.c_longlong)}
 
+# include/acg_b200_probe.h: only in libacg_b200_probe.so (profiling scripts, hardware-behaviour probes)
+PROBE_SIGNATURES = {
+    "acg_debug_phase_times": [_P],
+    "acg_debug_umma_shift": [_P, _I, _P, _I, _I, _I, _I, _P, _P],
+}
+
 _lib = None
+_probe = False
+
+
+def use_probe_library():
+    """Profiling scripts only: load libacg_b200_probe.so (same kernels compiled with -DACG_PROBES, which adds the
+    ACG_DBG_SKIP pipeline switches and the acg_debug_* entry points).  Must be called before the first load()."""
+    global LIB_PATH, _probe
+    if _lib is not None and not _probe:
+        raise RuntimeError("use_probe_library() must be called before the library is first used")
+    LIB_PATH = os.path.join(HERE, "libacg_b200_probe.so")
+    _probe = True
 
 
 def load():
@@ -112,6 +127,11 @@ def load():
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = restype
+    if _probe:
+        for name, argtypes in PROBE_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
     _lib = lib
     return lib
 

@@ -20,6 +20,10 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
 
 namespace acg {
@@ -66,8 +70,17 @@ struct Params {
     int splits, kb_per_split;
     float* ws;
     unsigned int* tickets;
-    int dbg_skip;               // profiling experiments (env ACG_DBG_SKIP): bit 3 = per-phase timing
+    int dbg_skip;               // probe library only (-DACG_PROBES, env ACG_DBG_SKIP): see ACG_DBG below
 };
+// Profiling probes (per-phase timing, pipelines with one stage switched off) exist only in libacg_b200_probe.so, which
+// scripts/ load explicitly; in the product library ACG_DBG() is a compile-time false and the code below it vanishes.
+//   1: no halo TMA   2: no weight TMA   4: no MMAs   8: per-phase %globaltimer stamps   16: epilogue loads TMEM only
+//   32: no epilogue work
+#ifdef ACG_PROBES
+#define ACG_DBG(p, bit) (((p).dbg_skip & (bit)) != 0)
+#else
+#define ACG_DBG(p, bit) false
+#endif
 
 // Column sums of a 32-lane x 16-column register tile: after the butterfly lane L holds the total of column L>>1.
 __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
@@ -364,7 +377,7 @@ struct alignas(64) ConvParams {
 enum { CONV = 0, ADJ = 1 };
 
 // timing experiments (ACG_DBG_SKIP bit 3): per-phase nanoseconds summed over CTAs
-__device__ unsigned long long g_phase_ns[8];
+__device__ unsigned long long g_phase_ns[8];      // written only under ACG_PROBES
 __device__ __forceinline__ unsigned long long gtime() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -397,7 +410,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smemA = smem_base, smemB = smem_base + STAGES * kStageA;
     if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
-    const bool timing = (p.dbg_skip & 8) && tid == 0;
+    const bool timing = ACG_DBG(p, 8) && tid == 0;
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     if (timing) t0 = gtime();
 
@@ -957,8 +970,8 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smemH = smem_base, smemB = smem_base + 2 * kHaloBuf;
     if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
-    const bool timing = (p.dbg_skip & 8) && tid == 0;
-    const bool mtiming = (p.dbg_skip & 8) && tid == 128;
+    const bool timing = ACG_DBG(p, 8) && tid == 0;
+    const bool mtiming = ACG_DBG(p, 8) && tid == 128;
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, w_halo = 0, w_b = 0;
     if (timing) t0 = gtime();
 
@@ -1113,10 +1126,10 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
         }
     }
     unsigned long long tb4 = 0;
-    if ((p.dbg_skip & 8) && lane == 0) tb4 = gtime();
+    if (ACG_DBG(p, 8) && lane == 0) tb4 = gtime();
     tc_fence_before();
     __syncthreads();
-    if ((p.dbg_skip & 8) && lane == 0 && warp == 1) atomicAdd(&g_phase_ns[7], gtime() - tb4);   // warp 1's barrier wait
+    if (ACG_DBG(p, 8) && lane == 0 && warp == 1) atomicAdd(&g_phase_ns[7], gtime() - tb4);   // warp 1's barrier wait
     if (warp == 4) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
@@ -1252,6 +1265,7 @@ conv_adj_halo_persistent_kernel(const __grid_constant__ HaloParams hp, int ntile
             for (int kc = 0; kc < nkc; ++kc, ++hcount) {
                 const int buf = hcount & 1, use = hcount >> 1;
                 if (use >= 1) mbar_wait(&halo_empty[buf], (uint32_t)((use - 1) & 1));
+                if (ACG_DBG(p, 1)) { mbar_arrive(&halo_full[buf]); continue; }      // probe: no halo traffic
                 mbar_expect_tx(&halo_full[buf], a_bytes);
                 tma_load_4d(smemH + buf * kHaloBuf, &hp.map_a, kc * 64, ow0, oh0, h.b0, &halo_full[buf]);
             }
@@ -1266,6 +1280,7 @@ conv_adj_halo_persistent_kernel(const __grid_constant__ HaloParams hp, int ntile
                 for (int tap = 0; tap < h.ntaps; ++tap, ++bcount) {
                     const int st = bcount % kHaloBStages, use = bcount / kHaloBStages;
                     if (use >= 1) mbar_wait(&b_empty[st], (uint32_t)((use - 1) & 1));
+                    if (ACG_DBG(p, 2)) { mbar_arrive(&b_full[st]); continue; }      // probe: no weight traffic
                     mbar_expect_tx(&b_full[st], b_bytes);
                     tma_load_2d(smemB + st * kHaloBStage, &hp.map_b[h.cls], tap * p.lda + kc * 64, 0, &b_full[st]);
                 }
@@ -1303,12 +1318,14 @@ conv_adj_halo_persistent_kernel(const __grid_constant__ HaloParams hp, int ntile
                     const int shift = (h.na - 1 - ta) * WH + (h.nc - 1 - tcc);
                     const uint32_t blo = blo0 + st * (kHaloBStage >> 4);
                     const uint32_t alo_t = desc_lo(hbase, 16) + (uint32_t)shift * 8u;
+                    if (!ACG_DBG(p, 4)) {                                             // probe: no MMAs
 #pragma unroll
                     for (int q = 0; q < HALO_ACC; ++q) {
                         const uint32_t alo = alo_t + acc_row8[q];
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             tc_mma2(tacc + q * N, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                    }
                     }
                     tc_commit(&b_empty[st]);
                 }
@@ -1326,13 +1343,14 @@ conv_adj_halo_persistent_kernel(const __grid_constant__ HaloParams hp, int ntile
             mbar_wait(&acc_full[abuf], (uint32_t)(ause & 1));
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(abuf * HALO_ACC * N);
-            for (int q = 0; q < HALO_ACC; ++q) {
+            for (int q = 0; q < HALO_ACC && !ACG_DBG(p, 32); ++q) {                  // probe bit 32: no epilogue work
                 const int tb = q / XG, xg = q - tb * XG;
                 const int ih = ((h.y0 + yy) << 1) + h.ph, iw = ((xg * 8 + xi) << 1) + h.pw;
                 const size_t row_off = ((size_t)((h.b0 + tb) * p.H + ih) * p.W + iw) * p.ldo;
                 for (int cb = 0; cb < N; cb += 16) {
                     uint32_t v[16];
                     tmem_ld16(tacc + q * N + cb, v);
+                    if (ACG_DBG(p, 16)) continue;                                    // probe bit 16: loads only
                     epilogue_chunk(p, v, cb, true, row_off, 0u, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
                 }
             }
@@ -1865,10 +1883,13 @@ int apply_split(Params* p, const acg_tc_args* t, const SplitPlan& pl) {
 }
 
 int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char* who) {
+    p->dbg_skip = 0;
+#ifdef ACG_PROBES
     {
         const char* e = getenv("ACG_DBG_SKIP");
         p->dbg_skip = e ? atoi(e) : 0;
     }
+#endif
     p->stats = t->stats;
     p->counter = nullptr;
     p->total_ctas = total_ctas;
@@ -1904,12 +1925,22 @@ int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char
     return ACG_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember (kernel, device) pairs, so a
+// process that drives several GPUs sets it on each of them.
 int set_smem(const void* kern, int bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    for (const auto& e : done)
+        if (e.first == kern && e.second == dev) return ACG_OK;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) {
         cudaError_t e = cudaGetLastError();
-        set_error("conv_tc: cannot set dynamic smem: %s", cudaGetErrorString(e));
+        set_error("conv_tc: cannot set %d B dynamic smem: %s", bytes, cudaGetErrorString(e));
         return ACG_ERR_CUDA;
     }
+    done.emplace_back(kern, dev);
     return ACG_OK;
 }
 
@@ -1918,6 +1949,7 @@ int set_smem(const void* kern, int bytes) {
 
 extern "C" {
 
+#ifdef ACG_PROBES
 /* timing experiments: returns {setup ns, main loop ns, epilogue ns, CTAs, K blocks} summed since the last call */
 int acg_debug_phase_times(unsigned long long* out5 /* 8 entries */) {
     using namespace acg::tc;
@@ -1926,6 +1958,7 @@ int acg_debug_phase_times(unsigned long long* out5 /* 8 entries */) {
     if (cudaMemcpyToSymbol(g_phase_ns, zero, sizeof(zero)) != cudaSuccess) return ACG_ERR_CUDA;
     return ACG_OK;
 }
+#endif
 
 long long acg_pack_size(const acg_conv_shape* s, int which, int ld_k) {
     using namespace acg::tc;
@@ -2041,13 +2074,9 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     int N = ru(s->Cout, 16);
     if (t->n_limit > 0 && ru(t->n_limit, 16) < N) N = ru(t->n_limit, 16);   // only the first n_limit output channels
     ACG_REQUIRE(t->ld_out >= s->Cout, ACG_ERR_INVALID, "acg_conv_fprop_tc: ld_out=%d < Cout=%d", t->ld_out, s->Cout);
-    static bool ready = false;
-    if (!ready) {
-        rc = set_smem((const void*)conv_tc_kernel<CONV, 3>, kSmemBytes);
-        if (!rc) rc = set_smem((const void*)conv_tc_kernel<CONV, 6>, kSmemBytes6);
-        if (rc) return rc;
-        ready = true;
-    }
+    rc = set_smem((const void*)conv_tc_kernel<CONV, 3>, kSmemBytes);
+    if (!rc) rc = set_smem((const void*)conv_tc_kernel<CONV, 6>, kSmemBytes6);
+    if (rc) return rc;
     Params p{};
     p.a_src = static_cast<const __nv_bfloat16*>(x_bf16); p.w_pack = static_cast<const __nv_bfloat16*>(w_pack);
     p.out = y; p.bias = t->bias;
@@ -2066,13 +2095,9 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
         const bool epi_ok = !t->bias && t->out_act == ACG_ACT_NONE && !t->red_z && t->ld_out % 8 == 0 &&
                             ((uintptr_t)y & 15) == 0;
         if (nkb <= kSmallKMaxKb && shape_ok && epi_ok && tiles >= 2ll * num_sms() && !getenv("ACG_NO_SMALLK")) {
-            static bool sready = false;
-            if (!sready) {
-                rc = set_smem((const void*)conv_smallk_persistent_kernel<32>, kSmallKSmem);
-                if (!rc) rc = set_smem((const void*)conv_smallk_persistent_kernel<64>, kSmallKSmem);
-                if (rc) return rc;
-                sready = true;
-            }
+            rc = set_smem((const void*)conv_smallk_persistent_kernel<32>, kSmallKSmem);
+            if (!rc) rc = set_smem((const void*)conv_smallk_persistent_kernel<64>, kSmallKSmem);
+            if (rc) return rc;
             p.splits = 1;
             p.total_ctas = (unsigned int)num_sms();
             ConvParams scp;
@@ -2112,13 +2137,9 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     int N = Npack;
     if (t->n_limit > 0 && ru(t->n_limit, 16) < N) N = ru(t->n_limit, 16);   // only the first n_limit input channels
     ACG_REQUIRE(t->ld_out >= s->Cin, ACG_ERR_INVALID, "acg_conv_dgrad_tc: ld_out=%d < Cin=%d", t->ld_out, s->Cin);
-    static bool ready = false;
-    if (!ready) {
-        rc = set_smem((const void*)conv_tc_kernel<ADJ, 3>, kSmemBytes);
-        if (!rc) rc = set_smem((const void*)conv_tc_kernel<ADJ, 6>, kSmemBytes6);
-        if (rc) return rc;
-        ready = true;
-    }
+    rc = set_smem((const void*)conv_tc_kernel<ADJ, 3>, kSmemBytes);
+    if (!rc) rc = set_smem((const void*)conv_tc_kernel<ADJ, 6>, kSmemBytes6);
+    if (rc) return rc;
     Params p{};
     p.a_src = static_cast<const __nv_bfloat16*>(dy_bf16); p.w_pack = static_cast<const __nv_bfloat16*>(w_pack);
     p.out = dx; p.bias = t->bias;
@@ -2142,31 +2163,15 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     const long long M = (long long)s->B * Hp * Wp;
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, ncls);
     if (N == Npack && halo_ok(s, t, N)) {
-        static bool halo_ready = false;
-        if (!halo_ready) {
-            if (cudaFuncSetAttribute(conv_adj_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem) !=
-                cudaSuccess) {
-                cudaError_t e = cudaGetLastError();
-                set_error("acg_conv_dgrad_tc: cannot set %d B dynamic smem: %s", kHaloSmem, cudaGetErrorString(e));
-                return ACG_ERR_CUDA;
-            }
-            halo_ready = true;
-        }
+        rc = set_smem((const void*)conv_adj_halo_kernel, kHaloSmem);
+        if (rc) return rc;
         const int TB = HALO_ACC / (s->W / 16);
         dim3 hgrid((unsigned)((s->B / TB) * (s->H / 32)), 1, 4);
         static const bool persistent = []() { const char* e = getenv("ACG_HALO_PERSISTENT"); return !e || atoi(e) != 0; }();
         if (persistent && !t->red_z) {
             // one CTA per SM walks the tile list: copies, MMAs and epilogue of consecutive tiles overlap
-            static bool pready = false;
-            if (!pready) {
-                if (cudaFuncSetAttribute(conv_adj_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kHaloSmem) != cudaSuccess) {
-                    cudaError_t e = cudaGetLastError();
-                    set_error("acg_conv_dgrad_tc: cannot set %d B dynamic smem: %s", kHaloSmem, cudaGetErrorString(e));
-                    return ACG_ERR_CUDA;
-                }
-                pready = true;
-            }
+            rc = set_smem((const void*)conv_adj_halo_persistent_kernel, kHaloSmem);
+            if (rc) return rc;
             const int ntiles = (int)hgrid.x * 4;
             const int ctas = ntiles < num_sms() ? ntiles : num_sms();
             rc = fill_bn(&p, t, (unsigned int)ctas, "acg_conv_dgrad_tc");
@@ -2220,8 +2225,7 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
     ACG_REQUIRE((long long)s->B * s->H * s->W * (long long)t->ld_in < (1ll << 40) &&
                     (long long)s->B * s->OH * s->OW < (1ll << 31),
                 ACG_ERR_UNSUPPORTED, "acg_conv_wgrad_tc: tensor too large");
-    static bool ready = false;
-    if (!ready) { int rc = set_smem((const void*)conv_wgrad_tc_kernel, kSmemBytes); if (rc) return rc; ready = true; }
+    { int rc = set_smem((const void*)conv_wgrad_tc_kernel, kSmemBytes); if (rc) return rc; }
     WgradParams p{};
     p.x = static_cast<const __nv_bfloat16*>(x_bf16); p.dy = static_cast<const __nv_bfloat16*>(dy_bf16); p.dw = dw;
     p.B = s->B; p.H = s->H; p.W = s->W; p.OH = s->OH; p.OW = s->OW; p.KH = s->KH; p.KW = s->KW;

@@ -1,6 +1,7 @@
 // Probe kernel (tests only): checks how tcgen05.mma addresses a 128-byte-swizzled K-major operand whose start is NOT
 // 1024-byte aligned and whose 8-row groups are spaced by an arbitrary pitch -- the "shifted window" access that lets
 // every filter tap of a transposed convolution read the same shared-memory halo patch.
+#ifdef ACG_PROBES
 #include "common.cuh"
 
 namespace acg {
@@ -101,3 +102,4 @@ extern "C" int acg_debug_umma_shift(const void* a_rows, int n_rows, const void* 
         base_offset_mode, out);
     return check_launch("acg_debug_umma_shift");
 }
+#endif  // ACG_PROBES

@@ -237,7 +237,10 @@ int launch(const void* logits, const float* img, const float* dy, float* out, vo
     using L = StageLayout<K, LT, BWD>;
     auto kern = dna_kernel<K, LT, BWD, STAGES, PADOUT>;
     const int smem = STAGES * L::bytes + (PADOUT ? 2 * kThreads * pad16(K * K) * 2 : 0);
-    static int occ = 0;  // per template instance
+    static int occ_dev[64] = {0};  // per template instance and device (the smem attribute is per device)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& occ = occ_dev[dev & 63];
     if (occ == 0) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
             cudaError_t e = cudaGetLastError();

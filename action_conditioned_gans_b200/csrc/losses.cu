@@ -97,29 +97,38 @@ dlogit_loss_kernel(const float* __restrict__ x, int n, int kind, float label_or_
     }
 }
 
+// sumsq_out != NULL: phase 1 of the data-parallel form -- only the LOCAL sum of squares is written (fp64), the caller
+// sums it over the ranks.  sumsq_in != NULL: the norm is sqrt(*sumsq_in) (the GLOBAL sum) instead of the local one, so
+// that loss and gradient are those of train.py:77's Frobenius norm over the whole batch.
 __global__ void __launch_bounds__(kThreads)
 state_loss_kernel(const float* __restrict__ s, const float* __restrict__ t, int n, float inv_batch,
-                  float grad_scale, float* __restrict__ loss_out, float* __restrict__ ds) {
+                  float grad_scale, float* __restrict__ loss_out, float* __restrict__ ds,
+                  double* __restrict__ sumsq_out, const double* __restrict__ sumsq_in) {
     pdl_prologue();
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < n; i += kThreads) {
-        const double d = (double)s[i] - (double)t[i];
-        acc += d * d;
-    }
     __shared__ double red[kThreads / 32];
     __shared__ float norm_sh;
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
+    if (!sumsq_in) {
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < n; i += kThreads) {
+            const double d = (double)s[i] - (double)t[i];
+            acc += d * d;
+        }
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         double tot = 0.0;
-        for (int w = 0; w < kThreads / 32; ++w) tot += red[w];
+        if (sumsq_in) tot = *sumsq_in;
+        else
+            for (int w = 0; w < kThreads / 32; ++w) tot += red[w];
+        if (sumsq_out) *sumsq_out = tot;
         const float norm = (float)sqrt(tot);
         norm_sh = norm;
-        loss_out[0] = norm * inv_batch;
+        if (loss_out) loss_out[0] = norm * inv_batch;
     }
     __syncthreads();
-    if (ds) {
+    if (ds && !sumsq_out) {
         const float k = norm_sh > 0.f ? grad_scale * inv_batch / norm_sh : 0.f;
         for (int i = threadIdx.x; i < n; i += kThreads) ds[i] = k * (s[i] - t[i]);
     }
@@ -155,12 +164,13 @@ int acg_dlogit_loss(const float* x, int n, int kind, float label_or_sign, float 
 }
 
 int acg_state_loss(const float* s, const float* t, int n, float inv_batch, float grad_scale, float* loss_out,
-                   float* dstate, void* stream) {
+                   float* dstate, double* sumsq_out, const double* sumsq_in, void* stream) {
     using namespace acg;
-    ACG_REQUIRE(s && t && loss_out, ACG_ERR_INVALID, "acg_state_loss: null pointer");
+    ACG_REQUIRE(s && t && (loss_out || sumsq_out), ACG_ERR_INVALID, "acg_state_loss: null pointer");
+    ACG_REQUIRE(!(sumsq_out && sumsq_in), ACG_ERR_INVALID, "acg_state_loss: sumsq_out and sumsq_in exclude each other");
     ACG_REQUIRE(n > 0, ACG_ERR_INVALID, "acg_state_loss: n=%d", n);
     launch_pdl(state_loss_kernel, 1, kThreads, 0, static_cast<cudaStream_t>(stream), s, t, n, inv_batch, grad_scale,
-                                                                            loss_out, dstate);
+                                                                            loss_out, dstate, sumsq_out, sumsq_in);
     return check_launch("acg_state_loss");
 }
 

@@ -214,7 +214,6 @@ def ru16(v):
     return (v + 15) // 16 * 16
 
 
-_DP_SKIP = set(filter(None, os.environ.get("ACG_DP_SKIP", "").split(",")))   # timing experiments (scripts/dp_step_time.py)
 FRAME_LD = 8        # channel stride of the bf16 frame operands (3 / 6 real channels): K of the first layers = 25 x 8
 
 
@@ -332,9 +331,7 @@ class NetRun:
     def _sync_moments(self, st, beta):
         """Sum the [2C] moments over the ranks and finalise mean / rstd / scale / shift over the global batch."""
         L, dp = st.spec, self.dp
-        if "bn" in _DP_SKIP:   # timing experiment: local statistics
-            K.bn_finalize(st.stats, beta, st.rows, L.cout, 1, st.mean, st.rstd, st.scale, st.shift, BN_EPS)
-        elif dp.peer_sync:     # one launch: push to the peers' mailboxes, wait, sum in rank order, finalise
+        if dp.peer_sync:       # one launch: push to the peers' mailboxes, wait, sum in rank order, finalise
             dp.mailbox.allreduce_f64(st.stats, 2 * L.cout, st.slot_f,
                                      bn=(L.cout, beta, st.rows * dp.world, BN_EPS, st.mean, st.rstd, st.scale, st.shift))
         else:
@@ -412,9 +409,7 @@ class NetRun:
             world = 1
             if self.dp is not None:
                 world = self.dp.world
-                if "bn" in _DP_SKIP:
-                    pass
-                elif L.bn and self.dp.peer_sync:
+                if L.bn and self.dp.peer_sync:
                     self.dp.mailbox.allreduce_f64(st.red, 2 * L.cout, st.slot_b)
                 elif L.bn:
                     self.dp.allreduce_sum(st.red)

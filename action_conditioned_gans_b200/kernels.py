@@ -207,8 +207,10 @@ def dlogit_loss(x, n, kind, label_or_sign, grad_scale, loss_out, dlogits=None):
          grad_scale, ptr(loss_out), ptr(dlogits), stream())
 
 
-def state_loss(s, t, n, inv_batch, grad_scale, loss_out, dstate=None):
-    call("acg_state_loss", ptr(s), ptr(t), n, inv_batch, grad_scale, ptr(loss_out), ptr(dstate), stream())
+def state_loss(s, t, n, inv_batch, grad_scale, loss_out, dstate=None, sumsq_out=None, sumsq_in=None):
+    """sumsq_out / sumsq_in (fp64 scalars): the two phases of the batch-sharded form, see include/acg_b200.h"""
+    call("acg_state_loss", ptr(s), ptr(t), n, inv_batch, grad_scale, ptr(loss_out), ptr(dstate), ptr(sumsq_out),
+         ptr(sumsq_in), stream())
 
 
 # ---- optimizers -----------------------------------------------------------------------------------

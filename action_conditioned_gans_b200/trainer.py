@@ -17,9 +17,7 @@ BATCH_SIZE = 64      # train.py:19
 L2_WEIGHT = 0.05     # train.py:22
 DNA_KSIZE = 6        # train.py:53-54 passes ksize=6
 
-# timing experiments only (scripts/dp_step_time.py): comma list of collectives to leave out -- results are then wrong
 import os as _os
-_DP_SKIP = set(filter(None, _os.environ.get("ACG_DP_SKIP", "").split(",")))
 
 # run train_d's optimizer part on a side stream under the next call's generator forward (ACG_OVERLAP_D_UPDATE=0: inline)
 OVERLAP_D_UPDATE = _os.environ.get("ACG_OVERLAP_D_UPDATE", "1") != "0"
@@ -100,6 +98,8 @@ class Trainer:
         self.fsum = torch.zeros(3, dtype=torch.float64, device=dev)
         self.sc = torch.zeros(4, dtype=torch.float32, device=dev)
         self.zero_state = torch.zeros(self.B, E.STATE_DIM, device=dev)
+        self.state_ss = torch.zeros(1, dtype=torch.float64, device=dev)     # sum of squares of the state residual
+        self._state_slot = dp.mailbox.new_slot(1) if dp is not None and dp.peer_sync else None
         self._have = set()
         # static feed buffers + one captured CUDA graph per step kind (the step is ~300 small launches; replaying a
         # graph removes the per-launch host cost and the idle gaps between tiny kernels)
@@ -226,27 +226,32 @@ class Trainer:
         K.frame_losses(g.g_out, nxt, self.fsum, g.dg_out if want_grad else None, w_l1,
                        1.0 if with_adv_grad else 0.0, dadv, dadv.shape[3] if dadv is not None else 0, 3)
         if self.arg_transform:
-            K.state_loss(g.state, state_gt, self.B * E.STATE_DIM, 1.0 / self.GB, 1.0, self.sc[3:4],
-                         g.dstate if want_grad else None)
-            if self.dp is not None and want_grad:
-                # train.py:77 is a Frobenius norm over the GLOBAL batch: rescale the local-norm gradient
-                n2 = (self.sc[3:4] * self.GB) ** 2
-                tot = n2.clone()
-                self.dp.allreduce_sum(tot)
-                g.dstate.mul_(torch.sqrt(n2 / tot.clamp_min(1e-30)))
+            n_st = self.B * E.STATE_DIM
+            if self.dp is None:
+                K.state_loss(g.state, state_gt, n_st, 1.0 / self.GB, 1.0, self.sc[3:4], g.dstate if want_grad else None)
+            else:
+                # train.py:77 is a Frobenius norm over the GLOBAL batch: local sum of squares -> sum over the ranks ->
+                # loss and gradient from the global norm (kernels + the exchange only; no torch op on the path)
+                K.state_loss(g.state, state_gt, n_st, 1.0 / self.GB, 1.0, None, None, sumsq_out=self.state_ss)
+                if self.dp.peer_sync:
+                    self.dp.mailbox.allreduce_f64(self.state_ss, 1, self._state_slot)
+                else:
+                    self.dp.allreduce_sum(self.state_ss)
+                K.state_loss(g.state, state_gt, n_st, 1.0 / self.GB, 1.0, self.sc[3:4], g.dstate if want_grad else None,
+                             sumsq_in=self.state_ss)
 
     def _scalars(self):
         """Host values of the loss scalars of the last step (synchronises; logging only)."""
+        self._wait_d_update()        # eager collectives below must not interleave with the side-stream gradient all-reduce
         fs = self.fsum.clone()
         sc = self.sc.clone().double()
         if self.dp is not None:
             self.dp.allreduce_sum(fs)
             loc = sc.clone()
             loc[:3] /= self.world        # means over the local logits -> global mean
-            # the state loss is a norm over the GLOBAL batch: combine squared local norms
-            loc[3] = (sc[3] * self.GB) ** 2
+            loc[3] = 0.0                 # the state loss is already the global norm on every rank (_g_losses)
             self.dp.allreduce_sum(loc)
-            loc[3] = torch.sqrt(loc[3]) / self.GB
+            loc[3] = sc[3]
             sc = loc
         fs = fs.cpu().numpy()
         sc = sc.cpu().numpy()
@@ -273,7 +278,7 @@ class Trainer:
         return {k: s[k] for k in SUMMARY_KEYS if k in s}
 
     def _sync_grads(self, store):
-        if self.dp is not None and "grad" not in _DP_SKIP:
+        if self.dp is not None:
             self.dp.allreduce_sum(store.grad)
 
     # ---- train.py:114-121 -------------------------------------------------------------------------------
@@ -373,7 +378,8 @@ class Trainer:
             self._run("train_d_state", lambda: self._body_train_d(True))
         else:
             self._run("train_d", lambda: self._body_train_d(False))
-        if not self.use_graphs or not OVERLAP_D_UPDATE:
+        nccl_bn = self.dp is not None and not self.dp.peer_sync    # batch-norm all-reduces share the communicator
+        if not self.use_graphs or not OVERLAP_D_UPDATE or nccl_bn:
             self._run("train_d_update", self._body_train_d_update)
         else:
             if self._d_update_stream is None:

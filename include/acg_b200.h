@@ -233,9 +233,11 @@ int acg_frame_losses(const float* g, const float* n, int B, int H, int W, double
  *   dlogits (may be NULL) = grad_scale * d loss / d x.   label is 1, 0.9 or 0; sign is +1/-1. */
 int acg_dlogit_loss(const float* x, int n, int kind, float label_or_sign, float grad_scale,
                     float* loss_out, float* dlogits, void* stream);
-/* state loss ||s - t||_F / B (train.py:77) over [B,5]; dstate (may be NULL) = grad_scale * d/ds. */
+/* state loss ||s - t||_F / B (train.py:77) over [B,5]; dstate (may be NULL) = grad_scale * d/ds.
+ * Batch-sharded form (the norm spans the GLOBAL batch): call once with sumsq_out != NULL (writes only the local
+ * fp64 sum of squares), sum that scalar over the ranks, call again with sumsq_in pointing at the global sum. */
 int acg_state_loss(const float* s, const float* t, int n, float inv_batch, float grad_scale,
-                   float* loss_out, float* dstate, void* stream);
+                   float* loss_out, float* dstate, double* sumsq_out, const double* sumsq_in, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizers: tf.train.AdamOptimizer / RMSPropOptimizer as TF 1.0 implements them
@@ -281,16 +283,6 @@ int acg_peer_allreduce_f64(double* vec, int n, int cap, long long slot_off, int 
                            void* const* host_mailboxes, unsigned long long* epoch, float timeout_s, int bn_C,
                            const float* beta, long long bn_rows, float eps, float* mean, float* rstd, float* scale,
                            float* shift, void* stream);
-
-/* Probe (tests only): D[128][N] = A_window * B^T where A_window's logical row m is shared-memory row
- * shift + (m/8)*pitch + (m%8) of a 128-byte-swizzled K-major [n_rows][64] bf16 tile (start not 1024 B aligned, 8-row
- * groups spaced by `pitch` rows).  base_offset_mode 1 sets the descriptor's base-offset field to (addr>>7)&7. */
-/* Probe (profiling experiments, ACG_DBG_SKIP=8): out[8] = {setup ns, main-loop ns, epilogue ns, CTAs, K blocks,
- * MMA-thread wait for halo ns, MMA-thread wait for weights ns, 0} of the conv_tc kernels summed over CTAs since the
- * previous call (synchronises the device). */
-int acg_debug_phase_times(unsigned long long* out8);
-int acg_debug_umma_shift(const void* a_rows, int n_rows, const void* b_rows, int N, int shift, int pitch,
-                         int base_offset_mode, float* out, void* stream);
 
 #ifdef __cplusplus
 }

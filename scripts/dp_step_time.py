@@ -18,7 +18,19 @@ dist.init_process_group("nccl", device_id=dev)
 dist.barrier()
 torch.cuda.synchronize()
 os.dup2(saved, 1)
+from action_conditioned_gans_b200 import engine as E
+from action_conditioned_gans_b200 import kernels as K
 from action_conditioned_gans_b200.trainer import DataParallel, Trainer
+
+# timing-only switches live HERE (monkeypatches), not in the product: results are wrong with them
+SKIP = set(filter(None, os.environ.get("ACG_DP_SKIP", "").split(",")))
+if "grad" in SKIP:
+    Trainer._sync_grads = lambda self, store: None
+if "bn" in SKIP:
+    def _local_moments(self, st, beta):
+        L = st.spec
+        K.bn_finalize(st.stats, beta, st.rows, L.cout, 1, st.mean, st.rstd, st.scale, st.shift, E.BN_EPS)
+    E.NetRun._sync_moments = _local_moments
 
 B = 256
 dp = DataParallel(device=dev)

@@ -1,0 +1,104 @@
+"""One launch of each conv-kernel variant of the bench step (B=256) for `ncu --set full`:
+
+    python scripts/ncu_kernels.py [batch] [names...]                   (plain run first, must exit 0)
+    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/r2_kernels \
+        python scripts/ncu_kernels.py
+
+Every case is launched twice (the first launch pays one-time attribute setup and warms L2 for the weights); the order of
+the launches is printed so that the ncu launch ids can be mapped back to layers.
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from action_conditioned_gans_b200 import engine as E  # noqa: E402
+from action_conditioned_gans_b200 import kernels as K  # noqa: E402
+
+CASES = [   # (label, layer, role)  role: f = forward, d = data gradient, w = weight gradient
+    ("halo_persistent N=128  g/tconv3 fwd", "g/tconv3", "f"),
+    ("halo_persistent N=48   g/tconv4 fwd", "g/tconv4", "f"),
+    ("conv_tc<CONV,3>        g/tconv4 dgrad", "g/tconv4", "d"),
+    ("conv_tc<CONV,3>        g/tconv3 dgrad", "g/tconv3", "d"),
+    ("conv_tc<CONV,3>        d/conv2 fwd", "d/conv2", "f"),
+    ("conv_tc<CONV,6>        g/conv3 fwd", "g/conv3", "f"),
+    ("conv_tc<CONV,6> splitK d/conv5 fwd", "d/conv5", "f"),
+    ("conv_tc<ADJ,6>         g/tconv1 fwd", "g/tconv1", "f"),
+    ("conv_tc<ADJ,*>         d/conv3 dgrad", "d/conv3", "d"),
+    ("smallk_persistent<64>  d/conv1 fwd", "d/conv1", "f"),
+    ("wgrad                  g/tconv3 wgrad", "g/tconv3", "w"),
+    ("wgrad                  g/tconv4 wgrad", "g/tconv4", "w"),
+    ("wgrad                  d/conv1 wgrad", "d/conv1", "w"),
+]
+
+
+def main():
+    args = sys.argv[1:]
+    B = int(args[0]) if args and args[0].isdigit() else 256
+    only = [a for a in args if not a.isdigit()]
+    dev = torch.device("cuda:0")
+    runs = {}
+    for spec, tag in ((E.g_dna_spec(6), "g"), (E.d_spec(), "d")):
+        store = E.ParamStore(spec, dev)
+        store.flat.normal_(0, 0.05)
+        run = E.GeneratorRun(store, B, dev, True, 6) if tag == "g" else E.DiscriminatorRun(store, B, dev)
+        store.refresh_packs()
+        runs[tag] = (store, run)
+    torch.cuda.synchronize()
+    n = 0
+    for label, lname, role in CASES:
+        if only and not any(o in label for o in only):
+            continue
+        store, run = runs[lname[0]]
+        st = run.layers[lname]
+        L, s = st.spec, st.shape
+        x = torch.randn(B, st.in_hw[0], st.in_hw[1], st.ld_in, device=dev).to(torch.bfloat16)
+        fp32_out = lname == "g/tconv4"
+        ldz = 36 if fp32_out else st.ldz
+        z = torch.empty(B, st.out_hw[0], st.out_hw[1], ldz, device=dev, dtype=torch.float32 if fp32_out else torch.bfloat16)
+        dz = torch.randn(B, st.out_hw[0], st.out_hw[1], st.ldz, device=dev).to(torch.bfloat16)
+        dx = torch.empty(B, st.in_hw[0], st.in_hw[1], st.ld_in, device=dev, dtype=torch.bfloat16)
+        dw = store.gviews[lname + "/weights"]
+        pk = store.packs[lname]
+        stats = st.stats if L.bn else None
+        for rep in range(2):
+            if rep == 1:
+                torch.cuda.cudart().cudaProfilerStart()     # ncu --profile-from-start off: only the second launch
+            if role == "f":
+                fn = K.conv_fprop_tc if L.kind == "conv" else K.conv_dgrad_tc
+                fn(s, x, pk[3], z, st.ld_in, ldz, stats=stats, splitk=st.splitk_f)
+            elif role == "d":
+                fn = K.conv_dgrad_tc if L.kind == "conv" else K.conv_fprop_tc
+                fn(s, dz, pk[6], dx, st.ldz, st.ld_in, splitk=st.splitk_b)
+            elif L.kind == "conv":
+                K.conv_wgrad_tc(s, x, dz, dw, st.ld_in, st.ldz)
+            else:
+                K.conv_wgrad_tc(s, dz, x, dw, st.ldz, st.ld_in)
+            torch.cuda.synchronize()
+            if rep == 1:
+                torch.cuda.cudart().cudaProfilerStop()
+                print("profiled launch %2d: %s" % (n, label), flush=True)
+                n += 1
+        del x, z, dz, dx
+    # DNA at the two bench sizes
+    for (b, k) in ((256, 6), (64, 5)):
+        lg = torch.randn(b, 64, 64, k * k, device=dev)
+        im = torch.rand(b, 64, 64, 3, device=dev) * 2 - 1
+        dy = torch.randn(b, 64, 64, 3, device=dev)
+        o = torch.empty(b, 64, 64, 3, device=dev)
+        dl = torch.empty(b, 64, 64, k * k, device=dev)
+        for rep in range(2):
+            if rep == 1:
+                torch.cuda.cudart().cudaProfilerStart()
+            K.dna_fwd(lg, im, o, k)
+            K.dna_bwd(lg, im, dy, dl, k)
+            torch.cuda.synchronize()
+            if rep == 1:
+                torch.cuda.cudart().cudaProfilerStop()
+                print("profiled launches %2d, %2d: dna fwd / bwd B=%d K=%d" % (n, n + 1, b, k), flush=True)
+                n += 2
+
+
+if __name__ == "__main__":
+    main()

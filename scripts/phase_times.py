@@ -1,7 +1,9 @@
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from action_conditioned_gans_b200 import engine as E, kernels as K, _lib
+from action_conditioned_gans_b200 import _lib
+_lib.use_probe_library()
+from action_conditioned_gans_b200 import engine as E, kernels as K
 dev = torch.device("cuda:0"); B = 256
 buf = (ctypes.c_ulonglong * 8)()
 def phases(tag, fn):

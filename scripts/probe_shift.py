@@ -2,6 +2,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from action_conditioned_gans_b200 import _lib
+_lib.use_probe_library()
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 R, N = 200, 64
