@@ -11,7 +11,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libacg_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, U8 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 LOSS_BCE, LOSS_WASS = 0, 1
 ACT_IDS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "lrelu": ACT_LRELU, "tanh": ACT_TANH}
@@ -75,6 +75,8 @@ SIGNATURES = {
     "acg_state_loss": [_P, _P, _I, _F, _F, _P, _P, _P, _P, _P],
     "acg_adam_step": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _P, _P],
     "acg_rmsprop_step": [_P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P, _P],
+    "acg_gather_frames": [_P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "acg_rollout_actions": [_P, _I, _I, _P, _P, _I, _I, _I, _P],
     "acg_peer_alloc": [_L, C.POINTER(C.c_void_p)],
     "acg_peer_free": [_P],
     "acg_peer_export": [_P, _P],

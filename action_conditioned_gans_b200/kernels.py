@@ -193,6 +193,32 @@ def tile_actions(actions, B, hw, dst, ld_dst, off):
     call("acg_tile_actions", ptr(actions), B, hw, A, ptr(dst), dtype_id(dst), ld_dst, off, stream())
 
 
+# ---- device-side feeder / rollout glue ---------------------------------------------------------------
+def gather_frames(frames, actions, sample, t0, img, nxt, act, next_state, pair_stride=1, geometry=None):
+    """frames [N,T,H,W,3] uint8 or fp32, actions [N,T,A] or None; sample / t0 int32 [B] (all on the device).
+    geometry = (N, T) overrides the leading dimensions (host-staged [2,B,...] batches: N=1, T=2B, pair_stride=B)."""
+    N, T = geometry if geometry is not None else (frames.shape[0], frames.shape[1])
+    fe = img[0].numel()
+    B = sample.numel()
+    if frames.dtype == torch.uint8:
+        fdt = _lib.U8
+    elif frames.dtype == torch.float32:
+        fdt = _lib.F32
+    else:
+        raise RuntimeError("frames must be uint8 or float32")
+    if sample.dtype != torch.int32 or t0.dtype != torch.int32:
+        raise RuntimeError("sample / t0 must be int32")
+    A = actions.shape[-1] if actions is not None else 0
+    S = next_state.shape[1] if next_state is not None else 0
+    call("acg_gather_frames", ptr(frames), fdt, ptr(actions), ptr(sample), ptr(t0), N, T, pair_stride, fe, max(A, 1),
+         S if actions is not None else 0, B, ptr(img), ptr(nxt), ptr(act), ptr(next_state), stream())
+
+
+def rollout_actions(acts, j, state, out, S=5):
+    B, T, A = acts.shape
+    call("acg_rollout_actions", ptr(acts), T, j, ptr(state), ptr(out), B, A, S, stream())
+
+
 # ---- losses -------------------------------------------------------------------------------------
 def frame_losses(g, n, sums, dg=None, w_l1=0.0, w_gdl=0.0, dadv=None, ld_adv=0, adv_off=0):
     B, H, W, _ = g.shape

@@ -5,6 +5,8 @@ Same constructor flags and methods as the reference (`Trainer(sess, arg_adv, arg
 session -- each method enqueues one device step).  Repairs R1-R6 of SURVEY.md section 0 are applied; the D step
 is update-THEN-clip (the reference leaves the order of train.py:140,143 unspecified).
 """
+import contextlib
+import functools
 import math
 
 import numpy as np
@@ -21,6 +23,20 @@ import os as _os
 
 # run train_d's optimizer part on a side stream under the next call's generator forward (ACG_OVERLAP_D_UPDATE=0: inline)
 OVERLAP_D_UPDATE = _os.environ.get("ACG_OVERLAP_D_UPDATE", "1") != "0"
+
+# replay train_g's generator forward on a second stream under the discriminator backward of the preceding train_d
+OVERLAP_G_FWD = _os.environ.get("ACG_OVERLAP_G_FWD", "1") != "0"
+
+
+def _on_device(fn):
+    """Every kernel is launched on torch's CURRENT stream of the CURRENT device: make the trainer's device current for
+    the duration of the call, so that Trainer(device='cuda:1') works without a global torch.cuda.set_device."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapped
+
 
 SUMMARY_KEYS = ["discriminator_direct_loss", "discriminator_gen_loss", "discriminator_loss", "g_loss",
                 "g_l2_loss", "g_adv_loss", "g_psnr"]
@@ -110,12 +126,19 @@ class Trainer:
         self.in_state = torch.zeros(self.B, E.STATE_DIM, device=dev)
         self._copy_stream = None
         self._staging = None
+        self._staging_u8 = None
+        self._u8_pair = None
+        self._arange = None
+        self._idx_ring = None
         self._frames_host = None
         self._pending_fetch = None
         # the discriminator update (gradient all-reduce, optimizer, weight packs) of train_d runs on its own stream so
         # that the generator forward of the following train_g overlaps it; everything that reads D weights waits
         self._d_update_stream = None
         self._d_update_done = None
+        self._g_stream = None           # train_g's generator forward under the preceding discriminator backward
+        self._d_fwd_done = None
+        self._rollout_bufs = {}
         self._graphs, self._calls, self._graph_launches = {}, {}, {}
         self.replayed_launches = 0      # kernels launched through graph replays (acg_launch_count sees eager ones)
 
@@ -124,16 +147,24 @@ class Trainer:
 
         Host feeds go through a COPY STREAM into one of two device staging sets, so the host->device transfer of this
         call overlaps the device work of the previous call (train_d's graph is still running when train_g's feeds
-        arrive); the compute stream then only does a device->device copy into the static buffers."""
+        arrive); the compute stream then only does a device->device copy into the static buffers.  uint8 frames
+        (what a decoded dataset holds) are shipped as uint8 -- a quarter of the bytes -- and scaled to [-1,1]
+        (ops.py:195) by acg_gather_frames on the device."""
         if self._pending_fetch is not None:
             torch.cuda.current_stream().wait_event(self._pending_fetch)
             self._pending_fetch = None
+        u8 = img.dtype == torch.uint8
+        if u8 != (nxt.dtype == torch.uint8):
+            raise ValueError("input_images and next_frame must have the same dtype (both uint8 or both float)")
         feeds = [(self.in_img, img), (self.in_next, nxt), (self.in_act, act)]
         if st is not None:
             feeds.append((self.in_state, st))
         else:
             self.in_state.zero_()
         if all(t.is_cuda for _, t in feeds):
+            if u8:
+                self._decode_u8(img.reshape(self.B, -1), nxt.reshape(self.B, -1))
+                feeds = feeds[2:]
             for dst, t in feeds:
                 dst.copy_(t.reshape(dst.shape), non_blocking=True)
             return
@@ -144,6 +175,9 @@ class Trainer:
                              for _ in range(2)]
             self._staging_free = [torch.cuda.Event(), torch.cuda.Event()]
             self._staging_idx = 0
+        if u8 and self._staging_u8 is None:
+            fe = E.IMG * E.IMG * 3
+            self._staging_u8 = [torch.empty(2, self.B, fe, dtype=torch.uint8, device=self.device) for _ in range(2)]
         k = self._staging_idx
         self._staging_idx ^= 1
         main, cs = torch.cuda.current_stream(), self._copy_stream
@@ -151,12 +185,57 @@ class Trainer:
         ready = torch.cuda.Event()
         with torch.cuda.stream(cs):
             for i, (dst, t) in enumerate(feeds):
-                self._staging[k][i].copy_(t.reshape(dst.shape), non_blocking=True)
+                if u8 and i < 2:
+                    self._staging_u8[k][i].copy_(t.reshape(self.B, -1), non_blocking=True)
+                else:
+                    self._staging[k][i].copy_(t.reshape(dst.shape), non_blocking=True)
             ready.record(cs)
         main.wait_event(ready)
         for i, (dst, t) in enumerate(feeds):
+            if u8 and i < 2:
+                continue
             dst.copy_(self._staging[k][i], non_blocking=True)
+        if u8:
+            self._decode_u8(self._staging_u8[k])
         self._staging_free[k].record(main)
+
+    def _decode_u8(self, a, b=None):
+        """uint8 frames -> the fp32 static feeds.  a: [2,B,F] (img | next) or a, b: [B,F] each."""
+        if b is not None:
+            if self._u8_pair is None:
+                self._u8_pair = torch.empty(2, self.B, a.shape[1], dtype=torch.uint8, device=self.device)
+            self._u8_pair[0].copy_(a, non_blocking=True)
+            self._u8_pair[1].copy_(b, non_blocking=True)
+            a = self._u8_pair
+        if self._arange is None:
+            self._arange = torch.arange(self.B, dtype=torch.int32, device=self.device)
+            self._zeros_i = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        K.gather_frames(a, None, self._zeros_i, self._arange, self.in_img, self.in_next, None, None,
+                        pair_stride=self.B, geometry=(1, 2 * self.B))
+
+    def _stage_indexed(self, feeder, sample, t0, with_state):
+        """Device-side feeder: the sequences are resident in HBM; a step ships 2 x B int32 indices and
+        one gather kernel writes all four static feeds (frame pair, action++state, next state)."""
+        if self._pending_fetch is not None:
+            torch.cuda.current_stream().wait_event(self._pending_fetch)
+            self._pending_fetch = None
+        if self._idx_ring is None:
+            self._idx_ring = [(torch.empty(2, self.B, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+                              for _ in range(8)]
+            self._idx_dev = torch.empty(2, self.B, dtype=torch.int32, device=self.device)
+            self._idx_k = 0
+        host, ev = self._idx_ring[self._idx_k]
+        self._idx_k = (self._idx_k + 1) % len(self._idx_ring)
+        ev.synchronize()                               # the copy that last used this pinned slot has completed
+        feeder.check(sample, t0, self.B)
+        host[0].copy_(torch.as_tensor(sample, dtype=torch.int32))
+        host[1].copy_(torch.as_tensor(t0, dtype=torch.int32))
+        self._idx_dev.copy_(host, non_blocking=True)
+        ev.record(torch.cuda.current_stream())
+        K.gather_frames(feeder.frames, feeder.actions, self._idx_dev[0], self._idx_dev[1], self.in_img, self.in_next,
+                        self.in_act, self.in_state)
+        if not with_state:
+            self.in_state.zero_()                      # train_d feeds zeros (train.py:137)
 
     def synchronize(self):
         """Block the host until every enqueued step (including a discriminator update on its side stream) is done."""
@@ -196,8 +275,11 @@ class Trainer:
     def _as_tensor(a):
         """numpy / torch (host or device) -> float32 torch tensor, no device copy yet"""
         if isinstance(a, torch.Tensor):
-            return a if a.dtype == torch.float32 else a.float()
-        return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float32)))
+            return a if a.dtype in (torch.float32, torch.uint8) else a.float()
+        a = np.asarray(a)
+        if a.dtype != np.uint8:
+            a = a.astype(np.float32, copy=False)
+        return torch.from_numpy(np.ascontiguousarray(a))
 
     def _dev(self, a, shape):
         return self._as_tensor(a).to(self.device, non_blocking=True).reshape(shape).contiguous()
@@ -287,9 +369,16 @@ class Trainer:
         self.enqueue_pretrain_g(img, nxt, act, st)
         return self._scalars()["g_loss"]
 
-    def enqueue_pretrain_g(self, img, nxt, act, st):
+    def pretrain_g_indexed(self, feeder, sample, t0):
+        """pretrain_g on frame pairs gathered on the device from a resident dataset (feeder.DeviceFeeder)."""
+        self.enqueue_pretrain_g(stager=lambda: self._stage_indexed(feeder, sample, t0, True))
+        return self._scalars()["g_loss"]
+
+    @_on_device
+    def enqueue_pretrain_g(self, img=None, nxt=None, act=None, st=None, stager=None):
         self._wait_d_update()
-        self._stage(img, nxt, act, st)
+        self._join_g_stream()
+        (stager or (lambda: self._stage(img, nxt, act, st)))()
         self.g_pretrain_opt.tick()
         self._run("pretrain_g", self._body_pretrain_g)
 
@@ -313,12 +402,32 @@ class Trainer:
         done.synchronize()          # only the device->host copy of the frames; the backward pass keeps running
         return self._frames_host[self._frames_idx].numpy()
 
-    def enqueue_train_g(self, img, nxt, act, st, fetch=False):
-        """The step is two captured graphs: (a) generator forward, (b) everything else.  With fetch=True the frames
-        leave for the host on the copy stream as soon as (a) is done, overlapping (b)."""
-        self._stage(img, nxt, act, st)
-        self.g_opt.tick()
-        self._run("train_g_a", self._body_train_g_a)
+    def train_g_indexed(self, feeder, sample, t0):
+        done = self.enqueue_train_g(fetch=True, stager=lambda: self._stage_indexed(feeder, sample, t0, True))
+        done.synchronize()
+        return self._frames_host[self._frames_idx].numpy()
+
+    @_on_device
+    def enqueue_train_g(self, img=None, nxt=None, act=None, st=None, fetch=False, stager=None):
+        """The step is two captured graphs: (a) generator forward, (b) everything else.  (a) reads nothing the
+        discriminator backward of a preceding train_d writes, so it is replayed on a second stream as soon as that
+        train_d's FORWARD graph is done and overlaps the discriminator backward (most kernels of either chain leave
+        SMs idle).  With fetch=True the frames leave for the host on the copy stream as soon as (a) is done,
+        overlapping (b)."""
+        main = torch.cuda.current_stream()
+        gs = self._g_stream_for_overlap()
+        if gs is not None and self._d_fwd_done is not None:
+            gs.wait_event(self._d_fwd_done)            # feeds + generator buffers are free; D backward still runs
+            self._d_fwd_done = None
+            ctx = torch.cuda.stream(gs)
+        else:
+            gs, ctx = None, contextlib.nullcontext()
+        with ctx:
+            (stager or (lambda: self._stage(img, nxt, act, st)))()
+            self.g_opt.tick()
+            self._run("train_g_a", self._body_train_g_a)
+            fwd_done = torch.cuda.Event()
+            fwd_done.record(torch.cuda.current_stream())
         done = None
         if fetch:
             if self._frames_host is None:
@@ -328,18 +437,31 @@ class Trainer:
                 if self._copy_stream is None:
                     self._copy_stream = torch.cuda.Stream(device=self.device)
             self._frames_idx = (self._frames_idx + 1) % 4
-            main, cs = torch.cuda.current_stream(), self._copy_stream
-            fwd_done = torch.cuda.Event()
-            fwd_done.record(main)
+            cs = self._copy_stream
             cs.wait_event(fwd_done)
             done = torch.cuda.Event()
             with torch.cuda.stream(cs):
                 self._frames_host[self._frames_idx].copy_(self.g_run.g_out, non_blocking=True)
                 done.record(cs)
             self._pending_fetch = done     # the NEXT step's forward overwrites g_out: it waits for this copy
+        if gs is not None:
+            main.wait_event(fwd_done)
         self._wait_d_update()              # D(generated) reads the discriminator weights / packs
         self._run("train_g_b", self._body_train_g_b)
         return done
+
+    def _g_stream_for_overlap(self):
+        nccl_bn = self.dp is not None and not self.dp.peer_sync    # NCCL batch-norm: one communicator, one stream
+        if not self.use_graphs or not OVERLAP_G_FWD or nccl_bn:
+            return None
+        if self._g_stream is None:
+            self._g_stream = torch.cuda.Stream(device=self.device)
+        return self._g_stream
+
+    def _join_g_stream(self):
+        """Steps other than train_g that follow a train_d: nothing is pending on the generator stream, but the marker of
+        the train_d forward must not leak into a later train_g."""
+        self._d_fwd_done = None
 
     def _body_train_g_a(self):
         self.g_store.grad.zero_()
@@ -359,25 +481,35 @@ class Trainer:
     def train_d(self, input_images, next_frame, actions, summarize=False):
         img, nxt, act, st = self._feed(input_images, next_frame, actions, None)
         self.enqueue_train_d(img, nxt, act, need_state=summarize)
-        if summarize:
-            # merged_summaries also holds the generator scalars (train.py:112,140)
-            self._g_losses(self.in_next, self.in_state, want_grad=False, with_adv_grad=False)
-            self._have = {"g", "d"}
-            return self.summaries()
-        return None
+        return self._d_summaries(summarize)
 
-    def enqueue_train_d(self, img, nxt, act, need_state=False):
+    def train_d_indexed(self, feeder, sample, t0, summarize=False):
+        self.enqueue_train_d(need_state=summarize, stager=lambda: self._stage_indexed(feeder, sample, t0, False))
+        return self._d_summaries(summarize)
+
+    def _d_summaries(self, summarize):
+        if not summarize:
+            return None
+        # merged_summaries also holds the generator scalars (train.py:112,140)
+        self._join_g_stream()
+        self._g_losses(self.in_next, self.in_state, want_grad=False, with_adv_grad=False)
+        self._have = {"g", "d"}
+        return self.summaries()
+
+    @_on_device
+    def enqueue_train_d(self, img=None, nxt=None, act=None, need_state=False, stager=None):
         """need_state: also run the generator's state head (only the summaries of train.py:140 read it).
-        Two graphs: (main) forward + backward of D on both pairs, (update) gradient all-reduce + optimizer + clip +
-        weight packs.  The update is replayed on a side stream: the next train_g's generator forward does not read D
-        weights and overlaps it (with data parallelism that hides the 19 MB gradient all-reduce)."""
+        Three graphs: (fwd) D(real), G, D(generated) forward + the logit losses, (bwd) the two discriminator backward
+        passes, (update) gradient all-reduce + optimizer + clip + weight packs.  The update is replayed on a side
+        stream: the next train_g's generator forward does not read D weights and overlaps it (with data parallelism
+        that hides the 19 MB gradient all-reduce); that generator forward itself may start right after (fwd)."""
         self._wait_d_update()
-        self._stage(img, nxt, act, None)
+        (stager or (lambda: self._stage(img, nxt, act, None)))()
         self.d_opt.tick()
-        if need_state:
-            self._run("train_d_state", lambda: self._body_train_d(True))
-        else:
-            self._run("train_d", lambda: self._body_train_d(False))
+        self._run("train_d_fwd_state" if need_state else "train_d_fwd", lambda: self._body_train_d_fwd(need_state))
+        self._d_fwd_done = torch.cuda.Event()
+        self._d_fwd_done.record(torch.cuda.current_stream())
+        self._run("train_d_bwd", self._body_train_d_bwd)
         nccl_bn = self.dp is not None and not self.dp.peer_sync    # batch-norm all-reduces share the communicator
         if not self.use_graphs or not OVERLAP_D_UPDATE or nccl_bn:
             self._run("train_d_update", self._body_train_d_update)
@@ -392,7 +524,7 @@ class Trainer:
                 self._d_update_done.record(side)
         self._have = {"d"}
 
-    def _body_train_d(self, need_state=False):
+    def _body_train_d_fwd(self, need_state=False):
         img, nxt, act = self.in_img, self.in_next, self.in_act
         self.d_store.grad.zero_()
         with self.real_branch:
@@ -407,6 +539,8 @@ class Trainer:
         else:                                                        # ops.py:43-45
             K.dlogit_loss(self.d_real.logits, self.d_real.n_logits, "wass", 1.0, gs, self.sc[1:2], self.d_real.dlogits)
             K.dlogit_loss(self.d_gen.logits, self.d_gen.n_logits, "wass", -1.0, gs, self.sc[2:3], self.d_gen.dlogits)
+
+    def _body_train_d_bwd(self):
         with self.real_branch:
             self.d_real.backward(need_dw=True, need_dinput=False)
         self.d_gen.backward(need_dw=True, need_dinput=False)
@@ -423,8 +557,10 @@ class Trainer:
         state = g_state.cpu().numpy() if g_state is not None else None
         return g_out.cpu().numpy(), state, self.summaries()
 
+    @_on_device
     def enqueue_test(self, img, nxt, act, st):
         self._wait_d_update()
+        self._join_g_stream()
         self._stage(img, nxt, act, st)
         self._run("test", self._body_test)
         self._have = {"g", "d"}
@@ -445,26 +581,54 @@ class Trainer:
             K.dlogit_loss(self.d_real.logits, self.d_real.n_logits, "wass", 1.0, 1.0, self.sc[1:2], None)
             K.dlogit_loss(self.d_gen.logits, self.d_gen.n_logits, "wass", -1.0, 1.0, self.sc[2:3], None)
 
-    # ---- train.py:157-176 -------------------------------------------------------------------------------
+    # ---- train.py:157-176, :286-299 ----------------------------------------------------------------------
     def test_sequence(self, input_images, test_next_frame, test_actions):
-        """6-step recursive rollout; frames and the predicted state stay on the device between steps
-        (the reference round-trips host<->device every step)."""
+        """train.py:157-176: 6 recursive steps with action index 2j; returns (predicted [B,6,64,64,3],
+        current_frame[1:7]).  The reference runs Trainer.test per step and throws its summaries away; here the rollout
+        is ONE captured graph of generator-only forwards (rollout())."""
+        pred = self.rollout(np.asarray(input_images)[:, 0], test_actions, steps=6, action_stride=2)
+        out = pred.permute(1, 0, 2, 3, 4).contiguous().cpu().numpy()
+        return out, pred[5][1:7].cpu().numpy()
+
+    @_on_device
+    def rollout(self, first_frame, actions, steps, action_stride=1):
+        """Recursive prediction: frame_{j+1} = G(frame_j, [actions[:, j*stride, :5] | state_j]) with the
+        generated frame AND the predicted state fed back on the device; state_0 = actions[:, 0, 5:].  The direct-pixel
+        generator predicts no state and keeps the fed one (repair R5).  One CUDA graph per (steps, stride, T): per step
+        one tiny kernel builds the action vector, the generator writes straight into predicted[j].
+        Returns the device tensor predicted [steps, B, 64, 64, 3]."""
         B = self.B
-        seq = self._dev(input_images, (B, -1, E.IMG, E.IMG, 3))
-        nxt = self._dev(test_next_frame, (B, -1, E.IMG, E.IMG, 3))
-        acts = self._dev(test_actions, (B, -1, E.ACTION_DIM))
-        predicted = torch.empty(6, B, E.IMG, E.IMG, 3, device=self.device)
-        current_frame = seq[:, 0].contiguous()
-        current_state = acts[:, 0, 5:].contiguous()
-        for j in range(6):
-            acs = torch.cat((acts[:, j * 2, :5], current_state), dim=1).contiguous()   # train.py:163
-            g_out, g_state = self.enqueue_test(current_frame, nxt[:, j * 2].contiguous(), acs, self.zero_state)
-            predicted[j].copy_(g_out)
-            current_frame = predicted[j]
-            if g_state is not None:                    # R5: the direct generator keeps the fed state
-                current_state = g_state.clone()
-        pred = predicted.permute(1, 0, 2, 3, 4).contiguous().cpu().numpy()
-        return pred, current_frame[1:7].cpu().numpy()
+        acts = self._dev(actions, (B, -1, E.ACTION_DIM))
+        T = acts.shape[1]
+        if (steps - 1) * action_stride >= T:
+            raise ValueError("rollout: %d steps with action stride %d need more than %d action frames"
+                             % (steps, action_stride, T))
+        self._wait_d_update()
+        self._join_g_stream()
+        if self._pending_fetch is not None:
+            torch.cuda.current_stream().wait_event(self._pending_fetch)
+            self._pending_fetch = None
+        key = ("rollout", steps, action_stride, T)
+        if key not in self._rollout_bufs:
+            self._rollout_bufs[key] = (torch.empty(B, T, E.ACTION_DIM, device=self.device),
+                                       torch.empty(steps, B, E.IMG, E.IMG, 3, device=self.device))
+        ro_acts, predicted = self._rollout_bufs[key]
+        ro_acts.copy_(acts, non_blocking=True)
+        f0 = self._as_tensor(first_frame)
+        if f0.dtype == torch.uint8:
+            f0 = f0.float() / 127.5 - 1.0
+        self.in_img.copy_(f0.reshape(self.in_img.shape), non_blocking=True)
+
+        def body():
+            frame = self.in_img
+            for j in range(steps):
+                state = self.g_run.state if (j > 0 and self.arg_transform) else None
+                K.rollout_actions(ro_acts, j * action_stride, state, self.in_act, E.STATE_DIM)
+                self.g_run.forward(frame, self.in_act, out=predicted[j])
+                frame = predicted[j]
+
+        self._run(key, body)
+        return predicted
 
     # ---- checkpoints (replaces tf.train.Saver, train.py:215,274 / test.py:29-30) -------------------------------
     def state_dict(self):

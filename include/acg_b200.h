@@ -34,6 +34,7 @@ extern "C" {
 /* element types of activation / logit buffers */
 #define ACG_F32 0
 #define ACG_BF16 1
+#define ACG_U8 2   /* acg_gather_frames only: frames stored as uint8, decoded to x/127.5 - 1 (ops.py:195) */
 
 /* activations (ops.py:22-26 lrelu; tf.nn.relu / tf.tanh at models.py:10,20,31,80) */
 #define ACG_ACT_NONE 0
@@ -283,6 +284,24 @@ int acg_peer_allreduce_f64(double* vec, int n, int cap, long long slot_off, int 
                            void* const* host_mailboxes, unsigned long long* epoch, float timeout_s, int bn_C,
                            const float* beta, long long bn_rows, float eps, float* mean, float* rstd, float* scale,
                            float* shift, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Device-side feeder and rollout glue.
+ * acg_gather_frames replaces the host gather of the training loop: util.py:10-16 (one-hot frame masks) applied at
+ * train.py:231-237,249-263 and the [-1,1] scaling of ops.py:195.  frames [N,T,frame_elems] uint8 (decoded as
+ * x/127.5-1) or fp32, actions [N,T,A] fp32 stay resident in device memory; sample[B], t0[B] (int32, device) pick
+ * sequence and frame index of every batch element:
+ *   img[b] = frames[sample[b], t0[b]], next[b] = frames[sample[b], t0[b]+p], act[b] = actions[sample[b], t0[b]],
+ *   next_state[b] = actions[sample[b], t0[b]+p, A-S:A]   (p = pair_stride, 1 for consecutive frames; next_state may
+ *   be NULL; actions NULL = frames only).  The same kernel decodes a host-staged uint8 batch laid out [2,B,...]
+ *   (N=1, T=2B, sample=0, t0=b, p=B).
+ * acg_rollout_actions: out[b] = [acts[b, j, 0:A-S] | state[b]] (train.py:163,290); state NULL = acts[b, 0, A-S:A].
+ * ------------------------------------------------------------------------------------------ */
+int acg_gather_frames(const void* frames, int frames_dtype, const float* actions, const int* sample, const int* t0,
+                      int N, int T, int pair_stride, int frame_elems, int A, int S, int B, float* img, float* next,
+                      float* act, float* next_state, void* stream);
+int acg_rollout_actions(const float* acts, int T, int j, const float* state, float* out, int B, int A, int S,
+                        void* stream);
 
 #ifdef __cplusplus
 }
