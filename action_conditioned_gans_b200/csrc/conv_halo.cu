@@ -1,0 +1,496 @@
+// Persistent halo-tile tcgen05 kernel for the stride-2 layers with 16- or 32-pixel-wide tile grids, in BOTH gather forms:
+//
+//   ADJ  (conv2d_transpose forward, conv2d data gradient; models.py:17-21,39-40,53-59 and TF autodiff of :12-15,34-37,
+//         82-86): every tap of an output-parity class is a pure 2-D shift of the small-grid input,
+//             out_class[b][y][x] = sum_{ta,tc,k} in[b][y + ea - ta][x + ec - tc][k] * W[class][n][(ta,tc)][k].
+//   CONV (conv2d forward, conv2d_transpose data gradient): the input is split into its 4 parity PLANES
+//         x_p[b][i][j] = x[b][2i+pi][2j+pj]; tap (a,c) of a stride-2 filter reads plane ((a-pad_t)&1, (c-pad_l)&1) at the
+//         shift (floor((a-pad_t)/2), floor((c-pad_l)/2)), so every tap is again a pure 2-D shift of a dense tile:
+//             y[b][oh][ow] = sum_{planes} sum_{taps of plane,k} x_p[b][oh+di][ow+dj][k] * W[n][(a,c)][k].
+//         A plane is addressed by a plain 4-D tensor map with doubled pixel strides and a shifted base pointer.
+//
+// One CTA per SM walks a tile list.  A tile is `NACC` accumulators of 128 pixels (8 columns x 16 rows each) = 16 rows x
+// TW columns of TB images.  Per 64-channel block (and, CONV form, per plane) the (16+2) x (TW+2) halo patch is ONE 4-D TMA
+// copy (hardware zero fill = SAME padding, hardware 128-byte swizzle); each tap's A operand is a shifted descriptor into
+// it, every streamed weight slice feeds NACC accumulators.  Roles (384 threads):
+//   warp 5 halo TMA producer | warp 6 weight-slice TMA producer | warp 4 tcgen05.mma issuer (+ TMEM owner)
+//   warps 0-3 and 8-11: two epilogue groups (accumulators q even / odd), tcgen05.ld -> bias / moments -> global stores
+// The accumulators are double buffered in tensor memory (2 x NACC x N <= 512 columns: NACC = 4 for N <= 64, NACC = 2 for
+// N <= 128), so copies, MMAs and epilogue of consecutive tiles overlap.
+//
+// Round-2 measurements that shaped this version (scripts/probe_r2.py, stage knock-out on B200):
+//   * the round-1 kernel issued its MMAs from `warp == 4 && lane == 0`: the compiler wrapped every UTCHMMA in a
+//     uniformisation loop and the issue thread needed ~95-105 clk per MMA for ANY N (g/tconv4 forward: MMA phase alone
+//     133 us of 143 us; math at N=48 is 24 clk).  Here a whole warp walks the loop and elect.sync picks the issuing lane.
+//   * with N = 128 there was one accumulator set: MMA (43 us) and epilogue (40 us) of g/tconv3 forward ran back to back.
+//   * 4 epilogue warps with one synchronous TMEM load per 16 columns took 83 us for g/tconv4's 151 MB of logits: now 8
+//     warps, TMEM loads issued in batches of up to 64 columns before one wait.
+#include "conv_tc.cuh"
+
+namespace acg {
+namespace tc {
+
+constexpr int kH2Threads = 384;
+constexpr int kH2Rows = 18;                         // staged halo rows per image: 16 output rows + 2
+constexpr int kH2Region = 4 * 41 * 1024;            // halo ring: 2 x (18 x 34 | 2 x 18 x 18) or 4 x (18 x 18) rows of 128 B
+constexpr int kH2BStage = BN * BK * 2;
+constexpr int kH2BStages = 3;
+constexpr int kH2Smem = kH2Region + kH2BStages * kH2BStage + 1024;
+constexpr int kMaxTaps = 9;
+constexpr int kEpiBatch = 3;                        // 16-column TMEM loads in flight per wait (48 columns = g/tconv4's N)
+
+struct TapProg {
+    int ntaps;
+    int oy, ox;                   // halo origin relative to the tile origin (rows, columns of the staged grid)
+    short shift_y[kMaxTaps], shift_x[kMaxTaps];   // tap -> row / column shift inside the halo patch
+    short wtap[kMaxTaps];         // tap -> tap index inside the weight pack ([N][tap][lda])
+};
+
+struct alignas(64) Halo2Params {
+    Params p;
+    CUtensorMap map_a[4];         // ADJ: [0];  CONV: one per input parity plane
+    CUtensorMap map_b[4];         // ADJ: one per output parity class;  CONV: [0]
+    TapProg prog[4];              // ADJ: per class;  CONV: per plane
+    int form;                     // 0 ADJ, 1 CONV
+    int Hs, Ws;                   // tile grid: ADJ class grid (= conv output grid), CONV output grid
+    int TW, TB;                   // tile width (16 | 32) and images per tile
+    int nkc, nk16_last;           // 64-channel blocks; K=16 steps of the last block (lda % 64 != 0 -> fewer MMAs)
+    int out_H, out_W;             // spatial size of the output tensor
+};
+
+struct H2Tile {
+    int b0, y0, x0, pg0, npg, cls;
+};
+__device__ __forceinline__ H2Tile h2_tile(const Halo2Params& hp, int t) {
+    H2Tile h;
+    int sp = t;
+    if (hp.form == 0) {
+        // the 4 parity classes of one spatial tile are adjacent in the list (they read the same input halo: neighbouring
+        // CTAs find it in L2) and the class is rotated by the wave index so that every CTA gets 9-, 6- and 4-tap tiles
+        sp = t >> 2;
+        h.cls = ((t & 3) + t / (int)gridDim.x) & 3;
+        h.pg0 = h.cls;
+        h.npg = 1;
+    } else {
+        h.cls = 0;
+        h.pg0 = 0;
+        h.npg = 4;
+    }
+    const int tiles_x = hp.Ws / hp.TW, tiles_y = hp.Hs >> 4;
+    const int per_img = tiles_x * tiles_y;
+    const int bi = sp / per_img, r = sp - bi * per_img;
+    h.b0 = bi * hp.TB;
+    h.y0 = (r / tiles_x) << 4;
+    h.x0 = (r % tiles_x) * hp.TW;
+    return h;
+}
+
+template <int NACC>
+__global__ void __launch_bounds__(kH2Threads, 1)
+conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
+    const Params& p = hp.p;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t halo_full[4], halo_empty[4], b_full[kH2BStages], b_empty[kH2BStages];
+    __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ float sm_stats[2][BN];
+    __shared__ int last_cta_sh;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smemH = smem_base, smemB = smem_base + kH2Region;
+    if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
+
+    const int N = p.N;
+    const int XG = hp.TW >> 3;                               // 8-column accumulator groups per tile row
+    const int WH = hp.TW + 2, HR = kH2Rows * WH;             // halo: 18 rows x (TW+2) pixels per image
+    const uint32_t halo_bytes = (uint32_t)(hp.TB * HR) * 128u;
+    const uint32_t halo_stride = (halo_bytes + 1023u) & ~1023u;        // buffers start on swizzle-atom boundaries
+    const int NH = halo_stride * 4u <= (uint32_t)kH2Region ? 4 : 2;     // halo ring depth
+    const int NB = (2 * NACC * N <= 512) ? 2 : 1;            // accumulator buffers in tensor memory
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(NB * NACC * N)) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
+        for (int i = 0; i < kH2BStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        fence_mbar_init();
+        for (int c = 0; c < 4; ++c) { tma_prefetch_desc(&hp.map_a[c]); tma_prefetch_desc(&hp.map_b[c]); }
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // PDL: dependents may be scheduled now that this CTA owns its tensor memory; nothing above touched global memory
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp == 5) {
+        // ================================ halo producer (whole warp walks, one elected lane issues) ================
+        int hcount = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const H2Tile h = h2_tile(hp, t);
+            for (int kc = 0; kc < hp.nkc; ++kc) {
+                for (int pg = h.pg0; pg < h.pg0 + h.npg; ++pg, ++hcount) {
+                    const int buf = hcount % NH, use = hcount / NH;
+                    if (use >= 1) mbar_wait(&halo_empty[buf], (uint32_t)((use - 1) & 1));
+                    if (elect_one()) {
+                        if (ACG_DBG(p, 1)) {
+                            mbar_arrive(&halo_full[buf]);                          // probe: no halo traffic
+                        } else {
+                            mbar_expect_tx(&halo_full[buf], halo_bytes);
+                            tma_load_4d(smemH + buf * halo_stride, &hp.map_a[hp.form ? pg : 0], kc * 64,
+                                        h.x0 + hp.prog[pg].ox, h.y0 + hp.prog[pg].oy, h.b0, &halo_full[buf]);
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ================================ weight producer ================================
+        const uint32_t b_bytes = (uint32_t)N * 128u;
+        int bcount = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const H2Tile h = h2_tile(hp, t);
+            for (int kc = 0; kc < hp.nkc; ++kc) {
+                for (int pg = h.pg0; pg < h.pg0 + h.npg; ++pg) {
+                    const TapProg& pr = hp.prog[pg];
+                    for (int tap = 0; tap < pr.ntaps; ++tap, ++bcount) {
+                        const int st = bcount % kH2BStages, use = bcount / kH2BStages;
+                        if (use >= 1) mbar_wait(&b_empty[st], (uint32_t)((use - 1) & 1));
+                        if (elect_one()) {
+                            if (ACG_DBG(p, 2)) {
+                                mbar_arrive(&b_full[st]);                          // probe: no weight traffic
+                            } else {
+                                mbar_expect_tx(&b_full[st], b_bytes);
+                                tma_load_2d(smemB + st * kH2BStage, &hp.map_b[hp.form ? 0 : pg],
+                                            (int)pr.wtap[tap] * p.lda + kc * 64, 0, &b_full[st]);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else if (warp == 4) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc = make_idesc(N, 0, 0);
+        const uint32_t ahi = desc_hi((uint32_t)WH * 128u), bhi = desc_hi(1024);
+        const uint32_t blo0 = desc_lo(smemB, 16);
+        uint32_t acc_row8[NACC];               // first halo row of accumulator q, in 16-byte units (8 per row)
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) {
+            const int tb = q / XG, xg = q - tb * XG;
+            acc_row8[q] = (uint32_t)(tb * HR + xg * 8) * 8u;
+        }
+        int hcount = 0, bcount = 0, tcount = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
+            const H2Tile h = h2_tile(hp, t);
+            const int abuf = tcount % NB, ause = tcount / NB;
+            if (ause >= 1) {      // the epilogue has drained this accumulator buffer
+                mbar_wait(&acc_empty[abuf], (uint32_t)((ause - 1) & 1));
+                tc_fence_after();
+            }
+            const uint32_t tacc = tmem_base + (uint32_t)(abuf * NACC * N);
+            uint32_t first = 0u;               // 0 until the first MMA of the tile has been issued
+            for (int kc = 0; kc < hp.nkc; ++kc) {
+                const int nk = kc == hp.nkc - 1 ? hp.nk16_last : BK / 16;
+                for (int pg = h.pg0; pg < h.pg0 + h.npg; ++pg, ++hcount) {
+                    const TapProg& pr = hp.prog[pg];
+                    const int buf = hcount % NH;
+                    mbar_wait(&halo_full[buf], (uint32_t)((hcount / NH) & 1));
+                    const uint32_t alo_h = desc_lo(smemH + buf * halo_stride, 16);
+                    for (int tap = 0; tap < pr.ntaps; ++tap, ++bcount) {
+                        const int st = bcount % kH2BStages;
+                        mbar_wait(&b_full[st], (uint32_t)((bcount / kH2BStages) & 1));
+                        tc_fence_after();
+                        const uint32_t blo = blo0 + st * (kH2BStage >> 4);
+                        const uint32_t alo_t = alo_h + (uint32_t)((int)pr.shift_y[tap] * WH + (int)pr.shift_x[tap]) * 8u;
+                        if (elect_one()) {
+                            if (!ACG_DBG(p, 4)) {                                  // probe: no MMAs
+                                // K step outer, accumulator inner: consecutive MMAs write different accumulators
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k) {
+                                    if (k < nk) {
+#pragma unroll
+                                        for (int q = 0; q < NACC; ++q)
+                                            tc_mma2(tacc + q * N, alo_t + acc_row8[q] + 2 * k, ahi, blo + 2 * k, bhi, idesc,
+                                                    first | (uint32_t)k);
+                                    }
+                                }
+                            }
+                            tc_commit(&b_empty[st]);
+                        }
+                        __syncwarp();
+                        first = 1u;
+                    }
+                    if (elect_one()) tc_commit(&halo_empty[buf]);
+                    __syncwarp();
+                }
+            }
+            if (elect_one()) tc_commit(&acc_full[abuf]);
+            __syncwarp();
+        }
+    } else if (warp < 4 || warp >= 8) {
+        // ================================ epilogue: two groups of 4 warps ================================
+        // warp w may read TMEM lanes 32*(w&3) .. +31; group 0 = warps 0-3 takes accumulators 0, 2, group 1 = warps 8-11
+        // takes 1, 3
+        const int grp = warp >> 3, wq = warp & 3;
+        const int ml = wq * 32 + lane, yy = ml >> 3, xi = ml & 7;
+        int tcount = 0;
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
+            const H2Tile h = h2_tile(hp, t);
+            const int abuf = tcount % NB, ause = tcount / NB;
+            mbar_wait(&acc_full[abuf], (uint32_t)(ause & 1));
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(abuf * NACC * N);
+            for (int q = grp; q < NACC && !ACG_DBG(p, 32); q += 2) {                  // probe bit 32: no epilogue work
+                const int tb = q / XG, xg = q - tb * XG;
+                int oy = h.y0 + yy, ox = h.x0 + xg * 8 + xi;
+                if (hp.form == 0) { oy = (oy << 1) + (h.cls >> 1); ox = (ox << 1) + (h.cls & 1); }
+                const size_t row_off = ((size_t)((h.b0 + tb) * hp.out_H + oy) * hp.out_W + ox) * p.ldo;
+                for (int cb0 = 0; cb0 < N; cb0 += 16 * kEpiBatch) {
+                    uint32_t v[kEpiBatch][16];
+#pragma unroll
+                    for (int i = 0; i < kEpiBatch; ++i)
+                        if (cb0 + 16 * i < N) tmem_ld16_nowait(tacc + q * N + cb0 + 16 * i, v[i]);
+                    tmem_ld_wait();
+                    if (ACG_DBG(p, 16)) continue;                                     // probe bit 16: loads only
+#pragma unroll
+                    for (int i = 0; i < kEpiBatch; ++i)
+                        if (cb0 + 16 * i < N)
+                            epilogue_chunk(p, v[i], cb0 + 16 * i, true, row_off, 0u, lane, &sm_stats[0][cb0 + 16 * i],
+                                           &sm_stats[1][cb0 + 16 * i]);
+                }
+            }
+            // this accumulator buffer may be overwritten by the MMAs of the tile after next
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[abuf]);
+            if (p.stats) {   // per-tile flush of the fp32 column sums into the fp64 accumulators (epilogue warps only)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (tid < N && tid < p.n_stat) {
+                    atomicAdd(&p.stats[tid], (double)sm_stats[0][tid]);
+                    atomicAdd(&p.stats[p.n_stat + tid], (double)sm_stats[1][tid]);
+                }
+                if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+    if (p.stats && p.counter) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last_cta_sh = (atomicAdd(p.counter, 1u) == p.total_ctas - 1u);
+        __syncthreads();
+        if (last_cta_sh) {
+            __threadfence();
+            const double inv = 1.0 / (double)p.bn_rows;
+            for (int c = tid; c < p.n_bias; c += kH2Threads) {
+                const double mu = __ldcg(&p.stats[c]) * inv;
+                double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
+                if (var < 0.0) var = 0.0;
+                const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+                const float b = p.beta ? p.beta[c] : 0.f;
+                p.bn_mean[c] = (float)mu;
+                p.bn_rstd[c] = rs;
+                p.bn_scale[c] = rs;
+                p.bn_shift[c] = b - (float)mu * rs;
+            }
+            if (tid == 0) *p.counter = 0u;
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+namespace {
+
+int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+               const cuuint32_t* box, const char* who) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    ACG_REQUIRE(enc, ACG_ERR_CUDA, "%s: cuTensorMapEncodeTiled is not available", who);
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    ACG_REQUIRE(r == CUDA_SUCCESS, ACG_ERR_CUDA, "%s: tensor map failed (%d)", who, (int)r);
+    return ACG_OK;
+}
+
+// tile shape for a grid of Hs x Ws pixels and N output columns; false when the kernel does not cover the shape
+bool pick_tile(int B, int Hs, int Ws, int N, int* nacc, int* TW, int* TB) {
+    if (Hs % 16 != 0 || (Ws != 16 && Ws != 32) || N > BN || N % 16 != 0) return false;
+    if (N > 64) { *nacc = 2; *TW = 16; *TB = 1; return true; }              // 2 x 2 x N <= 512 TMEM columns
+    *nacc = 4;
+    *TW = Ws;
+    *TB = Ws == 32 ? 1 : 2;
+    return B % *TB == 0;
+}
+
+}  // namespace
+
+// shape gates (also used by the dispatchers in conv_tc.cu)
+bool halo2_adj_ok(const acg_conv_shape* s, const acg_tc_args* t, int N) {
+    if (getenv("ACG_NO_HALO")) return false;
+    if (s->stride != 2 || s->KH > 6 || s->KW > 6 || s->KH < 2 || s->KW < 2) return false;
+    if (s->OH != s->H / 2 || s->OW != s->W / 2 || (s->H & 1) || (s->W & 1)) return false;
+    if (t->ld_in % 64 != 0) return false;
+    int nacc, TW, TB;
+    return pick_tile(s->B, s->OH, s->OW, N, &nacc, &TW, &TB);
+}
+bool halo2_conv_ok(const acg_conv_shape* s, const acg_tc_args* t, int N) {
+    if (getenv("ACG_NO_HALO") || getenv("ACG_NO_HALO_CONV")) return false;
+    if (s->stride != 2 || s->KH > 6 || s->KW > 6 || s->KH < 2 || s->KW < 2) return false;
+    if (s->OH != s->H / 2 || s->OW != s->W / 2 || (s->H & 1) || (s->W & 1)) return false;
+    if (t->ld_in % 16 != 0 || t->ld_in < 16) return false;
+    if (t->ld_in > 64 && t->ld_in % 64 != 0) return false;
+    // every plane's taps must fit the 3 x 3 window of the staged halo
+    for (int ax = 0; ax < 2; ++ax) {
+        const int K = ax ? s->KW : s->KH, pad = ax ? s->pad_l : s->pad_t;
+        for (int par = 0; par < 2; ++par) {
+            int dmin = 1 << 20, dmax = -(1 << 20);
+            for (int a = 0; a < K; ++a) {
+                const int r = a - pad, pi = ((r % 2) + 2) % 2, d = (r - pi) / 2;
+                if (pi != par) continue;
+                dmin = d < dmin ? d : dmin;
+                dmax = d > dmax ? d : dmax;
+            }
+            if (dmax >= dmin && dmax - dmin > 2) return false;
+        }
+    }
+    int nacc, TW, TB;
+    return pick_tile(s->B, s->OH, s->OW, N, &nacc, &TW, &TB);
+}
+
+// form 0: dx / deconv output [B,H,W,N] from dy [B,OH,OW,lda] (ADJ);  form 1: y [B,OH,OW,N] from x [B,H,W,lda] (CONV)
+int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const Params& p_in, const void* src,
+                 const void* w_pack, int N, cudaStream_t stream, const char* who) {
+    Halo2Params hp;
+    memset(&hp, 0, sizeof(hp));
+    hp.p = p_in;
+    hp.form = form;
+    hp.Hs = s->OH;
+    hp.Ws = s->OW;
+    int nacc = 4;
+    if (!pick_tile(s->B, s->OH, s->OW, N, &nacc, &hp.TW, &hp.TB)) {
+        set_error("%s: shape not covered by the halo kernel", who);
+        return ACG_ERR_UNSUPPORTED;
+    }
+    const int lda = t->ld_in;
+    hp.nkc = (lda + 63) / 64;
+    hp.nk16_last = ((lda - (hp.nkc - 1) * 64) + 15) / 16;
+    hp.out_H = form == 0 ? s->H : s->OH;
+    hp.out_W = form == 0 ? s->W : s->OW;
+    const cuuint32_t box_a[4] = {64, (cuuint32_t)(hp.TW + 2), (cuuint32_t)kH2Rows, (cuuint32_t)hp.TB};
+    int rc;
+    if (form == 0) {
+        const cuuint64_t dims[4] = {(cuuint64_t)lda, (cuuint64_t)s->OW, (cuuint64_t)s->OH, (cuuint64_t)s->B};
+        const cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)s->OW * lda * 2, (cuuint64_t)s->OH * s->OW * lda * 2};
+        rc = encode_map(&hp.map_a[0], src, 4, dims, strides, box_a, who);
+        if (rc) return rc;
+        for (int c = 1; c < 4; ++c) hp.map_a[c] = hp.map_a[0];
+        for (int cls = 0; cls < 4; ++cls) {
+            const int ph = cls >> 1, pw = cls & 1;
+            const int a0 = (ph + s->pad_t) & 1, c0 = (pw + s->pad_l) & 1;
+            const int na = (s->KH - a0 + 1) >> 1, nc = (s->KW - c0 + 1) >> 1;
+            const int ea = (ph + s->pad_t - a0) >> 1, ec = (pw + s->pad_l - c0) >> 1;
+            TapProg& pr = hp.prog[cls];
+            pr.ntaps = na * nc;
+            ACG_REQUIRE(pr.ntaps <= kMaxTaps && na <= 3 && nc <= 3, ACG_ERR_UNSUPPORTED, "%s: %d x %d class taps", who, na, nc);
+            pr.oy = ea - (na - 1);
+            pr.ox = ec - (nc - 1);
+            for (int ta = 0; ta < na; ++ta)
+                for (int tcx = 0; tcx < nc; ++tcx) {
+                    const int i = ta * nc + tcx;
+                    pr.shift_y[i] = (short)(na - 1 - ta);
+                    pr.shift_x[i] = (short)(nc - 1 - tcx);
+                    pr.wtap[i] = (short)i;
+                }
+            const cuuint64_t Kc = (cuuint64_t)pr.ntaps * lda;
+            const cuuint64_t wd[2] = {Kc, (cuuint64_t)N};
+            const cuuint64_t ws[1] = {Kc * 2};
+            const cuuint32_t wb[2] = {64, (cuuint32_t)N};
+            const void* base = static_cast<const __nv_bfloat16*>(w_pack) + p_in.w_class_off[cls];
+            rc = encode_map(&hp.map_b[cls], base, 2, wd, ws, wb, who);
+            if (rc) return rc;
+        }
+    } else {
+        const int Hp = s->H / 2, Wp = s->W / 2;
+        for (int pl = 0; pl < 4; ++pl) {
+            const int pi = pl >> 1, pj = pl & 1;
+            TapProg& pr = hp.prog[pl];
+            int dmin_i = 1 << 20, dmin_j = 1 << 20;
+            for (int a = 0; a < s->KH; ++a) {
+                const int r = a - s->pad_t, q = ((r % 2) + 2) % 2;
+                if (q == pi && (r - q) / 2 < dmin_i) dmin_i = (r - q) / 2;
+            }
+            for (int c = 0; c < s->KW; ++c) {
+                const int r = c - s->pad_l, q = ((r % 2) + 2) % 2;
+                if (q == pj && (r - q) / 2 < dmin_j) dmin_j = (r - q) / 2;
+            }
+            int n = 0;
+            for (int a = 0; a < s->KH; ++a) {
+                const int ra = a - s->pad_t, qa = ((ra % 2) + 2) % 2;
+                if (qa != pi) continue;
+                for (int c = 0; c < s->KW; ++c) {
+                    const int rc2 = c - s->pad_l, qc = ((rc2 % 2) + 2) % 2;
+                    if (qc != pj) continue;
+                    ACG_REQUIRE(n < kMaxTaps, ACG_ERR_UNSUPPORTED, "%s: more than %d taps per plane", who, kMaxTaps);
+                    pr.shift_y[n] = (short)((ra - qa) / 2 - dmin_i);
+                    pr.shift_x[n] = (short)((rc2 - qc) / 2 - dmin_j);
+                    pr.wtap[n] = (short)(a * s->KW + c);
+                    ++n;
+                }
+            }
+            pr.ntaps = n;
+            pr.oy = n ? dmin_i : 0;
+            pr.ox = n ? dmin_j : 0;
+            // plane (pi, pj) of x [B,H,W,lda]: x_p[b][i][j][k] = x[b][2i+pi][2j+pj][k]
+            const cuuint64_t dims[4] = {(cuuint64_t)lda, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)s->B};
+            const cuuint64_t strides[3] = {(cuuint64_t)2 * lda * 2, (cuuint64_t)2 * s->W * lda * 2,
+                                           (cuuint64_t)s->H * s->W * lda * 2};
+            const void* base = static_cast<const __nv_bfloat16*>(src) + ((size_t)pi * s->W + pj) * lda;
+            rc = encode_map(&hp.map_a[pl], base, 4, dims, strides, box_a, who);
+            if (rc) return rc;
+        }
+        const cuuint64_t Kt = (cuuint64_t)s->KH * s->KW * lda;
+        const cuuint64_t wd[2] = {Kt, (cuuint64_t)N};
+        const cuuint64_t ws[1] = {Kt * 2};
+        const cuuint32_t wb[2] = {64, (cuuint32_t)N};
+        rc = encode_map(&hp.map_b[0], w_pack, 2, wd, ws, wb, who);
+        if (rc) return rc;
+        for (int c = 1; c < 4; ++c) hp.map_b[c] = hp.map_b[0];
+    }
+    const int n_sp = (s->B / hp.TB) * (s->OH / 16) * (s->OW / hp.TW);
+    const int ntiles = form == 0 ? n_sp * 4 : n_sp;
+    const int ctas = ntiles < num_sms() ? ntiles : num_sms();
+    rc = fill_bn(&hp.p, t, (unsigned int)ctas, who);
+    if (rc) return rc;
+    ACG_REQUIRE(!hp.p.rz, ACG_ERR_UNSUPPORTED, "%s: the fused backward reduction is not available in the halo kernel", who);
+    if (nacc == 2) {
+        rc = set_smem((const void*)conv_halo2_kernel<2>, kH2Smem);
+        if (rc) return rc;
+        launch_pdl(conv_halo2_kernel<2>, ctas, kH2Threads, kH2Smem, stream, hp, ntiles);
+    } else {
+        rc = set_smem((const void*)conv_halo2_kernel<4>, kH2Smem);
+        if (rc) return rc;
+        launch_pdl(conv_halo2_kernel<4>, ctas, kH2Threads, kH2Smem, stream, hp, ntiles);
+    }
+    return check_launch(who);
+}
+
+}  // namespace tc
+}  // namespace acg

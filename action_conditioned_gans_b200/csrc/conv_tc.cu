@@ -17,326 +17,20 @@
 //   epilogue   tcgen05.ld 32 lanes x 16 columns per warp -> (+bias, tanh) -> bf16 / fp32 NHWC rows.
 // Two CTAs are resident per SM (3 stages x 32 KB, 128 TMEM columns each) so one CTA's epilogue overlaps the
 // other's main loop.
-#include <cuda.h>
-#include <stdlib.h>
-
 #include <mutex>
 #include <utility>
 #include <vector>
 
-#include "common.cuh"
+#include "conv_tc.cuh"
 
 namespace acg {
 namespace tc {
 
-constexpr int BM = 128, BK = 64, BN = 128, STAGES = 3;
-constexpr int kProducers = 128, kThreads = 160, kThreads6 = 288;
-constexpr int kStageA = BM * BK * 2, kStageB = BN * BK * 2;
-constexpr int kSmemBytes = STAGES * (kStageA + kStageB) + 1024;  // + alignment slack
-constexpr int kSmemBytes6 = 6 * (kStageA + kStageB) + 1024;
-
-struct Params {
-    const __nv_bfloat16* a_src;
-    const __nv_bfloat16* w_pack;
-    void* out;
-    const float* bias;
-    int B, H, W, OH, OW, KH, KW, stride, pad_t, pad_l;
-    int lda;         // channel stride of a_src == channels per tap in the packed K dimension (multiple of 8)
-    int ldo;         // channel stride of the output rows (>= N)
-    int N;           // GEMM N of this launch (multiple of 16)
-    int n_bias;      // bias entries (real output channels)
-    int n_store;     // output channels written per row: min(N, ldo)
-    int out_dtype, out_act;
-    long long w_class_off[4];   // ADJ: element offset of each parity class' [N][Kc] matrix inside w_pack
-    // fused batch-norm moments of THIS layer's output (optional)
-    double* stats;              // [2][n_bias] fp64 (sum | sum of squares), accumulated with atomics
-    unsigned int* counter;      // when non-NULL the last CTA to finish also finalises mean/rstd/scale/shift
-    unsigned int total_ctas;    // CTAs that reach the epilogue (smaller parity classes exit early)
-    const float* beta;
-    float* bn_mean; float* bn_rstd; float* bn_scale; float* bn_shift;
-    long long bn_rows;
-    float bn_eps;
-    // fused batch-norm BACKWARD reduction (optional; then `stats` is the consumer layer's `red` buffer): this launch
-    // computes dA = d loss / d activation of a layer with pre-activation rz [rows][rz_ld] (bf16), and the epilogue adds
-    // sum_r dzh and sum_r dzh*xhat (dzh = dA*act'(rz*rstd + shift), xhat = (rz - mean)*rstd) of its tile to stats[2][n_stat]
-    const __nv_bfloat16* rz;
-    int rz_ld, r_act;
-    const float* r_mean; const float* r_rstd; const float* r_shift;
-    int n_stat;                 // columns of stats (== n_bias for forward moments, the consumer's C for the reduction)
-    // split-K (generic kernel, launches with far fewer tiles than SMs: 4x4 / 2x2 feature maps, K up to 6400): grid.z
-    // carries `splits` K ranges of kb_per_split K blocks per tile; every CTA parks its fp32 accumulator tile in `ws`
-    // ([tile][split][16-column chunk][128 rows][16]) and takes a ticket; the LAST CTA of a tile adds the other
-    // partial tiles to its own accumulator and runs the normal epilogue (bias, moments, store).  No CTA ever waits.
-    int splits, kb_per_split;
-    float* ws;
-    unsigned int* tickets;
-    int dbg_skip;               // probe library only (-DACG_PROBES, env ACG_DBG_SKIP): see ACG_DBG below
-};
-// Profiling probes (per-phase timing, pipelines with one stage switched off) exist only in libacg_b200_probe.so, which
-// scripts/ load explicitly; in the product library ACG_DBG() is a compile-time false and the code below it vanishes.
-//   1: no halo TMA   2: no weight TMA   4: no MMAs   8: per-phase %globaltimer stamps   16: epilogue loads TMEM only
-//   32: no epilogue work
-#ifdef ACG_PROBES
-#define ACG_DBG(p, bit) (((p).dbg_skip & (bit)) != 0)
-#else
-#define ACG_DBG(p, bit) false
-#endif
-
-// Column sums of a 32-lane x 16-column register tile: after the butterfly lane L holds the total of column L>>1.
-__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
-    float w[8], x[4], y[2], z;
-    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float send = h16 ? v[i] : v[i + 8];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-        w[i] = (h16 ? v[i + 8] : v[i]) + recv;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float send = h8 ? w[i] : w[i + 4];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-        x[i] = (h8 ? w[i + 4] : w[i]) + recv;
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const float send = h4 ? x[i] : x[i + 2];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-        y[i] = (h4 ? x[i + 2] : x[i]) + recv;
-    }
-    {
-        const float send = h2 ? y[0] : y[1];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-        z = (h2 ? y[1] : y[0]) + recv;
-    }
-    z += __shfl_xor_sync(0xffffffffu, z, 1);
-    return z;
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// Same instruction with the two shared-memory descriptors passed as (lo, hi) 32-bit halves.  Only the low word
-// (start address >> 4 | LBO << 16) changes from MMA to MMA; the issuing thread adds a constant to it instead of
-// rebuilding a 64-bit descriptor with shifts and masks (the single issuing thread is latency bound: ~40 dependent
-// instructions per MMA made descriptor arithmetic, not the tensor pipe, the limiter of the first version).
-__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
-                                        uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
-        ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// descriptor halves for 128-byte swizzle: lo = start>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version 1 | SWIZZLE_128B
-__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
-    return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
-}
-__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
-    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// shared-memory matrix descriptor with 128-byte swizzle (atoms of 8 rows x 128 B = 1024 B, 1024 B aligned).
-//   K-major : a row is 64 consecutive K elements of one M/N index; SBO = stride between 8-row (M/N) groups;
-//             LBO is unused.
-//   MN-major: a row is 64 consecutive M/N elements of one K index; SBO = stride between 8-row (K) groups;
-//             LBO = stride between 64-element M/N atoms.
-__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset
-    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;  // stride byte offset
-    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
-    return d;
-}
-__device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t smem_addr) { return sw128_desc(smem_addr, 16, 1024); }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N runtime
-__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
-           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
-
-__device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// One 32-row x 16-column accumulator chunk: (+bias) (tanh) -> moments -> store.  All mode tests are kernel-uniform
-// and sit OUTSIDE the unrolled element loops so that they compile to branches, not to predicated instruction bloat
-// (a first version that tested bias / tanh per element spent ~800 issue slots per chunk on predicated-off code).
-__device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&v)[16], int ncol, bool row_ok,
-                                               size_t row_off, uint32_t z_smem, int lane, float* sm_sum, float* sm_sq) {
-    float f[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-    if (p.bias) {
-        if (ncol + 16 <= p.n_bias) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + ncol);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 b = b4[i];
-                f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (ncol + i < p.n_bias) f[i] += p.bias[ncol + i];
-        }
-    }
-    if (p.out_act == ACG_ACT_TANH) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = tanh_fast(f[i]);
-    }
-    const bool bf16_out = p.out_dtype == ACG_BF16;
-    uint32_t w[8];
-    if (bf16_out) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-            w[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
-    }
-    if (p.stats && ncol < p.n_stat) {      // n_stat % 16 == 0 in the reduction mode (host check)
-        // batch-norm moments of exactly what is stored (bf16-rounded when the output is bf16)
-        float q[16], q2[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float t = f[i];
-            if (bf16_out) t = __uint_as_float((i & 1) ? (w[i >> 1] & 0xffff0000u) : (w[i >> 1] << 16));
-            t = row_ok ? t : 0.f;
-            q[i] = t;
-        }
-        if (p.rz) {
-            // backward reduction terms of the layer that consumes this gradient (same arithmetic as
-            // vec_col_reduce_kernel<1>): q = dA*act'(u), q2 = q*xhat
-            // z_smem: this row's 16 pre-activations, staged in shared memory by stage_z_row (zero filled for rows
-            // outside the tensor, whose q is zero anyway)
-            float zf[16];
-            {
-                uint32_t zw[8];
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(zw[0]), "=r"(zw[1]), "=r"(zw[2]), "=r"(zw[3]) : "r"(z_smem));
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(zw[4]), "=r"(zw[5]), "=r"(zw[6]), "=r"(zw[7]) : "r"(z_smem + 16u));
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    zf[2 * i] = __uint_as_float(zw[i] << 16);
-                    zf[2 * i + 1] = __uint_as_float(zw[i] & 0xffff0000u);
-                }
-            }
-            const float4* mu4 = reinterpret_cast<const float4*>(p.r_mean + ncol);
-            const float4* rs4 = reinterpret_cast<const float4*>(p.r_rstd + ncol);
-            const float4* sh4 = reinterpret_cast<const float4*>(p.r_shift + ncol);
-            if (p.r_act == ACG_ACT_RELU) {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const float4 mu = mu4[g], rs = rs4[g], sh = sh4[g];
-                    const float m_[4] = {mu.x, mu.y, mu.z, mu.w}, r_[4] = {rs.x, rs.y, rs.z, rs.w},
-                                s_[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = 4 * g + k;
-                        const float u = zf[i] * r_[k] + s_[k];
-                        const float d = u > 0.f ? q[i] : 0.f;
-                        q[i] = d;
-                        q2[i] = d * ((zf[i] - m_[k]) * r_[k]);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const float4 mu = mu4[g], rs = rs4[g], sh = sh4[g];
-                    const float m_[4] = {mu.x, mu.y, mu.z, mu.w}, r_[4] = {rs.x, rs.y, rs.z, rs.w},
-                                s_[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int i = 4 * g + k;
-                        const float u = zf[i] * r_[k] + s_[k];
-                        const float d = q[i] * act_bwd(u, p.r_act);
-                        q[i] = d;
-                        q2[i] = d * ((zf[i] - m_[k]) * r_[k]);
-                    }
-                }
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) q2[i] = q[i] * q[i];
-        }
-        const float cs = warp_colsum16(q, lane), cs2 = warp_colsum16(q2, lane);
-        if ((lane & 1) == 0) {
-            atomicAdd(sm_sum + (lane >> 1), cs);
-            atomicAdd(sm_sq + (lane >> 1), cs2);
-        }
-    }
-    if (!row_ok) return;
-    const bool full = ncol + 16 <= p.n_store;
-    if (bf16_out) {
-        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + row_off + ncol;
-        if (full && (p.ldo & 7) == 0) {
-            reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
-            reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
-        } else {
-            for (int i = 0; i < 16; ++i)
-                if (ncol + i < p.n_store) o[i] = __float2bfloat16_rn(f[i]);
-        }
-    } else {
-        float* o = static_cast<float*>(p.out) + row_off + ncol;
-        if (full && (p.ldo & 3) == 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-        } else {
-            for (int i = 0; i < 16; ++i)
-                if (ncol + i < p.n_store) o[i] = f[i];
-        }
-    }
-}
-
-// Fused backward reduction: the consumer's pre-activation rows of a tile are staged in the (by then idle) pipeline
-// shared memory with cp.async right after the accumulator barrier -- one exposed L2 latency per tile instead of one
-// global-load latency per 16-column chunk; the rows were pulled into L2 by a prefetch at kernel start.
-constexpr int kZRowBytes = BN * 2 + 16;     // +16 B: 16-byte row accesses of a quarter warp hit distinct banks
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-__device__ __forceinline__ void stage_z_row(uint32_t dst, const __nv_bfloat16* src, int ncols, bool ok) {
-    for (int c = 0; c < ncols; c += 8) cp_async16(dst + 2 * c, ok ? (const void*)(src + c) : (const void*)src, ok ? 16u : 0u);
-}
+// persistent halo-tile kernel in both gather forms (conv_halo.cu)
+bool halo2_adj_ok(const acg_conv_shape* s, const acg_tc_args* t, int N);
+bool halo2_conv_ok(const acg_conv_shape* s, const acg_tc_args* t, int N);
+int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const Params& p_in, const void* src,
+                 const void* w_pack, int N, cudaStream_t stream, const char* who);
 
 constexpr int HALO_ACC = 4;
 constexpr int HALO_H = 18;    // staged halo rows per image: 16 output rows + (na-1) <= 2
@@ -347,22 +41,6 @@ struct alignas(64) HaloParams {
     CUtensorMap map_b[4];     // per parity class: bf16 [N][Kc], box {64, N}, 128B swizzle
 };
 
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
-                                            uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
 constexpr int kHaloBuf = 648 * 128;                       // 18 x 34 (one image) or 2 x 18 x 18 rows of 128 B
 constexpr int kHaloBStage = BN * BK * 2;
 constexpr int kHaloBStages = 3;
@@ -550,8 +228,10 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
             ci += BK;
             while (ci >= p.lda) { ci -= p.lda; ++tap; }
         }
-    } else if (warp == PW && lane == 0) {
+    } else if (warp == PW) {
         // ================================ MMA issuer ================================
+        // the whole warp walks the loop, elect.sync picks the issuing lane (see elect_one() in conv_tc.cuh: a plain
+        // `lane == 0` branch costs ~95 clk of uniformisation code per MMA)
         const uint32_t idesc = make_idesc(n_cta, 0, 0);
         const uint32_t hi = desc_hi(1024);
         const uint32_t alo0 = desc_lo(smemA, 16), blo0 = desc_lo(smemB, 16);
@@ -560,12 +240,16 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
             mbar_wait(&full_bar[stage], (uint32_t)((kb / STAGES) & 1));
             tc_fence_after();
             const uint32_t alo = alo0 + stage * (kStageA >> 4), blo = blo0 + stage * (kStageB >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the swizzle atom
-                tc_mma2(tmem_base, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
-            tc_commit(&empty_bar[stage]);   // arrives when the MMAs above have finished reading this stage
+                for (int k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the swizzle atom
+                    tc_mma2(tmem_base, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                tc_commit(&empty_bar[stage]);   // arrives when the MMAs above have finished reading this stage
+            }
+            __syncwarp();
         }
-        tc_commit(&acc_bar);
+        if (elect_one()) tc_commit(&acc_bar);
+        __syncwarp();
     }
 
     // ================================ epilogue (warps 0-3) ================================
@@ -881,8 +565,8 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
                 }
             }
         }
-    } else if (warp == 4 && lane == 0) {
-        // ================================ MMA issuer ================================
+    } else if (warp == 4) {
+        // ================================ MMA issuer (whole warp walks, elect.sync issues) ================================
         const uint32_t idesc = make_idesc(NT, 0, 0);
         const uint32_t hi = desc_hi(1024);
         const uint32_t alo0 = desc_lo(smemA, 16), blo0 = desc_lo(smemB, 16);
@@ -900,12 +584,16 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
                 mbar_wait(&full_bar[stage], (uint32_t)((cnt / kSmallKRing) & 1));
                 tc_fence_after();
                 const uint32_t alo = alo0 + stage * (kStageA >> 4), blo = blo0 + kb * (kStageB >> 4);
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)
-                    tc_mma2(tacc, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                tc_commit(&empty_bar[stage]);
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc_mma2(tacc, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit(&empty_bar[stage]);
+                }
+                __syncwarp();
             }
-            tc_commit(&acc_full[abuf]);
+            if (elect_one()) tc_commit(&acc_full[abuf]);
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -1174,231 +862,6 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
 }
 
 
-// ---- ADJ gather, PERSISTENT halo-tile variant ---------------------------------------------------------------------
-// Same tile, operand staging and MMA schedule as conv_adj_halo_kernel, but one CTA per SM walks a list of tiles and the
-// three phases of a tile (halo + weight copies, MMAs, epilogue) belong to different warps, so they overlap ACROSS tiles:
-//   warp 5 (one lane): halo TMA producer      warp 6 (one lane): weight-slice TMA producer
-//   warp 4 (one lane): tcgen05.mma issuer     warps 0-3: epilogue (tcgen05.ld -> bias/moments -> global stores)
-// The producers run ahead into the next tile as soon as a halo buffer / weight stage has drained, i.e. while the
-// epilogue of the current tile is still storing; with N <= 64 (g/tconv4: 4 accumulators x 48 columns) the accumulators
-// are double buffered in tensor memory as well, so the MMAs of tile i+1 run under the epilogue of tile i.  The
-// non-persistent kernel serialises copy -> MMA -> epilogue within its single CTA per SM (ncu: tensor pipe idle during
-// 33 % epilogue + the halo wait).  Tiles are ordered class-major (9-tap classes first), CTA b takes tiles b, b+grid, ...
-constexpr int kHaloPThreads = 224;
-
-struct HaloTile {
-    int ph, pw, na, nc, ea, ec, ntaps, b0, y0, cls;
-};
-__device__ __forceinline__ HaloTile halo_tile(const Params& p, int t, int n_sp, int tiles_y, int TB) {
-    HaloTile h;
-    // Tile order: the 4 parity classes of one spatial tile are adjacent (they read the same input halo: neighbouring
-    // CTAs find it in L2 -- class-major order re-read the input from DRAM once per class, ncu: 167 MB for a 67 MB
-    // input), and the class is rotated by the wave index so that every CTA gets 9-, 6- and 4-tap tiles in turn.
-    const int sp = t >> 2;
-    h.cls = ((t & 3) + t / (int)gridDim.x) & 3;
-    (void)n_sp;
-    h.ph = h.cls >> 1; h.pw = h.cls & 1;
-    const int a0 = (h.ph + p.pad_t) & 1, c0 = (h.pw + p.pad_l) & 1;
-    h.na = (p.KH - a0 + 1) >> 1; h.nc = (p.KW - c0 + 1) >> 1;
-    h.ea = (h.ph + p.pad_t - a0) >> 1; h.ec = (h.pw + p.pad_l - c0) >> 1;
-    h.ntaps = h.na * h.nc;
-    h.b0 = (sp / tiles_y) * TB; h.y0 = (sp % tiles_y) << 4;
-    return h;
-}
-
-__global__ void __launch_bounds__(kHaloPThreads, 1)
-conv_adj_halo_persistent_kernel(const __grid_constant__ HaloParams hp, int ntiles) {
-    const Params& p = hp.p;
-    extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t halo_full[2], halo_empty[2], b_full[kHaloBStages], b_empty[kHaloBStages];
-    __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
-    __shared__ uint32_t tmem_base_sh;
-    __shared__ float sm_stats[2][BN];
-    __shared__ int last_cta_sh;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t smemH = smem_base, smemB = smem_base + 2 * kHaloBuf;
-    if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
-
-    const int Hs = p.H >> 1, Ws = p.W >> 1;
-    const int XG = Ws >> 3, TB = HALO_ACC / XG;
-    const int WH = Ws + 2, HR = HALO_H * WH;
-    const int tiles_y = Hs >> 4;
-    const int n_sp = (p.B / TB) * tiles_y;                  // tiles per parity class
-    const int N = p.N;
-    const int nkc = p.lda >> 6;
-    const int NB = (2 * HALO_ACC * N <= 512) ? 2 : 1;       // accumulator buffers in tensor memory
-    uint32_t tmem_cols = 32;
-    while (tmem_cols < (uint32_t)(NB * HALO_ACC * N)) tmem_cols <<= 1;
-
-    if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
-        }
-        for (int i = 0; i < kHaloBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        fence_mbar_init();
-        tma_prefetch_desc(&hp.map_a);
-        for (int c = 0; c < 4; ++c) tma_prefetch_desc(&hp.map_b[c]);
-    }
-    if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
-                     "r"(tmem_cols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    // PDL: dependents may be scheduled now that this CTA owns its tensor memory; nothing above touched global memory
-    pdl_launch_dependents();
-    pdl_wait();
-    const uint32_t tmem_base = tmem_base_sh;
-
-    if (warp == 5 && lane == 0) {
-        // ================================ halo producer ================================
-        const uint32_t a_bytes = (uint32_t)(TB * HR) * 128u;
-        int hcount = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const HaloTile h = halo_tile(p, t, n_sp, tiles_y, TB);
-            const int oh0 = h.y0 + h.ea - (h.na - 1), ow0 = h.ec - (h.nc - 1);
-            for (int kc = 0; kc < nkc; ++kc, ++hcount) {
-                const int buf = hcount & 1, use = hcount >> 1;
-                if (use >= 1) mbar_wait(&halo_empty[buf], (uint32_t)((use - 1) & 1));
-                if (ACG_DBG(p, 1)) { mbar_arrive(&halo_full[buf]); continue; }      // probe: no halo traffic
-                mbar_expect_tx(&halo_full[buf], a_bytes);
-                tma_load_4d(smemH + buf * kHaloBuf, &hp.map_a, kc * 64, ow0, oh0, h.b0, &halo_full[buf]);
-            }
-        }
-    } else if (warp == 6 && lane == 0) {
-        // ================================ weight producer ================================
-        const uint32_t b_bytes = (uint32_t)N * 128u;
-        int bcount = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-            const HaloTile h = halo_tile(p, t, n_sp, tiles_y, TB);
-            for (int kc = 0; kc < nkc; ++kc) {
-                for (int tap = 0; tap < h.ntaps; ++tap, ++bcount) {
-                    const int st = bcount % kHaloBStages, use = bcount / kHaloBStages;
-                    if (use >= 1) mbar_wait(&b_empty[st], (uint32_t)((use - 1) & 1));
-                    if (ACG_DBG(p, 2)) { mbar_arrive(&b_full[st]); continue; }      // probe: no weight traffic
-                    mbar_expect_tx(&b_full[st], b_bytes);
-                    tma_load_2d(smemB + st * kHaloBStage, &hp.map_b[h.cls], tap * p.lda + kc * 64, 0, &b_full[st]);
-                }
-            }
-        }
-    } else if (warp == 4 && lane == 0) {
-        // ================================ MMA issuer ================================
-        const uint32_t idesc = make_idesc(N, 0, 0);
-        const uint32_t ahi = desc_hi((uint32_t)WH * 128u), bhi = desc_hi(1024);
-        const uint32_t blo0 = desc_lo(smemB, 16);
-        uint32_t acc_row8[HALO_ACC];
-#pragma unroll
-        for (int q = 0; q < HALO_ACC; ++q) {
-            const int tb = q / XG, xg = q - tb * XG;
-            acc_row8[q] = (uint32_t)(tb * HR + xg * 8) * 8u;
-        }
-        int hcount = 0, bcount = 0, tcount = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
-            const HaloTile h = halo_tile(p, t, n_sp, tiles_y, TB);
-            const int abuf = tcount % NB, ause = tcount / NB;
-            if (ause >= 1) {      // the epilogue has drained this accumulator buffer
-                mbar_wait(&acc_empty[abuf], (uint32_t)((ause - 1) & 1));
-                tc_fence_after();
-            }
-            const uint32_t tacc = tmem_base + (uint32_t)(abuf * HALO_ACC * N);
-            for (int kc = 0; kc < nkc; ++kc, ++hcount) {
-                const int buf = hcount & 1;
-                mbar_wait(&halo_full[buf], (uint32_t)((hcount >> 1) & 1));
-                const uint32_t hbase = smemH + buf * kHaloBuf;
-                for (int tap = 0; tap < h.ntaps; ++tap, ++bcount) {
-                    const int st = bcount % kHaloBStages;
-                    mbar_wait(&b_full[st], (uint32_t)((bcount / kHaloBStages) & 1));
-                    tc_fence_after();
-                    const int ta = tap / h.nc, tcc = tap - ta * h.nc;
-                    const int shift = (h.na - 1 - ta) * WH + (h.nc - 1 - tcc);
-                    const uint32_t blo = blo0 + st * (kHaloBStage >> 4);
-                    const uint32_t alo_t = desc_lo(hbase, 16) + (uint32_t)shift * 8u;
-                    if (!ACG_DBG(p, 4)) {                                             // probe: no MMAs
-#pragma unroll
-                    for (int q = 0; q < HALO_ACC; ++q) {
-                        const uint32_t alo = alo_t + acc_row8[q];
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            tc_mma2(tacc + q * N, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, (kc | tap | k) != 0 ? 1u : 0u);
-                    }
-                    }
-                    tc_commit(&b_empty[st]);
-                }
-                tc_commit(&halo_empty[buf]);
-            }
-            tc_commit(&acc_full[abuf]);
-        }
-    } else if (warp < 4) {
-        // ================================ epilogue ================================
-        const int ml = warp * 32 + lane, yy = ml >> 3, xi = ml & 7;
-        int tcount = 0;
-        for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
-            const HaloTile h = halo_tile(p, t, n_sp, tiles_y, TB);
-            const int abuf = tcount % NB, ause = tcount / NB;
-            mbar_wait(&acc_full[abuf], (uint32_t)(ause & 1));
-            tc_fence_after();
-            const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(abuf * HALO_ACC * N);
-            for (int q = 0; q < HALO_ACC && !ACG_DBG(p, 32); ++q) {                  // probe bit 32: no epilogue work
-                const int tb = q / XG, xg = q - tb * XG;
-                const int ih = ((h.y0 + yy) << 1) + h.ph, iw = ((xg * 8 + xi) << 1) + h.pw;
-                const size_t row_off = ((size_t)((h.b0 + tb) * p.H + ih) * p.W + iw) * p.ldo;
-                for (int cb = 0; cb < N; cb += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(tacc + q * N + cb, v);
-                    if (ACG_DBG(p, 16)) continue;                                    // probe bit 16: loads only
-                    epilogue_chunk(p, v, cb, true, row_off, 0u, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
-                }
-            }
-            // this accumulator buffer may be overwritten by the MMAs of the tile after next
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[abuf]);
-            if (p.stats) {   // per-tile flush of the fp32 column sums into the fp64 accumulators (epilogue warps only)
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (tid < N && tid < p.n_stat) {
-                    atomicAdd(&p.stats[tid], (double)sm_stats[0][tid]);
-                    atomicAdd(&p.stats[p.n_stat + tid], (double)sm_stats[1][tid]);
-                }
-                if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 4) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
-    }
-    if (p.stats && p.counter) {
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) last_cta_sh = (atomicAdd(p.counter, 1u) == p.total_ctas - 1u);
-        __syncthreads();
-        if (last_cta_sh) {
-            __threadfence();
-            const double inv = 1.0 / (double)p.bn_rows;
-            for (int c = tid; c < p.n_bias; c += kHaloPThreads) {
-                const double mu = __ldcg(&p.stats[c]) * inv;
-                double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
-                if (var < 0.0) var = 0.0;
-                const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
-                const float b = p.beta ? p.beta[c] : 0.f;
-                p.bn_mean[c] = (float)mu;
-                p.bn_rstd[c] = rs;
-                p.bn_scale[c] = rs;
-                p.bn_shift[c] = b - (float)mu * rs;
-            }
-            if (tid == 0) *p.counter = 0u;
-        }
-    }
-}
-
 // ---- all packs of a parameter store in ONE launch ---------------------------------------------------------------
 // After every optimizer step ~22 weight tensors x 2 packs have to be refreshed; one launch per pack costs more in
 // launch latency than in work.  The job table and a TILE table live in device memory (built once by the host,
@@ -1453,10 +916,6 @@ void class_taps(const acg_conv_shape* s, int cls, int* na, int* nc) {
     *na = a0 < s->KH ? (s->KH - a0 + s->stride - 1) / s->stride : 0;
     *nc = c0 < s->KW ? (s->KW - c0 + s->stride - 1) / s->stride : 0;
 }
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn encode_tiled_fn() {
     static EncodeTiledFn fn = nullptr;
@@ -1701,7 +1160,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
             cp_async_arrive_noinc(&full_bar[stage]);
         }
         }
-    } else if (lane == 0) {
+    } else {
+        // MMA issuer: the whole warp walks the loop, elect.sync picks the issuing lane
         const uint32_t idesc = make_idesc(n_cta, 1, 1);
         const uint32_t hi = desc_hi(1024);
         const uint32_t alo0 = desc_lo(smemA, BK * 128), blo0 = desc_lo(smemB, BK * 128);
@@ -1710,12 +1170,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
             mbar_wait(&full_bar[stage], (uint32_t)((kb / STAGES) & 1));
             tc_fence_after();
             const uint32_t alo = alo0 + stage * (kStageA >> 4), blo = blo0 + stage * (kStageB >> 4);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)   // 16 pixels = two 8-row groups (2048 B) further down each atom
-                tc_mma2(tmem_base, alo + 128 * k, hi, blo + 128 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
-            tc_commit(&empty_bar[stage]);
+                for (int k = 0; k < BK / 16; ++k)   // 16 pixels = two 8-row groups (2048 B) further down each atom
+                    tc_mma2(tmem_base, alo + 128 * k, hi, blo + 128 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                tc_commit(&empty_bar[stage]);
+            }
+            __syncwarp();
         }
-        tc_commit(&acc_bar);
+        if (elect_one()) tc_commit(&acc_bar);
+        __syncwarp();
     }
 
     if (warp < 4) {
@@ -2113,6 +1577,9 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
             return check_launch("acg_conv_fprop_tc(small K, persistent)");
         }
     }
+    if (N == ru(s->Cout, 16) && !t->red_z && halo2_conv_ok(s, t, N))
+        // stride-2 layers with a 16- or 32-wide output: parity planes staged by TMA, every tap a shifted descriptor
+        return launch_halo2(1, s, t, p, x_bf16, w_pack, N, static_cast<cudaStream_t>(stream), "acg_conv_fprop_tc(halo)");
     grid.z = (unsigned)apply_split(&p, t, plan_fprop(s, t->ld_in));
     ConvParams cp;
     cp.p = p;
@@ -2162,27 +1629,15 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     const int Hp = (s->H + s->stride - 1) / s->stride, Wp = (s->W + s->stride - 1) / s->stride;
     const long long M = (long long)s->B * Hp * Wp;
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, ncls);
+    if (N == Npack && !t->red_z && halo2_adj_ok(s, t, N))
+        // one CTA per SM walks the tile list: copies, MMAs and epilogue of consecutive tiles overlap (conv_halo.cu)
+        return launch_halo2(0, s, t, p, dy_bf16, w_pack, N, static_cast<cudaStream_t>(stream), "acg_conv_dgrad_tc(halo)");
     if (N == Npack && halo_ok(s, t, N)) {
+        // fused backward reduction requested: the one-tile-per-CTA predecessor stages the consumer's pre-activations
         rc = set_smem((const void*)conv_adj_halo_kernel, kHaloSmem);
         if (rc) return rc;
         const int TB = HALO_ACC / (s->W / 16);
         dim3 hgrid((unsigned)((s->B / TB) * (s->H / 32)), 1, 4);
-        static const bool persistent = []() { const char* e = getenv("ACG_HALO_PERSISTENT"); return !e || atoi(e) != 0; }();
-        if (persistent && !t->red_z) {
-            // one CTA per SM walks the tile list: copies, MMAs and epilogue of consecutive tiles overlap
-            rc = set_smem((const void*)conv_adj_halo_persistent_kernel, kHaloSmem);
-            if (rc) return rc;
-            const int ntiles = (int)hgrid.x * 4;
-            const int ctas = ntiles < num_sms() ? ntiles : num_sms();
-            rc = fill_bn(&p, t, (unsigned int)ctas, "acg_conv_dgrad_tc");
-            if (rc) return rc;
-            HaloParams hp;
-            hp.p = p;
-            rc = encode_halo_maps(&hp, s, t, N, TB, dy_bf16, w_pack);
-            if (rc) return rc;
-            launch_pdl(conv_adj_halo_persistent_kernel, ctas, kHaloPThreads, kHaloSmem, static_cast<cudaStream_t>(stream), hp, ntiles);
-            return check_launch("acg_conv_dgrad_tc(halo, persistent)");
-        }
         rc = fill_bn(&p, t, hgrid.x * 4u, "acg_conv_dgrad_tc");
         if (rc) return rc;
         HaloParams hp;

@@ -1,0 +1,368 @@
+// Shared pieces of the tcgen05 / TMEM implicit-GEMM convolution kernels (conv_tc.cu, conv_halo.cu): tile constants,
+// the launch parameter block, PTX wrappers (cp.async, tcgen05.mma / commit / ld, TMA tensor copies, elect.sync),
+// shared-memory matrix descriptors and the common epilogue (bias / tanh / bf16 rounding / batch-norm moments / store).
+#pragma once
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace acg {
+namespace tc {
+
+constexpr int BM = 128, BK = 64, BN = 128, STAGES = 3;
+constexpr int kProducers = 128, kThreads = 160, kThreads6 = 288;
+constexpr int kStageA = BM * BK * 2, kStageB = BN * BK * 2;
+constexpr int kSmemBytes = STAGES * (kStageA + kStageB) + 1024;  // + alignment slack
+constexpr int kSmemBytes6 = 6 * (kStageA + kStageB) + 1024;
+
+struct Params {
+    const __nv_bfloat16* a_src;
+    const __nv_bfloat16* w_pack;
+    void* out;
+    const float* bias;
+    int B, H, W, OH, OW, KH, KW, stride, pad_t, pad_l;
+    int lda;         // channel stride of a_src == channels per tap in the packed K dimension (multiple of 8)
+    int ldo;         // channel stride of the output rows (>= N)
+    int N;           // GEMM N of this launch (multiple of 16)
+    int n_bias;      // bias entries (real output channels)
+    int n_store;     // output channels written per row: min(N, ldo)
+    int out_dtype, out_act;
+    long long w_class_off[4];   // ADJ: element offset of each parity class' [N][Kc] matrix inside w_pack
+    // fused batch-norm moments of THIS layer's output (optional)
+    double* stats;              // [2][n_bias] fp64 (sum | sum of squares), accumulated with atomics
+    unsigned int* counter;      // when non-NULL the last CTA to finish also finalises mean/rstd/scale/shift
+    unsigned int total_ctas;    // CTAs that reach the epilogue (smaller parity classes exit early)
+    const float* beta;
+    float* bn_mean; float* bn_rstd; float* bn_scale; float* bn_shift;
+    long long bn_rows;
+    float bn_eps;
+    // fused batch-norm BACKWARD reduction (optional; then `stats` is the consumer layer's `red` buffer): this launch
+    // computes dA = d loss / d activation of a layer with pre-activation rz [rows][rz_ld] (bf16), and the epilogue adds
+    // sum_r dzh and sum_r dzh*xhat (dzh = dA*act'(rz*rstd + shift), xhat = (rz - mean)*rstd) of its tile to stats[2][n_stat]
+    const __nv_bfloat16* rz;
+    int rz_ld, r_act;
+    const float* r_mean; const float* r_rstd; const float* r_shift;
+    int n_stat;                 // columns of stats (== n_bias for forward moments, the consumer's C for the reduction)
+    // split-K (generic kernel, launches with far fewer tiles than SMs: 4x4 / 2x2 feature maps, K up to 6400): grid.z
+    // carries `splits` K ranges of kb_per_split K blocks per tile; every CTA parks its fp32 accumulator tile in `ws`
+    // ([tile][split][16-column chunk][128 rows][16]) and takes a ticket; the LAST CTA of a tile adds the other
+    // partial tiles to its own accumulator and runs the normal epilogue (bias, moments, store).  No CTA ever waits.
+    int splits, kb_per_split;
+    float* ws;
+    unsigned int* tickets;
+    int dbg_skip;               // probe library only (-DACG_PROBES, env ACG_DBG_SKIP): see ACG_DBG below
+};
+// Profiling probes (per-phase timing, pipelines with one stage switched off) exist only in libacg_b200_probe.so, which
+// scripts/ load explicitly; in the product library ACG_DBG() is a compile-time false and the code below it vanishes.
+//   1: no halo TMA   2: no weight TMA   4: no MMAs   8: per-phase %globaltimer stamps   16: epilogue loads TMEM only
+//   32: no epilogue work
+#ifdef ACG_PROBES
+#define ACG_DBG(p, bit) (((p).dbg_skip & (bit)) != 0)
+#else
+#define ACG_DBG(p, bit) false
+#endif
+
+// Column sums of a 32-lane x 16-column register tile: after the butterfly lane L holds the total of column L>>1.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+    float w[8], x[4], y[2], z;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = h16 ? v[i] : v[i + 8];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+        w[i] = (h16 ? v[i + 8] : v[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h8 ? w[i] : w[i + 4];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+        x[i] = (h8 ? w[i + 4] : w[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h4 ? x[i] : x[i + 2];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        y[i] = (h4 ? x[i + 2] : x[i]) + recv;
+    }
+    {
+        const float send = h2 ? y[0] : y[1];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+        z = (h2 ? y[1] : y[0]) + recv;
+    }
+    z += __shfl_xor_sync(0xffffffffu, z, 1);
+    return z;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// Same instruction with the two shared-memory descriptors passed as (lo, hi) 32-bit halves.  Only the low word
+// (start address >> 4 | LBO << 16) changes from MMA to MMA; the issuing thread adds a constant to it instead of
+// rebuilding a 64-bit descriptor with shifts and masks (the single issuing thread is latency bound: ~40 dependent
+// instructions per MMA made descriptor arithmetic, not the tensor pipe, the limiter of the first version).
+__device__ __forceinline__ void tc_mma2(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                        uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// descriptor halves for 128-byte swizzle: lo = start>>4 | (LBO>>4)<<16 ; hi = SBO>>4 | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor with 128-byte swizzle (atoms of 8 rows x 128 B = 1024 B, 1024 B aligned).
+//   K-major : a row is 64 consecutive K elements of one M/N index; SBO = stride between 8-row (M/N) groups;
+//             LBO is unused.
+//   MN-major: a row is 64 consecutive M/N elements of one K index; SBO = stride between 8-row (K) groups;
+//             LBO = stride between 64-element M/N atoms.
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;  // stride byte offset
+    d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ uint64_t kmajor_sw128_desc(uint32_t smem_addr) { return sw128_desc(smem_addr, 16, 1024); }
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N runtime
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// One 32-row x 16-column accumulator chunk: (+bias) (tanh) -> moments -> store.  All mode tests are kernel-uniform
+// and sit OUTSIDE the unrolled element loops so that they compile to branches, not to predicated instruction bloat
+// (a first version that tested bias / tanh per element spent ~800 issue slots per chunk on predicated-off code).
+__device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&v)[16], int ncol, bool row_ok,
+                                               size_t row_off, uint32_t z_smem, int lane, float* sm_sum, float* sm_sq) {
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+    if (p.bias) {
+        if (ncol + 16 <= p.n_bias) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + ncol);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 b = b4[i];
+                f[4 * i] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (ncol + i < p.n_bias) f[i] += p.bias[ncol + i];
+        }
+    }
+    if (p.out_act == ACG_ACT_TANH) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = tanh_fast(f[i]);
+    }
+    const bool bf16_out = p.out_dtype == ACG_BF16;
+    uint32_t w[8];
+    if (bf16_out) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+    }
+    if (p.stats && ncol < p.n_stat) {      // n_stat % 16 == 0 in the reduction mode (host check)
+        // batch-norm moments of exactly what is stored (bf16-rounded when the output is bf16)
+        float q[16], q2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float t = f[i];
+            if (bf16_out) t = __uint_as_float((i & 1) ? (w[i >> 1] & 0xffff0000u) : (w[i >> 1] << 16));
+            t = row_ok ? t : 0.f;
+            q[i] = t;
+        }
+        if (p.rz) {
+            // backward reduction terms of the layer that consumes this gradient (same arithmetic as
+            // vec_col_reduce_kernel<1>): q = dA*act'(u), q2 = q*xhat
+            // z_smem: this row's 16 pre-activations, staged in shared memory by stage_z_row (zero filled for rows
+            // outside the tensor, whose q is zero anyway)
+            float zf[16];
+            {
+                uint32_t zw[8];
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(zw[0]), "=r"(zw[1]), "=r"(zw[2]), "=r"(zw[3]) : "r"(z_smem));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(zw[4]), "=r"(zw[5]), "=r"(zw[6]), "=r"(zw[7]) : "r"(z_smem + 16u));
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    zf[2 * i] = __uint_as_float(zw[i] << 16);
+                    zf[2 * i + 1] = __uint_as_float(zw[i] & 0xffff0000u);
+                }
+            }
+            const float4* mu4 = reinterpret_cast<const float4*>(p.r_mean + ncol);
+            const float4* rs4 = reinterpret_cast<const float4*>(p.r_rstd + ncol);
+            const float4* sh4 = reinterpret_cast<const float4*>(p.r_shift + ncol);
+            if (p.r_act == ACG_ACT_RELU) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 mu = mu4[g], rs = rs4[g], sh = sh4[g];
+                    const float m_[4] = {mu.x, mu.y, mu.z, mu.w}, r_[4] = {rs.x, rs.y, rs.z, rs.w},
+                                s_[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = 4 * g + k;
+                        const float u = zf[i] * r_[k] + s_[k];
+                        const float d = u > 0.f ? q[i] : 0.f;
+                        q[i] = d;
+                        q2[i] = d * ((zf[i] - m_[k]) * r_[k]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 mu = mu4[g], rs = rs4[g], sh = sh4[g];
+                    const float m_[4] = {mu.x, mu.y, mu.z, mu.w}, r_[4] = {rs.x, rs.y, rs.z, rs.w},
+                                s_[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = 4 * g + k;
+                        const float u = zf[i] * r_[k] + s_[k];
+                        const float d = q[i] * act_bwd(u, p.r_act);
+                        q[i] = d;
+                        q2[i] = d * ((zf[i] - m_[k]) * r_[k]);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) q2[i] = q[i] * q[i];
+        }
+        const float cs = warp_colsum16(q, lane), cs2 = warp_colsum16(q2, lane);
+        if ((lane & 1) == 0) {
+            atomicAdd(sm_sum + (lane >> 1), cs);
+            atomicAdd(sm_sq + (lane >> 1), cs2);
+        }
+    }
+    if (!row_ok) return;
+    const bool full = ncol + 16 <= p.n_store;
+    if (bf16_out) {
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + row_off + ncol;
+        if (full && (p.ldo & 7) == 0) {
+            reinterpret_cast<uint4*>(o)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4*>(o)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+            for (int i = 0; i < 16; ++i)
+                if (ncol + i < p.n_store) o[i] = __float2bfloat16_rn(f[i]);
+        }
+    } else {
+        float* o = static_cast<float*>(p.out) + row_off + ncol;
+        if (full && (p.ldo & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(o)[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+        } else {
+            for (int i = 0; i < 16; ++i)
+                if (ncol + i < p.n_store) o[i] = f[i];
+        }
+    }
+}
+
+// Fused backward reduction: the consumer's pre-activation rows of a tile are staged in the (by then idle) pipeline
+// shared memory with cp.async right after the accumulator barrier -- one exposed L2 latency per tile instead of one
+// global-load latency per 16-column chunk; the rows were pulled into L2 by a prefetch at kernel start.
+constexpr int kZRowBytes = BN * 2 + 16;     // +16 B: 16-byte row accesses of a quarter warp hit distinct banks
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ void stage_z_row(uint32_t dst, const __nv_bfloat16* src, int ncols, bool ok) {
+    for (int c = 0; c < ncols; c += 8) cp_async16(dst + 2 * c, ok ? (const void*)(src + c) : (const void*)src, ok ? 16u : 0u);
+}
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// One lane of a CONVERGED warp (elect.sync).  tcgen05.mma / TMA instructions take uniform-register operands; under a
+// plain `lane == 0` branch the compiler wraps EVERY such instruction in a uniformisation loop (ELECT / PLOP3 / BRA.U.ANY,
+// ~10 extra instructions at ~8 clk each: measured 95-105 clk per MMA regardless of N, round 2 knock-out probe), while
+// code under an elect.sync predicate in warp-uniform control flow compiles to bare UTCHMMA + 2-3 uniform adds.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// host helpers defined in conv_tc.cu
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn();
+int ru(int v, int m);
+void class_taps(const acg_conv_shape* s, int cls, int* na, int* nc);
+int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char* who);
+int set_smem(const void* kern, int bytes);
+
+}  // namespace tc
+}  // namespace acg

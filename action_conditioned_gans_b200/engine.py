@@ -496,8 +496,10 @@ class GeneratorRun(NetRun):
         else:
             self.state = None
 
-    def forward(self, img, actions, need_state=True):
-        """need_state=False skips the state head (sconv3-5): train_d only fetches the frame (train.py:132-144)."""
+    def forward(self, img, actions, need_state=True, out=None):
+        """need_state=False skips the state head (sconv3-5): train_d only fetches the frame (train.py:132-144).
+        out: write the generated frame there instead of self.g_out (recursive rollout: predicted[j])."""
+        g_out = self.g_out if out is None else out
         self.zero_reductions()
         self.img = img
         Ls = self.layers
@@ -526,11 +528,11 @@ class GeneratorRun(NetRun):
         if self.dna:
             kk = self.ksize * self.ksize
             self.layer_fwd("g/tconv4", Ls["g/tconv3"].a, self.logits, kk)        # logits (+bias), fp32 dense
-            K.dna_fwd(self.logits, img, self.g_out, self.ksize)                  # models.py:60-72
+            K.dna_fwd(self.logits, img, g_out, self.ksize)                       # models.py:60-72
         else:
-            self.layer_fwd("g/tconv4", Ls["g/tconv3"].a, self.g_out, 3)          # tanh image
+            self.layer_fwd("g/tconv4", Ls["g/tconv3"].a, g_out, 3)               # tanh image
         self.side_branch.join()
-        return self.g_out, self.state
+        return g_out, self.state
 
     def backward(self, with_state):
         """dg_out (and dstate when with_state) must be filled; accumulates into store.grad."""

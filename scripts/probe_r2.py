@@ -96,7 +96,9 @@ def main():
     print("\nPERSISTENT HALO KERNEL, stage knock-out (ACG_DBG_SKIP bits: 1 halo TMA, 2 weight TMA, 4 MMA, 16 epilogue "
           "stores, 32 epilogue)")
     cases = [("g/tconv3 fwd", launches["g/tconv3"][0]), ("g/tconv4 fwd", launches["g/tconv4"][0]),
-             ("d/conv2 dgrad", launches["d/conv2"][1]), ("d/conv1 dgrad", launches["d/conv1"][1])]
+             ("d/conv2 dgrad", launches["d/conv2"][1]), ("d/conv1 dgrad", launches["d/conv1"][1]),
+             ("g/tconv4 dgrad", launches["g/tconv4"][1]), ("g/tconv3 dgrad", launches["g/tconv3"][1]),
+             ("d/conv2 fwd", launches["d/conv2"][0]), ("g/conv2 fwd", launches["g/conv2"][0])]
     masks = [0, 1, 2, 3, 4, 16, 32, 1 | 2 | 32, 4 | 32, 1 | 2 | 4, 1 | 4 | 32, 2 | 4 | 32]
     print("%-14s " % "skip mask" + " ".join("%7d" % m for m in masks))
     for name, fn in cases:

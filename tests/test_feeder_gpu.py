@@ -1,0 +1,133 @@
+"""Device-side feeder (N4) and graph rollout (N1): the gather kernel against the host gather it replaces
+(util.py:10-16 / train.py:231-237), indexed and uint8-fed training steps against the reference-signature calls, and the
+one-graph recursive rollout (train.py:157-176, :286-299) against the CPU oracle in fp32 AND in the bf16 product mode."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_ref, torch_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(N, T, seed):
+    rng = np.random.RandomState(seed)
+    frames = rng.randint(0, 256, size=(N, T, 64, 64, 3)).astype(np.uint8)
+    actions = rng.randn(N, T, 10).astype(np.float32)
+    return frames, actions
+
+
+def _params(dna, ksize=6, seed=7):
+    rng = np.random.RandomState(seed)
+    p = np_ref.init_params(np_ref.g_dna_spec(ksize) if dna else np_ref.g_direct_spec(), rng)
+    p.update(np_ref.init_params(np_ref.d_spec(), rng))
+    for k in p:
+        if not k.endswith("weights"):
+            p[k] = (rng.randn(*p[k].shape) * 0.05).astype(np.float32)
+    return p
+
+
+@pytest.mark.parametrize("as_u8", [True, False])
+def test_gather_kernel_equals_host_gather(cuda, as_u8):
+    from action_conditioned_gans_b200 import kernels as Kn
+    from action_conditioned_gans_b200.feeder import DeviceFeeder
+    from action_conditioned_gans_b200.util import build_all_mask
+    N, T, B = 9, 7, 6
+    frames, actions = _data(N, T, 0)
+    src = frames if as_u8 else (frames.astype(np.float32) / 127.5 - 1.0).astype(np.float32)
+    fd = DeviceFeeder(src, actions, cuda)
+    rng = np.random.RandomState(1)
+    sample, t0 = fd.sample(B, rng)
+    assert t0.max() <= T - 2
+    img = torch.empty(B, 64, 64, 3, device=cuda)
+    nxt = torch.empty_like(img)
+    act = torch.empty(B, 10, device=cuda)
+    st = torch.empty(B, 5, device=cuda)
+    t = lambda a: torch.from_numpy(a).to(cuda)
+    Kn.gather_frames(fd.frames, fd.actions, t(sample), t(t0), img, nxt, act, st)
+    torch.cuda.synchronize()
+    # the reference's formulation: one-hot masks over the frame axis of the gathered sequences
+    mask = build_all_mask(T)[t0]
+    seq = src[sample]
+    ref_img, ref_nxt = seq[mask], seq[np.roll(mask, 1, axis=1)]
+    if as_u8:
+        ref_img = ref_img.astype(np.float32) / 127.5 - 1.0
+        ref_nxt = ref_nxt.astype(np.float32) / 127.5 - 1.0
+    assert np.abs(img.cpu().numpy() - ref_img).max() <= 2e-7
+    assert np.abs(nxt.cpu().numpy() - ref_nxt).max() <= 2e-7
+    assert np.array_equal(act.cpu().numpy(), actions[sample][mask])
+    assert np.array_equal(st.cpu().numpy(), actions[sample][:, :, 5:][np.roll(mask, 1, axis=1)])
+    h = fd.host_pair(sample, t0)
+    assert np.abs(h[0] - ref_img).max() <= 2e-7 and np.array_equal(h[3], st.cpu().numpy())
+    with pytest.raises(IndexError):
+        fd.check(sample, np.full(B, T - 1, np.int32), B)
+
+
+def test_indexed_and_uint8_steps_equal_the_reference_signature_calls(cuda):
+    """train_d / train_g fed (a) float arrays, (b) uint8 arrays decoded on the device, (c) indices into a resident
+    dataset: same losses and frames (fp32 engine, identical weights)."""
+    from action_conditioned_gans_b200.feeder import DeviceFeeder
+    from action_conditioned_gans_b200.trainer import Trainer
+    N, T, B = 8, 7, 4
+    frames, actions = _data(N, T, 3)
+    fd = DeviceFeeder(frames, actions, cuda)
+    sample, t0 = fd.sample(B, np.random.RandomState(4))
+    img, nxt, act, st = fd.host_pair(sample, t0)
+    params = _params(True)
+    res = []
+    for mode in ("float", "uint8", "indexed"):
+        trn = Trainer(None, True, "bce", "adam", True, batch_size=B, params=params, precision="fp32")
+        for it in range(3):      # eager, capture, replay
+            if mode == "float":
+                s = trn.train_d(img, nxt, act, summarize=True)
+                f = trn.train_g(img, nxt, act, st)
+            elif mode == "uint8":
+                s = trn.train_d(frames[sample, t0], frames[sample, t0 + 1], act, summarize=True)
+                f = trn.train_g(frames[sample, t0], frames[sample, t0 + 1], act, st)
+            else:
+                s = trn.train_d_indexed(fd, sample, t0, summarize=True)
+                f = trn.train_g_indexed(fd, sample, t0)
+        res.append((s, f.copy(), trn.summaries()))
+    for s, f, sg in res[1:]:
+        for k in ("discriminator_loss", "g_loss", "g_l2_loss"):
+            assert abs(s[k] - res[0][0][k]) <= 1e-5 * max(1.0, abs(res[0][0][k])), k
+        assert np.abs(f - res[0][1]).max() <= 1e-5
+        assert abs(sg["g_loss"] - res[0][2]["g_loss"]) <= 1e-5 * abs(res[0][2]["g_loss"])
+
+
+@pytest.mark.parametrize("dna", [True, False])
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-3), ("bf16", 3e-2)])
+def test_graph_rollout_matches_oracle(cuda, dna, prec, tol):
+    """test_sequence (6 steps, action index 2j) and the in-loop evaluation (T-1 steps, action index j) as ONE captured
+    graph each, state fed back on the device.  bf16 tolerance: mean absolute frame error (six recursive applications of
+    a ~5e-3-accurate generator; the direct generator's tanh image is the looser of the two)."""
+    from action_conditioned_gans_b200.trainer import Trainer
+    B = 5
+    rng = np.random.RandomState(3)
+    seq = rng.uniform(-1, 1, (B, 13, 64, 64, 3)).astype(np.float32)
+    acts = rng.randn(B, 13, 10).astype(np.float32)
+    params = _params(dna)
+    ora = torch_ref.Trainer(params, True, "bce", "adam", dna, ksize=6)
+    trn = Trainer(None, True, "bce", "adam", dna, batch_size=B, ksize=6, params=params, precision=prec)
+    p_ref, tail_ref = ora.test_sequence(seq, seq, acts)
+    for rep in range(3):          # eager, capture, replay: all three must agree
+        p, tail = trn.test_sequence(seq, seq, acts)
+        assert p.shape == (B, 6, 64, 64, 3)
+        if prec == "fp32":
+            assert np.abs(p - p_ref).max() <= tol and np.abs(tail - tail_ref).max() <= tol
+        else:
+            assert np.abs(p - p_ref).mean() <= tol
+            assert np.abs(p[:, 0] - p_ref[:, 0]).mean() <= tol / 3      # first step: a single generator application
+    # in-loop evaluation of train.py:286-299: T-1 recursive steps, stride 1
+    T = 7
+    pred = trn.rollout(seq[:, 0], acts[:, :T], steps=T - 1, action_stride=1).cpu().numpy()
+    cur, state = seq[:, 0], acts[:, 0, 5:]
+    for j in range(T - 1):
+        a = np.concatenate((acts[:, j, :5], state), axis=1)
+        cur, st, _ = ora.test(cur, seq[:, j + 1], a)
+        if st is not None:
+            state = st
+        err = np.abs(pred[j] - cur)
+        assert (err.max() <= tol) if prec == "fp32" else (err.mean() <= tol), (j, err.max(), err.mean())
+    with pytest.raises(ValueError):
+        trn.rollout(seq[:, 0], acts[:, :3], steps=6, action_stride=2)
