@@ -32,10 +32,9 @@ namespace tc {
 
 constexpr int kH2Threads = 384;
 constexpr int kH2Rows = 18;                         // staged halo rows per image: 16 output rows + 2
-constexpr int kH2Region = 4 * 41 * 1024;            // halo ring: 2 x (18 x 34 | 2 x 18 x 18) or 4 x (18 x 18) rows of 128 B
-constexpr int kH2BStage = BN * BK * 2;
-constexpr int kH2BStages = 3;
-constexpr int kH2Smem = kH2Region + kH2BStages * kH2BStage + 1024;
+constexpr int kH2Data = 222 * 1024;                 // operand staging: 2 halo buffers + the weight-slice ring
+constexpr int kH2Smem = kH2Data + 1024;             // + alignment slack (227 KB per CTA is the hardware limit)
+constexpr int kH2MaxBStages = 8;
 constexpr int kMaxTaps = 9;
 constexpr int kEpiBatch = 3;                        // 16-column TMEM loads in flight per wait (48 columns = g/tconv4's N)
 
@@ -90,7 +89,7 @@ __global__ void __launch_bounds__(kH2Threads, 1)
 conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
     const Params& p = hp.p;
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t halo_full[4], halo_empty[4], b_full[kH2BStages], b_empty[kH2BStages];
+    __shared__ __align__(8) uint64_t halo_full[2], halo_empty[2], b_full[kH2MaxBStages], b_empty[kH2MaxBStages];
     __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_sh;
     __shared__ float sm_stats[2][BN];
@@ -98,7 +97,7 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t smemH = smem_base, smemB = smem_base + kH2Region;
+    const uint32_t smemH = smem_base;
     if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
 
     const int N = p.N;
@@ -106,15 +105,24 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
     const int WH = hp.TW + 2, HR = kH2Rows * WH;             // halo: 18 rows x (TW+2) pixels per image
     const uint32_t halo_bytes = (uint32_t)(hp.TB * HR) * 128u;
     const uint32_t halo_stride = (halo_bytes + 1023u) & ~1023u;        // buffers start on swizzle-atom boundaries
-    const int NH = halo_stride * 4u <= (uint32_t)kH2Region ? 4 : 2;     // halo ring depth
+    constexpr int NH = 2;                                    // halo ring: a patch feeds >= 4 taps, two in flight are enough
+    // The weight-slice ring takes the rest.  A stage is recycled by tcgen05.commit -> mbarrier -> producer -> TMA -> MMA
+    // warp: ~3000 clk round trip (probe: 620 clk per tap with 3 stages and NO MMAs), against 384-512 clk of MMA work
+    // per tap -- so the ring must hold ~8 taps or the tensor pipe idles (3 stages: 1032-1296 clk per tap measured).
+    const uint32_t smemB = smemH + NH * halo_stride;
+    const uint32_t b_stride = ((uint32_t)N * 128u + 1023u) & ~1023u;
+    int NBS = (int)(((uint32_t)kH2Data - NH * halo_stride) / b_stride);
+    NBS = NBS > kH2MaxBStages ? kH2MaxBStages : NBS;
     const int NB = (2 * NACC * N <= 512) ? 2 : 1;            // accumulator buffers in tensor memory
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(NB * NACC * N)) tmem_cols <<= 1;
 
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
-        for (int i = 0; i < kH2BStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8);
+        }
+        for (int i = 0; i < kH2MaxBStages; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         fence_mbar_init();
         for (int c = 0; c < 4; ++c) { tma_prefetch_desc(&hp.map_a[c]); tma_prefetch_desc(&hp.map_b[c]); }
     }
@@ -163,14 +171,14 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
                 for (int pg = h.pg0; pg < h.pg0 + h.npg; ++pg) {
                     const TapProg& pr = hp.prog[pg];
                     for (int tap = 0; tap < pr.ntaps; ++tap, ++bcount) {
-                        const int st = bcount % kH2BStages, use = bcount / kH2BStages;
+                        const int st = bcount % NBS, use = bcount / NBS;
                         if (use >= 1) mbar_wait(&b_empty[st], (uint32_t)((use - 1) & 1));
                         if (elect_one()) {
                             if (ACG_DBG(p, 2)) {
                                 mbar_arrive(&b_full[st]);                          // probe: no weight traffic
                             } else {
                                 mbar_expect_tx(&b_full[st], b_bytes);
-                                tma_load_2d(smemB + st * kH2BStage, &hp.map_b[hp.form ? 0 : pg],
+                                tma_load_2d(smemB + st * b_stride, &hp.map_b[hp.form ? 0 : pg],
                                             (int)pr.wtap[tap] * p.lda + kc * 64, 0, &b_full[st]);
                             }
                         }
@@ -208,10 +216,10 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
                     mbar_wait(&halo_full[buf], (uint32_t)((hcount / NH) & 1));
                     const uint32_t alo_h = desc_lo(smemH + buf * halo_stride, 16);
                     for (int tap = 0; tap < pr.ntaps; ++tap, ++bcount) {
-                        const int st = bcount % kH2BStages;
-                        mbar_wait(&b_full[st], (uint32_t)((bcount / kH2BStages) & 1));
+                        const int st = bcount % NBS;
+                        mbar_wait(&b_full[st], (uint32_t)((bcount / NBS) & 1));
                         tc_fence_after();
-                        const uint32_t blo = blo0 + st * (kH2BStage >> 4);
+                        const uint32_t blo = blo0 + st * (b_stride >> 4);
                         const uint32_t alo_t = alo_h + (uint32_t)((int)pr.shift_y[tap] * WH + (int)pr.shift_x[tap]) * 8u;
                         if (elect_one()) {
                             if (!ACG_DBG(p, 4)) {                                  // probe: no MMAs

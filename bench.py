@@ -1,17 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- the driver's benchmark contract for the acg_b200 hot path.
 
-Workload (BASELINE.json configs[2], the one the headline metric "GAN train frames/sec" is quoted on): one full
+Default workload (BASELINE.json configs[2], the one the headline metric "GAN train frames/sec" is quoted on): one full
 adversarial DNA training iteration, --loss bce --opt adam --dna, = 1 x Trainer.train_d + 1 x Trainer.train_g
 (train.py:241-263) at batch 256 PER GPU (weak scaling), 64x64 RGB frames, 10-D action++state, ksize=6 (what
-train.py:53-54 passes), random-init weights, synthetic Push-shaped data.
+train.py:53-54 passes), random-init weights, synthetic Push-shaped data.  --config wass_rmsprop is configs[3]
+(5 x train_d + 1 x train_g, train.py:217-218), --config direct_rollout is configs[4] (6-step rollout, batch 512).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one rank per GPU under torchrun)
-  python bench.py --impl reference [...]                         the reference's CPU path (oracle port)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config C]   our arm (one rank per GPU under torchrun)
+  python bench.py --impl reference [...]                             the reference's CPU path (oracle port)
 
-One JSON line on stdout (rank 0).  `value` = frames/s with the feeds resident in HBM; `e2e` = the same metric
-through the public Trainer.train_d / Trainer.train_g calls with HOST (pinned) feeds, H2D copies and the D2H
-fetch of the generated frames that train_g returns (train.py:124,130) inside the timed region.
+One JSON line on stdout (rank 0).  `value` = frames/s with the feeds resident in HBM (K steps between CUDA events, max
+over ranks; `step_ms_median` / `step_ms_max` from one event per step boundary); `e2e` = the same metric through the
+public Trainer calls with HOST (pinned) feeds, H2D copies and the D2H fetch of the generated frames that train_g
+returns (train.py:124,130) inside the timed region; with N > 1 `strong_scaling` times the same GLOBAL batch split over
+the ranks.
 """
 import argparse
 import json
@@ -162,50 +165,92 @@ def synth_batch(B, seed, pinned):
     return ts
 
 
-def flops_per_iter(B, K):
-    """Nominal 2*M*N*K FLOPs of one train_d + train_g."""
-    per = 4.28e9 if K == 6 else 3.99e9
-    return per * B
+# ----------------------------------------------------------------------------------------------------------------
+# workloads (BASELINE.json configs[2], [3], [4])
+# ----------------------------------------------------------------------------------------------------------------
+CONFIGS = {
+    # name: (dna, loss, opt, default batch per GPU, D steps per iteration, description)
+    "dna_bce_adam": (True, "bce", "adam", 256, 1,
+                     "full adversarial DNA step bce+adam: 1 x train_d + 1 x train_g per step (BASELINE configs[2])"),
+    "wass_rmsprop": (True, "wass", "rmsprop", 256, 5,
+                     "Wasserstein + RMSProp variant: 5 x train_d + 1 x train_g per step (BASELINE configs[3])"),
+    "direct_rollout": (False, "bce", "adam", 512, 0,
+                       "non-DNA direct-pixel generator, 6-step recursive rollout (test_sequence) per step "
+                       "(BASELINE configs[4]); frames/s counts generated frames"),
+}
+# nominal 2*M*N*K FLOPs per sample, ksize 6: train_d 1975.3 MF, train_g 2303.0 MF;
+# direct generator forward 650.9 MF per rollout step
+TRAIN_D_MF, TRAIN_G_MF, DIRECT_FWD_MF = 1975.3, 2303.0, 650.9
+
+
+def flops_per_iter(config, B):
+    dna, loss, opt, _, d_steps, _ = CONFIGS[config]
+    if config == "direct_rollout":
+        return DIRECT_FWD_MF * 1e6 * 6 * B
+    return (d_steps * TRAIN_D_MF + TRAIN_G_MF) * 1e6 * B
+
+
+def frames_per_iter(config, B):
+    return 6 * B if config == "direct_rollout" else B
+
+
+def synth_sequences(B, seed, pinned, T=13):
+    rng = np.random.RandomState(seed)
+    base = rng.uniform(-1, 1, (B, 1, 64, 64, 3)).astype(np.float32)
+    seq = np.clip(base + np.cumsum(0.05 * rng.randn(B, T, 64, 64, 3).astype(np.float32), axis=1), -1, 1)
+    acts = rng.randn(B, T, 10).astype(np.float32)
+    ts = [torch.from_numpy(seq), torch.from_numpy(acts)]
+    if pinned:
+        ts = [t.pin_memory() for t in ts]
+    return ts
 
 
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port of the reference's CPU path, all host threads
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(steps, warmup, B=CPU_BATCH):
+def cpu_reference_run(steps, warmup, config="dna_bce_adam", B=CPU_BATCH):
     from oracle import np_ref, torch_ref
+    dna, loss, opt, _, d_steps, _ = CONFIGS[config]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     rng = np.random.RandomState(7)
-    params = np_ref.init_params(np_ref.g_dna_spec(KSIZE), rng)
+    params = np_ref.init_params(np_ref.g_dna_spec(KSIZE) if dna else np_ref.g_direct_spec(), rng)
     params.update(np_ref.init_params(np_ref.d_spec(), rng))
-    ora = torch_ref.Trainer(params, True, "bce", "adam", True, ksize=KSIZE, dtype=torch.float32)
+    ora = torch_ref.Trainer(params, True, loss, opt, dna, ksize=KSIZE, dtype=torch.float32)
     img, nxt, act, state = [t.numpy() for t in synth_batch(B, 1, False)]
+    seq, acts = [t.numpy() for t in synth_sequences(B, 2, False)]
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        ora.train_d(img, nxt, act)
-        ora.train_g(img, nxt, act, state)
+        if config == "direct_rollout":
+            ora.test_sequence(seq, seq, acts)
+        else:
+            for _ in range(d_steps):
+                ora.train_d(img, nxt, act)
+            ora.train_g(img, nxt, act, state)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     total = sum(times)
-    return {"value": B * len(times) / total, "ms_per_step": 1e3 * total / len(times), "cores": cores,
-            "sample": "%d iteration(s) of train_d+train_g at batch %d (configs[0] size), fp32 torch-CPU oracle port of "
-                      "models.py/ops.py/train.py, %d threads" % (len(times), B, cores)}
+    what = "6-step rollout" if config == "direct_rollout" else "%d x train_d + train_g" % d_steps
+    return {"value": frames_per_iter(config, B) * len(times) / total, "ms_per_step": 1e3 * total / len(times),
+            "cores": cores,
+            "sample": "%d iteration(s) of %s at batch %d (configs[0] size), fp32 torch-CPU oracle port of "
+                      "models.py/ops.py/train.py, %d threads" % (len(times), what, B, cores)}
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 5))
-    res = cpu_reference_run(steps, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    res = cpu_reference_run(steps, warmup, args.config)
     line = {
         "impl": "reference", "metric": "GAN train frames/sec", "value": res["value"], "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": res["ms_per_step"],
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": res["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "full adversarial DNA step bce+adam (train_d + train_g), 64x64x3, ksize=6; CPU sample "
-                               "at batch %d" % CPU_BATCH, "global_batch": CPU_BATCH},
+        "config": {"workload": CONFIGS[args.config][5] + ", 64x64x3, ksize=6; CPU sample at batch %d" % CPU_BATCH,
+                   "name": args.config, "global_batch": CPU_BATCH},
         "cpu_baseline": {"value": res["value"], "unit": "frames/s", "cores": res["cores"], "kind": "port",
                          "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -242,7 +287,7 @@ def time_kernel(fn, iters, flush=None):
 
 def dna_microbench(dev, peaks, B=256, K=KSIZE):
     """BASELINE configs[1]: DNA transform fwd / bwd alone.  B=256 makes the working set (176 / 317 MB at K=6)
-    larger than the 126 MB L2; B=64 rotates 8 buffer sets for the same reason."""
+    larger than the 126 MB L2; B=64 rotates 12 buffer sets for the same reason."""
     from action_conditioned_gans_b200 import kernels as Kn
     out = {}
     for (b, k, nset) in ((B, K, 4), (64, 5, 12)):
@@ -265,7 +310,7 @@ def dna_microbench(dev, peaks, B=256, K=KSIZE):
             it[0] += 1
             Kn.dna_bwd(lg, im, dy, dl, k)
 
-        tf, tb = time_kernel(fwd, 20), time_kernel(bwd, 20)
+        tf, tb = time_kernel(fwd, 24), time_kernel(bwd, 24)
         bytes_f = b * 4096 * (k * k + 6) * 4
         bytes_b = b * 4096 * (2 * k * k + 6) * 4
         out["B%d_K%d" % (b, k)] = {
@@ -273,6 +318,84 @@ def dna_microbench(dev, peaks, B=256, K=KSIZE):
             "bwd_us": 1e3 * tb, "bwd_gbs": bytes_b / tb / 1e6, "bwd_frac": bytes_b / tb / 1e6 / peaks["hbm_gbs"],
             "buffer_sets": nset}
     return out
+
+
+def load_traffic():
+    """DRAM bytes of the conv-family kernels of one iteration, from the committed ncu capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except ValueError:
+            return None
+    return None
+
+
+class Workload:
+    """One benchmark configuration: device-resident iteration, end-to-end iteration through the public API."""
+
+    def __init__(self, config, B, dev, dp, rank, branches=True):
+        from action_conditioned_gans_b200.trainer import Trainer
+        self.config, self.B, self.dev = config, B, dev
+        dna, loss, opt, _, self.d_steps, _ = CONFIGS[config]
+        self.trn = Trainer(None, True, loss, opt, dna, batch_size=B, ksize=KSIZE, device=dev, seed=7, dp=dp,
+                           branches=branches)
+        self.nfeeds = 2
+        if config == "direct_rollout":
+            self.host = [synth_sequences(B, 100 + rank * 10 + i, True) for i in range(self.nfeeds)]
+            self.resident = [[t.to(dev) for t in hb] for hb in self.host]
+        else:
+            self.host = [synth_batch(B, 100 + rank * 10 + i, True) for i in range(self.nfeeds)]
+            self.resident = [[t.to(dev) for t in hb] for hb in self.host]
+            # uint8 copies of the frames (what a decoded dataset holds): a quarter of the H2D bytes
+            q = lambda t: ((t + 1.0) * 127.5).round().clamp(0, 255).to(torch.uint8).pin_memory()
+            self.host_u8 = [[q(hb[0]), q(hb[1]), hb[2], hb[3]] for hb in self.host]
+
+    def resident_step(self, i):
+        trn = self.trn
+        if self.config == "direct_rollout":
+            seq, acts = self.resident[i % self.nfeeds]
+            trn.rollout(seq[:, 0], acts, steps=6, action_stride=2)
+            return
+        img, nxt, act, state = self.resident[i % self.nfeeds]
+        for _ in range(self.d_steps):
+            trn.enqueue_train_d(img, nxt, act)
+        trn.enqueue_train_g(img, nxt, act, state)
+
+    def e2e_step(self, i, u8):
+        trn = self.trn
+        if self.config == "direct_rollout":
+            seq, acts = self.host[i % self.nfeeds]
+            pred, _ = trn.test_sequence(seq, seq, acts)
+            return pred
+        img, nxt, act, state = (self.host_u8 if u8 else self.host)[i % self.nfeeds]
+        for _ in range(self.d_steps):
+            trn.train_d(img, nxt, act)
+        return trn.train_g(img, nxt, act, state)          # returns the generated frames on the host
+
+    def e2e_bytes(self, u8):
+        if self.config == "direct_rollout":
+            seq, acts = self.host[0]
+            return seq[:, 0].numel() * 4 + acts.numel() * 4, 6 * self.B * 64 * 64 * 3 * 4
+        img, nxt, act, state = (self.host_u8 if u8 else self.host)[0]
+        per_d = img.numel() * img.element_size() + nxt.numel() * nxt.element_size() + act.numel() * 4
+        per_g = per_d + state.numel() * 4
+        return self.d_steps * per_d + per_g, self.B * 64 * 64 * 3 * 4
+
+
+def timed_steps(step_fn, steps, barrier, sampler=None, rank=0):
+    """K steps between CUDA events on the launching stream, one event per step boundary: total, median and max."""
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    barrier()
+    evs[0].record()
+    for i in range(steps):
+        step_fn(i)
+        evs[i + 1].record()
+        if sampler is not None and rank == 0 and (i == steps // 2 or i == steps - 1):
+            sampler.sample_now()      # the device is busy with the queued iterations at this point
+    barrier()
+    per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    return evs[0].elapsed_time(evs[steps]), per
 
 
 def main_ours(args):
@@ -284,7 +407,7 @@ def main_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     from action_conditioned_gans_b200 import _lib
-    from action_conditioned_gans_b200.trainer import DataParallel, Trainer
+    from action_conditioned_gans_b200.trainer import DataParallel
     _lib.load()
     dp = None
     if world > 1:
@@ -304,109 +427,107 @@ def main_ours(args):
             os.close(saved)
         dp = DataParallel()
     peaks = load_peaks()
-    B = args.batch
-    trn = Trainer(None, True, "bce", "adam", True, batch_size=B, ksize=KSIZE, device=dev, seed=7, dp=dp,
-                  branches=not args.no_branches)
-
-    # feeds: a few distinct host batches (pinned), rotated; device copies for the HBM-resident measurement
-    nfeeds = 2
-    host = [synth_batch(B, 100 + rank * 10 + i, True) for i in range(nfeeds)]
-    resident = [[t.to(dev) for t in hb] for hb in host]
-
-    def iteration_resident(i):
-        img, nxt, act, state = resident[i % nfeeds]
-        trn.enqueue_train_d(img, nxt, act)
-        trn.enqueue_train_g(img, nxt, act, state)
+    config = args.config
+    B = args.batch if args.batch > 0 else CONFIGS[config][3]
+    wl = Workload(config, B, dev, dp, rank, branches=not args.no_branches)
+    trn = wl.trn
 
     def barrier():
         if dp is not None:
             dp.dist.barrier()
         torch.cuda.synchronize()
 
-    # W >= 3 warm-up iterations (eager, graph capture, first replay) + 5 more replays so that the timed region starts
-    # with captured graphs and settled clocks
-    n_warm = max(args.warmup, 3) + 5
+    def max_over_ranks(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if dp is not None:
+            dp.dist.all_reduce(t, op=dp.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # warm-up: W >= 3 (first call eager, second captures the graphs, third is the first replay)
+    n_warm = max(args.warmup, 3)
     for i in range(n_warm):
-        iteration_resident(i)
+        wl.resident_step(i)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count() + trn.replayed_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        iteration_resident(i)
-        if rank == 0 and (i == args.steps // 2 or i == args.steps - 1):
-            sampler.sample_now()      # the device is busy with the queued iterations at this point
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms, per = timed_steps(wl.resident_step, args.steps, barrier, sampler, rank)
     launches = _lib.launch_count() + trn.replayed_launches - launches0
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    if dp is not None:
-        dp.dist.all_reduce(t, op=dp.dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = B * world * args.steps / (ms / 1e3)
+    ms = max_over_ranks(ms)
+    step_med, step_max = max_over_ranks(float(np.median(per))), max_over_ranks(float(np.max(per)))
+    fpi = frames_per_iter(config, B)
+    value = fpi * world * args.steps / (ms / 1e3)
 
-    # ---- end to end through the public API with host feeds ---------------------------------------------------
-    def iteration_e2e(i):
-        img, nxt, act, state = host[i % nfeeds]
-        trn.train_d(img, nxt, act)
-        return trn.train_g(img, nxt, act, state)          # returns the generated frames on the host
+    # ---- end to end through the public API with pinned HOST feeds (uint8 frames, then fp32 frames) ---------------
+    def e2e(u8):
+        wl.e2e_step(0, u8)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            out = wl.e2e_step(i, u8)
+        barrier()
+        return fpi * world * args.steps / max_over_ranks(time.perf_counter() - t0), out
 
-    e2e_steps = max(2, min(args.steps, 10))
-    iteration_e2e(0)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        frames = iteration_e2e(i)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if dp is not None:
-        dp.dist.all_reduce(t, op=dp.dist.ReduceOp.MAX)
-    e2e_value = B * world * e2e_steps / float(t.item())
-    h2d = sum(x.numel() * 4 for x in host[0][:3]) + sum(x.numel() * 4 for x in host[0])
-    d2h = frames.nbytes
+    e2e_u8, frames = e2e(True)
+    h2d_u8, d2h = wl.e2e_bytes(True)
+    e2e_f32, h2d_f32 = None, None
+    if config != "direct_rollout":
+        e2e_f32, _ = e2e(False)
+        h2d_f32, _ = wl.e2e_bytes(False)
+
+    # ---- strong scaling: the SAME global batch split over the ranks (BASELINE configs[2]: "batch 256 on 1/2/4/8") ---
+    strong = None
+    if world > 1 and B % world == 0 and config != "direct_rollout":
+        ws = Workload(config, B // world, dev, dp, rank, branches=not args.no_branches)
+        for i in range(n_warm):
+            ws.resident_step(i)
+        barrier()
+        ms_s, per_s = timed_steps(ws.resident_step, args.steps, barrier)
+        ms_s = max_over_ranks(ms_s)
+        strong = {"global_batch": B, "batch_per_gpu": B // world, "ms_per_step": ms_s / args.steps,
+                  "value": B * args.steps / (ms_s / 1e3), "unit": "frames/s",
+                  "step_ms_median": max_over_ranks(float(np.median(per_s)))}
+        del ws
 
     # ---- per-kernel breakdown of one iteration (instrumented pass, right after the timed region; every rank
     # takes part because the step contains collectives) -----------------------------------------------------
-    breakdown = kernel_breakdown(trn, resident[0])
+    breakdown = kernel_breakdown(wl)
     barrier()
     if rank != 0:
         hard_exit()       # no collective is issued after this point; see hard_exit()
     dna = dna_microbench(dev, peaks)
-    flops = flops_per_iter(B, KSIZE)
+    flops = flops_per_iter(config, B)
     conv_ms = sum(v["ms"] for k, v in breakdown.items() if k.startswith("acg_conv"))
-    top = max(breakdown.items(), key=lambda kv: kv[1]["ms"])
-    if top[0].startswith("acg_conv"):
-        tens_peak = peaks["bf16_tflops_sustained"]
-        achieved = flops / (conv_ms / 1e3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "conv family (%s largest)" % top[0], "achieved": achieved,
-                    "peak": tens_peak, "unit": "TFLOP/s", "frac": achieved / tens_peak, "traffic": None,
-                    "peak_src": peaks["src"] + " (sustained cuBLAS bf16)",
-                    "note": "nominal conv FLOPs of one iteration / summed conv-kernel device time"}
-    else:
-        k = "B%d_K%d" % (256, KSIZE)
-        roofline = {"bound": "hbm", "kernel": "dna_bwd", "achieved": dna[k]["bwd_gbs"], "peak": peaks["hbm_gbs"],
-                    "unit": "GB/s", "frac": dna[k]["bwd_frac"], "traffic": None, "peak_src": peaks["src"]}
-    cpu = cpu_reference_run(1, 1)
+    traffic = load_traffic()
+    tens_peak = peaks["bf16_tflops_sustained"]
+    achieved = flops / (conv_ms / 1e3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "conv family (tcgen05 implicit GEMM: conv_halo2 / conv_tc / conv_wgrad_tc)",
+                "achieved": achieved, "peak": tens_peak, "unit": "TFLOP/s", "frac": achieved / tens_peak,
+                "traffic": traffic["conv_dram_bytes_per_iteration"] if traffic and config == "dna_bce_adam" else None,
+                "traffic_note": (traffic or {}).get("note"),
+                "peak_src": peaks["src"] + " (sustained cuBLAS bf16)",
+                "step_frac": flops / (ms / args.steps / 1e3) / 1e12 / tens_peak,
+                "note": "achieved = nominal conv FLOPs of one iteration / summed conv-kernel device time (eager, one "
+                        "stream); step_frac = the same FLOPs / the graph-replayed step time"}
+    cpu = cpu_reference_run(20 if config != "direct_rollout" else 5, 1, config)
     line = {
         "metric": "GAN train frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": n_warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": n_warm, "ms_per_step": ms / args.steps, "step_ms_median": step_med, "step_ms_max": step_max,
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": trn.precision, "data": "synthetic",
-        "config": {"workload": "full adversarial DNA step bce+adam: 1 x train_d + 1 x train_g per step "
-                               "(BASELINE configs[2]), 64x64x3 frames, 10-D action++state, ksize=6, batch 256 per GPU",
-                   "global_batch": B * world, "batch_per_gpu": B, "parallelism": "dp%d" % world,
-                   "l2": "activations of one step (>1 GB) exceed the 126 MB L2; %d feed sets rotated" % nfeeds},
+        "config": {"workload": CONFIGS[config][5] + ", 64x64x3 frames, 10-D action++state, ksize=6, batch %d per GPU" % B,
+                   "name": config, "global_batch": B * world, "batch_per_gpu": B, "parallelism": "dp%d" % world,
+                   "l2": "activations of one step (>1 GB) exceed the 126 MB L2; %d feed sets rotated" % wl.nfeeds},
         "clocks": clocks, "gpu_launches": launches,
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps,
-                "note": "separately timed through Trainer.train_d/train_g with pinned HOST feeds; the H2D copies ride a "
+        "e2e": {"value": e2e_u8, "unit": "frames/s", "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": d2h,
+                "steps": args.steps, "feed_dtype": "uint8 frames (decoded to [-1,1] on the device), fp32 actions",
+                "note": "separately timed through the public Trainer calls with pinned HOST feeds; the H2D copies ride a "
                         "copy stream under the previous call's kernels and the frames leave while the backward pass runs"},
+        "e2e_fp32_feeds": ({"value": e2e_f32, "unit": "frames/s", "h2d_bytes_per_step": h2d_f32,
+                            "d2h_bytes_per_step": d2h} if e2e_f32 is not None else None),
+        "strong_scaling": strong,
         "roofline": roofline,
         "dna_roofline": dna,
         "kernel_breakdown_ms": {k: round(v["ms"], 4) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])},
@@ -426,9 +547,10 @@ def hard_exit():
     os._exit(0)
 
 
-def kernel_breakdown(trn, feeds):
+def kernel_breakdown(wl):
     """Device time per C-ABI entry point over ONE iteration: CUDA events around every call (instrumented pass)."""
     from action_conditioned_gans_b200 import kernels as Kn
+    trn = wl.trn
     records = []
     orig = Kn.call
 
@@ -444,9 +566,7 @@ def kernel_breakdown(trn, feeds):
     from action_conditioned_gans_b200 import engine as En
     En.Branch.enabled = False                             # ... on ONE stream (no overlapping kernels)
     try:
-        img, nxt, act, state = feeds
-        trn.enqueue_train_d(img, nxt, act)
-        trn.enqueue_train_g(img, nxt, act, state)
+        wl.resident_step(0)
         torch.cuda.synchronize()
     finally:
         Kn.call = orig
@@ -463,9 +583,10 @@ def kernel_breakdown(trn, feeds):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=0, help="batch per GPU (default: the configuration's)")
+    ap.add_argument("--config", type=str, default="dna_bce_adam", choices=sorted(CONFIGS))
     ap.add_argument("--no-branches", action="store_true", help="every chain of a step on one stream (A/B switch)")
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     a = ap.parse_args()

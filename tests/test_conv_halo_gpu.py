@@ -21,7 +21,7 @@ CONV_CASES = [
     (5, 64, 64, 64, 48, 5),       # N = 48, 32-wide tiles, one image per tile
     (3, 32, 32, 128, 128, 3),     # 3x3 stride 2 (pad 0/1): planes with 4 / 2 / 2 / 1 taps, two channel blocks
     (2, 64, 64, 192, 96, 5),      # three channel blocks
-    (4, 32, 32, 16, 32, 6),       # even filter (pad 2/2): 3 x 3 taps in every plane, 16-channel rows
+    (4, 32, 32, 16, 32, 4),       # even filter (pad 1/1): 2 x 2 taps in every plane, 16-channel rows
 ]
 ADJ_CASES = [
     (40, 32, 32, 128, 128, 5),    # g/tconv3 forward (as the dgrad of a 128 -> 128 conv): N = 128, NACC 2
