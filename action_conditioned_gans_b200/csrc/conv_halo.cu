@@ -41,8 +41,8 @@ constexpr int kEpiBatch = 3;                        // 16-column TMEM loads in f
 struct TapProg {
     int ntaps;
     int oy, ox;                   // halo origin relative to the tile origin (rows, columns of the staged grid)
-    short shift_y[kMaxTaps], shift_x[kMaxTaps];   // tap -> row / column shift inside the halo patch
-    short wtap[kMaxTaps];         // tap -> tap index inside the weight pack ([N][tap][lda])
+    int a_off[kMaxTaps];          // tap -> offset of its shifted window inside the halo patch, in 16-byte units
+    int w_off[kMaxTaps];          // tap -> K coordinate of its slice in the weight pack ([N][tap][lda]): tap index * lda
 };
 
 struct alignas(64) Halo2Params {
@@ -82,6 +82,17 @@ __device__ __forceinline__ H2Tile h2_tile(const Halo2Params& hp, int t) {
     h.y0 = (r / tiles_x) << 4;
     h.x0 = (r % tiles_x) * hp.TW;
     return h;
+}
+
+// MMAs of one tap: K step outer, accumulator inner, so that consecutive MMAs write different accumulators
+template <int NACC, int NK>
+__device__ __forceinline__ void issue_tap(uint32_t tacc, int N, uint32_t alo_t, const uint32_t (&acc_row8)[NACC],
+                                          uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t first) {
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+#pragma unroll
+        for (int q = 0; q < NACC; ++q)
+            tc_mma2(tacc + q * N, alo_t + acc_row8[q] + 2 * k, ahi, blo + 2 * k, bhi, idesc, first | (uint32_t)k);
 }
 
 template <int NACC>
@@ -141,64 +152,76 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
 
     if (warp == 5) {
         // ================================ halo producer (whole warp walks, one elected lane issues) ================
-        int hcount = 0;
+        int hb = 0;
+        uint32_t eph = 1u;                     // first use of every buffer passes at once
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const H2Tile h = h2_tile(hp, t);
             for (int kc = 0; kc < hp.nkc; ++kc) {
-                for (int pg = h.pg0; pg < h.pg0 + h.npg; ++pg, ++hcount) {
-                    const int buf = hcount % NH, use = hcount / NH;
-                    if (use >= 1) mbar_wait(&halo_empty[buf], (uint32_t)((use - 1) & 1));
+                for (int pg = h.pg0; pg < h.pg0 + h.npg; ++pg) {
+                    mbar_wait(&halo_empty[hb], eph);
                     if (elect_one()) {
                         if (ACG_DBG(p, 1)) {
-                            mbar_arrive(&halo_full[buf]);                          // probe: no halo traffic
+                            mbar_arrive(&halo_full[hb]);                           // probe: no halo traffic
                         } else {
-                            mbar_expect_tx(&halo_full[buf], halo_bytes);
-                            tma_load_4d(smemH + buf * halo_stride, &hp.map_a[hp.form ? pg : 0], kc * 64,
-                                        h.x0 + hp.prog[pg].ox, h.y0 + hp.prog[pg].oy, h.b0, &halo_full[buf]);
+                            mbar_expect_tx(&halo_full[hb], halo_bytes);
+                            tma_load_4d(smemH + hb * halo_stride, &hp.map_a[hp.form ? pg : 0], kc * 64,
+                                        h.x0 + hp.prog[pg].ox, h.y0 + hp.prog[pg].oy, h.b0, &halo_full[hb]);
                         }
                     }
                     __syncwarp();
+                    if (++hb == NH) { hb = 0; eph ^= 1u; }
                 }
             }
         }
     } else if (warp == 6) {
         // ================================ weight producer ================================
         const uint32_t b_bytes = (uint32_t)N * 128u;
-        int bcount = 0;
+        int st = 0;
+        uint32_t eph = 1u;                     // parity a wait on b_empty[st] must see: passes at once in the first round
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
             const H2Tile h = h2_tile(hp, t);
             for (int kc = 0; kc < hp.nkc; ++kc) {
                 for (int pg = h.pg0; pg < h.pg0 + h.npg; ++pg) {
                     const TapProg& pr = hp.prog[pg];
-                    for (int tap = 0; tap < pr.ntaps; ++tap, ++bcount) {
-                        const int st = bcount % NBS, use = bcount / NBS;
-                        if (use >= 1) mbar_wait(&b_empty[st], (uint32_t)((use - 1) & 1));
+                    for (int tap = 0; tap < pr.ntaps; ++tap) {
+                        mbar_wait(&b_empty[st], eph);
                         if (elect_one()) {
                             if (ACG_DBG(p, 2)) {
                                 mbar_arrive(&b_full[st]);                          // probe: no weight traffic
                             } else {
                                 mbar_expect_tx(&b_full[st], b_bytes);
                                 tma_load_2d(smemB + st * b_stride, &hp.map_b[hp.form ? 0 : pg],
-                                            (int)pr.wtap[tap] * p.lda + kc * 64, 0, &b_full[st]);
+                                            pr.w_off[tap] + kc * 64, 0, &b_full[st]);
                             }
                         }
                         __syncwarp();
+                        if (++st == NBS) { st = 0; eph ^= 1u; }
                     }
                 }
             }
         }
     } else if (warp == 4) {
         // ================================ MMA issuer ================================
+        // The tensor pipe queues only a few MMAs: whatever the issuing warp does between two taps is time the pipe
+        // idles (round-2 probe: ~165 SASS instructions = ~700 clk per tap against 384-512 clk of MMA work per tap).
+        // So everything here is warp-UNIFORM by construction -- loop counters, descriptor words and the TMEM base
+        // (__reduce_or_sync lands in a uniform register; a plain shared-memory load does not) -- which lets the
+        // compiler keep the operands of UTCHMMA in uniform registers instead of moving them there for every MMA, the
+        // ring positions are running counters (no division), and the tap offsets come precomputed from the host.
+        const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
         const uint32_t idesc = make_idesc(N, 0, 0);
         const uint32_t ahi = desc_hi((uint32_t)WH * 128u), bhi = desc_hi(1024);
-        const uint32_t blo0 = desc_lo(smemB, 16);
+        const uint32_t blo0 = desc_lo(smemB, 16), bstep = b_stride >> 4;
+        const uint32_t alo0 = desc_lo(smemH, 16), hstep = halo_stride >> 4;
         uint32_t acc_row8[NACC];               // first halo row of accumulator q, in 16-byte units (8 per row)
 #pragma unroll
         for (int q = 0; q < NACC; ++q) {
             const int tb = q / XG, xg = q - tb * XG;
             acc_row8[q] = (uint32_t)(tb * HR + xg * 8) * 8u;
         }
-        int hcount = 0, bcount = 0, tcount = 0;
+        const uint32_t bar_bfull = smem_u32(&b_full[0]), bar_bempty = smem_u32(&b_empty[0]);
+        int st = 0, hb = 0, tcount = 0;
+        uint32_t bph = 0u, hph = 0u;           // parities of the weight ring / halo ring
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
             const H2Tile h = h2_tile(hp, t);
             const int abuf = tcount % NB, ause = tcount / NB;
@@ -206,41 +229,39 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
                 mbar_wait(&acc_empty[abuf], (uint32_t)((ause - 1) & 1));
                 tc_fence_after();
             }
-            const uint32_t tacc = tmem_base + (uint32_t)(abuf * NACC * N);
+            const uint32_t tacc = tmem_u + (uint32_t)(abuf * NACC * N);
             uint32_t first = 0u;               // 0 until the first MMA of the tile has been issued
             for (int kc = 0; kc < hp.nkc; ++kc) {
                 const int nk = kc == hp.nkc - 1 ? hp.nk16_last : BK / 16;
-                for (int pg = h.pg0; pg < h.pg0 + h.npg; ++pg, ++hcount) {
+                for (int pg = h.pg0; pg < h.pg0 + h.npg; ++pg) {
                     const TapProg& pr = hp.prog[pg];
-                    const int buf = hcount % NH;
-                    mbar_wait(&halo_full[buf], (uint32_t)((hcount / NH) & 1));
-                    const uint32_t alo_h = desc_lo(smemH + buf * halo_stride, 16);
-                    for (int tap = 0; tap < pr.ntaps; ++tap, ++bcount) {
-                        const int st = bcount % NBS;
-                        mbar_wait(&b_full[st], (uint32_t)((bcount / NBS) & 1));
+                    mbar_wait(&halo_full[hb], hph);
+                    const uint32_t alo_h = alo0 + (uint32_t)hb * hstep;
+                    const int ntaps = pr.ntaps;
+                    for (int tap = 0; tap < ntaps; ++tap) {
+                        mbar_wait_addr(bar_bfull + 8u * (uint32_t)st, bph);
                         tc_fence_after();
-                        const uint32_t blo = blo0 + st * (b_stride >> 4);
-                        const uint32_t alo_t = alo_h + (uint32_t)((int)pr.shift_y[tap] * WH + (int)pr.shift_x[tap]) * 8u;
+                        const uint32_t blo = blo0 + (uint32_t)st * bstep;
+                        const uint32_t alo_t = alo_h + (uint32_t)pr.a_off[tap];
                         if (elect_one()) {
                             if (!ACG_DBG(p, 4)) {                                  // probe: no MMAs
                                 // K step outer, accumulator inner: consecutive MMAs write different accumulators
-#pragma unroll
-                                for (int k = 0; k < BK / 16; ++k) {
-                                    if (k < nk) {
-#pragma unroll
-                                        for (int q = 0; q < NACC; ++q)
-                                            tc_mma2(tacc + q * N, alo_t + acc_row8[q] + 2 * k, ahi, blo + 2 * k, bhi, idesc,
-                                                    first | (uint32_t)k);
-                                    }
+                                switch (nk) {      // straight-line code per K-step count (uniform branch)
+                                    case 4: issue_tap<NACC, 4>(tacc, N, alo_t, acc_row8, ahi, blo, bhi, idesc, first); break;
+                                    case 3: issue_tap<NACC, 3>(tacc, N, alo_t, acc_row8, ahi, blo, bhi, idesc, first); break;
+                                    case 2: issue_tap<NACC, 2>(tacc, N, alo_t, acc_row8, ahi, blo, bhi, idesc, first); break;
+                                    default: issue_tap<NACC, 1>(tacc, N, alo_t, acc_row8, ahi, blo, bhi, idesc, first); break;
                                 }
                             }
-                            tc_commit(&b_empty[st]);
+                            tc_commit_addr(bar_bempty + 8u * (uint32_t)st);
                         }
                         __syncwarp();
                         first = 1u;
+                        if (++st == NBS) { st = 0; bph ^= 1u; }
                     }
-                    if (elect_one()) tc_commit(&halo_empty[buf]);
+                    if (elect_one()) tc_commit(&halo_empty[hb]);
                     __syncwarp();
+                    if (++hb == NH) { hb = 0; hph ^= 1u; }
                 }
             }
             if (elect_one()) tc_commit(&acc_full[abuf]);
@@ -423,9 +444,8 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
             for (int ta = 0; ta < na; ++ta)
                 for (int tcx = 0; tcx < nc; ++tcx) {
                     const int i = ta * nc + tcx;
-                    pr.shift_y[i] = (short)(na - 1 - ta);
-                    pr.shift_x[i] = (short)(nc - 1 - tcx);
-                    pr.wtap[i] = (short)i;
+                    pr.a_off[i] = ((na - 1 - ta) * (hp.TW + 2) + (nc - 1 - tcx)) * 8;
+                    pr.w_off[i] = i * lda;
                 }
             const cuuint64_t Kc = (cuuint64_t)pr.ntaps * lda;
             const cuuint64_t wd[2] = {Kc, (cuuint64_t)N};
@@ -457,9 +477,8 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
                     const int rc2 = c - s->pad_l, qc = ((rc2 % 2) + 2) % 2;
                     if (qc != pj) continue;
                     ACG_REQUIRE(n < kMaxTaps, ACG_ERR_UNSUPPORTED, "%s: more than %d taps per plane", who, kMaxTaps);
-                    pr.shift_y[n] = (short)((ra - qa) / 2 - dmin_i);
-                    pr.shift_x[n] = (short)((rc2 - qc) / 2 - dmin_j);
-                    pr.wtap[n] = (short)(a * s->KW + c);
+                    pr.a_off[n] = (((ra - qa) / 2 - dmin_i) * (hp.TW + 2) + ((rc2 - qc) / 2 - dmin_j)) * 8;
+                    pr.w_off[n] = (a * s->KW + c) * lda;
                     ++n;
                 }
             }

@@ -235,6 +235,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
         const uint32_t idesc = make_idesc(n_cta, 0, 0);
         const uint32_t hi = desc_hi(1024);
         const uint32_t alo0 = desc_lo(smemA, 16), blo0 = desc_lo(smemB, 16);
+        const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);    // warp-uniform register (see conv_halo.cu)
         for (int kb = 0; kb < nkb; ++kb) {
             const int stage = kb % STAGES;
             mbar_wait(&full_bar[stage], (uint32_t)((kb / STAGES) & 1));
@@ -243,7 +244,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
             if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)   // +32 B per K=16 step inside the swizzle atom
-                    tc_mma2(tmem_base, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_mma2(tmem_u, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
                 tc_commit(&empty_bar[stage]);   // arrives when the MMAs above have finished reading this stage
             }
             __syncwarp();
@@ -578,7 +579,7 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
                 mbar_wait(&acc_empty[abuf], (uint32_t)(((it >> 1) - 1) & 1));
                 tc_fence_after();
             }
-            const uint32_t tacc = tmem_base + (uint32_t)(abuf * NT);
+            const uint32_t tacc = __reduce_or_sync(0xffffffffu, tmem_base) + (uint32_t)(abuf * NT);
             for (int kb = 0; kb < nkb; ++kb, ++cnt) {
                 const int stage = cnt % kSmallKRing;
                 mbar_wait(&full_bar[stage], (uint32_t)((cnt / kSmallKRing) & 1));
@@ -1165,6 +1166,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
         const uint32_t idesc = make_idesc(n_cta, 1, 1);
         const uint32_t hi = desc_hi(1024);
         const uint32_t alo0 = desc_lo(smemA, BK * 128), blo0 = desc_lo(smemB, BK * 128);
+        const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);    // warp-uniform register
         for (int kb = 0; kb < nkb; ++kb) {
             const int stage = kb % STAGES;
             mbar_wait(&full_bar[stage], (uint32_t)((kb / STAGES) & 1));
@@ -1173,7 +1175,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
             if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)   // 16 pixels = two 8-row groups (2048 B) further down each atom
-                    tc_mma2(tmem_base, alo + 128 * k, hi, blo + 128 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_mma2(tmem_u, alo + 128 * k, hi, blo + 128 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
                 tc_commit(&empty_bar[stage]);
             }
             __syncwarp();

@@ -5,20 +5,36 @@ TF's variable scopes are mirrored by a module-level variable table keyed by scop
 creates the variables (xavier-uniform weights, zero beta / biases: slim defaults) unless reuse=True, a second call
 without reuse raises ValueError like tf.get_variable does.  `actions` may be the tiled map the reference feeds
 ([B,4,4,10]; [B,16,16,10] for the discriminator after repair R3) or the raw [B,10] vector.
+
+The functions are differentiable: they call the `acg::generator_transform` / `acg::generator` / `acg::discriminator`
+custom ops (torch_ops.py), whose backward is the engine's hand-scheduled backward pass.  `trainable(scope)` returns
+the scope's flat parameter tensor (a leaf sharing storage with the ParamStore) -- the analogue of
+`tf.get_collection(TRAINABLE_VARIABLES, scope)` at train.py:87-88 -- and `variables(scope)` its named views.
 """
 import numpy as np
 import torch
 
 from . import engine as E
+from . import torch_ops as T
 
 VARIABLES = {}     # scope -> ParamStore
-_RUNS = {}         # (scope, batch, flags) -> NetRun
+_LEAVES = {}       # scope -> flat parameter leaf (requires_grad, same storage as the store)
 _SEED = 7          # train.py:14
 
 
 def reset_default_graph():
     VARIABLES.clear()
-    _RUNS.clear()
+    _LEAVES.clear()
+
+
+def trainable(scope):
+    """Flat fp32 parameter tensor of scope 'g' / 'd' (requires_grad; `.grad` is filled by backward())."""
+    return _LEAVES[scope]
+
+
+def variables(scope):
+    """{tf variable name: view into the flat buffer} of a scope (HWIO weights, beta / biases)."""
+    return VARIABLES[scope].views
 
 
 def _actions(a):
@@ -42,6 +58,8 @@ def _store(scope, spec, reuse, device):
     rng = np.random.RandomState(_SEED + len(VARIABLES))
     st = E.ParamStore(spec, device, E.xavier_init(spec, rng))
     VARIABLES[scope] = st
+    T.register_store(st)
+    _LEAVES[scope] = st.flat.detach().requires_grad_(True)      # same storage: optimizer kernels update it in place
     return st
 
 
@@ -54,14 +72,8 @@ def _need_cuda(t):
 def build_generator(images, actions, reuse=False):
     """models.py:8-22 -> tanh image [B,64,64,3]."""
     images = _need_cuda(images)
-    spec = E.g_direct_spec()
-    store = _store("g", spec, reuse, images.device)
-    key = ("g", images.shape[0], "direct")
-    if key not in _RUNS:
-        _RUNS[key] = E.GeneratorRun(store, images.shape[0], images.device, False, 5)
-        store.refresh_packs()
-    out, _ = _RUNS[key].forward(images, _actions(actions).to(images.device))
-    return out.clone()
+    _store("g", E.g_direct_spec(), reuse, images.device)
+    return T.generator(images, _actions(actions).to(images.device), _LEAVES["g"])
 
 
 def build_generator_transform(images, actions, batch_size, reuse=False, color_channels=3, ksize=5):
@@ -69,23 +81,13 @@ def build_generator_transform(images, actions, batch_size, reuse=False, color_ch
     images = _need_cuda(images)
     if color_channels != 3 or images.shape[0] != batch_size:
         raise ValueError("build_generator_transform: color_channels must be 3 and batch_size must match images")
-    spec = E.g_dna_spec(ksize)
-    store = _store("g", spec, reuse, images.device)
-    key = ("g", batch_size, "dna", ksize)
-    if key not in _RUNS:
-        _RUNS[key] = E.GeneratorRun(store, batch_size, images.device, True, ksize)
-        store.refresh_packs()
-    out, state = _RUNS[key].forward(images, _actions(actions).to(images.device))
-    return out.clone(), state.clone()
+    _store("g", E.g_dna_spec(ksize), reuse, images.device)
+    out, state = T.generator_transform(images, _actions(actions).to(images.device), _LEAVES["g"], ksize)
+    return out, state
 
 
 def build_discriminator(inputs, actions, reuse=False):
     """models.py:76-88: inputs = concat([frame_t, frame_t+1], 3) [B,64,64,6] -> logits [B,2,2,1]."""
     inputs = _need_cuda(inputs)
-    store = _store("d", E.d_spec(), reuse, inputs.device)
-    key = ("d", inputs.shape[0])
-    if key not in _RUNS:
-        _RUNS[key] = E.DiscriminatorRun(store, inputs.shape[0], inputs.device)
-        store.refresh_packs()
-    img, frame = inputs[..., :3].contiguous(), inputs[..., 3:].contiguous()
-    return _RUNS[key].forward(img, frame, _actions(actions).to(inputs.device)).clone()
+    _store("d", E.d_spec(), reuse, inputs.device)
+    return T.discriminator(inputs, _actions(actions).to(inputs.device), _LEAVES["d"])

@@ -1,14 +1,15 @@
 """`ops.py` surface of the reference (ops.py:19-50,100-120) on the acg_b200 kernels.
 
 Every function takes CUDA float32 torch tensors (NHWC) and returns a 0-d CUDA tensor (the losses) or a tensor
-(lrelu).  They are the forward values; the training step (trainer.py) uses the fused value+gradient kernels
-directly.  Unknown `arg_loss` raises ValueError('unexpected loss argument') exactly like the reference.
+(lrelu).  They are differentiable `acg::` custom ops (torch_ops.py) whose backward is the same fused kernel; the
+training step (trainer.py) calls the fused value+gradient kernels directly.  Unknown `arg_loss` raises
+ValueError('unexpected loss argument') exactly like the reference.
 """
 import math
 
 import torch
 
-from . import kernels as K
+from . import torch_ops as T
 
 
 def _check(t):
@@ -23,38 +24,26 @@ def lrelu(x, leak=0.2, name="lrelu"):
     if abs(leak - 0.2) > 1e-12:
         raise RuntimeError("lrelu: only leak=0.2 is compiled in")
     x = _check(x)
-    out = torch.empty_like(x)
-    C = x.shape[-1]
-    K.bn_act_fwd(x, x.numel() // C, C, C, 1, None, None, "lrelu", out, C)
-    return out
-
-
-def _frame_sums(a, b):
-    a, b = _check(a), _check(b)
-    sums = torch.zeros(3, dtype=torch.float64, device=a.device)
-    K.frame_losses(a, b, sums)
-    return sums
+    return T.bias_act(x, torch.zeros(x.shape[-1], device=x.device), "lrelu")
 
 
 def build_psnr(true, pred):
     """ops.py:19-20: 10*log10(1 / mean((true-pred)^2))."""
-    s = _frame_sums(pred, true)
+    s = T.frame_losses(_check(pred), _check(true))
     return (10.0 * torch.log(true.numel() / s[1]) / math.log(10.0)).float()
 
 
 def build_gdl(g_out, next_frames, alpha=1):
     """ops.py:100-120 with the reference's call order build_gdl(next_frame_ph, g_next_frame) in mind: the value is
-    symmetric in its two arguments.  Only alpha=1 (the default, the only value used) is compiled in."""
+    symmetric in its two arguments; the gradient flows to the first one.  Only alpha=1 (the default, the only value
+    used) is compiled in."""
     if alpha != 1:
         raise RuntimeError("build_gdl: only alpha=1 is compiled in")
-    return _frame_sums(next_frames, g_out)[2].float()
+    return T.frame_losses(_check(g_out), _check(next_frames))[2].float()
 
 
 def _logit_loss(x, kind, label_or_sign):
-    x = _check(x)
-    out = torch.zeros(1, device=x.device)
-    K.dlogit_loss(x, x.numel(), kind, label_or_sign, 1.0, out, None)
-    return out[0]
+    return T.dlogit_loss(_check(x), kind, float(label_or_sign))
 
 
 def build_g_adv_loss(d_out_gen, arg_loss):

@@ -109,3 +109,19 @@ def test_peer_slot_plan_is_symmetric(built_lib):
     small.take(64)
     with pytest.raises(RuntimeError, match="exhausted"):
         small.take(1024)
+
+
+def test_custom_ops_are_registered_and_cuda_only():
+    """The acg:: torch.library ops exist with schemas and fake (shape) kernels, and refuse CPU tensors: there is no CPU
+    fallback behind the PyTorch boundary."""
+    from action_conditioned_gans_b200 import torch_ops  # noqa: F401
+    for name in ("dna", "conv2d", "conv2d_dgrad", "conv2d_wgrad", "bn_act", "bias_act", "frame_losses", "dlogit_loss",
+                 "adam_step", "rmsprop_step", "generator_transform", "generator", "discriminator"):
+        assert hasattr(torch.ops.acg, name), name
+    assert "Tensor logits, Tensor img, SymInt ksize" in str(torch.ops.acg.dna.default._schema) or \
+        "Tensor logits, Tensor img, int ksize" in str(torch.ops.acg.dna.default._schema)
+    with pytest.raises(NotImplementedError):
+        torch.ops.acg.dna(torch.randn(1, 8, 8, 25), torch.randn(1, 8, 8, 3), 5)
+    # shape inference without a device (fake kernels)
+    meta = torch.ops.acg.conv2d(torch.empty(2, 64, 64, 3, device="meta"), torch.empty(5, 5, 3, 32, device="meta"), 2, True, False)
+    assert tuple(meta.shape) == (2, 32, 32, 32)
