@@ -3,8 +3,15 @@
     python train.py IN OUT [--adv [True|False]] [--loss bce|wass] [--opt adam|rmsprop] [--dna [True|False]]
 
 Repair R6: --adv / --dna accept `--adv`, `--adv True`, `--adv False` and default to True (README.md:30-49).
-IN is a directory of .npz shards {images [N,T,64,64,3] in [-1,1], actions [N,T,10]}, or the word `synthetic`
-(the Push TFRecords of ops.py:141-223 are not available offline; only their output shapes matter here).
+IN is a directory of .npz shards {images [N,T,64,64,3] (uint8, or float in [-1,1]), actions [N,T,10]}, or the word
+`synthetic` (the Push TFRecords of ops.py:141-223 are not available offline; only their output shapes matter here).
+90 % of the shards train, the last 10 % are held out for the in-loop rollout, as `build_tfrecord_input(..., .9, ...)`
+does (train.py:189-196).
+
+The sequences are uploaded once and stay resident in device memory (feeder.DeviceFeeder): every step ships 2 x B
+indices and a gather kernel does the frame-pair sampling of util.py:10-16 / train.py:231-237 on the device.  Scalars go
+to `OUT/logs/train.jsonl` and, as the reference's `tf.summary.FileWriter` does (train.py:211-214,275), to TensorBoard
+event files in `OUT/logs`; checkpoints keep the newest 5 like `tf.train.Saver()` and are written atomically.
 """
 import argparse
 import glob
@@ -14,13 +21,15 @@ import time
 
 import numpy as np
 
-from .trainer import BATCH_SIZE, Trainer
-from .util import build_all_mask, save_samples
+from .feeder import DeviceFeeder
+from .trainer import BATCH_SIZE, SUMMARY_KEYS, Trainer
+from .util import save_samples
 
 HISTORY_LENGTH = 1      # train.py:16
 PRETRAIN_ITER = 20      # train.py:24
 TRAIN_ITER = 60000      # train.py:25
-NUM_FRAMES = 7          # ops.py: frames 6,8,...,18
+NUM_FRAMES = 7          # ops.py: frames 6,8,...,18 (synthetic data only; real shards carry their own T)
+MAX_TO_KEEP = 5         # tf.train.Saver() default
 
 
 def str2bool(v):
@@ -50,47 +59,93 @@ def build_parser():
     return p
 
 
-class SyntheticPush:
-    """Push-shaped synthetic sequences: img [B,7,64,64,3] in [-1,1], action++state [B,7,10]."""
-
-    def __init__(self, batch, seed):
-        self.B, self.rng = batch, np.random.RandomState(seed)
-
-    def get_batch(self):
-        B = self.B
-        base = self.rng.uniform(-1, 1, (B, 1, 64, 64, 3)).astype(np.float32)
-        drift = np.cumsum(0.05 * self.rng.randn(B, NUM_FRAMES, 64, 64, 3).astype(np.float32), axis=1)
-        img = np.clip(base + drift, -1, 1)
-        act = self.rng.randn(B, NUM_FRAMES, 10).astype(np.float32)
-        return img, act
+def synthetic_push(n_seq, seed, T=NUM_FRAMES):
+    """Push-shaped synthetic sequences as a decoded dataset holds them: uint8 frames [N,T,64,64,3], action++state
+    [N,T,10]."""
+    rng = np.random.RandomState(seed)
+    base = rng.uniform(-1, 1, (n_seq, 1, 64, 64, 3)).astype(np.float32)
+    drift = np.cumsum(0.05 * rng.randn(n_seq, T, 64, 64, 3).astype(np.float32), axis=1)
+    return DeviceFeeder.quantize(np.clip(base + drift, -1, 1)), rng.randn(n_seq, T, 10).astype(np.float32)
 
 
-class NpzShards:
-    def __init__(self, path, batch, seed):
-        self.files = sorted(glob.glob(os.path.join(path, "*.npz")))
-        if not self.files:
-            raise FileNotFoundError("no .npz shards under %s" % path)
-        self.B, self.rng = batch, np.random.RandomState(seed)
-
-    def get_batch(self):
-        with np.load(self.files[self.rng.randint(len(self.files))]) as f:
-            img, act = f["images"], f["actions"]
-        idx = self.rng.randint(0, img.shape[0], size=self.B)
-        return img[idx].astype(np.float32), act[idx].astype(np.float32)
+def load_shards(files):
+    imgs, acts = [], []
+    for f in files:
+        with np.load(f) as z:
+            im, ac = z["images"], z["actions"]
+        imgs.append(im if im.dtype == np.uint8 else DeviceFeeder.quantize(im))
+        acts.append(ac.astype(np.float32))
+    return np.concatenate(imgs), np.concatenate(acts)
 
 
-def open_data(input_path, batch, seed):
+def open_data(input_path, batch, seed, device):
+    """-> (train feeder, held-out feeder).  ops.py:189-196: the first 90 % of the (sorted) files train, the rest test."""
     if input_path == "synthetic" or not os.path.isdir(input_path):
         print("input_path %r is not a directory of .npz shards: using synthetic Push-shaped data" % input_path)
-        return SyntheticPush(batch, seed)
-    return NpzShards(input_path, batch, seed)
+        tr, te = synthetic_push(max(4 * batch, 64), seed), synthetic_push(max(batch, 16), seed + 1)
+    else:
+        files = sorted(glob.glob(os.path.join(input_path, "*.npz")))
+        if not files:
+            raise FileNotFoundError("no .npz shards under %s" % input_path)
+        split = int(np.floor(0.9 * len(files)))
+        split = min(max(split, 1), len(files) - 1) if len(files) > 1 else 1
+        tr = load_shards(files[:split])
+        te = load_shards(files[split:]) if len(files) > 1 else tr
+    return DeviceFeeder(tr[0], tr[1], device), DeviceFeeder(te[0], te[1], device)
+
+
+def _ckpt_step(f):
+    return int(os.path.basename(f)[5:-4])
 
 
 def latest_checkpoint(model_dir):
     files = glob.glob(os.path.join(model_dir, "model*.npz"))
     if not files:
         return None
-    return max(files, key=lambda f: int(os.path.basename(f)[5:-4]))
+    return max(files, key=_ckpt_step)
+
+
+def save_checkpoint(trainer, model_dir, step, max_to_keep=MAX_TO_KEEP):
+    """tf.train.Saver().save (train.py:215,274): the file appears atomically (temp file + os.replace, so a crash
+    mid-write never leaves a truncated model*.npz for latest_checkpoint to pick up) and only the newest `max_to_keep`
+    checkpoints stay on disk (each is ~115 MB: weights + three sets of optimizer slots)."""
+    final = os.path.join(model_dir, "model{:d}.npz".format(step))
+    tmp = final + ".tmp.npz"
+    trainer.save(tmp)
+    os.replace(tmp, final)
+    files = sorted(glob.glob(os.path.join(model_dir, "model*.npz")), key=_ckpt_step)
+    files = [f for f in files if not f.endswith(".tmp.npz")]
+    for f in files[:-max_to_keep]:
+        os.remove(f)
+    return final
+
+
+class SummaryLog:
+    """The 7 scalars of train.py:104-112 to JSONL and to TensorBoard event files (tf.summary.FileWriter, train.py:211)."""
+
+    def __init__(self, log_dir):
+        os.makedirs(log_dir, exist_ok=True)
+        self.jsonl = open(os.path.join(log_dir, "train.jsonl"), "a")
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            self.tb = SummaryWriter(log_dir)
+        except Exception as e:                      # tensorboard missing: the JSONL still has everything
+            print("TensorBoard writer unavailable (%s): scalars go to train.jsonl only" % e)
+            self.tb = None
+
+    def add(self, scalars, step, **extra):
+        self.jsonl.write(json.dumps(dict(scalars or {}, iteration=step, **extra)) + "\n")
+        self.jsonl.flush()
+        if self.tb is not None:
+            for k in SUMMARY_KEYS:
+                if scalars and k in scalars:
+                    self.tb.add_scalar(k, scalars[k], step)
+            self.tb.flush()
+
+    def close(self):
+        self.jsonl.close()
+        if self.tb is not None:
+            self.tb.close()
 
 
 def train(input_path, output_path, test_output_path, log_dir, model_dir, arg_adv, arg_loss, arg_opt, arg_transform,
@@ -98,67 +153,61 @@ def train(input_path, output_path, test_output_path, log_dir, model_dir, arg_adv
     """train.py:179-309: 20 pre-train G iterations, then per iteration D_per_G x train_d (5 for wass, else 1) on fresh
     batches and one train_g on the last D batch with a re-drawn frame index (train.py:217-263)."""
     np.random.seed(seed)                                         # train.py:14
-    data = open_data(input_path, batch_size, seed)
-    test_data = open_data(input_path, batch_size, seed + 1)
-    boolean_mask = build_all_mask(NUM_FRAMES)                    # train.py:202
     trainer = Trainer(None, arg_adv, arg_loss, arg_opt, arg_transform, batch_size=batch_size, seed=seed,
                       precision=precision)
-    os.makedirs(log_dir, exist_ok=True)
-    log = open(os.path.join(log_dir, "train.jsonl"), "a")
+    data, test_data = open_data(input_path, batch_size, seed, trainer.device)
+    log = SummaryLog(log_dir)
     D_per_G = 5 if arg_loss == "wass" else 1                     # train.py:217-220
     B = batch_size
-
-    def draw(img, act):
-        start_mask = boolean_mask[np.random.randint(0, len(boolean_mask), size=B)]
-        end_mask = np.roll(start_mask, 1, axis=1)
-        state = act[:, :, 5:]                                    # next_state_train, train.py:199
-        return img[start_mask], img[end_mask], act[start_mask], state[end_mask]
 
     t0 = time.time()
     for i in range(iters):
         if i < pretrain_iters:
-            img, act = data.get_batch()
-            a, b, c, d = draw(img, act)
-            trainer.pretrain_g(a, b, c, d)
+            sample, t = data.sample(B)                           # get_batch + boolean_mask[randint] (train.py:226-230)
+            trainer.pretrain_g_indexed(data, sample, t)
             print("pre-train iter: " + str(i))
             continue
         summ = None
         for j in range(D_per_G):
-            img, act = data.get_batch()
-            a, b, c, d = draw(img, act)
+            sample, t = data.sample(B)
             make_summ = (i % 100 == 0) and (j == D_per_G - 1)
-            summ = trainer.train_d(a, b, c, summarize=make_summ)
-        a, b, c, d = draw(img, act)
-        gen_next_frames = trainer.train_g(a, b, c, d)
+            summ = trainer.train_d_indexed(data, sample, t, summarize=make_summ)
+        sample, t = data.redraw(sample)                          # same sequences, new frame index (train.py:258-263)
+        gen_next_frames = trainer.train_g_indexed(data, sample, t)
         if i % 100 == 0:
             print("Iteration {:d}".format(i))
-            save_samples(output_path, np.expand_dims(a[:32], 1), np.expand_dims(gen_next_frames[:32], 1),
-                         np.expand_dims(b[:32], 1), i)
-            trainer.save(os.path.join(model_dir, "model{:d}.npz".format(i)))
-            rec = dict(summ or {}, iteration=i, wall_s=time.time() - t0)
-            log.write(json.dumps(rec) + "\n")
-            log.flush()
+            a, b, _, _ = data.host_pair(sample[:32], t[:32])
+            save_samples(output_path, np.expand_dims(a, 1), np.expand_dims(gen_next_frames[:32], 1),
+                         np.expand_dims(b, 1), i)
+            save_checkpoint(trainer, model_dir, i)
+            log.add(summ, i, wall_s=time.time() - t0)
         if i % 500 == 0:
-            timg, tact = test_data.get_batch()
-            predicted, _ = rollout(trainer, timg, tact)
-            save_samples(test_output_path, timg[:16], predicted[:16], timg[:16], i)
+            idx = np.random.randint(0, test_data.N, size=B)
+            timg = test_data.frames[torch_index(idx, test_data)]
+            tact = test_data.actions[torch_index(idx, test_data)]
+            predicted, truth = rollout(trainer, timg, tact)
+            save_samples(test_output_path, truth[:16], predicted[:16], truth[:16], i)
     log.close()
     return trainer
 
 
+def torch_index(idx, feeder):
+    import torch
+    return torch.as_tensor(idx, dtype=torch.long, device=feeder.device)
+
+
 def rollout(trainer, test_input, test_actions):
-    """The in-loop evaluation of train.py:286-299: T-1 recursive steps with action index j."""
-    predicted = []
-    current_frame = test_input[:, 0]
-    current_state = test_actions[:, 0, 5:]
-    for j in range(test_input.shape[1] - 1):
-        acs = np.concatenate((test_actions[:, j, :5], current_state), axis=1)
-        out, st, _ = trainer.test(current_frame, test_input[:, j + 1], acs)
-        predicted.append(out)
-        current_frame = out
-        if st is not None:
-            current_state = st
-    return np.transpose(np.array(predicted), (1, 0, 2, 3, 4)), None
+    """The in-loop evaluation of train.py:286-299: T-1 recursive steps with action index j, as ONE captured graph with
+    frames and state fed back on the device (Trainer.rollout).  test_input: device frames [B,T,64,64,3] (uint8 or float),
+    test_actions [B,T,10].  Returns (predicted [B,T-1,64,64,3], ground truth [B,T,64,64,3]) as float NumPy arrays."""
+    import torch
+    T = int(test_input.shape[1])
+    first = test_input[:, 0]
+    pred = trainer.rollout(first.contiguous(), test_actions.contiguous(), steps=T - 1, action_stride=1)
+    truth = test_input
+    if truth.dtype == torch.uint8:
+        truth = truth.float() / 127.5 - 1.0
+    return pred.permute(1, 0, 2, 3, 4).contiguous().cpu().numpy(), truth.cpu().numpy()
 
 
 def main(argv=None):
