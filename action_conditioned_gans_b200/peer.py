@@ -3,6 +3,7 @@
 One `Mailbox` per process: a device segment every peer maps through a cudaIpc handle.  `new_slot()` hands out exchange
 slots; every rank creates its slots in the same order, so a slot has the same byte offset in every mailbox."""
 import ctypes as C
+import os
 
 import torch
 
@@ -37,7 +38,13 @@ class SlotPlan:
 
 
 class Mailbox:
-    def __init__(self, dist, group, device, timeout_s=30.0):
+    def __init__(self, dist, group, device, timeout_s=None):
+        """timeout_s: how long an exchange kernel spins for a peer before it traps (a lost rank must not hang the GPU).
+        Default 120 s, ACG_PEER_TIMEOUT_S overrides: rank skew beyond that (a rank-0-only checkpoint, a slow loader,
+        a debugger) would otherwise kill a healthy job."""
+        if timeout_s is None:
+            timeout_s = float(os.environ.get("ACG_PEER_TIMEOUT_S", "120"))
+        self._dist, self._group, self._own = dist, group, None
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if self.world > MAX_PEERS:
             raise RuntimeError("peer exchange supports at most %d ranks (one NVSwitch domain)" % MAX_PEERS)
@@ -46,6 +53,7 @@ class Mailbox:
         own = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.call("acg_peer_alloc", SEGMENT_BYTES, C.byref(own))
+            self._own = own
             handle = C.create_string_buffer(64)
             _lib.call("acg_peer_export", own, handle)
             handles = [None] * self.world
@@ -61,6 +69,22 @@ class Mailbox:
         self.plan = SlotPlan(self.world)
         self.epochs = torch.zeros(MAX_SLOTS, dtype=torch.int64, device=self.device)
         dist.barrier(group=group)       # every segment is mapped everywhere before the first push
+
+    def close(self):
+        """Unmap the peers' segments and free the own one (after a barrier: nobody may still push into it)."""
+        if self._own is None:
+            return
+        own, self._own = self._own, None
+        try:
+            torch.cuda.synchronize(self.device)
+            self._dist.barrier(group=self._group)
+        except Exception:
+            pass                      # process group already gone: still release the local mappings
+        with torch.cuda.device(self.device):
+            for r in range(self.world):
+                if r != self.rank and self.ptrs[r]:
+                    _lib.call("acg_peer_close", C.c_void_p(self.ptrs[r]))
+            _lib.call("acg_peer_free", own)
 
     def new_slot(self, cap):
         off, idx = self.plan.take(cap)

@@ -75,10 +75,48 @@ def test_frame_pair_masks_and_schedule():
 
 
 def test_synthetic_data_shapes():
-    from action_conditioned_gans_b200.train import SyntheticPush
-    img, act = SyntheticPush(4, 0).get_batch()
+    from action_conditioned_gans_b200.feeder import DeviceFeeder
+    from action_conditioned_gans_b200.train import synthetic_push
+    img, act = synthetic_push(4, 0)
     assert img.shape == (4, 7, 64, 64, 3) and act.shape == (4, 7, 10)
-    assert img.min() >= -1 and img.max() <= 1 and img.dtype == np.float32
+    assert img.dtype == np.uint8 and act.dtype == np.float32          # frames as a decoded dataset holds them
+    back = img.astype(np.float32) / 127.5 - 1.0
+    assert np.array_equal(DeviceFeeder.quantize(back), img)            # decode / quantize round trip
+
+
+def test_feeder_host_logic():
+    """Frame-pair sampling of util.py:10-16 / train.py:226-263 as index draws: t in [0, T-2], paired with t+1; train_g
+    re-draws the frame index on the same sequences; out-of-range indices are refused before any kernel runs."""
+    from action_conditioned_gans_b200.feeder import DeviceFeeder
+    from action_conditioned_gans_b200.train import synthetic_push
+    img, act = synthetic_push(6, 1)
+    fd = DeviceFeeder(img, act, "cpu")                                 # host logic only: no kernel is called
+    rng = np.random.RandomState(0)
+    sample, t0 = fd.sample(64, rng)
+    assert sample.dtype == np.int32 and t0.dtype == np.int32 and sample.max() < 6 and t0.max() <= 5 and t0.min() >= 0
+    s2, t2 = fd.redraw(sample, rng)
+    assert np.array_equal(s2, sample) and not np.array_equal(t2, t0)
+    a, b, ac, st = fd.host_pair(sample, t0)
+    assert a.shape == (64, 64, 64, 3) and np.array_equal(st, act[sample, t0 + 1, 5:]) and np.array_equal(ac, act[sample, t0])
+    with pytest.raises(IndexError):
+        fd.check(sample, np.full(64, 6, np.int32), 64)
+    with pytest.raises(ValueError):
+        DeviceFeeder(img[:, :1], act[:, :1], "cpu")
+
+
+def test_checkpoint_pruning_is_atomic_and_keeps_five(tmp_path):
+    from action_conditioned_gans_b200 import train as T
+
+    class FakeTrainer:
+        def save(self, path):
+            np.savez(path, x=np.zeros(3))
+
+    for step in range(0, 900, 100):
+        T.save_checkpoint(FakeTrainer(), str(tmp_path), step)
+    left = sorted(p.name for p in tmp_path.iterdir())
+    assert left == ["model%d.npz" % s for s in (400, 500, 600, 700, 800)]          # tf.train.Saver max_to_keep=5
+    assert T.latest_checkpoint(str(tmp_path)).endswith("model800.npz")
+    assert not any(n.endswith(".tmp.npz") for n in left)
 
 
 def test_save_samples_layout(tmp_path):

@@ -90,33 +90,32 @@ def test_argument_checks(cuda):
                   None, None, None, None, None)
 
 
-def _dp_worker(rank, world, port, out_dir):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+def _dp_worker(rank, world, port, out_dir, iters, sync):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      ACG_DP_SYNC=sync)
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     from action_conditioned_gans_b200.trainer import DataParallel, Trainer
     dp = DataParallel(device=dev)
-    assert dp.peer_sync and dp.mailbox is not None
+    assert dp.peer_sync == (sync == "peer") and (dp.mailbox is not None) == (sync == "peer")
     B = 4
-    rng = np.random.RandomState(5)
-    img = rng.uniform(-1, 1, (world * B, 64, 64, 3)).astype(np.float32)
-    nxt = np.clip(img + 0.1 * rng.randn(*img.shape), -1, 1).astype(np.float32)
-    act = rng.randn(world * B, 10).astype(np.float32)
-    st = rng.randn(world * B, 5).astype(np.float32)
+    img, nxt, act, st = _dp_feeds(world * B)
     sl = slice(rank * B, (rank + 1) * B)
     trn = Trainer(None, True, "bce", "adam", True, batch_size=B, device=dev, seed=7, dp=dp)
-    for _ in range(3):          # eager, capture, replay
+    for _ in range(iters):      # eager, capture, then replays of the captured graphs
         trn.train_d(img[sl], nxt[sl], act[sl])
         trn.train_g(img[sl], nxt[sl], act[sl], st[sl])
     s = trn.train_d(img[sl], nxt[sl], act[sl], summarize=True)
     trn.synchronize()
-    w = trn.d_store.flat.clone()
+    w = torch.cat([trn.d_store.flat, trn.g_store.flat]).clone()
     ws = [torch.empty_like(w) for _ in range(world)]
     dist.all_gather(ws, w)
     same = all(torch.equal(ws[0], t) for t in ws)
-    res = [rank, bool(same), s["discriminator_loss"], s["g_loss"], trn.g_store.flat.double().sum().item()]
+    finite = bool(torch.isfinite(w).all())
+    res = [rank, bool(same), s["discriminator_loss"], s["g_loss"], trn.g_store.flat.double().sum().item(), finite,
+           s["g_l2_loss"]]
     torch.cuda.synchronize()
     with open(os.path.join(out_dir, "rank%d.json" % rank), "w") as fh:
         json.dump(res, fh)
@@ -125,38 +124,70 @@ def _dp_worker(rank, world, port, out_dir):
     os._exit(0)     # NCCL collectives captured in CUDA graphs: skip the communicator teardown (see bench.py)
 
 
-def test_data_parallel_step_two_gpus(cuda, tmp_path):
-    """Two processes, two GPUs, peer-memory SyncBN + NCCL gradient bucket: replicas stay bit-identical and agree with
-    a single-GPU run over the global batch (bf16 tolerance)."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def _dp_feeds(n):
+    rng = np.random.RandomState(5)
+    img = rng.uniform(-1, 1, (n, 64, 64, 3)).astype(np.float32)
+    nxt = np.clip(img + 0.1 * rng.randn(*img.shape), -1, 1).astype(np.float32)
+    return img, nxt, rng.randn(n, 10).astype(np.float32), rng.randn(n, 5).astype(np.float32)
+
+
+def _run_dp(world, tmp_path, iters, sync, timeout):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
-    port = 29600 + os.getpid() % 1000
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    port = 29600 + (os.getpid() * 7 + world * 13 + iters) % 1000
+    procs = [ctx.Process(target=_dp_worker, args=(r, world, port, str(tmp_path), iters, sync)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
-        p.join(timeout=180)
+        p.join(timeout=timeout)
         if p.is_alive():
-            p.kill()
-            pytest.fail("data-parallel worker did not finish")
+            for q in procs:
+                q.kill()
+            pytest.fail("data-parallel worker did not finish (world %d, %s)" % (world, sync))
         assert p.exitcode == 0
-    res = [json.load(open(os.path.join(str(tmp_path), "rank%d.json" % r))) for r in range(2)]
+    res = [json.load(open(os.path.join(str(tmp_path), "rank%d.json" % r))) for r in range(world)]
     assert all(r[1] for r in res), "replica weights diverged"
-    assert res[0][2] == pytest.approx(res[1][2], rel=1e-6) and res[0][4] == res[1][4]
-    # single process over the global batch
+    assert all(r[5] for r in res), "non-finite weights"
+    for r in res[1:]:
+        assert r[2] == pytest.approx(res[0][2], rel=1e-6) and r[4] == res[0][4]
+    return res
+
+
+def _single_gpu_reference(cuda, world, iters):
     from action_conditioned_gans_b200.trainer import Trainer
-    B, world = 4, 2
-    rng = np.random.RandomState(5)
-    img = rng.uniform(-1, 1, (world * B, 64, 64, 3)).astype(np.float32)
-    nxt = np.clip(img + 0.1 * rng.randn(*img.shape), -1, 1).astype(np.float32)
-    act = rng.randn(world * B, 10).astype(np.float32)
-    st = rng.randn(world * B, 5).astype(np.float32)
+    B = 4
+    img, nxt, act, st = _dp_feeds(world * B)
     trn = Trainer(None, True, "bce", "adam", True, batch_size=world * B, device=cuda, seed=7)
-    for _ in range(3):
+    for _ in range(iters):
         trn.train_d(img, nxt, act)
         trn.train_g(img, nxt, act, st)
-    s = trn.train_d(img, nxt, act, summarize=True)
-    assert res[0][2] == pytest.approx(s["discriminator_loss"], rel=5e-2)
-    assert res[0][3] == pytest.approx(s["g_loss"], rel=5e-2)
+    return trn.train_d(img, nxt, act, summarize=True)
+
+
+# Tolerance of the sharded run against ONE GPU over the global batch: the north-star bf16 bound (1e-2 relative).  The
+# two runs execute the same arithmetic up to the summation order of the batch-norm moments and gradient buckets.
+DP_TOL = 1e-2
+
+
+@pytest.mark.parametrize("world,sync", [(2, "peer"), (2, "nccl"), (4, "peer")])
+def test_data_parallel_step_matches_single_gpu(cuda, tmp_path, world, sync):
+    """`world` processes, one GPU each: SyncBN through the NVLink peer-memory exchange (or NCCL, with the captured
+    graphs on), NCCL gradient buckets, the global state-loss norm.  Replicas stay bit-identical and losses agree with a
+    single-GPU run over the global batch within DP_TOL (train.py:63-70: per-branch full-batch batch-norm;
+    train.py:123-144)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    res = _run_dp(world, tmp_path, 3, sync, 240)
+    s = _single_gpu_reference(cuda, world, 3)
+    assert res[0][2] == pytest.approx(s["discriminator_loss"], rel=DP_TOL)
+    assert res[0][3] == pytest.approx(s["g_loss"], rel=DP_TOL)
+    assert res[0][6] == pytest.approx(s["g_l2_loss"], rel=DP_TOL)
+
+
+def test_data_parallel_soak_100_iterations(cuda, tmp_path):
+    """100 replays of the captured graphs on 2 GPUs (the spin-exchange / programmatic-dependent-launch deadlock family
+    shows up as a timeout here): the run finishes, replicas are bit-identical, everything stays finite."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    res = _run_dp(2, tmp_path, 100, "peer", 400)
+    assert np.isfinite(res[0][2]) and np.isfinite(res[0][3])
