@@ -49,7 +49,10 @@ template <int K, typename LT, bool BWD, int STAGES, bool PADOUT>
 __global__ void __launch_bounds__(kThreads)
 dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const float* __restrict__ dy,
            float* __restrict__ out, void* __restrict__ dlogits_v, int B, int H, int W) {
-    pdl_prologue();
+    // PDL: dependents may be scheduled at once; the wait for the producer grid comes AFTER the shared-memory setup below
+    // (barrier init, pad zeroing: no global memory involved), so that setup hides under the previous kernel's tail.  At
+    // the small bench size (B=64, K=5: 10 us per launch against 5 us of HBM time) the prologue was 10 % of the kernel.
+    pdl_launch_dependents();
     using L = StageLayout<K, LT, BWD>;
     constexpr int KK = K * K;
     constexpr int LDO = pad16(KK);
@@ -70,7 +73,13 @@ dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const f
     const uint32_t lbytes = (uint32_t)(npx * KK * sizeof(LT));
     const uint32_t rbytes = (uint32_t)(W * 3 * 4);
 
-    // zero the pad columns of every staged image row once (bulk copies never touch them)
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
+        fence_mbar_init();
+    }
+    // zero the pad columns of every staged image row once (bulk copies never touch them: the first loads, issued by
+    // thread 0 below, run concurrently with this loop on disjoint bytes)
+    auto zero_pads = [&]() {
     for (int idx = tid; idx < STAGES * L::NR * 2 * kPadCols * 3; idx += kThreads) {
         int s = idx / (L::NR * 2 * kPadCols * 3);
         int rem = idx % (L::NR * 2 * kPadCols * 3);
@@ -80,11 +89,7 @@ dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const f
         int col = c < kPadCols * 3 ? c : (kPadCols + W) * 3 + (c - kPadCols * 3);
         row[col] = 0.f;
     }
-    if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
+    };
 
     auto issue = [&](int band, int stage) {
         unsigned char* st = smem + (size_t)stage * L::bytes;
@@ -107,12 +112,15 @@ dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const f
         if (BWD) bulk_g2s(st + L::off_dy, dy + (size_t)band * npx * 3, (uint32_t)npx * 12u, &full_bar[stage]);
     };
 
+    pdl_wait();                 // the producer grid has completed: global memory may be read from here on
     if (tid == 0) {
         for (int p = 0; p < PREFETCH; ++p) {
             int band = blockIdx.x + p * gridDim.x;
             if (band < nbands) issue(band, p % STAGES);
         }
     }
+    zero_pads();
+    __syncthreads();
 
     const int il = tid / W;   // row of this thread's pixel inside the band
     const int j = tid - il * W;
