@@ -284,7 +284,10 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
                 const int tb = q / XG, xg = q - tb * XG;
                 int oy = h.y0 + yy, ox = h.x0 + xg * 8 + xi;
                 if (hp.form == 0) { oy = (oy << 1) + (h.cls >> 1); ox = (ox << 1) + (h.cls & 1); }
-                const size_t row_off = ((size_t)((h.b0 + tb) * hp.out_H + oy) * hp.out_W + ox) * p.ldo;
+                const size_t pix = (size_t)((h.b0 + tb) * hp.out_H + oy) * hp.out_W + ox;
+                const size_t row_off = pix * p.ldo;
+                // fused batch-norm backward reduction of the layer that consumes this gradient: its pre-activation row
+                const __nv_bfloat16* zrow = p.rz ? p.rz + pix * p.rz_ld : nullptr;
                 for (int cb0 = 0; cb0 < N; cb0 += 16 * kEpiBatch) {
                     uint32_t v[kEpiBatch][16];
 #pragma unroll
@@ -296,7 +299,8 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
                     for (int i = 0; i < kEpiBatch; ++i)
                         if (cb0 + 16 * i < N)
                             epilogue_chunk(p, v[i], cb0 + 16 * i, true, row_off, 0u, lane, &sm_stats[0][cb0 + 16 * i],
-                                           &sm_stats[1][cb0 + 16 * i]);
+                                           &sm_stats[1][cb0 + 16 * i],
+                                           (zrow && cb0 + 16 * i < p.n_stat) ? zrow + cb0 + 16 * i : nullptr);
                 }
             }
             // this accumulator buffer may be overwritten by the MMAs of the tile after next
@@ -506,7 +510,6 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
     const int ctas = ntiles < num_sms() ? ntiles : num_sms();
     rc = fill_bn(&hp.p, t, (unsigned int)ctas, who);
     if (rc) return rc;
-    ACG_REQUIRE(!hp.p.rz, ACG_ERR_UNSUPPORTED, "%s: the fused backward reduction is not available in the halo kernel", who);
     if (nacc == 2) {
         rc = set_smem((const void*)conv_halo2_kernel<2>, kH2Smem);
         if (rc) return rc;

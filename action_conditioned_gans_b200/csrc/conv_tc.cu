@@ -1579,7 +1579,7 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
             return check_launch("acg_conv_fprop_tc(small K, persistent)");
         }
     }
-    if (N == ru(s->Cout, 16) && !t->red_z && halo2_conv_ok(s, t, N))
+    if (N == ru(s->Cout, 16) && halo2_conv_ok(s, t, N))
         // stride-2 layers with a 16- or 32-wide output: parity planes staged by TMA, every tap a shifted descriptor
         return launch_halo2(1, s, t, p, x_bf16, w_pack, N, static_cast<cudaStream_t>(stream), "acg_conv_fprop_tc(halo)");
     grid.z = (unsigned)apply_split(&p, t, plan_fprop(s, t->ld_in));
@@ -1631,7 +1631,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     const int Hp = (s->H + s->stride - 1) / s->stride, Wp = (s->W + s->stride - 1) / s->stride;
     const long long M = (long long)s->B * Hp * Wp;
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, ncls);
-    if (N == Npack && !t->red_z && halo2_adj_ok(s, t, N))
+    if (N == Npack && halo2_adj_ok(s, t, N))
         // one CTA per SM walks the tile list: copies, MMAs and epilogue of consecutive tiles overlap (conv_halo.cu)
         return launch_halo2(0, s, t, p, dy_bf16, w_pack, N, static_cast<cudaStream_t>(stream), "acg_conv_dgrad_tc(halo)");
     if (N == Npack && halo_ok(s, t, N)) {

@@ -181,7 +181,8 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // and sit OUTSIDE the unrolled element loops so that they compile to branches, not to predicated instruction bloat
 // (a first version that tested bias / tanh per element spent ~800 issue slots per chunk on predicated-off code).
 __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (&v)[16], int ncol, bool row_ok,
-                                               size_t row_off, uint32_t z_smem, int lane, float* sm_sum, float* sm_sq) {
+                                               size_t row_off, uint32_t z_smem, int lane, float* sm_sum, float* sm_sq,
+                                               const __nv_bfloat16* z_gmem = nullptr) {
     float f[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
@@ -230,10 +231,17 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
             float zf[16];
             {
                 uint32_t zw[8];
+                if (z_gmem) {     // halo kernel: dedicated epilogue warps read the row's 32 bytes straight from global
+                    const uint4 z0 = __ldg(reinterpret_cast<const uint4*>(z_gmem));
+                    const uint4 z1 = __ldg(reinterpret_cast<const uint4*>(z_gmem) + 1);
+                    zw[0] = z0.x; zw[1] = z0.y; zw[2] = z0.z; zw[3] = z0.w;
+                    zw[4] = z1.x; zw[5] = z1.y; zw[6] = z1.z; zw[7] = z1.w;
+                } else {
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(zw[0]), "=r"(zw[1]), "=r"(zw[2]), "=r"(zw[3]) : "r"(z_smem));
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(zw[4]), "=r"(zw[5]), "=r"(zw[6]), "=r"(zw[7]) : "r"(z_smem + 16u));
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     zf[2 * i] = __uint_as_float(zw[i] << 16);

@@ -173,6 +173,9 @@ RED_CASES = [
     ("dgrad", 2, 64, 64, 64, 128, 64, "lrelu"),      # halo-tile kernel, 64-wide rows
     ("fprop", 3, 16, 16, 48, 128, 128, "relu"),      # data gradient of a conv2d_transpose = forward conv form
     ("fprop", 2, 8, 8, 272, 128, 128, "relu"),
+    ("fprop", 4, 32, 32, 64, 128, 128, "relu"),      # CONV-form halo kernel (g/tconv3's data gradient shape), NACC 2
+    ("fprop", 2, 64, 64, 48, 128, 128, "lrelu"),     # CONV-form halo kernel, 48-channel rows (g/tconv4's data gradient)
+    ("dgrad", 6, 32, 32, 32, 64, 32, "relu"),        # ADJ halo kernel, N = 32, two images per tile (g/conv2 -> g/conv1)
 ]
 
 
