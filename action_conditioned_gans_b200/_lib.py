@@ -60,6 +60,7 @@ SIGNATURES = {
     "acg_pack_weights": [_SP, _P, _I, _I, _P, _P],
     "acg_pack_weights_batched": [_P, _I, _P, _I, _P],
     "acg_conv_tc_supported": [_SP, _I],
+    "acg_conv_kernel_kind": [_SP, _I, _I, _I],
     "acg_conv_splitk_plan": [_SP, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_int)],
     "acg_bn_stats": [_P, _I, _L, _I, _I, _I, _P, _P],
     "acg_bn_finalize": [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _P],

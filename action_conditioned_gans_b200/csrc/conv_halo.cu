@@ -52,7 +52,11 @@ struct alignas(64) Halo2Params {
     TapProg prog[4];              // ADJ: per class;  CONV: per plane
     int form;                     // 0 ADJ, 1 CONV
     int Hs, Ws;                   // tile grid: ADJ class grid (= conv output grid), CONV output grid
-    int TW, TB;                   // tile width (16 | 32) and images per tile
+    int TW, TB;                   // tile width (8 | 16 | 32) and images per tile
+    int rows;                     // staged halo rows per image: 16 + 2, or 8 + 2 in the interleaved 8 x 8 mode
+    int il;                       // 1: 8 x 8 grids -- the TB images of a tile are interleaved BY ROW in the halo patch
+                                  // (patch row index = y * TB + b), so that the 16 row groups of an accumulator (8 pixels
+                                  // each) keep ONE stride although they come from different images
     int nkc, nk16_last;           // 64-channel blocks; K=16 steps of the last block (lda % 64 != 0 -> fewer MMAs)
     int out_H, out_W;             // spatial size of the output tensor
 };
@@ -75,7 +79,7 @@ __device__ __forceinline__ H2Tile h2_tile(const Halo2Params& hp, int t) {
         h.pg0 = 0;
         h.npg = 4;
     }
-    const int tiles_x = hp.Ws / hp.TW, tiles_y = hp.Hs >> 4;
+    const int tiles_x = hp.il ? 1 : hp.Ws / hp.TW, tiles_y = hp.il ? 1 : hp.Hs >> 4;
     const int per_img = tiles_x * tiles_y;
     const int bi = sp / per_img, r = sp - bi * per_img;
     h.b0 = bi * hp.TB;
@@ -113,7 +117,7 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
 
     const int N = p.N;
     const int XG = hp.TW >> 3;                               // 8-column accumulator groups per tile row
-    const int WH = hp.TW + 2, HR = kH2Rows * WH;             // halo: 18 rows x (TW+2) pixels per image
+    const int WH = hp.TW + 2, HR = hp.rows * WH;             // halo: (16|8)+2 rows x (TW+2) pixels per image
     const uint32_t halo_bytes = (uint32_t)(hp.TB * HR) * 128u;
     const uint32_t halo_stride = (halo_bytes + 1023u) & ~1023u;        // buffers start on swizzle-atom boundaries
     constexpr int NH = 2;                                    // halo ring: a patch feeds >= 4 taps, two in flight are enough
@@ -164,8 +168,12 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
                             mbar_arrive(&halo_full[hb]);                           // probe: no halo traffic
                         } else {
                             mbar_expect_tx(&halo_full[hb], halo_bytes);
-                            tma_load_4d(smemH + hb * halo_stride, &hp.map_a[hp.form ? pg : 0], kc * 64,
-                                        h.x0 + hp.prog[pg].ox, h.y0 + hp.prog[pg].oy, h.b0, &halo_full[hb]);
+                            if (hp.il)      // tensor map dimensions (C, X, B, Y): images interleaved by row
+                                tma_load_4d(smemH + hb * halo_stride, &hp.map_a[hp.form ? pg : 0], kc * 64,
+                                            hp.prog[pg].ox, h.b0, hp.prog[pg].oy, &halo_full[hb]);
+                            else
+                                tma_load_4d(smemH + hb * halo_stride, &hp.map_a[hp.form ? pg : 0], kc * 64,
+                                            h.x0 + hp.prog[pg].ox, h.y0 + hp.prog[pg].oy, h.b0, &halo_full[hb]);
                         }
                     }
                     __syncwarp();
@@ -217,7 +225,7 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
 #pragma unroll
         for (int q = 0; q < NACC; ++q) {
             const int tb = q / XG, xg = q - tb * XG;
-            acc_row8[q] = (uint32_t)(tb * HR + xg * 8) * 8u;
+            acc_row8[q] = hp.il ? (uint32_t)(16 * q * WH) * 8u : (uint32_t)(tb * HR + xg * 8) * 8u;
         }
         const uint32_t bar_bfull = smem_u32(&b_full[0]), bar_bempty = smem_u32(&b_empty[0]);
         int st = 0, hb = 0, tcount = 0;
@@ -281,8 +289,17 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(abuf * NACC * N);
             for (int q = grp; q < NACC && !ACG_DBG(p, 32); q += 2) {                  // probe bit 32: no epilogue work
-                const int tb = q / XG, xg = q - tb * XG;
-                int oy = h.y0 + yy, ox = h.x0 + xg * 8 + xi;
+                int tb = q / XG, oy, ox;
+                if (hp.il) {          // patch row G = 16 q + yy of the interleaved tile: image G % TB, row G / TB
+                    const int G = 16 * q + yy;
+                    tb = G % hp.TB;
+                    oy = G / hp.TB;
+                    ox = xi;
+                } else {
+                    const int xg = q - tb * XG;
+                    oy = h.y0 + yy;
+                    ox = h.x0 + xg * 8 + xi;
+                }
                 if (hp.form == 0) { oy = (oy << 1) + (h.cls >> 1); ox = (ox << 1) + (h.cls & 1); }
                 const size_t pix = (size_t)((h.b0 + tb) * hp.out_H + oy) * hp.out_W + ox;
                 const size_t row_off = pix * p.ldo;
@@ -364,8 +381,17 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
 }
 
 // tile shape for a grid of Hs x Ws pixels and N output columns; false when the kernel does not cover the shape
-bool pick_tile(int B, int Hs, int Ws, int N, int* nacc, int* TW, int* TB) {
-    if (Hs % 16 != 0 || (Ws != 16 && Ws != 32) || N > BN || N % 16 != 0) return false;
+bool pick_tile(int B, int Hs, int Ws, int N, int* nacc, int* TW, int* TB, int* il) {
+    *il = 0;
+    if (N > BN || N % 16 != 0) return false;
+    if (Hs == 8 && Ws == 8) {        // interleaved mode: one accumulator = two whole 8 x 8 images (B x 64 pixels are too
+        *il = 1;                      // few to give every SM more than one accumulator)
+        *nacc = 1;
+        *TW = 8;
+        *TB = 2;
+        return B % 2 == 0;
+    }
+    if (Hs % 16 != 0 || (Ws != 16 && Ws != 32)) return false;
     if (N > 64) { *nacc = 2; *TW = 16; *TB = 1; return true; }              // 2 x 2 x N <= 512 TMEM columns
     *nacc = 4;
     *TW = Ws;
@@ -381,15 +407,14 @@ bool halo2_adj_ok(const acg_conv_shape* s, const acg_tc_args* t, int N) {
     if (s->stride != 2 || s->KH > 6 || s->KW > 6 || s->KH < 2 || s->KW < 2) return false;
     if (s->OH != s->H / 2 || s->OW != s->W / 2 || (s->H & 1) || (s->W & 1)) return false;
     if (t->ld_in % 64 != 0) return false;
-    int nacc, TW, TB;
-    return pick_tile(s->B, s->OH, s->OW, N, &nacc, &TW, &TB);
+    int nacc, TW, TB, il;
+    return pick_tile(s->B, s->OH, s->OW, N, &nacc, &TW, &TB, &il);
 }
 bool halo2_conv_ok(const acg_conv_shape* s, const acg_tc_args* t, int N) {
     if (getenv("ACG_NO_HALO") || getenv("ACG_NO_HALO_CONV")) return false;
     if (s->stride != 2 || s->KH > 6 || s->KW > 6 || s->KH < 2 || s->KW < 2) return false;
     if (s->OH != s->H / 2 || s->OW != s->W / 2 || (s->H & 1) || (s->W & 1)) return false;
-    if (t->ld_in % 16 != 0 || t->ld_in < 16) return false;
-    if (t->ld_in > 64 && t->ld_in % 64 != 0) return false;
+    if (t->ld_in % 16 != 0 || t->ld_in < 16) return false;     // a ragged last 64-channel block issues fewer K steps
     // every plane's taps must fit the 3 x 3 window of the staged halo
     for (int ax = 0; ax < 2; ++ax) {
         const int K = ax ? s->KW : s->KH, pad = ax ? s->pad_l : s->pad_t;
@@ -404,8 +429,8 @@ bool halo2_conv_ok(const acg_conv_shape* s, const acg_tc_args* t, int N) {
             if (dmax >= dmin && dmax - dmin > 2) return false;
         }
     }
-    int nacc, TW, TB;
-    return pick_tile(s->B, s->OH, s->OW, N, &nacc, &TW, &TB);
+    int nacc, TW, TB, il;
+    return pick_tile(s->B, s->OH, s->OW, N, &nacc, &TW, &TB, &il);
 }
 
 // form 0: dx / deconv output [B,H,W,N] from dy [B,OH,OW,lda] (ADJ);  form 1: y [B,OH,OW,N] from x [B,H,W,lda] (CONV)
@@ -418,7 +443,7 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
     hp.Hs = s->OH;
     hp.Ws = s->OW;
     int nacc = 4;
-    if (!pick_tile(s->B, s->OH, s->OW, N, &nacc, &hp.TW, &hp.TB)) {
+    if (!pick_tile(s->B, s->OH, s->OW, N, &nacc, &hp.TW, &hp.TB, &hp.il)) {
         set_error("%s: shape not covered by the halo kernel", who);
         return ACG_ERR_UNSUPPORTED;
     }
@@ -427,11 +452,18 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
     hp.nk16_last = ((lda - (hp.nkc - 1) * 64) + 15) / 16;
     hp.out_H = form == 0 ? s->H : s->OH;
     hp.out_W = form == 0 ? s->W : s->OW;
-    const cuuint32_t box_a[4] = {64, (cuuint32_t)(hp.TW + 2), (cuuint32_t)kH2Rows, (cuuint32_t)hp.TB};
+    hp.rows = hp.il ? 10 : kH2Rows;
+    const int WHh = hp.TW + 2;                       // halo row pitch in pixels
+    const int ystep = hp.il ? hp.TB * WHh : WHh;     // patch rows per unit of vertical shift
+    // box: (C, X, Y, B), or (C, X, B, Y) in the interleaved mode
+    const cuuint32_t box_a[4] = {64, (cuuint32_t)WHh, (cuuint32_t)(hp.il ? hp.TB : hp.rows),
+                                 (cuuint32_t)(hp.il ? hp.rows : hp.TB)};
     int rc;
     if (form == 0) {
-        const cuuint64_t dims[4] = {(cuuint64_t)lda, (cuuint64_t)s->OW, (cuuint64_t)s->OH, (cuuint64_t)s->B};
-        const cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)s->OW * lda * 2, (cuuint64_t)s->OH * s->OW * lda * 2};
+        const cuuint64_t row_b = (cuuint64_t)s->OW * lda * 2, img_b = (cuuint64_t)s->OH * s->OW * lda * 2;
+        const cuuint64_t dims[4] = {(cuuint64_t)lda, (cuuint64_t)s->OW, (cuuint64_t)(hp.il ? s->B : s->OH),
+                                    (cuuint64_t)(hp.il ? s->OH : s->B)};
+        const cuuint64_t strides[3] = {(cuuint64_t)lda * 2, hp.il ? img_b : row_b, hp.il ? row_b : img_b};
         rc = encode_map(&hp.map_a[0], src, 4, dims, strides, box_a, who);
         if (rc) return rc;
         for (int c = 1; c < 4; ++c) hp.map_a[c] = hp.map_a[0];
@@ -448,7 +480,7 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
             for (int ta = 0; ta < na; ++ta)
                 for (int tcx = 0; tcx < nc; ++tcx) {
                     const int i = ta * nc + tcx;
-                    pr.a_off[i] = ((na - 1 - ta) * (hp.TW + 2) + (nc - 1 - tcx)) * 8;
+                    pr.a_off[i] = ((na - 1 - ta) * ystep + (nc - 1 - tcx)) * 8;
                     pr.w_off[i] = i * lda;
                 }
             const cuuint64_t Kc = (cuuint64_t)pr.ntaps * lda;
@@ -481,7 +513,7 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
                     const int rc2 = c - s->pad_l, qc = ((rc2 % 2) + 2) % 2;
                     if (qc != pj) continue;
                     ACG_REQUIRE(n < kMaxTaps, ACG_ERR_UNSUPPORTED, "%s: more than %d taps per plane", who, kMaxTaps);
-                    pr.a_off[n] = (((ra - qa) / 2 - dmin_i) * (hp.TW + 2) + ((rc2 - qc) / 2 - dmin_j)) * 8;
+                    pr.a_off[n] = (((ra - qa) / 2 - dmin_i) * ystep + ((rc2 - qc) / 2 - dmin_j)) * 8;
                     pr.w_off[n] = (a * s->KW + c) * lda;
                     ++n;
                 }
@@ -490,9 +522,10 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
             pr.oy = n ? dmin_i : 0;
             pr.ox = n ? dmin_j : 0;
             // plane (pi, pj) of x [B,H,W,lda]: x_p[b][i][j][k] = x[b][2i+pi][2j+pj][k]
-            const cuuint64_t dims[4] = {(cuuint64_t)lda, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)s->B};
-            const cuuint64_t strides[3] = {(cuuint64_t)2 * lda * 2, (cuuint64_t)2 * s->W * lda * 2,
-                                           (cuuint64_t)s->H * s->W * lda * 2};
+            const cuuint64_t row_b = (cuuint64_t)2 * s->W * lda * 2, img_b = (cuuint64_t)s->H * s->W * lda * 2;
+            const cuuint64_t dims[4] = {(cuuint64_t)lda, (cuuint64_t)Wp, (cuuint64_t)(hp.il ? s->B : Hp),
+                                        (cuuint64_t)(hp.il ? Hp : s->B)};
+            const cuuint64_t strides[3] = {(cuuint64_t)2 * lda * 2, hp.il ? img_b : row_b, hp.il ? row_b : img_b};
             const void* base = static_cast<const __nv_bfloat16*>(src) + ((size_t)pi * s->W + pj) * lda;
             rc = encode_map(&hp.map_a[pl], base, 4, dims, strides, box_a, who);
             if (rc) return rc;
@@ -505,12 +538,16 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
         if (rc) return rc;
         for (int c = 1; c < 4; ++c) hp.map_b[c] = hp.map_b[0];
     }
-    const int n_sp = (s->B / hp.TB) * (s->OH / 16) * (s->OW / hp.TW);
+    const int n_sp = hp.il ? s->B / hp.TB : (s->B / hp.TB) * (s->OH / 16) * (s->OW / hp.TW);
     const int ntiles = form == 0 ? n_sp * 4 : n_sp;
     const int ctas = ntiles < num_sms() ? ntiles : num_sms();
     rc = fill_bn(&hp.p, t, (unsigned int)ctas, who);
     if (rc) return rc;
-    if (nacc == 2) {
+    if (nacc == 1) {
+        rc = set_smem((const void*)conv_halo2_kernel<1>, kH2Smem);
+        if (rc) return rc;
+        launch_pdl(conv_halo2_kernel<1>, ctas, kH2Threads, kH2Smem, stream, hp, ntiles);
+    } else if (nacc == 2) {
         rc = set_smem((const void*)conv_halo2_kernel<2>, kH2Smem);
         if (rc) return rc;
         launch_pdl(conv_halo2_kernel<2>, ctas, kH2Threads, kH2Smem, stream, hp, ntiles);

@@ -1523,6 +1523,17 @@ int acg_conv_splitk_plan(const acg_conv_shape* s, int which, int ld_in, int* spl
     return ACG_OK;
 }
 
+int acg_conv_kernel_kind(const acg_conv_shape* s, int which, int ld_in, int n_limit) {
+    using namespace acg::tc;
+    if (!s || ld_in <= 0 || (which != 0 && which != 1)) return -1;
+    acg_tc_args t{};
+    t.ld_in = ld_in;
+    int N = ru(which == 0 ? s->Cout : s->Cin, 16);
+    if (n_limit > 0 && ru(n_limit, 16) < N) N = ru(n_limit, 16);
+    if (which == 0) return (N == ru(s->Cout, 16) && halo2_conv_ok(s, &t, N)) ? 1 : 0;
+    return halo2_adj_ok(s, &t, N) ? 1 : 0;
+}
+
 int acg_conv_tc_supported(const acg_conv_shape* s, int which) {
     if (!s) return 0;
     if (s->stride != 1 && s->stride != 2) return 0;
@@ -1631,7 +1642,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     const int Hp = (s->H + s->stride - 1) / s->stride, Wp = (s->W + s->stride - 1) / s->stride;
     const long long M = (long long)s->B * Hp * Wp;
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, ncls);
-    if (N == Npack && halo2_adj_ok(s, t, N))
+    if (halo2_adj_ok(s, t, N))        // N < Npack (n_limit): the first N rows of every class' weight matrix
         // one CTA per SM walks the tile list: copies, MMAs and epilogue of consecutive tiles overlap (conv_halo.cu)
         return launch_halo2(0, s, t, p, dy_bf16, w_pack, N, static_cast<cudaStream_t>(stream), "acg_conv_dgrad_tc(halo)");
     if (N == Npack && halo_ok(s, t, N)) {

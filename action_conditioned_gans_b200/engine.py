@@ -21,11 +21,11 @@ ACTION_DIM = 10     # train.py:39-42 (5-D action ++ 5-D state)
 STATE_DIM = 5       # train.py:43-46
 BN_EPS = 1e-3       # slim.batch_norm default
 # batch-norm backward sums in the epilogue of the producing data-gradient kernel (bf16 path) instead of the separate
-# acg_bn_act_bwd_reduce pass.  Measured on B200 at B=256 (scripts/step_time.py): 5.91 ms fused vs 5.89 ms separate --
-# the ~1 us the epilogue gains per tile costs what the 28 removed launches saved, because the epilogue warps are also
-# the gather producers of the generic kernel.  Kept (parity-tested) for a kernel with dedicated epilogue warps; off by
-# default (ACG_FUSE_BWD_REDUCE=1 switches it on).
-FUSE_BWD_REDUCE = os.environ.get("ACG_FUSE_BWD_REDUCE", "0") != "0"
+# acg_bn_act_bwd_reduce pass.  In the generic kernel the epilogue warps are also the gather producers and the fusion
+# costs more than the removed pass saves (B200, B=256: 3.81 ms with every layer fused vs 3.59 ms); the halo-tile kernel
+# has dedicated epilogue warps with slack under its MMA phase.  ACG_FUSE_BWD_REDUCE = "halo" (default): only where the
+# producer is the halo kernel; "1": everywhere; "0": nowhere.
+FUSE_BWD_REDUCE = os.environ.get("ACG_FUSE_BWD_REDUCE", "halo")
 
 
 @dataclass(frozen=True)
@@ -371,16 +371,32 @@ class NetRun:
             K.bn_act_fwd(st.z, st.rows, L.cout, st.ldz, 1, None, bias, L.act, out, ld_out)
 
     # -- one layer backward ----------------------------------------------------------------------------
-    def _fused_red(self, consumer):
+    def _fused_red(self, consumer, producer=None):
         """Arguments of the batch-norm backward reduction of layer `consumer` for the epilogue of the data-gradient
-        kernel that produces its dA (None when the separate acg_bn_act_bwd_reduce pass has to run)."""
-        if consumer is None or not self.bf16 or not FUSE_BWD_REDUCE:
+        kernel (of layer state `producer`) that produces its dA (None when the separate acg_bn_act_bwd_reduce pass has
+        to run)."""
+        if consumer is None or not self.bf16 or FUSE_BWD_REDUCE == "0":
             return None
+        if FUSE_BWD_REDUCE == "halo":
+            if producer is None:
+                return None
+            if not hasattr(producer, "dgrad_kind"):
+                which = 1 if producer.spec.kind == "conv" else 0
+                producer.dgrad_kind = K.kernel_kind(producer.shape, which, producer.ldz,
+                                                    getattr(producer, "dx_channels", 0))
+            if producer.dgrad_kind != 1:
+                return None
         sc = self.layers[consumer]
         Lc = sc.spec
         if not Lc.bn or Lc.cout % 16 != 0 or sc.z is None:
             return None
-        sc.red_ready = True
+        # the producer's dx tensor is (one of) the consumer's dA: remember that its share of the sums is taken care of
+        if not hasattr(sc, "red_fused"):
+            sc.red_fused = set()
+        if producer is not None and producer.dx is not None:
+            sc.red_fused.add(producer.dx.data_ptr())
+        else:
+            sc.red_fused.add(None)          # legacy "everything fused" mode
         return (sc.red, sc.z, sc.ldz, Lc.cout, Lc.act, sc.mean, sc.rstd, sc.shift)
 
     def layer_bwd(self, name, dA, ld_d, dA2=None, need_dx=True, need_dw=True, dx_dtype=None, consumer=None):
@@ -402,10 +418,13 @@ class NetRun:
                                         "none", st.red)
                     K.bias_grad(st.red, L.cout, 1.0, self.store.gviews[name + "/biases"])
         else:
-            if getattr(st, "red_ready", False):
-                st.red_ready = False        # the producer(s) of dA already accumulated st.red
-            else:
-                K.bn_act_bwd_reduce(dA, dA2, ld_d, st.z, st.ldz, st.rows, L.cout, 1, mean, rstd, shift, L.act, st.red)
+            # batch-norm backward sums: the share of a gradient tensor whose producing kernel accumulated it in its
+            # epilogue is already in st.red; the others go through the reduction pass (it accumulates as well)
+            fused = getattr(st, "red_fused", set())
+            todo = [d for d in (dA, dA2) if d is not None and not (None in fused or d.data_ptr() in fused)]
+            if todo:
+                K.bn_act_bwd_reduce(todo[0], todo[1] if len(todo) > 1 else None, ld_d, st.z, st.ldz, st.rows, L.cout, 1,
+                                    mean, rstd, shift, L.act, st.red)
             world = 1
             if self.dp is not None:
                 world = self.dp.world
@@ -440,7 +459,7 @@ class NetRun:
                 pk = self.store.packs[name]
                 fn = K.conv_dgrad_tc if L.kind == "conv" else K.conv_fprop_tc
                 # dx_channels: the input is a concat buffer whose tail (tiled actions) needs no gradient
-                fn(st.shape, st.dz, pk[6], st.dx, st.ldz, st.ld_in, red=self._fused_red(consumer), splitk=st.splitk_b,
+                fn(st.shape, st.dz, pk[6], st.dx, st.ldz, st.ld_in, red=self._fused_red(consumer, st), splitk=st.splitk_b,
                    n_limit=getattr(st, "dx_channels", 0))
             else:
                 w = self.store.views[name + "/weights"]

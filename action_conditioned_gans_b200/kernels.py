@@ -64,6 +64,11 @@ def tc_supported(shape, which):
     return bool(_lib.load().acg_conv_tc_supported(C.byref(shape), which))
 
 
+def kernel_kind(shape, which, ld_in, n_limit=0):
+    """1 when a conv_fprop_tc (which=0) / conv_dgrad_tc (which=1) launch of this shape takes the halo-tile kernel"""
+    return int(_lib.load().acg_conv_kernel_kind(C.byref(shape), which, ld_in, int(n_limit)))
+
+
 def splitk_workspace(shape, which, ld_in, device):
     """(workspace, tickets) tensors a conv_fprop_tc (which=0) / conv_dgrad_tc (which=1) launch of this shape wants for
     split-K, or None when it never splits (acg_conv_splitk_plan)."""

@@ -22,6 +22,10 @@ CONV_CASES = [
     (3, 32, 32, 128, 128, 3),     # 3x3 stride 2 (pad 0/1): planes with 4 / 2 / 2 / 1 taps, two channel blocks
     (2, 64, 64, 192, 96, 5),      # three channel blocks
     (4, 32, 32, 16, 32, 4),       # even filter (pad 1/1): 2 x 2 taps in every plane, 16-channel rows
+    (8, 16, 16, 64, 128, 5),      # g/conv3 forward: 8 x 8 output, two images interleaved by row per accumulator
+    (6, 16, 16, 138, 128, 5),     # d/conv3 forward: 144-channel rows = two full blocks + a 16-channel one
+    (300, 16, 16, 128, 128, 5),   # g/tconv2 data gradient at a batch with more tiles than SMs (150 tiles)
+    (4, 16, 16, 128, 32, 3),      # g/sconv3: 3x3 stride 2, N = 32
 ]
 ADJ_CASES = [
     (40, 32, 32, 128, 128, 5),    # g/tconv3 forward (as the dgrad of a 128 -> 128 conv): N = 128, NACC 2
@@ -29,6 +33,9 @@ ADJ_CASES = [
     (6, 64, 64, 128, 192, 5),     # N = 128 on a 32-wide class grid: 16-wide tiles, three channel blocks
     (8, 32, 32, 64, 128, 5),      # d/conv2 data gradient: N = 64, two images per tile
     (5, 64, 64, 6, 64, 5),        # d/conv1 data gradient: N = 16
+    (8, 16, 16, 128, 128, 5),     # g/tconv2 forward: 8 x 8 class grid, interleaved images
+    (6, 16, 16, 64, 128, 5),      # g/conv3 data gradient: N = 64 on the 8 x 8 grid
+    (80, 16, 16, 138, 128, 5),    # d/conv3 data gradient (N = 144 > 128: generic kernel) -- fallback must still agree
 ]
 
 
