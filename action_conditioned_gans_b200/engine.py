@@ -22,10 +22,13 @@ STATE_DIM = 5       # train.py:43-46
 BN_EPS = 1e-3       # slim.batch_norm default
 # batch-norm backward sums in the epilogue of the producing data-gradient kernel (bf16 path) instead of the separate
 # acg_bn_act_bwd_reduce pass.  In the generic kernel the epilogue warps are also the gather producers and the fusion
-# costs more than the removed pass saves (B200, B=256: 3.81 ms with every layer fused vs 3.59 ms); the halo-tile kernel
-# has dedicated epilogue warps with slack under its MMA phase.  ACG_FUSE_BWD_REDUCE = "halo" (default): only where the
-# producer is the halo kernel; "1": everywhere; "0": nowhere.
-FUSE_BWD_REDUCE = os.environ.get("ACG_FUSE_BWD_REDUCE", "halo")
+# costs more than the removed pass saves (B200, B=256: 3.81 ms with every layer fused vs 3.59 ms).  The halo-tile kernel
+# has dedicated epilogue warps, but there each thread reads its pixel's 32 bytes of z per 16-column chunk straight from
+# global memory -- 32 different cache lines per warp instruction, the same L1 tag-stage cost that bounds its stores -- and
+# the data-gradient kernels sit on the critical path: 3.74 ms with the halo producers fused vs 3.54 ms without.  So the
+# default is "0" (separate acg_bn_act_bwd_reduce pass, which streams at 4.4-5.8 TB/s); "halo" fuses where the producer is
+# the halo kernel, "1" everywhere (both parity-tested, tests/test_conv_tc_gpu.py).
+FUSE_BWD_REDUCE = os.environ.get("ACG_FUSE_BWD_REDUCE", "0")
 
 
 @dataclass(frozen=True)

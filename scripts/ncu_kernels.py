@@ -17,19 +17,22 @@ from action_conditioned_gans_b200 import engine as E  # noqa: E402
 from action_conditioned_gans_b200 import kernels as K  # noqa: E402
 
 CASES = [   # (label, layer, role)  role: f = forward, d = data gradient, w = weight gradient
-    ("halo_persistent N=128  g/tconv3 fwd", "g/tconv3", "f"),
-    ("halo_persistent N=48   g/tconv4 fwd", "g/tconv4", "f"),
-    ("conv_tc<CONV,3>        g/tconv4 dgrad", "g/tconv4", "d"),
-    ("conv_tc<CONV,3>        g/tconv3 dgrad", "g/tconv3", "d"),
-    ("conv_tc<CONV,3>        d/conv2 fwd", "d/conv2", "f"),
-    ("conv_tc<CONV,6>        g/conv3 fwd", "g/conv3", "f"),
+    ("halo2<2> ADJ N=128     g/tconv3 fwd", "g/tconv3", "f"),
+    ("halo2<4> ADJ N=48      g/tconv4 fwd", "g/tconv4", "f"),
+    ("halo2<2> CONV ld48     g/tconv4 dgrad", "g/tconv4", "d"),
+    ("halo2<2> CONV N=128    g/tconv3 dgrad", "g/tconv3", "d"),
+    ("halo2<2> CONV N=128    d/conv2 fwd", "d/conv2", "f"),
+    ("halo2<4> ADJ N=64      d/conv2 dgrad", "d/conv2", "d"),
+    ("halo2<1> CONV 8x8      g/conv3 fwd", "g/conv3", "f"),
+    ("halo2<1> ADJ 8x8       g/tconv2 fwd", "g/tconv2", "f"),
     ("conv_tc<CONV,6> splitK d/conv5 fwd", "d/conv5", "f"),
+    ("conv_tc<CONV,*>        d/conv4 fwd", "d/conv4", "f"),
     ("conv_tc<ADJ,6>         g/tconv1 fwd", "g/tconv1", "f"),
-    ("conv_tc<ADJ,*>         d/conv3 dgrad", "d/conv3", "d"),
+    ("conv_tc<ADJ,*>         d/conv4 dgrad", "d/conv4", "d"),
     ("smallk_persistent<64>  d/conv1 fwd", "d/conv1", "f"),
     ("wgrad                  g/tconv3 wgrad", "g/tconv3", "w"),
     ("wgrad                  g/tconv4 wgrad", "g/tconv4", "w"),
-    ("wgrad                  d/conv1 wgrad", "d/conv1", "w"),
+    ("wgrad                  d/conv2 wgrad", "d/conv2", "w"),
 ]
 
 
