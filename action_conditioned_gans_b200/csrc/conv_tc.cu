@@ -1011,29 +1011,20 @@ struct alignas(64) WgradTmaParams {
     CUtensorMap map_a;        // dy as bf16 [Kd][ldy], box {64 channels, 64 pixels}, 128B swizzle, zero OOB fill
 };
 
-// Round 2: the N tile is 256 columns (two 128-column halves of (tap, ci)).  The kernel sat on the L2 -> SM bandwidth
-// (32 KB of operands per 128 x 128 x 64 slice, 0.52 us per slice per SM = 9 TB/s) and, like every cta_group::1 MMA, on
-// the operand fetch of the tensor core ((128 + N) / 2 clk per K=16 step, see conv_halo.cu).  With N = 256 one dy slice
-// (the A operand, identical for every (tap, ci) tile) feeds both halves: 48 KB instead of 64 KB per two tiles, and ONE
-// M=128 x N=256 MMA (192 clk) instead of two N=128 MMAs (256 clk).  One CTA per SM, 4 stages of 48 KB.
-constexpr int kWgN = 256;                                  // N tile: (tap, ci) columns per CTA
-constexpr int kWgStages = 4;
-constexpr int kWgStage = kStageA + 2 * kStageB;            // 48 KB: dy slice + two x slices
-constexpr int kWgSmem = kWgStages * kWgStage + 1024;
-
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
     const WgradParams& p = wp.p;
     extern __shared__ unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[kWgStages], empty_bar[kWgStages], acc_bar;
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
     __shared__ uint32_t tmem_base_sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smemA = smem_base, smemB = smem_base + STAGES * kStageA;
 
     const int Ntot = p.KH * p.KW * p.ldx;
-    const int n0 = blockIdx.x * kWgN;
-    const int n_valid = min(kWgN, Ntot - n0);        // multiple of 8 (ldx % 8 == 0)
+    const int n0 = blockIdx.x * BN;
+    const int n_valid = min(BN, Ntot - n0);          // multiple of 8 (ldx % 8 == 0)
     const int n_cta = (n_valid + 15) & ~15;          // MMA N: multiple of 16, columns past n_valid are zero filled
     const int co0 = blockIdx.y * BM;
     const int Kd = p.B * p.OH * p.OW;
@@ -1043,17 +1034,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
     if (nkb == 0) return;
 
     if (tid == 0) {
-        for (int i = 0; i < kWgStages; ++i) {
-            mbar_init(&full_bar[i], kProducers + (p.a_tma ? 1 : 0));
-            mbar_init(&empty_bar[i], 1);
-        }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], kProducers + (p.a_tma ? 1 : 0)); mbar_init(&empty_bar[i], 1); }
         if (p.a_tma) tma_prefetch_desc(&wp.map_a);
         mbar_init(&acc_bar, 1);
         fence_mbar_init();
     }
     if (warp == 4) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
-                     "r"((uint32_t)kWgN) : "memory");
+                     "r"((uint32_t)BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -1065,45 +1053,36 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
     const uint32_t tmem_base = tmem_base_sh;
 
     if (warp < 4) {
-        // producers: thread = (16-byte channel chunk c16 of a 128-wide half tile, pixel slot)
+        // producers: thread = (16-byte channel chunk c16 of the 128-wide tile, pixel slot)
         const int c16 = tid & 15, pslot = tid >> 4;
         const int atom = c16 >> 3, jc = c16 & 7;
         // A: dy channels co0 + c16*8 .. +8
         const int a_ch = co0 + c16 * 8;
         const bool a_ch_ok = a_ch + 8 <= p.ldy;
-        // B: n = n0 + h*128 + c16*8 -> (tap, ci) fixed for the whole kernel, for both halves h
-        bool b_ch_ok[2];
-        int ta[2], tcc[2], ci[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int nn = n0 + h * 128 + c16 * 8;
-            b_ch_ok[h] = h * 128 + c16 * 8 < n_valid;
-            const int tap = nn / p.ldx;
-            ci[h] = nn - tap * p.ldx;
-            ta[h] = tap / p.KW;
-            tcc[h] = tap - ta[h] * p.KW;
-        }
+        // B: n = n0 + c16*8 -> (tap, ci) fixed for the whole kernel
+        const int nn = n0 + c16 * 8;
+        const bool b_ch_ok = c16 * 8 < n_valid;
+        const int tap = nn / p.ldx, ci = nn - tap * p.ldx;
+        const int ta = tap / p.KW, tcc = tap - ta * p.KW;
         const int S = p.OH * p.OW;
         const int soff0 = pslot * 128 + ((jc ^ pslot) << 4);       // k & 7 == pslot for every k = pslot + 8 i
         if (p.fast) {
             // Regular geometry (a 64-pixel K slice is whole rows of one image, or whole images): everything about the
             // slice-relative position q = pslot + 8 i of this thread's 8 pixels is a constant of the kernel -- source
             // offset relative to the slice's first pixel, the input row delta, whether the input column is inside the
-            // image.  A K slice then costs ~12 instructions per 16-byte copy instead of ~59 (the running decode with
-            // its wrap-around loops and divergent branches made the producers, not the tensor pipe, the limiter).
+            // image.  A K slice then costs ~12 instructions per 16-byte copy pair instead of ~59 (the running decode
+            // with its wrap-around loops and divergent branches made the producers, not the tensor pipe, the limiter:
+            // ncu source view, 61 % of the samples in this loop).
             int offB[8], dih[8];
-            uint32_t iw_ok[2] = {0u, 0u};
+            uint32_t iw_ok = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int q = pslot + 8 * i;
                 int db = 0, rem = q;
                 if (S < BK) { db = q / S; rem = q - db * S; }
                 const int doh = rem / p.OW, dow = rem - doh * p.OW;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int iw = dow * p.stride + tcc[h] - p.pad_l;
-                    if ((unsigned)iw < (unsigned)p.W) iw_ok[h] |= 1u << i;
-                }
+                const int iw = dow * p.stride + tcc - p.pad_l;
+                if ((unsigned)iw < (unsigned)p.W) iw_ok |= 1u << i;
                 dih[i] = doh * p.stride;
                 offB[i] = ((db * p.H + doh * p.stride) * p.W + dow * p.stride) * p.ldx;
             }
@@ -1113,43 +1092,32 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
             const int rows_per_slice = S >= BK ? BK / p.OW : 0;   // rows a slice advances inside an image
             const int imgs_per_slice = S >= BK ? 0 : BK / S;
             const __nv_bfloat16* dyP = p.dy + (long long)(k_begin + pslot) * p.ldy + a_ch;
-            long long tap_off[2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h)
-                tap_off[h] = ((long long)(ta[h] - p.pad_t) * p.W + (tcc[h] - p.pad_l)) * p.ldx + ci[h];
+            const long long tap_off = ((long long)(ta - p.pad_t) * p.W + (tcc - p.pad_l)) * p.ldx + ci;
             int kleft = k_end - k_begin;                          // valid pixels from the slice base on
-            int stage = 0;
-            uint32_t eph = 1u;
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&empty_bar[stage], eph);
-                const uint32_t sA = smem_base + stage * kWgStage, sB = sA + kStageA;
-                const uint32_t dstA = sA + atom * (BK * 128) + soff0;
-                const __nv_bfloat16* xP = p.x + ((long long)(bP * p.H + ohP * p.stride) * p.W) * p.ldx;
+                const int stage = kb % STAGES;
+                if (kb >= STAGES) mbar_wait(&empty_bar[stage], (uint32_t)(((kb / STAGES) - 1) & 1));
+                const uint32_t dstA = smemA + stage * kStageA + atom * (BK * 128) + soff0;
+                const uint32_t dstB = smemB + stage * kStageB + atom * (BK * 128) + soff0;
+                const __nv_bfloat16* xP = p.x + ((long long)(bP * p.H + ohP * p.stride) * p.W) * p.ldx + tap_off;
+                const int ihP = ohP * p.stride + ta - p.pad_t;
                 if (p.a_tma) {
                     if (tid == 0) {     // dy slice: two 64-channel atoms x 64 pixels, hardware swizzle / zero fill
                         mbar_expect_tx(&full_bar[stage], (uint32_t)kStageA);
-                        tma_load_2d(sA, &wp.map_a, co0, k_begin + kb * BK, &full_bar[stage]);
-                        tma_load_2d(sA + BK * 128, &wp.map_a, co0 + 64, k_begin + kb * BK, &full_bar[stage]);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool aok = (pslot + 8 * i < kleft) && a_ch_ok;
-                        cp_async16(dstA + i * 1024, aok ? (const void*)(dyP + (long long)(8 * i) * p.ldy) : (const void*)p.dy,
-                                   aok ? 16u : 0u);
+                        tma_load_2d(smemA + stage * kStageA, &wp.map_a, co0, k_begin + kb * BK, &full_bar[stage]);
+                        tma_load_2d(smemA + stage * kStageA + BK * 128, &wp.map_a, co0 + 64, k_begin + kb * BK, &full_bar[stage]);
                     }
                 }
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t dstB = sB + h * kStageB + atom * (BK * 128) + soff0;
-                    const int ihP = ohP * p.stride + ta[h] - p.pad_t;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool bok = (pslot + 8 * i < kleft) && b_ch_ok[h] && ((iw_ok[h] >> i) & 1u) &&
-                                         (unsigned)(ihP + dih[i]) < (unsigned)p.H;
-                        cp_async16(dstB + i * 1024, bok ? (const void*)(xP + tap_off[h] + offB[i]) : (const void*)p.x,
-                                   bok ? 16u : 0u);
+                for (int i = 0; i < 8; ++i) {
+                    const bool pv = pslot + 8 * i < kleft;
+                    if (!p.a_tma) {
+                        const bool aok = pv && a_ch_ok;
+                        cp_async16(dstA + i * 1024, aok ? (const void*)(dyP + (long long)(8 * i) * p.ldy) : (const void*)p.dy,
+                                   aok ? 16u : 0u);
                     }
+                    const bool bok = pv && b_ch_ok && ((iw_ok >> i) & 1u) && (unsigned)(ihP + dih[i]) < (unsigned)p.H;
+                    cp_async16(dstB + i * 1024, bok ? (const void*)(xP + offB[i]) : (const void*)p.x, bok ? 16u : 0u);
                 }
                 cp_async_arrive_noinc(&full_bar[stage]);
                 dyP += (long long)BK * p.ldy;
@@ -1157,62 +1125,53 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
                 ohP += rows_per_slice;
                 if (ohP >= p.OH) { ohP = 0; ++bP; }
                 bP += imgs_per_slice;
-                if (++stage == kWgStages) { stage = 0; eph ^= 1u; }
             }
         } else {
-            // running decode of this thread's pixel (it advances by 8 per step, 64 per K slice): no divisions in the loop
-            int pix = k_begin + pslot;
-            int pb = pix / (p.OH * p.OW), pr = pix - pb * p.OH * p.OW;
-            int poh = pr / p.OW, pow_ = pr - poh * p.OW;
-            int stage = 0;
-            uint32_t eph = 1u;
-            for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&empty_bar[stage], eph);
-                const uint32_t sA = smem_base + stage * kWgStage, sB = sA + kStageA;
-                const uint32_t dstA = sA + atom * (BK * 128) + soff0;
-                if (p.a_tma && tid == 0) {
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)kStageA);
-                    tma_load_2d(sA, &wp.map_a, co0, k_begin + kb * BK, &full_bar[stage]);
-                    tma_load_2d(sA + BK * 128, &wp.map_a, co0 + 64, k_begin + kb * BK, &full_bar[stage]);
-                }
-#pragma unroll
-                for (int i = 0; i < BK / 8; ++i) {
-                    const bool pv = pix < k_end;
-                    if (!p.a_tma) {
-                        const bool aok = pv && a_ch_ok;
-                        cp_async16(dstA + i * 1024, aok ? (const void*)(p.dy + (long long)pix * p.ldy + a_ch) : (const void*)p.dy,
-                                   aok ? 16u : 0u);
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int ih = poh * p.stride + ta[h] - p.pad_t, iw = pow_ * p.stride + tcc[h] - p.pad_l;
-                        const bool bok = pv && b_ch_ok[h] && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
-                        const long long boff = ((long long)(pb * p.H + ih) * p.W + iw) * p.ldx + ci[h];
-                        cp_async16(sB + h * kStageB + atom * (BK * 128) + soff0 + i * 1024,
-                                   bok ? (const void*)(p.x + boff) : (const void*)p.x, bok ? 16u : 0u);
-                    }
-                    pix += 8;
-                    pow_ += 8;
-                    while (pow_ >= p.OW) { pow_ -= p.OW; ++poh; }
-                    while (poh >= p.OH) { poh -= p.OH; ++pb; }
-                }
-                cp_async_arrive_noinc(&full_bar[stage]);
-                if (++stage == kWgStages) { stage = 0; eph ^= 1u; }
+        // running decode of this thread's pixel (it advances by 8 per step, 64 per K slice): no divisions in the loop
+        int pix = k_begin + pslot;
+        int pb = pix / (p.OH * p.OW), pr = pix - pb * p.OH * p.OW;
+        int poh = pr / p.OW, pow_ = pr - poh * p.OW;
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int stage = kb % STAGES;
+            if (kb >= STAGES) mbar_wait(&empty_bar[stage], (uint32_t)(((kb / STAGES) - 1) & 1));
+            const uint32_t dstA = smemA + stage * kStageA + atom * (BK * 128) + soff0;
+            const uint32_t dstB = smemB + stage * kStageB + atom * (BK * 128) + soff0;
+            if (p.a_tma && tid == 0) {
+                mbar_expect_tx(&full_bar[stage], (uint32_t)kStageA);
+                tma_load_2d(smemA + stage * kStageA, &wp.map_a, co0, k_begin + kb * BK, &full_bar[stage]);
+                tma_load_2d(smemA + stage * kStageA + BK * 128, &wp.map_a, co0 + 64, k_begin + kb * BK, &full_bar[stage]);
             }
+#pragma unroll
+            for (int i = 0; i < BK / 8; ++i) {
+                const bool pv = pix < k_end;
+                if (!p.a_tma) {
+                    const bool aok = pv && a_ch_ok;
+                    cp_async16(dstA + i * 1024, aok ? (const void*)(p.dy + (long long)pix * p.ldy + a_ch) : (const void*)p.dy,
+                               aok ? 16u : 0u);
+                }
+                const int ih = poh * p.stride + ta - p.pad_t, iw = pow_ * p.stride + tcc - p.pad_l;
+                const bool bok = pv && b_ch_ok && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+                const long long boff = ((long long)(pb * p.H + ih) * p.W + iw) * p.ldx + ci;
+                cp_async16(dstB + i * 1024, bok ? (const void*)(p.x + boff) : (const void*)p.x, bok ? 16u : 0u);
+                pix += 8;
+                pow_ += 8;
+                while (pow_ >= p.OW) { pow_ -= p.OW; ++poh; }
+                while (poh >= p.OH) { poh -= p.OH; ++pb; }
+            }
+            cp_async_arrive_noinc(&full_bar[stage]);
+        }
         }
     } else {
-        // MMA issuer: the whole warp walks the loop, elect.sync picks the issuing lane; ONE M=128 x N=n_cta (<= 256) MMA
-        // per K=16 step -- the B operand's 64-column atoms sit BK*128 bytes apart (LBO), both halves back to back
+        // MMA issuer: the whole warp walks the loop, elect.sync picks the issuing lane
         const uint32_t idesc = make_idesc(n_cta, 1, 1);
         const uint32_t hi = desc_hi(1024);
-        const uint32_t alo0 = desc_lo(smem_base, BK * 128), blo0 = desc_lo(smem_base + kStageA, BK * 128);
+        const uint32_t alo0 = desc_lo(smemA, BK * 128), blo0 = desc_lo(smemB, BK * 128);
         const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);    // warp-uniform register
-        int stage = 0;
-        uint32_t fph = 0u;
         for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&full_bar[stage], fph);
+            const int stage = kb % STAGES;
+            mbar_wait(&full_bar[stage], (uint32_t)((kb / STAGES) & 1));
             tc_fence_after();
-            const uint32_t alo = alo0 + stage * (kWgStage >> 4), blo = blo0 + stage * (kWgStage >> 4);
+            const uint32_t alo = alo0 + stage * (kStageA >> 4), blo = blo0 + stage * (kStageB >> 4);
             if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k)   // 16 pixels = two 8-row groups (2048 B) further down each atom
@@ -1220,7 +1179,6 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
                 tc_commit(&empty_bar[stage]);
             }
             __syncwarp();
-            if (++stage == kWgStages) { stage = 0; fph ^= 1u; }
         }
         if (elect_one()) tc_commit(&acc_bar);
         __syncwarp();
@@ -1241,9 +1199,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
                     const int tap = nn / p.ldx, ci0 = nn - tap * p.ldx;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const int cix = ci0 + i;
-                        if (cix < p.Cin)
-                            atomicAdd(p.dw + ((size_t)tap * p.Cin + cix) * p.Cout + co, __uint_as_float(v[8 * h + i]));
+                        const int ci = ci0 + i;
+                        if (ci < p.Cin)
+                            atomicAdd(p.dw + ((size_t)tap * p.Cin + ci) * p.Cout + co, __uint_as_float(v[8 * h + i]));
                     }
                 }
             }
@@ -1253,7 +1211,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
     __syncthreads();
     if (warp == 4) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)kWgN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
     }
 }
 
@@ -1735,17 +1693,17 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
     ACG_REQUIRE((long long)s->B * s->H * s->W * (long long)t->ld_in < (1ll << 40) &&
                     (long long)s->B * s->OH * s->OW < (1ll << 31),
                 ACG_ERR_UNSUPPORTED, "acg_conv_wgrad_tc: tensor too large");
-    { int rc = set_smem((const void*)conv_wgrad_tc_kernel, kWgSmem); if (rc) return rc; }
+    { int rc = set_smem((const void*)conv_wgrad_tc_kernel, kSmemBytes); if (rc) return rc; }
     WgradParams p{};
     p.x = static_cast<const __nv_bfloat16*>(x_bf16); p.dy = static_cast<const __nv_bfloat16*>(dy_bf16); p.dw = dw;
     p.B = s->B; p.H = s->H; p.W = s->W; p.OH = s->OH; p.OW = s->OW; p.KH = s->KH; p.KW = s->KW;
     p.stride = s->stride; p.pad_t = s->pad_t; p.pad_l = s->pad_l;
     p.Cin = s->Cin; p.Cout = s->Cout; p.ldx = t->ld_in; p.ldy = t->ld_out;
     const int Ntot = s->KH * s->KW * t->ld_in;
-    const int gx = (Ntot + kWgN - 1) / kWgN, gy = (s->Cout + BM - 1) / BM;
+    const int gx = (Ntot + BN - 1) / BN, gy = (s->Cout + BM - 1) / BM;
     const long long Kd = (long long)s->B * s->OH * s->OW;
-    // split the pixel reduction so that ~2 waves of CTAs exist (one CTA per SM), at least 4 K blocks per split
-    long long splits = ((long long)num_sms() * 2 + (long long)gx * gy - 1) / ((long long)gx * gy);
+    // split the pixel reduction so that ~2 waves of CTAs exist, at least 4 K blocks per split
+    long long splits = ((long long)num_sms() * 4 + (long long)gx * gy - 1) / ((long long)gx * gy);
     const long long max_splits = (Kd + 4 * BK - 1) / (4 * BK);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -1778,7 +1736,7 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
         }
     }
     if (!wp.p.a_tma) memset(&wp.map_a, 0, sizeof(wp.map_a));
-    launch_pdl(conv_wgrad_tc_kernel, grid, kThreads, kWgSmem, static_cast<cudaStream_t>(stream), wp);
+    launch_pdl(conv_wgrad_tc_kernel, grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream), wp);
     return check_launch("acg_conv_wgrad_tc");
 }
 
