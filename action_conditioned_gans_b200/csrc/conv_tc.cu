@@ -1011,7 +1011,11 @@ struct alignas(64) WgradTmaParams {
     CUtensorMap map_a;        // dy as bf16 [Kd][ldy], box {64 channels, 64 pixels}, 128B swizzle, zero OOB fill
 };
 
-__global__ void __launch_bounds__(kThreads, 2)
+// Producers: EIGHT warps (the cp.async gather is issue-latency bound: a variant with half the producer warps per SM ran 2x
+// slower), 4 pixels of a K slice per thread; warps 0-3 are also the epilogue, warp 8 issues the MMAs and owns the TMEM.
+constexpr int kWgProd = 256, kWgThreads = kWgProd + 32, kWgPx = BK / (kWgProd / 16);
+
+__global__ void __launch_bounds__(kWgThreads, 2)
 conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
     const WgradParams& p = wp.p;
     extern __shared__ unsigned char smem_raw[];
@@ -1034,12 +1038,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
     if (nkb == 0) return;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], kProducers + (p.a_tma ? 1 : 0)); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], kWgProd + (p.a_tma ? 1 : 0)); mbar_init(&empty_bar[i], 1); }
         if (p.a_tma) tma_prefetch_desc(&wp.map_a);
         mbar_init(&acc_bar, 1);
         fence_mbar_init();
     }
-    if (warp == 4) {
+    if (warp == kWgProd / 32) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
                      "r"((uint32_t)BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -1052,8 +1056,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
     pdl_wait();
     const uint32_t tmem_base = tmem_base_sh;
 
-    if (warp < 4) {
-        // producers: thread = (16-byte channel chunk c16 of the 128-wide tile, pixel slot)
+    if (warp < kWgProd / 32) {
+        // producers: thread = (16-byte channel chunk c16 of the 128-wide tile, pixel slot 0..15)
         const int c16 = tid & 15, pslot = tid >> 4;
         const int atom = c16 >> 3, jc = c16 & 7;
         // A: dy channels co0 + c16*8 .. +8
@@ -1065,7 +1069,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
         const int tap = nn / p.ldx, ci = nn - tap * p.ldx;
         const int ta = tap / p.KW, tcc = tap - ta * p.KW;
         const int S = p.OH * p.OW;
-        const int soff0 = pslot * 128 + ((jc ^ pslot) << 4);       // k & 7 == pslot for every k = pslot + 8 i
+        const int soff0 = pslot * 128 + ((jc ^ (pslot & 7)) << 4);  // k & 7 == pslot & 7 for every k = pslot + 16 i
         if (p.fast) {
             // Regular geometry (a 64-pixel K slice is whole rows of one image, or whole images): everything about the
             // slice-relative position q = pslot + 8 i of this thread's 8 pixels is a constant of the kernel -- source
@@ -1073,11 +1077,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
             // image.  A K slice then costs ~12 instructions per 16-byte copy pair instead of ~59 (the running decode
             // with its wrap-around loops and divergent branches made the producers, not the tensor pipe, the limiter:
             // ncu source view, 61 % of the samples in this loop).
-            int offB[8], dih[8];
+            int offB[kWgPx], dih[kWgPx];
             uint32_t iw_ok = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int q = pslot + 8 * i;
+            for (int i = 0; i < kWgPx; ++i) {
+                const int q = pslot + (kWgProd / 16) * i;
                 int db = 0, rem = q;
                 if (S < BK) { db = q / S; rem = q - db * S; }
                 const int doh = rem / p.OW, dow = rem - doh * p.OW;
@@ -1109,15 +1113,17 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool pv = pslot + 8 * i < kleft;
+                for (int i = 0; i < kWgPx; ++i) {
+                    const bool pv = pslot + (kWgProd / 16) * i < kleft;
                     if (!p.a_tma) {
                         const bool aok = pv && a_ch_ok;
-                        cp_async16(dstA + i * 1024, aok ? (const void*)(dyP + (long long)(8 * i) * p.ldy) : (const void*)p.dy,
+                        cp_async16(dstA + i * (kWgProd / 16) * 128,
+                                   aok ? (const void*)(dyP + (long long)((kWgProd / 16) * i) * p.ldy) : (const void*)p.dy,
                                    aok ? 16u : 0u);
                     }
                     const bool bok = pv && b_ch_ok && ((iw_ok >> i) & 1u) && (unsigned)(ihP + dih[i]) < (unsigned)p.H;
-                    cp_async16(dstB + i * 1024, bok ? (const void*)(xP + offB[i]) : (const void*)p.x, bok ? 16u : 0u);
+                    cp_async16(dstB + i * (kWgProd / 16) * 128, bok ? (const void*)(xP + offB[i]) : (const void*)p.x,
+                               bok ? 16u : 0u);
                 }
                 cp_async_arrive_noinc(&full_bar[stage]);
                 dyP += (long long)BK * p.ldy;
@@ -1142,19 +1148,19 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
                 tma_load_2d(smemA + stage * kStageA + BK * 128, &wp.map_a, co0 + 64, k_begin + kb * BK, &full_bar[stage]);
             }
 #pragma unroll
-            for (int i = 0; i < BK / 8; ++i) {
+            for (int i = 0; i < kWgPx; ++i) {
                 const bool pv = pix < k_end;
                 if (!p.a_tma) {
                     const bool aok = pv && a_ch_ok;
-                    cp_async16(dstA + i * 1024, aok ? (const void*)(p.dy + (long long)pix * p.ldy + a_ch) : (const void*)p.dy,
-                               aok ? 16u : 0u);
+                    cp_async16(dstA + i * (kWgProd / 16) * 128,
+                               aok ? (const void*)(p.dy + (long long)pix * p.ldy + a_ch) : (const void*)p.dy, aok ? 16u : 0u);
                 }
                 const int ih = poh * p.stride + ta - p.pad_t, iw = pow_ * p.stride + tcc - p.pad_l;
                 const bool bok = pv && b_ch_ok && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
                 const long long boff = ((long long)(pb * p.H + ih) * p.W + iw) * p.ldx + ci;
-                cp_async16(dstB + i * 1024, bok ? (const void*)(p.x + boff) : (const void*)p.x, bok ? 16u : 0u);
-                pix += 8;
-                pow_ += 8;
+                cp_async16(dstB + i * (kWgProd / 16) * 128, bok ? (const void*)(p.x + boff) : (const void*)p.x, bok ? 16u : 0u);
+                pix += kWgProd / 16;
+                pow_ += kWgProd / 16;
                 while (pow_ >= p.OW) { pow_ -= p.OW; ++poh; }
                 while (poh >= p.OH) { poh -= p.OH; ++pb; }
             }
@@ -1209,7 +1215,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kWgProd / 32) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
     }
@@ -1736,7 +1742,7 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
         }
     }
     if (!wp.p.a_tma) memset(&wp.map_a, 0, sizeof(wp.map_a));
-    launch_pdl(conv_wgrad_tc_kernel, grid, kThreads, kSmemBytes, static_cast<cudaStream_t>(stream), wp);
+    launch_pdl(conv_wgrad_tc_kernel, grid, kWgThreads, kSmemBytes, static_cast<cudaStream_t>(stream), wp);
     return check_launch("acg_conv_wgrad_tc");
 }
 
