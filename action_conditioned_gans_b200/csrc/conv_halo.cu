@@ -32,7 +32,8 @@ namespace tc {
 
 constexpr int kH2Threads = 384;
 constexpr int kH2Rows = 18;                         // staged halo rows per image: 16 output rows + 2
-constexpr int kH2Data = 222 * 1024;                 // operand staging: 2 halo buffers + the weight-slice ring
+constexpr int kH2Data = 214 * 1024;                 // operand staging: 2 halo buffers + the weight-slice ring (the per-warp
+                                                    // moment slots and the CTA totals take 10 KB of static shared memory)
 constexpr int kH2Smem = kH2Data + 1024;             // + alignment slack (227 KB per CTA is the hardware limit)
 constexpr int kH2MaxBStages = 8;
 constexpr int kMaxTaps = 9;
@@ -107,13 +108,15 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
     __shared__ __align__(8) uint64_t halo_full[2], halo_empty[2], b_full[kH2MaxBStages], b_empty[kH2MaxBStages];
     __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_sh;
-    __shared__ float sm_stats[2][BN];
+    __shared__ float sm_stats[8][2][BN];       // per epilogue warp: no atomics, fixed summation order
+    __shared__ double cta_acc[2][BN];          // this CTA's column totals over all of its tiles
     __shared__ int last_cta_sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smemH = smem_base;
-    if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
+    for (int i = tid; i < 8 * 2 * BN; i += kH2Threads) (&sm_stats[0][0][0])[i] = 0.f;
+    if (tid < BN) { cta_acc[0][tid] = 0.0; cta_acc[1][tid] = 0.0; }
 
     const int N = p.N;
     const int XG = hp.TW >> 3;                               // 8-column accumulator groups per tile row
@@ -279,7 +282,7 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
         // ================================ epilogue: two groups of 4 warps ================================
         // warp w may read TMEM lanes 32*(w&3) .. +31; group 0 = warps 0-3 takes accumulators 0, 2, group 1 = warps 8-11
         // takes 1, 3
-        const int grp = warp >> 3, wq = warp & 3;
+        const int grp = warp >> 3, wq = warp & 3, ew = grp * 4 + wq;     // ew: epilogue warp index 0..7
         const int ml = wq * 32 + lane, yy = ml >> 3, xi = ml & 7;
         int tcount = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
@@ -315,8 +318,8 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
 #pragma unroll
                     for (int i = 0; i < kEpiBatch; ++i)
                         if (cb0 + 16 * i < N)
-                            epilogue_chunk(p, v[i], cb0 + 16 * i, true, row_off, 0u, lane, &sm_stats[0][cb0 + 16 * i],
-                                           &sm_stats[1][cb0 + 16 * i],
+                            epilogue_chunk(p, v[i], cb0 + 16 * i, true, row_off, 0u, lane, &sm_stats[ew][0][cb0 + 16 * i],
+                                           &sm_stats[ew][1][cb0 + 16 * i],
                                            (zrow && cb0 + 16 * i < p.n_stat) ? zrow + cb0 + 16 * i : nullptr);
                 }
             }
@@ -324,13 +327,18 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[abuf]);
-            if (p.stats) {   // per-tile flush of the fp32 column sums into the fp64 accumulators (epilogue warps only)
+            if (p.stats) {   // per-tile flush of the eight warps' fp32 column sums into the CTA's fp64 totals, fixed order
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (tid < N && tid < p.n_stat) {
-                    atomicAdd(&p.stats[tid], (double)sm_stats[0][tid]);
-                    atomicAdd(&p.stats[p.n_stat + tid], (double)sm_stats[1][tid]);
+                    float a = 0.f, b = 0.f;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        a += sm_stats[w][0][tid]; b += sm_stats[w][1][tid];
+                        sm_stats[w][0][tid] = 0.f; sm_stats[w][1][tid] = 0.f;
+                    }
+                    cta_acc[0][tid] += (double)a;
+                    cta_acc[1][tid] += (double)b;
                 }
-                if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
@@ -341,27 +349,11 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
-    if (p.stats && p.counter) {
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) last_cta_sh = (atomicAdd(p.counter, 1u) == p.total_ctas - 1u);
-        __syncthreads();
-        if (last_cta_sh) {
-            __threadfence();
-            const double inv = 1.0 / (double)p.bn_rows;
-            for (int c = tid; c < p.n_bias; c += kH2Threads) {
-                const double mu = __ldcg(&p.stats[c]) * inv;
-                double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
-                if (var < 0.0) var = 0.0;
-                const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
-                const float b = p.beta ? p.beta[c] : 0.f;
-                p.bn_mean[c] = (float)mu;
-                p.bn_rstd[c] = rs;
-                p.bn_scale[c] = rs;
-                p.bn_shift[c] = b - (float)mu * rs;
-            }
-            if (tid == 0) *p.counter = 0u;
-        }
+    if (p.stats) {
+        const bool has_col = tid < N && tid < p.n_stat;
+        cta_stats_finish(p, tid, kH2Threads, (int)blockIdx.x, has_col, tid, has_col ? cta_acc[0][tid] : 0.0,
+                         has_col ? cta_acc[1][tid] : 0.0, &last_cta_sh,
+                         reinterpret_cast<double*>(smem_raw + (smem_base - smem_u32(smem_raw))));
     }
 }
 
@@ -543,6 +535,7 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
     const int ctas = ntiles < num_sms() ? ntiles : num_sms();
     rc = fill_bn(&hp.p, t, (unsigned int)ctas, who);
     if (rc) return rc;
+    set_stats_ws(&hp.p, t, ctas);
     if (nacc == 1) {
         rc = set_smem((const void*)conv_halo2_kernel<1>, kH2Smem);
         if (rc) return rc;

@@ -81,13 +81,13 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
     __shared__ uint32_t tmem_base_sh;
-    __shared__ float sm_stats[2][BN];
+    __shared__ float sm_stats[4][2][BN];       // per epilogue warp: no atomics, fixed summation order
     __shared__ int last_cta_sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smemA = smem_base, smemB = smem_base + STAGES * kStageA;
-    if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
+    for (int i = tid; i < 4 * 2 * BN; i += NTHREADS) (&sm_stats[0][0][0])[i] = 0.f;
     const bool timing = ACG_DBG(p, 8) && tid == 0;
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0;
     if (timing) t0 = gtime();
@@ -305,14 +305,14 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
         }
         for (int cb = 0; cb < n_cta; cb += 16) {
             uint32_t v[16];
-            if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + cb, v);
+            if (nkb > 0 && p.splits == 1) tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + cb, v);
             else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0u;
             }
-            if (p.splits > 1) {     // add the other CTAs' partial tiles (L2-resident; bypass L1)
+            if (p.splits > 1) {     // add ALL partial tiles in split order (L2-resident; bypass L1) -- this CTA's own one is
+                                    // read back from the workspace too, so the sum does not depend on which CTA came last
                 for (int sp = 0; sp < p.splits; ++sp) {
-                    if (sp == split) continue;
                     const float4* o = reinterpret_cast<const float4*>(
                         ws_tile + (size_t)sp * (BM * BN) + (size_t)(cb >> 4) * (BM * 16) + (warp * 32 + lane) * 16);
 #pragma unroll
@@ -325,7 +325,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
                     }
                 }
             }
-            epilogue_chunk(p, v, n0 + cb, m < M, row_off, zrow + 2 * cb, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
+            epilogue_chunk(p, v, n0 + cb, m < M, row_off, zrow + 2 * cb, lane, &sm_stats[warp][0][cb], &sm_stats[warp][1][cb]);
         }
     }
     tc_fence_before();
@@ -343,33 +343,18 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
         atomicAdd(&g_phase_ns[4], (unsigned long long)nkb);
     }
     if (p.stats && final_cta) {
-        if (tid < n_cta && n0 + tid < p.n_stat) {
-            atomicAdd(&p.stats[n0 + tid], (double)sm_stats[0][tid]);
-            atomicAdd(&p.stats[p.n_stat + n0 + tid], (double)sm_stats[1][tid]);
+        const bool has_col = tid < n_cta && n0 + tid < p.n_stat;
+        double s0 = 0.0, s1 = 0.0;
+        if (has_col) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { a += sm_stats[w][0][tid]; b += sm_stats[w][1][tid]; }
+            s0 = (double)a;
+            s1 = (double)b;
         }
-        if (p.counter) {
-            // last CTA of the launch turns the moments into mean / rstd / scale / shift (slim.batch_norm, eps 1e-3)
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) last_cta_sh = (atomicAdd(p.counter, 1u) == p.total_ctas - 1u);
-            __syncthreads();
-            if (last_cta_sh) {
-                __threadfence();
-                const double inv = 1.0 / (double)p.bn_rows;
-                for (int c = tid; c < p.n_bias; c += NTHREADS) {
-                    const double mu = __ldcg(&p.stats[c]) * inv;
-                    double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
-                    if (var < 0.0) var = 0.0;
-                    const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
-                    const float b = p.beta ? p.beta[c] : 0.f;
-                    p.bn_mean[c] = (float)mu;
-                    p.bn_rstd[c] = rs;
-                    p.bn_scale[c] = rs;
-                    p.bn_shift[c] = b - (float)mu * rs;
-                }
-                if (tid == 0) *p.counter = 0u;   // ready for the next launch
-            }
-        }
+        // workspace slot = M tile (x parity class); the N tiles of one M tile fill different columns of the same slot
+        cta_stats_finish(p, tid, NTHREADS, (int)(blockIdx.x + gridDim.x * (unsigned)zcls), has_col, n0 + tid, s0, s1,
+                         &last_cta_sh, reinterpret_cast<double*>(smem_raw + (smem_base - smem_u32(smem_raw))));
     }
 }
 
@@ -399,13 +384,13 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kSmallKRing], empty_bar[kSmallKRing], b_full, acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_sh;
-    __shared__ float sm_stats[2][BN];
+    __shared__ float sm_stats[4][2][BN];       // per epilogue warp
     __shared__ int last_cta_sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smemB = smem_base, smemA = smem_base + kSmallKMaxKb * kStageB;
-    if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
+    for (int i = tid; i < 4 * 2 * BN; i += kSmallKThreads) (&sm_stats[0][0][0])[i] = 0.f;
 
     const int s = p.stride;
     const int M = p.B * p.OH * p.OW;
@@ -561,8 +546,8 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
                 for (int i = 0; i < 16; ++i) { a16[i] = q1[cb + i]; b16[i] = q2[cb + i]; }
                 const float cs = warp_colsum16(a16, lane), cs2 = warp_colsum16(b16, lane);
                 if ((lane & 1) == 0) {
-                    atomicAdd(&sm_stats[0][cb + (lane >> 1)], cs);
-                    atomicAdd(&sm_stats[1][cb + (lane >> 1)], cs2);
+                    sm_stats[warp][0][cb + (lane >> 1)] = cs;
+                    sm_stats[warp][1][cb + (lane >> 1)] = cs2;
                 }
             }
         }
@@ -604,32 +589,14 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
     }
     if (p.stats) {
-        if (tid < NT && tid < p.n_stat) {
-            atomicAdd(&p.stats[tid], (double)sm_stats[0][tid]);
-            atomicAdd(&p.stats[p.n_stat + tid], (double)sm_stats[1][tid]);
+        const bool has_col = tid < NT && tid < p.n_stat;
+        double s0 = 0.0, s1 = 0.0;
+        if (has_col) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { s0 += (double)sm_stats[w][0][tid]; s1 += (double)sm_stats[w][1][tid]; }
         }
-        if (p.counter) {
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) last_cta_sh = (atomicAdd(p.counter, 1u) == p.total_ctas - 1u);
-            __syncthreads();
-            if (last_cta_sh) {
-                __threadfence();
-                const double inv = 1.0 / (double)p.bn_rows;
-                for (int c = tid; c < p.n_bias; c += kSmallKThreads) {
-                    const double mu = __ldcg(&p.stats[c]) * inv;
-                    double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
-                    if (var < 0.0) var = 0.0;
-                    const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
-                    const float b = p.beta ? p.beta[c] : 0.f;
-                    p.bn_mean[c] = (float)mu;
-                    p.bn_rstd[c] = rs;
-                    p.bn_scale[c] = rs;
-                    p.bn_shift[c] = b - (float)mu * rs;
-                }
-                if (tid == 0) *p.counter = 0u;
-            }
-        }
+        cta_stats_finish(p, tid, kSmallKThreads, (int)blockIdx.x, has_col, tid, s0, s1, &last_cta_sh,
+                         reinterpret_cast<double*>(smem_raw + (smem_base - smem_u32(smem_raw))));
     }
 }
 
@@ -652,13 +619,13 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t halo_full[2], halo_empty[2], b_full[kHaloBStages], b_empty[kHaloBStages], acc_bar;
     __shared__ uint32_t tmem_base_sh;
-    __shared__ float sm_stats[2][BN];
+    __shared__ float sm_stats[4][2][BN];       // per epilogue warp
     __shared__ int last_cta_sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smemH = smem_base, smemB = smem_base + 2 * kHaloBuf;
-    if (tid < BN) { sm_stats[0][tid] = 0.f; sm_stats[1][tid] = 0.f; }
+    for (int i = tid; i < 4 * 2 * BN; i += kThreads) (&sm_stats[0][0][0])[i] = 0.f;
     const bool timing = ACG_DBG(p, 8) && tid == 0;
     const bool mtiming = ACG_DBG(p, 8) && tid == 128;
     unsigned long long t0 = 0, t1 = 0, t2 = 0, t3 = 0, w_halo = 0, w_b = 0;
@@ -810,7 +777,7 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
             for (int cb = 0; cb < N; cb += 16) {
                 uint32_t v[16];
                 tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + q * N + cb, v);
-                epilogue_chunk(p, v, cb, true, row_off, zrow + 2 * cb, lane, &sm_stats[0][cb], &sm_stats[1][cb]);
+                epilogue_chunk(p, v, cb, true, row_off, zrow + 2 * cb, lane, &sm_stats[warp][0][cb], &sm_stats[warp][1][cb]);
             }
         }
     }
@@ -833,32 +800,14 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
         atomicAdd(&g_phase_ns[4], (unsigned long long)(nkc * ntaps));
     }
     if (p.stats) {
-        if (tid < N && tid < p.n_stat) {
-            atomicAdd(&p.stats[tid], (double)sm_stats[0][tid]);
-            atomicAdd(&p.stats[p.n_stat + tid], (double)sm_stats[1][tid]);
+        const bool has_col = tid < N && tid < p.n_stat;
+        double s0 = 0.0, s1 = 0.0;
+        if (has_col) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { s0 += (double)sm_stats[w][0][tid]; s1 += (double)sm_stats[w][1][tid]; }
         }
-        if (p.counter) {
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) last_cta_sh = (atomicAdd(p.counter, 1u) == p.total_ctas - 1u);
-            __syncthreads();
-            if (last_cta_sh) {
-                __threadfence();
-                const double inv = 1.0 / (double)p.bn_rows;
-                for (int c = tid; c < p.n_bias; c += kThreads) {
-                    const double mu = __ldcg(&p.stats[c]) * inv;
-                    double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
-                    if (var < 0.0) var = 0.0;
-                    const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
-                    const float b = p.beta ? p.beta[c] : 0.f;
-                    p.bn_mean[c] = (float)mu;
-                    p.bn_rstd[c] = rs;
-                    p.bn_scale[c] = rs;
-                    p.bn_shift[c] = b - (float)mu * rs;
-                }
-                if (tid == 0) *p.counter = 0u;
-            }
-        }
+        cta_stats_finish(p, tid, kThreads, (int)(blockIdx.x + gridDim.x * blockIdx.z), has_col, tid, s0, s1, &last_cta_sh,
+                         reinterpret_cast<double*>(smem_raw + (smem_base - smem_u32(smem_raw))));
     }
 }
 
@@ -1385,8 +1334,13 @@ int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char
         p->r_mean = t->red_mean; p->r_rstd = t->red_rstd; p->r_shift = t->red_shift;
         p->n_stat = t->red_C;
     }
+    p->stats_ws = nullptr;
+    p->ws_slots = 0;
+    p->bn_rows = 0;
     if (t->stats && t->bn_counter) {
-        ACG_REQUIRE(t->bn_mean && t->bn_rstd && t->bn_scale && t->bn_shift && t->bn_rows > 0, ACG_ERR_INVALID,
+        // bn_rows == 0: the last CTA only completes the totals (deterministic workspace sum), the caller finalises
+        ACG_REQUIRE(t->bn_rows == 0 || (t->bn_mean && t->bn_rstd && t->bn_scale && t->bn_shift && t->bn_rows > 0),
+                    ACG_ERR_INVALID,
                     "%s: in-kernel batch-norm finalize needs mean/rstd/scale/shift buffers and the row count", who);
         p->counter = t->bn_counter;
         p->beta = t->bn_beta;
@@ -1399,6 +1353,16 @@ int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember (kernel, device) pairs, so a
 // process that drives several GPUs sets it on each of them.
+// deterministic moments: use the caller's workspace when it has a slot for every contributing CTA and a ticket exists
+void set_stats_ws(Params* p, const acg_tc_args* t, int slots) {
+    p->stats_ws = nullptr;
+    p->ws_slots = 0;
+    if (p->stats && p->counter && !p->rz && t->stats_ws && slots > 0 && t->stats_ws_slots >= slots) {
+        p->stats_ws = t->stats_ws;
+        p->ws_slots = slots;
+    }
+}
+
 int set_smem(const void* kern, int bytes) {
     static std::mutex mu;
     static std::vector<std::pair<const void*, int>> done;
@@ -1540,6 +1504,21 @@ int acg_conv_kernel_kind(const acg_conv_shape* s, int which, int ld_in, int n_li
     return halo2_adj_ok(s, &t, N) ? 1 : 0;
 }
 
+int acg_conv_stats_slots(const acg_conv_shape* s, int which, int ld_in, int n_limit) {
+    using namespace acg;
+    using namespace acg::tc;
+    if (!s || ld_in <= 0 || (which != 0 && which != 1)) return -1;
+    if (acg_conv_kernel_kind(s, which, ld_in, n_limit) == 1) return num_sms();     // persistent: one slot per CTA
+    if (which == 0) {
+        const long long M = (long long)s->B * s->OH * s->OW;
+        const long long tiles = (M + BM - 1) / BM;
+        return (int)(tiles > num_sms() ? tiles : num_sms());          // generic: one per M tile; small-K: one per CTA
+    }
+    const int Hp = (s->H + s->stride - 1) / s->stride, Wp = (s->W + s->stride - 1) / s->stride;
+    const long long M = (long long)s->B * Hp * Wp;
+    return (int)(((M + BM - 1) / BM) * s->stride * s->stride);
+}
+
 int acg_conv_tc_supported(const acg_conv_shape* s, int which) {
     if (!s) return 0;
     if (s->stride != 1 && s->stride != 2) return 0;
@@ -1583,6 +1562,7 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
             if (rc) return rc;
             p.splits = 1;
             p.total_ctas = (unsigned int)num_sms();
+            set_stats_ws(&p, t, num_sms());
             ConvParams scp;
             scp.p = p;
             rc = encode_weight_map(&scp.map_b[0], w_pack, (long long)s->KH * s->KW * t->ld_in, N, "acg_conv_fprop_tc");
@@ -1600,6 +1580,7 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
         // stride-2 layers with a 16- or 32-wide output: parity planes staged by TMA, every tap a shifted descriptor
         return launch_halo2(1, s, t, p, x_bf16, w_pack, N, static_cast<cudaStream_t>(stream), "acg_conv_fprop_tc(halo)");
     grid.z = (unsigned)apply_split(&p, t, plan_fprop(s, t->ld_in));
+    set_stats_ws(&p, t, (int)grid.x);
     ConvParams cp;
     cp.p = p;
     rc = encode_weight_map(&cp.map_b[0], w_pack, (long long)s->KH * s->KW * t->ld_in, N, "acg_conv_fprop_tc");
@@ -1659,6 +1640,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
         dim3 hgrid((unsigned)((s->B / TB) * (s->H / 32)), 1, 4);
         rc = fill_bn(&p, t, hgrid.x * 4u, "acg_conv_dgrad_tc");
         if (rc) return rc;
+        set_stats_ws(&p, t, (int)hgrid.x * 4);
         HaloParams hp;
         hp.p = p;
         rc = encode_halo_maps(&hp, s, t, N, TB, dy_bf16, w_pack);
@@ -1669,6 +1651,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     rc = fill_bn(&p, t, active, "acg_conv_dgrad_tc");
     if (rc) return rc;
     grid.z = (unsigned)(ncls * apply_split(&p, t, plan_dgrad(s, t->ld_in)));
+    set_stats_ws(&p, t, (int)grid.x * ncls);
     ConvParams cp;
     cp.p = p;
     for (int cls = 0; cls < ncls; ++cls) {

@@ -51,6 +51,10 @@ struct Params {
     int splits, kb_per_split;
     float* ws;
     unsigned int* tickets;
+    // deterministic moments (optional): every CTA writes its fp64 column partials to slot `its index` of stats_ws
+    // ([ws_slots][2][n_stat]) instead of adding them to `stats` with atomics; the last CTA adds the slots in index order
+    double* stats_ws;
+    int ws_slots;
     int dbg_skip;               // probe library only (-DACG_PROBES, env ACG_DBG_SKIP): see ACG_DBG below
 };
 // Profiling probes (per-phase timing, pipelines with one stage switched off) exist only in libacg_b200_probe.so, which
@@ -286,10 +290,11 @@ __device__ __forceinline__ void epilogue_chunk(const Params& p, const uint32_t (
 #pragma unroll
             for (int i = 0; i < 16; ++i) q2[i] = q[i] * q[i];
         }
+        // sm_sum / sm_sq point into THIS WARP's slot (single writer per column: no atomics, fixed summation order)
         const float cs = warp_colsum16(q, lane), cs2 = warp_colsum16(q2, lane);
         if ((lane & 1) == 0) {
-            atomicAdd(sm_sum + (lane >> 1), cs);
-            atomicAdd(sm_sq + (lane >> 1), cs2);
+            sm_sum[lane >> 1] += cs;
+            sm_sq[lane >> 1] += cs2;
         }
     }
     if (!row_ok) return;
@@ -344,6 +349,76 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// CTA-level end of the fused batch-norm moments; called by ALL threads of the CTA.  s0 / s1: the fp64 totals of column
+// `col` over this CTA's rows, held by the calling thread when has_col.  Without a workspace they are added to p.stats
+// with fp64 atomics (the order, hence the last bits, vary from run to run); with p.stats_ws the CTA writes them to ITS
+// slot and the last CTA of the launch (ticket) adds the slots in index order -- bitwise reproducible.  The last CTA also
+// finalises mean / rstd / scale / shift (slim.batch_norm, eps 1e-3) when p.bn_rows > 0.  `scratch`: 2 * nthreads doubles
+// of shared memory that are free at this point (the operand staging area: every pipeline has drained).
+__device__ __forceinline__ void cta_stats_finish(const Params& p, int tid, int nthreads, int slot, bool has_col, int col,
+                                                 double s0, double s1, int* last_sh, double* scratch) {
+    if (has_col) {
+        if (p.stats_ws) {
+            double* w = p.stats_ws + (size_t)slot * 2 * p.n_stat;
+            w[col] = s0;
+            w[p.n_stat + col] = s1;
+        } else {
+            atomicAdd(&p.stats[col], s0);
+            atomicAdd(&p.stats[p.n_stat + col], s1);
+        }
+    }
+    if (!p.counter) return;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) *last_sh = (atomicAdd(p.counter, 1u) == p.total_ctas - 1u);
+    __syncthreads();
+    if (!*last_sh) return;
+    __threadfence();
+    if (p.stats_ws) {
+        // thread (pair, part) adds slots part, part + parts, ... of one column pair in that order (independent 16-byte
+        // L2 loads, several in flight); the parts of a column are then added in part order.  The grouping depends only
+        // on the launch geometry, so the result is the same in every run.
+        const int ncols = 2 * p.n_stat, npair = ncols >> 1;
+        int parts = nthreads / npair;
+        parts = parts < 1 ? 1 : (parts > p.ws_slots ? p.ws_slots : parts);
+        for (int idx = tid; idx < npair * parts; idx += nthreads) {
+            const int pr = idx % npair, part = idx / npair;
+            double tx = 0.0, ty = 0.0;
+#pragma unroll 8
+            for (int sl = part; sl < p.ws_slots; sl += parts) {
+                const double2 v = __ldcg(reinterpret_cast<const double2*>(p.stats_ws + (size_t)sl * ncols) + pr);
+                tx += v.x;
+                ty += v.y;
+            }
+            scratch[part * ncols + 2 * pr] = tx;
+            scratch[part * ncols + 2 * pr + 1] = ty;
+        }
+        __syncthreads();
+        for (int c = tid; c < ncols; c += nthreads) {
+            double t = 0.0;
+            for (int part = 0; part < parts; ++part) t += scratch[part * ncols + c];
+            p.stats[c] = t;
+        }
+        __threadfence();
+        __syncthreads();
+    }
+    if (p.bn_rows > 0) {
+        const double inv = 1.0 / (double)p.bn_rows;
+        for (int c = tid; c < p.n_bias; c += nthreads) {
+            const double mu = __ldcg(&p.stats[c]) * inv;
+            double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
+            if (var < 0.0) var = 0.0;
+            const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
+            const float b = p.beta ? p.beta[c] : 0.f;
+            p.bn_mean[c] = (float)mu;
+            p.bn_rstd[c] = rs;
+            p.bn_scale[c] = rs;
+            p.bn_shift[c] = b - (float)mu * rs;
+        }
+    }
+    if (tid == 0) *p.counter = 0u;   // ready for the next launch
+}
+
 // One lane of a CONVERGED warp (elect.sync).  tcgen05.mma / TMA instructions take uniform-register operands; under a
 // plain `lane == 0` branch the compiler wraps EVERY such instruction in a uniformisation loop (ELECT / PLOP3 / BRA.U.ANY,
 // ~10 extra instructions at ~8 clk each: measured 95-105 clk per MMA regardless of N, round 2 knock-out probe), while
@@ -390,6 +465,7 @@ EncodeTiledFn encode_tiled_fn();
 int ru(int v, int m);
 void class_taps(const acg_conv_shape* s, int cls, int* na, int* nc);
 int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char* who);
+void set_stats_ws(Params* p, const acg_tc_args* t, int slots);
 int set_smem(const void* kern, int bytes);
 
 }  // namespace tc
