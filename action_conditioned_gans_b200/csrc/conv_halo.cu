@@ -351,9 +351,8 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
     }
     if (p.stats) {
         const bool has_col = tid < N && tid < p.n_stat;
-        cta_stats_finish(p, tid, kH2Threads, (int)blockIdx.x, has_col, tid, has_col ? cta_acc[0][tid] : 0.0,
-                         has_col ? cta_acc[1][tid] : 0.0, &last_cta_sh,
-                         reinterpret_cast<double*>(smem_raw + (smem_base - smem_u32(smem_raw))));
+        cta_stats_finish(p, tid, kH2Threads, has_col, tid, has_col ? cta_acc[0][tid] : 0.0,
+                         has_col ? cta_acc[1][tid] : 0.0, &last_cta_sh);
     }
 }
 
@@ -535,7 +534,7 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
     const int ctas = ntiles < num_sms() ? ntiles : num_sms();
     rc = fill_bn(&hp.p, t, (unsigned int)ctas, who);
     if (rc) return rc;
-    set_stats_ws(&hp.p, t, ctas);
+    set_stats_fix(&hp.p, t);
     if (nacc == 1) {
         rc = set_smem((const void*)conv_halo2_kernel<1>, kH2Smem);
         if (rc) return rc;

@@ -352,9 +352,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
             s0 = (double)a;
             s1 = (double)b;
         }
-        // workspace slot = M tile (x parity class); the N tiles of one M tile fill different columns of the same slot
-        cta_stats_finish(p, tid, NTHREADS, (int)(blockIdx.x + gridDim.x * (unsigned)zcls), has_col, n0 + tid, s0, s1,
-                         &last_cta_sh, reinterpret_cast<double*>(smem_raw + (smem_base - smem_u32(smem_raw))));
+        cta_stats_finish(p, tid, NTHREADS, has_col, n0 + tid, s0, s1, &last_cta_sh);
     }
 }
 
@@ -595,8 +593,7 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
 #pragma unroll
             for (int w = 0; w < 4; ++w) { s0 += (double)sm_stats[w][0][tid]; s1 += (double)sm_stats[w][1][tid]; }
         }
-        cta_stats_finish(p, tid, kSmallKThreads, (int)blockIdx.x, has_col, tid, s0, s1, &last_cta_sh,
-                         reinterpret_cast<double*>(smem_raw + (smem_base - smem_u32(smem_raw))));
+        cta_stats_finish(p, tid, kSmallKThreads, has_col, tid, s0, s1, &last_cta_sh);
     }
 }
 
@@ -806,8 +803,7 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
 #pragma unroll
             for (int w = 0; w < 4; ++w) { s0 += (double)sm_stats[w][0][tid]; s1 += (double)sm_stats[w][1][tid]; }
         }
-        cta_stats_finish(p, tid, kThreads, (int)(blockIdx.x + gridDim.x * blockIdx.z), has_col, tid, s0, s1, &last_cta_sh,
-                         reinterpret_cast<double*>(smem_raw + (smem_base - smem_u32(smem_raw))));
+        cta_stats_finish(p, tid, kThreads, has_col, tid, s0, s1, &last_cta_sh);
     }
 }
 
@@ -1334,8 +1330,7 @@ int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char
         p->r_mean = t->red_mean; p->r_rstd = t->red_rstd; p->r_shift = t->red_shift;
         p->n_stat = t->red_C;
     }
-    p->stats_ws = nullptr;
-    p->ws_slots = 0;
+    p->stats_fix = nullptr;
     p->bn_rows = 0;
     if (t->stats && t->bn_counter) {
         // bn_rows == 0: the last CTA only completes the totals (deterministic workspace sum), the caller finalises
@@ -1353,14 +1348,12 @@ int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember (kernel, device) pairs, so a
 // process that drives several GPUs sets it on each of them.
-// deterministic moments: use the caller's workspace when it has a slot for every contributing CTA and a ticket exists
-void set_stats_ws(Params* p, const acg_tc_args* t, int slots) {
-    p->stats_ws = nullptr;
-    p->ws_slots = 0;
-    if (p->stats && p->counter && !p->rz && t->stats_ws && slots > 0 && t->stats_ws_slots >= slots) {
-        p->stats_ws = t->stats_ws;
-        p->ws_slots = slots;
-    }
+// reproducible moments: use the caller's limb accumulators when a ticket exists (the last CTA converts them)
+void set_stats_fix(Params* p, const acg_tc_args* t) {
+    p->stats_fix = nullptr;
+    if (p->stats && p->counter && !p->rz && t->stats_fix && t->stats_fix_len >= 6LL * p->n_stat &&
+        ((uintptr_t)t->stats_fix & 7) == 0)
+        p->stats_fix = t->stats_fix;
 }
 
 int set_smem(const void* kern, int bytes) {
@@ -1504,21 +1497,6 @@ int acg_conv_kernel_kind(const acg_conv_shape* s, int which, int ld_in, int n_li
     return halo2_adj_ok(s, &t, N) ? 1 : 0;
 }
 
-int acg_conv_stats_slots(const acg_conv_shape* s, int which, int ld_in, int n_limit) {
-    using namespace acg;
-    using namespace acg::tc;
-    if (!s || ld_in <= 0 || (which != 0 && which != 1)) return -1;
-    if (acg_conv_kernel_kind(s, which, ld_in, n_limit) == 1) return num_sms();     // persistent: one slot per CTA
-    if (which == 0) {
-        const long long M = (long long)s->B * s->OH * s->OW;
-        const long long tiles = (M + BM - 1) / BM;
-        return (int)(tiles > num_sms() ? tiles : num_sms());          // generic: one per M tile; small-K: one per CTA
-    }
-    const int Hp = (s->H + s->stride - 1) / s->stride, Wp = (s->W + s->stride - 1) / s->stride;
-    const long long M = (long long)s->B * Hp * Wp;
-    return (int)(((M + BM - 1) / BM) * s->stride * s->stride);
-}
-
 int acg_conv_tc_supported(const acg_conv_shape* s, int which) {
     if (!s) return 0;
     if (s->stride != 1 && s->stride != 2) return 0;
@@ -1562,7 +1540,7 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
             if (rc) return rc;
             p.splits = 1;
             p.total_ctas = (unsigned int)num_sms();
-            set_stats_ws(&p, t, num_sms());
+            set_stats_fix(&p, t);
             ConvParams scp;
             scp.p = p;
             rc = encode_weight_map(&scp.map_b[0], w_pack, (long long)s->KH * s->KW * t->ld_in, N, "acg_conv_fprop_tc");
@@ -1580,7 +1558,7 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
         // stride-2 layers with a 16- or 32-wide output: parity planes staged by TMA, every tap a shifted descriptor
         return launch_halo2(1, s, t, p, x_bf16, w_pack, N, static_cast<cudaStream_t>(stream), "acg_conv_fprop_tc(halo)");
     grid.z = (unsigned)apply_split(&p, t, plan_fprop(s, t->ld_in));
-    set_stats_ws(&p, t, (int)grid.x);
+    set_stats_fix(&p, t);
     ConvParams cp;
     cp.p = p;
     rc = encode_weight_map(&cp.map_b[0], w_pack, (long long)s->KH * s->KW * t->ld_in, N, "acg_conv_fprop_tc");
@@ -1640,7 +1618,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
         dim3 hgrid((unsigned)((s->B / TB) * (s->H / 32)), 1, 4);
         rc = fill_bn(&p, t, hgrid.x * 4u, "acg_conv_dgrad_tc");
         if (rc) return rc;
-        set_stats_ws(&p, t, (int)hgrid.x * 4);
+        set_stats_fix(&p, t);
         HaloParams hp;
         hp.p = p;
         rc = encode_halo_maps(&hp, s, t, N, TB, dy_bf16, w_pack);
@@ -1651,7 +1629,7 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     rc = fill_bn(&p, t, active, "acg_conv_dgrad_tc");
     if (rc) return rc;
     grid.z = (unsigned)(ncls * apply_split(&p, t, plan_dgrad(s, t->ld_in)));
-    set_stats_ws(&p, t, (int)grid.x * ncls);
+    set_stats_fix(&p, t);
     ConvParams cp;
     cp.p = p;
     for (int cls = 0; cls < ncls; ++cls) {

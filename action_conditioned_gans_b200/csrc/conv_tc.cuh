@@ -51,10 +51,8 @@ struct Params {
     int splits, kb_per_split;
     float* ws;
     unsigned int* tickets;
-    // deterministic moments (optional): every CTA writes its fp64 column partials to slot `its index` of stats_ws
-    // ([ws_slots][2][n_stat]) instead of adding them to `stats` with atomics; the last CTA adds the slots in index order
-    double* stats_ws;
-    int ws_slots;
+    // reproducible moments (optional): integer limb accumulators [3][2][n_stat], see fix_add / cta_stats_finish
+    unsigned long long* stats_fix;
     int dbg_skip;               // probe library only (-DACG_PROBES, env ACG_DBG_SKIP): see ACG_DBG below
 };
 // Profiling probes (per-phase timing, pipelines with one stage switched off) exist only in libacg_b200_probe.so, which
@@ -349,19 +347,40 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// Order-independent accumulation of fp64 values: v is split into three integer limbs,
+//     v ~= H * 2^24 + M * 2^-8 + L * 2^-40     (H signed, M and L in [0, 2^32); truncation < 2^-40),
+// each added to its own 64-bit accumulator with an integer atomic.  Integer addition is associative, so the totals do not
+// depend on the order in which the CTAs arrive -- unlike fp64 atomics -- and the launch stays fire-and-forget.  The
+// mapping v -> (H, M, L) is a pure function of v (its roundings need not be exact, only repeatable).  Range |v| < 2^80;
+// beyond it, and for inf / nan, the value goes to the fp64 total directly so that a diverged run still shows up as such.
+__device__ __forceinline__ void fix_add(const Params& p, int c, double v) {
+    if (!(fabs(v) < 0x1p80)) {
+        atomicAdd(&p.stats[c], v);
+        return;
+    }
+    const int ncols = 2 * p.n_stat;
+    const double h = floor(v * 0x1p-24);
+    const double r = (v - h * 0x1p24) * 0x1p8;
+    const double m = floor(r);
+    const double l = floor((r - m) * 0x1p32);
+    atomicAdd(p.stats_fix + c, (unsigned long long)(long long)h);
+    atomicAdd(p.stats_fix + ncols + c, (unsigned long long)m);
+    atomicAdd(p.stats_fix + 2 * ncols + c, (unsigned long long)l);
+}
+
 // CTA-level end of the fused batch-norm moments; called by ALL threads of the CTA.  s0 / s1: the fp64 totals of column
-// `col` over this CTA's rows, held by the calling thread when has_col.  Without a workspace they are added to p.stats
-// with fp64 atomics (the order, hence the last bits, vary from run to run); with p.stats_ws the CTA writes them to ITS
-// slot and the last CTA of the launch (ticket) adds the slots in index order -- bitwise reproducible.  The last CTA also
-// finalises mean / rstd / scale / shift (slim.batch_norm, eps 1e-3) when p.bn_rows > 0.  `scratch`: 2 * nthreads doubles
-// of shared memory that are free at this point (the operand staging area: every pipeline has drained).
-__device__ __forceinline__ void cta_stats_finish(const Params& p, int tid, int nthreads, int slot, bool has_col, int col,
-                                                 double s0, double s1, int* last_sh, double* scratch) {
+// `col` over this CTA's rows (added in a fixed order inside the CTA), held by the calling thread when has_col.
+//   p.stats_fix == NULL: fp64 atomics into p.stats (the order, hence the last bits, vary from run to run);
+//   p.stats_fix: integer limb accumulators (fix_add) -> the totals are bitwise reproducible; the last CTA of the launch
+//     (ticket p.counter) converts them to fp64 in p.stats and leaves the accumulators zeroed for the next launch.
+// The last CTA also finalises mean / rstd / scale / shift (slim.batch_norm, eps 1e-3) when p.bn_rows > 0.
+__device__ __forceinline__ void cta_stats_finish(const Params& p, int tid, int nthreads, bool has_col, int col, double s0,
+                                                 double s1, int* last_sh) {
+    const int ncols = 2 * p.n_stat;
     if (has_col) {
-        if (p.stats_ws) {
-            double* w = p.stats_ws + (size_t)slot * 2 * p.n_stat;
-            w[col] = s0;
-            w[p.n_stat + col] = s1;
+        if (p.stats_fix) {
+            fix_add(p, col, s0);
+            fix_add(p, p.n_stat + col, s1);
         } else {
             atomicAdd(&p.stats[col], s0);
             atomicAdd(&p.stats[p.n_stat + col], s1);
@@ -374,30 +393,14 @@ __device__ __forceinline__ void cta_stats_finish(const Params& p, int tid, int n
     __syncthreads();
     if (!*last_sh) return;
     __threadfence();
-    if (p.stats_ws) {
-        // thread (pair, part) adds slots part, part + parts, ... of one column pair in that order (independent 16-byte
-        // L2 loads, several in flight); the parts of a column are then added in part order.  The grouping depends only
-        // on the launch geometry, so the result is the same in every run.
-        const int ncols = 2 * p.n_stat, npair = ncols >> 1;
-        int parts = nthreads / npair;
-        parts = parts < 1 ? 1 : (parts > p.ws_slots ? p.ws_slots : parts);
-        for (int idx = tid; idx < npair * parts; idx += nthreads) {
-            const int pr = idx % npair, part = idx / npair;
-            double tx = 0.0, ty = 0.0;
-#pragma unroll 8
-            for (int sl = part; sl < p.ws_slots; sl += parts) {
-                const double2 v = __ldcg(reinterpret_cast<const double2*>(p.stats_ws + (size_t)sl * ncols) + pr);
-                tx += v.x;
-                ty += v.y;
-            }
-            scratch[part * ncols + 2 * pr] = tx;
-            scratch[part * ncols + 2 * pr + 1] = ty;
-        }
-        __syncthreads();
+    if (p.stats_fix) {
         for (int c = tid; c < ncols; c += nthreads) {
-            double t = 0.0;
-            for (int part = 0; part < parts; ++part) t += scratch[part * ncols + c];
-            p.stats[c] = t;
+            unsigned long long* a = p.stats_fix + c;
+            const long long H = (long long)__ldcg(a);
+            const unsigned long long M = __ldcg(a + ncols), L = __ldcg(a + 2 * ncols);
+            a[0] = 0ull; a[ncols] = 0ull; a[2 * ncols] = 0ull;
+            // p.stats[c] is zero on entry unless a non-finite value was added to it
+            p.stats[c] = __ldcg(&p.stats[c]) + ((double)H * 0x1p24 + ((double)M * 0x1p-8 + (double)L * 0x1p-40));
         }
         __threadfence();
         __syncthreads();
@@ -465,7 +468,7 @@ EncodeTiledFn encode_tiled_fn();
 int ru(int v, int m);
 void class_taps(const acg_conv_shape* s, int cls, int* na, int* nc);
 int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char* who);
-void set_stats_ws(Params* p, const acg_tc_args* t, int slots);
+void set_stats_fix(Params* p, const acg_tc_args* t);
 int set_smem(const void* kern, int bytes);
 
 }  // namespace tc

@@ -29,7 +29,7 @@ BN_EPS = 1e-3       # slim.batch_norm default
 # default is "0" (separate acg_bn_act_bwd_reduce pass, which streams at 4.4-5.8 TB/s); "halo" fuses where the producer is
 # the halo kernel, "1" everywhere (both parity-tested, tests/test_conv_tc_gpu.py).
 FUSE_BWD_REDUCE = os.environ.get("ACG_FUSE_BWD_REDUCE", "0")
-# Fused batch-norm moments through per-CTA workspace slots added in a fixed order (bitwise reproducible forward pass).
+# Fused batch-norm moments through integer limb accumulators (order-independent: bitwise reproducible forward pass).
 # "0": fp64 atomics instead (order varies from run to run; kept to measure what reproducibility costs).
 DETERMINISTIC = os.environ.get("ACG_DETERMINISTIC", "1") != "0"
 
@@ -312,10 +312,9 @@ class NetRun:
             fwd_w, bwd_w = (0, 1) if L.kind == "conv" else (1, 0)
             st.splitk_f = K.splitk_workspace(st.shape, fwd_w, ld_in, self.device)
             st.splitk_b = K.splitk_workspace(st.shape, bwd_w, st.ldz, self.device) if dx else None
-            # per-CTA partials of the fused batch-norm moments, added in a fixed order by the launch's last CTA: the
-            # forward pass is bitwise reproducible (ACG_DETERMINISTIC=0: fp64 atomics, for A/B timing only)
-            st.stats_ws = (K.stats_workspace(st.shape, fwd_w, ld_in, ru16(L.cout), self.device)
-                           if L.bn and DETERMINISTIC else None)
+            # integer limb accumulators of the fused batch-norm moments (order-independent atomics): the forward pass
+            # is bitwise reproducible (ACG_DETERMINISTIC=0: fp64 atomics, for A/B timing only)
+            st.stats_fix = K.stats_accumulators(ru16(L.cout), self.device) if L.bn and DETERMINISTIC else None
         if self.bf16 and name not in self.store.packs:
             # forward / backward-data packs; conv2d_transpose swaps the roles (see include/acg_b200.h)
             fwd_which, bwd_which = (0, 1) if L.kind == "conv" else (1, 0)
@@ -334,7 +333,7 @@ class NetRun:
             pk = self.store.packs[L.name]
             fn = K.conv_fprop_tc if L.kind == "conv" else K.conv_dgrad_tc
             fn(st.shape, x, pk[3], out, st.ld_in, ld_out, bias=bias, stats=stats, bn=bn, splitk=st.splitk_f,
-               stats_ws=st.stats_ws if stats is not None else None)
+               stats_fix=st.stats_fix if stats is not None else None)
         else:
             w = self.store.views[L.name + "/weights"]
             (K.conv_fprop_f32 if L.kind == "conv" else K.conv_dgrad_f32)(st.shape, x, w, out)
@@ -366,7 +365,7 @@ class NetRun:
             else:
                 # the ticket alone (rows 0): this rank's totals in a fixed order, finalised after the exchange
                 self._conv_fwd(st, x, st.z, st.ldz, stats=st.stats,
-                               bn=(st.counter, None, None, None, None, None, 0, BN_EPS) if st.stats_ws else None)
+                               bn=(st.counter, None, None, None, None, None, 0, BN_EPS) if st.stats_fix is not None else None)
                 self._sync_moments(st, beta)           # SyncBN: statistics over the GLOBAL batch
             K.bn_act_fwd(st.z, st.rows, L.cout, st.ldz, 1, st.scale, st.shift, L.act, out, ld_out)
             return

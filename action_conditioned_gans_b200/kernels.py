@@ -80,15 +80,15 @@ def splitk_workspace(shape, which, ld_in, device):
             torch.zeros(ntick.value, dtype=torch.int32, device=device))
 
 
-def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, splitk=None, n_limit=0, stats_ws=None):
+def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, splitk=None, n_limit=0, stats_fix=None):
     """bn = (counter, beta, mean, rstd, scale, shift, rows, eps): finalise the moments in-kernel (single GPU); rows == 0
       with only the counter set: the last CTA completes the totals and the caller finalises (data parallel)
     red = (red_buffer, z, ldz, C, act, mean, rstd, shift): fused batch-norm backward reduction of the consumer layer
-    stats_ws = (fp64 workspace, slots): reproducible moments (per-CTA partials added in a fixed order; needs bn)"""
+    stats_fix: int64 tensor of >= 6*C zeros: reproducible moments (integer limb accumulators; needs bn's ticket)"""
     t = TcArgs(ld_in, ld_out, ptr(bias), dtype_id(out), ACT_IDS[out_act], ptr(stats))
     t.n_limit = int(n_limit)
-    if stats_ws is not None:
-        t.stats_ws, t.stats_ws_slots = ptr(stats_ws[0]), int(stats_ws[1])
+    if stats_fix is not None:
+        t.stats_fix, t.stats_fix_len = ptr(stats_fix), stats_fix.numel()
     if splitk is not None:
         ws, tickets = splitk
         t.splitk_ws, t.splitk_ws_bytes = ptr(ws), ws.numel() * 4
@@ -107,14 +107,14 @@ def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, s
 
 
 def conv_fprop_tc(shape, x, w_pack, y, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None,
-                  splitk=None, n_limit=0, stats_ws=None):
-    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn, red, splitk, n_limit, stats_ws)
+                  splitk=None, n_limit=0, stats_fix=None):
+    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn, red, splitk, n_limit, stats_fix)
     call("acg_conv_fprop_tc", C.byref(shape), ptr(x), ptr(w_pack), ptr(y), C.byref(t), stream())
 
 
 def conv_dgrad_tc(shape, dy, w_pack, dx, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None,
-                  splitk=None, n_limit=0, stats_ws=None):
-    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn, red, splitk, n_limit, stats_ws)
+                  splitk=None, n_limit=0, stats_fix=None):
+    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn, red, splitk, n_limit, stats_fix)
     call("acg_conv_dgrad_tc", C.byref(shape), ptr(dy), ptr(w_pack), ptr(dx), C.byref(t), stream())
 
 
@@ -123,12 +123,9 @@ def conv_wgrad_tc(shape, x, dy, dw, ld_x, ld_dy):
     call("acg_conv_wgrad_tc", C.byref(shape), ptr(x), ptr(dy), ptr(dw), C.byref(t), stream())
 
 
-def stats_workspace(shape, which, ld_in, channels, device, n_limit=0):
-    """(zeroed fp64 workspace, slots) for reproducible fused batch-norm moments of a launch of this shape"""
-    slots = int(_lib.load().acg_conv_stats_slots(C.byref(shape), which, ld_in, n_limit))
-    if slots <= 0:
-        raise RuntimeError("acg_conv_stats_slots: invalid arguments")
-    return torch.zeros(slots * 2 * channels, dtype=torch.float64, device=device), slots
+def stats_accumulators(channels, device):
+    """zeroed integer limb accumulators for reproducible fused batch-norm moments of a layer with `channels` outputs"""
+    return torch.zeros(6 * channels, dtype=torch.int64, device=device)
 
 
 def pack_size(shape, which, ld_k):

@@ -134,13 +134,14 @@ typedef struct acg_tc_args {
     /* optional: compute only the first n_limit output channels (0 = all).  The data gradient w.r.t. a concat buffer
      * whose tail is the tiled action map (models.py:16,38,84) is only needed for the feature channels. */
     int n_limit;
-    /* optional: run-to-run reproducible moments.  With a ticket (bn_counter) AND this workspace -- stats_ws_slots slots
-     * of [2][C] fp64, zeroed once by the caller, acg_conv_stats_slots says how many a shape wants -- every CTA writes
-     * its column partials to its own slot and the last CTA adds the slots in index order into `stats` (overwriting
-     * it) instead of fp64 atomics whose order varies.  bn_rows == 0 with a ticket: totals only, no finalize (the
-     * data-parallel path finalises after its exchange). */
-    double* stats_ws;
-    int stats_ws_slots;
+    /* optional: run-to-run reproducible moments.  With a ticket (bn_counter) AND stats_fix -- 6*C uint64 integer
+     * accumulators (stats_fix_len elements >= 6*C), zeroed once by the caller and left zeroed by every launch -- the
+     * per-CTA column totals are added as fixed-point limbs with integer atomics (associative: the CTA arrival order
+     * does not matter) and the last CTA converts them into `stats` (which must be zero on entry).  Without it: fp64
+     * atomics whose order varies.  bn_rows == 0 with a ticket: totals only, no finalize (the data-parallel path
+     * finalises after its exchange). */
+    unsigned long long* stats_fix;
+    long long stats_fix_len;
 } acg_tc_args;
 
 /* y = conv(x): x [B,H,W,ld_in] -> y [B,OH,OW,ld_out]; w_pack = acg_pack_weights(which=0, ld_k=ld_in) */
@@ -180,8 +181,6 @@ int acg_conv_splitk_plan(const acg_conv_shape* s, int which, int ld_in, int* spl
 /* which kernel a launch of this shape takes: 1 = the persistent halo-tile kernel (dedicated epilogue warps: the fused
  * batch-norm backward reduction costs nothing there), 0 = the generic kernel, -1 = bad argument.  Host only. */
 int acg_conv_kernel_kind(const acg_conv_shape* s, int which, int ld_in, int n_limit);
-/* HOST: slots of acg_tc_args.stats_ws a launch of this shape uses at most (which: 0 fprop, 1 dgrad); -1 = bad argument */
-int acg_conv_stats_slots(const acg_conv_shape* s, int which, int ld_in, int n_limit);
 int acg_conv_tc_supported(const acg_conv_shape* s, int which);
 
 /* ------------------------------------------------------------------------------------------

@@ -1,7 +1,7 @@
 """Run-to-run reproducibility of the forward pass.  The batch-norm moments fused into the conv
-epilogues go through per-CTA workspace slots that the launch's last CTA adds in index order, and split-K tiles are
-added in split order -- so a rerun on the same inputs is BITWISE identical, for every kernel family, and so is the whole
-generator / discriminator forward.  (The backward pass still accumulates weight gradients with fp32 atomics; see
+epilogues are added in a fixed order inside a CTA and across CTAs as fixed-point integer limbs (integer atomics are
+associative), and split-K tiles are added in split order -- so a rerun on the same inputs is BITWISE identical, for every
+kernel family, and so is the whole generator / discriminator forward.  (The backward pass still accumulates weight gradients with fp32 atomics; see
 DESIGN.md section 7.)"""
 import numpy as np
 import pytest
@@ -18,7 +18,7 @@ def ru(v, m):
 CASES = [
     (8, 32, 32, 64, 128, 5, 0, 1),       # halo CONV form, two accumulators
     (6, 64, 64, 32, 64, 5, 0, 1),        # halo CONV form, 32-wide tiles
-    (16, 16, 16, 128, 256, 5, 0, 1),     # halo CONV form, 8x8 output grid (images interleaved by row)
+    (16, 16, 16, 128, 256, 5, 0, None),  # 8x8 output grid
     (8, 32, 32, 64, 128, 5, 1, 1),       # halo ADJ form (g/tconv2-like: 16x16x128 -> 32x32x64)
     (4, 64, 64, 32, 64, 5, 1, 1),        # halo ADJ form, 64-wide rows
     (40, 64, 64, 6, 64, 5, 0, 0),        # persistent small-K kernel
@@ -51,18 +51,18 @@ def test_fused_moments_are_bitwise_reproducible(cuda, case):
     pack = torch.empty(Kn.pack_size(shape, which, ld_in), dtype=torch.bfloat16, device=cuda)
     Kn.pack_weights(shape, w, which, ld_in, pack)
     wsp = Kn.splitk_workspace(shape, which, ld_in, cuda)
-    ws = Kn.stats_workspace(shape, which, ld_in, n_out, cuda)
+    ws = Kn.stats_accumulators(n_out, cuda)
     beta = torch.randn(n_out, device=cuda, generator=g)
     counter = torch.zeros(1, dtype=torch.int32, device=cuda)
     runs = []
     for rep in range(6):
         out = torch.zeros(rows, ld_out, dtype=torch.bfloat16, device=cuda)
-        stats = torch.full((2 * n_out,), 123.0, dtype=torch.float64, device=cuda)   # overwritten, not accumulated
+        stats = torch.zeros(2 * n_out, dtype=torch.float64, device=cuda)
         mean, rstd, scale, shift = (torch.zeros(n_out, device=cuda) for _ in range(4))
         fn(shape, src, pack, out, ld_in, ld_out, stats=stats, bn=(counter, beta, mean, rstd, scale, shift, rows, 1e-3),
-           splitk=wsp, stats_ws=ws)
+           splitk=wsp, stats_fix=ws)
         torch.cuda.synchronize()
-        assert int(counter.item()) == 0
+        assert int(counter.item()) == 0 and int(ws.abs().sum()) == 0          # left ready for the next launch
         runs.append((out, stats, torch.stack([mean, rstd, scale, shift])))
     for out, stats, fin in runs[1:]:
         assert torch.equal(out, runs[0][0]) and torch.equal(stats, runs[0][1]) and torch.equal(fin, runs[0][2])
@@ -78,19 +78,25 @@ def test_fused_moments_are_bitwise_reproducible(cuda, case):
     # totals only (ticket with rows == 0: what the data-parallel path asks for), then the atomics path for comparison
     stats2 = torch.zeros(2 * n_out, dtype=torch.float64, device=cuda)
     fn(shape, src, pack, out, ld_in, ld_out, stats=stats2, bn=(counter, None, None, None, None, None, 0, 1e-3),
-       splitk=wsp, stats_ws=ws)
+       splitk=wsp, stats_fix=ws)
     assert torch.equal(stats2, stats)
     stats3 = torch.zeros(2 * n_out, dtype=torch.float64, device=cuda)
     fn(shape, src, pack, out, ld_in, ld_out, stats=stats3, splitk=wsp)
     assert float((stats3 - stats).abs().max()) <= 1e-9 * max(1.0, float(stats.abs().max()))
-    # a workspace that is too small is ignored (atomics), never overrun
-    small = (torch.zeros(2 * n_out, dtype=torch.float64, device=cuda), 1)
-    if ws[1] > 1:
-        stats4 = torch.zeros(2 * n_out, dtype=torch.float64, device=cuda)
-        fn(shape, src, pack, out, ld_in, ld_out, stats=stats4, bn=(counter, None, None, None, None, None, 0, 1e-3),
-           splitk=wsp, stats_ws=small)
-        assert float((stats4 - stats).abs().max()) <= 1e-9 * max(1.0, float(stats.abs().max()))
-        assert int(counter.item()) == 0
+    # accumulators that are too short are ignored (fp64 atomics), never overrun
+    stats4 = torch.zeros(2 * n_out, dtype=torch.float64, device=cuda)
+    short = torch.zeros(6 * n_out - 1, dtype=torch.int64, device=cuda)
+    fn(shape, src, pack, out, ld_in, ld_out, stats=stats4, bn=(counter, None, None, None, None, None, 0, 1e-3),
+       splitk=wsp, stats_fix=short)
+    assert float((stats4 - stats).abs().max()) <= 1e-9 * max(1.0, float(stats.abs().max()))
+    assert int(counter.item()) == 0 and int(short.abs().sum()) == 0
+    # a diverged layer still reads as diverged: inf in the input -> non-finite totals
+    bad = src.clone()
+    bad.view(-1)[0] = float("inf")
+    stats5 = torch.zeros(2 * n_out, dtype=torch.float64, device=cuda)
+    fn(shape, bad, pack, out, ld_in, ld_out, stats=stats5, bn=(counter, None, None, None, None, None, 0, 1e-3),
+       splitk=wsp, stats_fix=ws)
+    assert not bool(torch.isfinite(stats5).all()) and int(ws.abs().sum()) == 0
 
 
 @pytest.mark.parametrize("B", [3, 16])
