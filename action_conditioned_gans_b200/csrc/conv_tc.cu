@@ -877,7 +877,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // bf16 [rows][K] row-major weight pack -> 2-D map with a {64 x 128} box (128B swizzle, zero fill out of bounds)
-int encode_weight_map(CUtensorMap* map, const void* base, long long K, int rows, const char* who, int n_used = 0) {
+int encode_weight_map(CUtensorMap* map, const void* base, long long K, int rows, const char* who, int n_used) {
     EncodeTiledFn enc = encode_tiled_fn();
     ACG_REQUIRE(enc, ACG_ERR_CUDA, "%s: cuTensorMapEncodeTiled is not available", who);
     if (n_used <= 0 || n_used > rows) n_used = rows;                 // rows of the matrix the launch actually reads
@@ -1483,6 +1483,16 @@ int acg_conv_splitk_plan(const acg_conv_shape* s, int which, int ld_in, int* spl
     *splits = pl.splits;
     *ws_bytes = pl.splits > 1 ? pl.ws_bytes : 0;
     *n_tickets = pl.splits > 1 ? pl.tickets : 0;
+    acg_tc_args t{};
+    t.ld_in = ld_in;
+    if (px_ok(s, &t, which)) {      // the pixel-major kernel may take the launch: room for whichever plan is larger
+        int sp, tk;
+        long long wb;
+        px_split_plan(s, which, ld_in, ru(which == 0 ? s->Cout : s->Cin, 16), &sp, &wb, &tk);
+        if (sp > *splits) *splits = sp;
+        if (wb > *ws_bytes) *ws_bytes = wb;
+        if (tk > *n_tickets) *n_tickets = tk;
+    }
     return ACG_OK;
 }
 
@@ -1493,6 +1503,7 @@ int acg_conv_kernel_kind(const acg_conv_shape* s, int which, int ld_in, int n_li
     t.ld_in = ld_in;
     int N = ru(which == 0 ? s->Cout : s->Cin, 16);
     if (n_limit > 0 && ru(n_limit, 16) < N) N = ru(n_limit, 16);
+    if (px_ok(s, &t, which)) return 2;
     if (which == 0) return (N == ru(s->Cout, 16) && halo2_conv_ok(s, &t, N)) ? 1 : 0;
     return halo2_adj_ok(s, &t, N) ? 1 : 0;
 }
@@ -1554,6 +1565,10 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
             return check_launch("acg_conv_fprop_tc(small K, persistent)");
         }
     }
+    if (px_ok(s, t, 0))
+        // small feature maps: one output pixel x 128 images per tile, operands by TMA only (conv_px.cu)
+        return launch_px(0, s, t, p, x_bf16, w_pack, N, ru(s->Cout, 16), static_cast<cudaStream_t>(stream),
+                         "acg_conv_fprop_tc(pixel-major)");
     if (N == ru(s->Cout, 16) && halo2_conv_ok(s, t, N))
         // stride-2 layers with a 16- or 32-wide output: parity planes staged by TMA, every tap a shifted descriptor
         return launch_halo2(1, s, t, p, x_bf16, w_pack, N, static_cast<cudaStream_t>(stream), "acg_conv_fprop_tc(halo)");
@@ -1607,6 +1622,9 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
     const int Hp = (s->H + s->stride - 1) / s->stride, Wp = (s->W + s->stride - 1) / s->stride;
     const long long M = (long long)s->B * Hp * Wp;
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, ncls);
+    if (px_ok(s, t, 1))
+        return launch_px(1, s, t, p, dy_bf16, w_pack, N, Npack, static_cast<cudaStream_t>(stream),
+                         "acg_conv_dgrad_tc(pixel-major)");
     if (halo2_adj_ok(s, t, N))        // N < Npack (n_limit): the first N rows of every class' weight matrix
         // one CTA per SM walks the tile list: copies, MMAs and epilogue of consecutive tiles overlap (conv_halo.cu)
         return launch_halo2(0, s, t, p, dy_bf16, w_pack, N, static_cast<cudaStream_t>(stream), "acg_conv_dgrad_tc(halo)");

@@ -469,6 +469,12 @@ int ru(int v, int m);
 void class_taps(const acg_conv_shape* s, int cls, int* na, int* nc);
 int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char* who);
 void set_stats_fix(Params* p, const acg_tc_args* t);
+int encode_weight_map(CUtensorMap* map, const void* base, long long K, int rows, const char* who, int n_used = 0);
+// pixel-major kernel for small feature maps (conv_px.cu)
+bool px_ok(const acg_conv_shape* s, const acg_tc_args* t, int form);
+void px_split_plan(const acg_conv_shape* s, int form, int ld_in, int N, int* splits, long long* ws_bytes, int* tickets);
+int launch_px(int form, const acg_conv_shape* s, const acg_tc_args* t, const Params& p_in, const void* src,
+              const void* w_pack, int N, int Npack, cudaStream_t stream, const char* who);
 int set_smem(const void* kern, int bytes);
 
 }  // namespace tc

@@ -65,7 +65,8 @@ def tc_supported(shape, which):
 
 
 def kernel_kind(shape, which, ld_in, n_limit=0):
-    """1 when a conv_fprop_tc (which=0) / conv_dgrad_tc (which=1) launch of this shape takes the halo-tile kernel"""
+    """which kernel a conv_fprop_tc (which=0) / conv_dgrad_tc (which=1) launch of this shape takes: 2 pixel-major (small
+    feature maps), 1 halo-tile, 0 generic"""
     return int(_lib.load().acg_conv_kernel_kind(C.byref(shape), which, ld_in, int(n_limit)))
 
 

@@ -178,8 +178,8 @@ long long acg_pack_plan(const acg_pack_job* host_jobs, int njobs, int* host_tile
 int acg_conv_splitk_plan(const acg_conv_shape* s, int which, int ld_in, int* splits, long long* ws_bytes,
                          int* n_tickets);
 /* 1 when the tcgen05 kernels accept the shape, 0 otherwise (which: 0 fprop, 1 dgrad, 2 wgrad) */
-/* which kernel a launch of this shape takes: 1 = the persistent halo-tile kernel (dedicated epilogue warps: the fused
- * batch-norm backward reduction costs nothing there), 0 = the generic kernel, -1 = bad argument.  Host only. */
+/* which kernel a launch of this shape takes: 2 = the pixel-major kernel for small feature maps, 1 = the persistent
+ * halo-tile kernel (dedicated epilogue warps), 0 = the generic kernel, -1 = bad argument.  Host only. */
 int acg_conv_kernel_kind(const acg_conv_shape* s, int which, int ld_in, int n_limit);
 int acg_conv_tc_supported(const acg_conv_shape* s, int which);
 

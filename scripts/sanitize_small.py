@@ -67,6 +67,8 @@ def main():
     conv_family(2, 64, 64, 36, 128, 5, "halo: CONV 48-channel rows / ADJ N=48, 32-wide tiles")
     conv_family(2, 32, 32, 128, 128, 5, "halo: ADJ N=128 NACC=2")
     conv_family(40, 64, 64, 6, 64, 5, "small-K persistent forward (320 tiles) / halo ADJ N=16")
+    conv_family(130, 8, 8, 128, 256, 5, "pixel-major kernel: 4x4 / 8x8 grids, ragged batch tile, two N tiles")
+    conv_family(64, 4, 4, 256, 512, 5, "pixel-major kernel + split-K (2x2 grid)")
     torch.cuda.synchronize()
     # feeder + one whole iteration, eager then captured + replayed (all elementwise / loss / optimizer kernels)
     rng = np.random.RandomState(0)

@@ -23,7 +23,9 @@ CASES = [
     (4, 64, 64, 32, 64, 5, 1, 1),        # halo ADJ form, 64-wide rows
     (40, 64, 64, 6, 64, 5, 0, 0),        # persistent small-K kernel
     (3, 64, 64, 6, 64, 5, 0, 0),         # generic kernel, CONV gather (too few tiles for the small-K kernel)
-    (64, 4, 4, 256, 512, 5, 0, 0),       # generic kernel + split-K
+    (64, 4, 4, 256, 512, 5, 0, 2),       # pixel-major kernel + split-K
+    (256, 8, 8, 128, 256, 5, 1, 2),      # pixel-major kernel, ADJ gather
+    (32, 4, 4, 256, 512, 5, 0, 0),       # generic kernel + split-K
     (5, 8, 8, 128, 256, 5, 1, None),     # ADJ gather at an odd batch
 ]
 
