@@ -25,6 +25,7 @@ constexpr int kPxStages = 6;
 constexpr int kPxThreads = 192;
 constexpr int kPxSmem = kPxStages * (kStageA + kStageB) + 1024;
 constexpr int kPxMaxTaps = 32;
+constexpr int kPxMaxSplits = 4;
 
 struct alignas(64) PxParams {
     Params p;
@@ -191,29 +192,57 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
         const int b = b0 + warp * 32 + lane;
         const bool row_ok = b < p.B;
         const size_t row_off = ((size_t)((size_t)b * pp.DY + py) * pp.DX + px) * p.ldo;
-        for (int cb = 0; cb < n_cta; cb += 16) {
-            uint32_t v[16];
-            if (nkb > 0 && p.splits == 1) tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + cb, v);
-            else {
+        if (p.splits > 1) {
+            // all partial tiles in split order (this CTA's own one included: the sum does not depend on which CTA came
+            // last).  The 16-column chunk after the current one is already in flight while this one goes through the
+            // epilogue (one exposed L2 latency per tile instead of one per chunk); splits <= kPxMaxSplits.
+            const float* mine = ws_tile + (warp * 32 + lane) * 16;
+            float4 nxt[kPxMaxSplits][4];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0u;
-            }
-            if (p.splits > 1) {     // all partial tiles in split order (this CTA's own one included: the sum does not
-                                    // depend on which CTA came last)
-                for (int sp = 0; sp < p.splits; ++sp) {
-                    const float4* o = reinterpret_cast<const float4*>(
-                        ws_tile + (size_t)sp * (BM * BN) + (size_t)(cb >> 4) * (BM * 16) + (warp * 32 + lane) * 16);
+            for (int j = 0; j < kPxMaxSplits; ++j)
+                if (j < p.splits) {
+                    const float4* o = reinterpret_cast<const float4*>(mine + (size_t)j * (BM * BN));
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 t4 = __ldcg(o + i);
-                        v[4 * i] = __float_as_uint(__uint_as_float(v[4 * i]) + t4.x);
-                        v[4 * i + 1] = __float_as_uint(__uint_as_float(v[4 * i + 1]) + t4.y);
-                        v[4 * i + 2] = __float_as_uint(__uint_as_float(v[4 * i + 2]) + t4.z);
-                        v[4 * i + 3] = __float_as_uint(__uint_as_float(v[4 * i + 3]) + t4.w);
-                    }
+                    for (int i = 0; i < 4; ++i) nxt[j][i] = __ldcg(o + i);
                 }
+            for (int cb = 0; cb < n_cta; cb += 16) {
+                float f[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) f[i] = 0.f;
+#pragma unroll
+                for (int j = 0; j < kPxMaxSplits; ++j)
+                    if (j < p.splits) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            f[4 * i] += nxt[j][i].x; f[4 * i + 1] += nxt[j][i].y;
+                            f[4 * i + 2] += nxt[j][i].z; f[4 * i + 3] += nxt[j][i].w;
+                        }
+                    }
+                if (cb + 16 < n_cta) {
+#pragma unroll
+                    for (int j = 0; j < kPxMaxSplits; ++j)
+                        if (j < p.splits) {
+                            const float4* o = reinterpret_cast<const float4*>(mine + (size_t)j * (BM * BN) +
+                                                                              (size_t)((cb + 16) >> 4) * (BM * 16));
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) nxt[j][i] = __ldcg(o + i);
+                        }
+                }
+                uint32_t v[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(f[i]);
+                epilogue_chunk(p, v, n0 + cb, row_ok, row_off, 0u, lane, &sm_stats[warp][0][cb], &sm_stats[warp][1][cb]);
             }
-            epilogue_chunk(p, v, n0 + cb, row_ok, row_off, 0u, lane, &sm_stats[warp][0][cb], &sm_stats[warp][1][cb]);
+        } else {
+            for (int cb = 0; cb < n_cta; cb += 16) {
+                uint32_t v[16];
+                if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + cb, v);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0u;
+                }
+                epilogue_chunk(p, v, n0 + cb, row_ok, row_off, 0u, lane, &sm_stats[warp][0][cb], &sm_stats[warp][1][cb]);
+            }
         }
     }
     tc_fence_before();
@@ -276,7 +305,7 @@ void px_split_plan(const acg_conv_shape* s, int form, int ld_in, int N, int* spl
     if (!getenv("ACG_NO_SPLITK") && items * 2 <= num_sms() && max_nkb >= 16) {
         sp = (int)(num_sms() / items);
         if (sp > max_nkb / 8) sp = max_nkb / 8;         // at least 8 K slices per CTA on the longest pixel
-        if (sp > 8) sp = 8;
+        if (sp > kPxMaxSplits) sp = kPxMaxSplits;
         if (sp < 2) sp = 1;
     }
     *splits = sp;

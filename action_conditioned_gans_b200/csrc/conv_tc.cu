@@ -950,10 +950,13 @@ struct WgradParams {
     int k_chunk;     // pixels per split (multiple of BK)
     int fast;        // 1: a 64-pixel K slice is whole rows of one image (OW | 64 | OH*OW) or whole images (OH*OW | 64)
     int a_tma;       // 1: the dy operand (a plain [pixels][ldy] matrix) arrives by TMA: two 64 x 64 boxes per K slice
+    int b_tma;       // 1: the x operand arrives by TMA too (ldx % 64 == 0, regular geometry): per 64-channel atom ONE box
+                     //    {64 channels, bw, bh, bn pixels} of the tap's input-parity plane, zero fill outside the image
 };
 struct alignas(64) WgradTmaParams {
     WgradParams p;
     CUtensorMap map_a;        // dy as bf16 [Kd][ldy], box {64 channels, 64 pixels}, 128B swizzle, zero OOB fill
+    CUtensorMap map_x[4];     // x parity planes (stride 2; entry 0 alone for stride 1) as (C, X, Y, B)
 };
 
 // Producers: EIGHT warps (the cp.async gather is issue-latency bound: a variant with half the producer warps per SM ran 2x
@@ -983,7 +986,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
     if (nkb == 0) return;
 
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], kWgProd + (p.a_tma ? 1 : 0)); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], p.b_tma ? 1 : kWgProd + (p.a_tma ? 1 : 0));
+            mbar_init(&empty_bar[i], 1);
+        }
         if (p.a_tma) tma_prefetch_desc(&wp.map_a);
         mbar_init(&acc_bar, 1);
         fence_mbar_init();
@@ -1001,7 +1007,55 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
     pdl_wait();
     const uint32_t tmem_base = tmem_base_sh;
 
-    if (warp < kWgProd / 32) {
+    if (p.b_tma && warp < kWgProd / 32) {
+        // ---- both operands by TMA: warp 0 is the whole producer (warps 1-7 go straight to the epilogue / exit) ----
+        // A K slice is 64 consecutive output pixels = whole rows of one image or whole images; for filter tap (ta, tc) the
+        // matching input pixels are a box of the parity plane ((ta - pad_t) & 1, (tc - pad_l) & 1) of x, shifted by
+        // floor((ta - pad_t) / 2) rows and floor((tc - pad_l) / 2) columns -- out-of-image pixels are zero filled by the
+        // copy engine.  Each 64-column atom of the N tile is one tap (ldx % 64 == 0).
+        if (warp == 0) {
+            const int S = p.OH * p.OW;
+            const int natoms = n_valid > 64 ? 2 : 1;
+            int pl[2], dj[2], di[2], cc[2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                const int nn = n0 + 64 * a;
+                const int tap = nn / p.ldx;
+                cc[a] = nn - tap * p.ldx;
+                const int ta = tap / p.KW, tcx = tap - ta * p.KW;
+                const int ry = ta - p.pad_t, rx = tcx - p.pad_l;
+                if (p.stride == 2) {
+                    const int qy = ry & 1, qx = rx & 1;
+                    pl[a] = qy * 2 + qx;
+                    di[a] = (ry - qy) >> 1;       // floor(ry / 2): ry - qy is even
+                    dj[a] = (rx - qx) >> 1;
+                } else {
+                    pl[a] = 0; di[a] = ry; dj[a] = rx;
+                }
+            }
+            const uint32_t tx = (uint32_t)kStageA + (uint32_t)natoms * (BK * 128);
+            int bP = k_begin / S;
+            int ohP = (k_begin - bP * S) / p.OW;
+            const int rows_per_slice = S >= BK ? BK / p.OW : 0, imgs_per_slice = S >= BK ? 0 : BK / S;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int stage = kb % STAGES;
+                if (kb >= STAGES) mbar_wait(&empty_bar[stage], (uint32_t)(((kb / STAGES) - 1) & 1));
+                if (elect_one()) {
+                    mbar_expect_tx(&full_bar[stage], tx);
+                    tma_load_2d(smemA + stage * kStageA, &wp.map_a, co0, k_begin + kb * BK, &full_bar[stage]);
+                    tma_load_2d(smemA + stage * kStageA + BK * 128, &wp.map_a, co0 + 64, k_begin + kb * BK, &full_bar[stage]);
+                    tma_load_4d(smemB + stage * kStageB, &wp.map_x[pl[0]], cc[0], dj[0], ohP + di[0], bP, &full_bar[stage]);
+                    if (natoms == 2)
+                        tma_load_4d(smemB + stage * kStageB + BK * 128, &wp.map_x[pl[1]], cc[1], dj[1], ohP + di[1], bP,
+                                    &full_bar[stage]);
+                }
+                __syncwarp();
+                ohP += rows_per_slice;
+                if (ohP >= p.OH) { ohP = 0; ++bP; }
+                bP += imgs_per_slice;
+            }
+        }
+    } else if (warp < kWgProd / 32) {
         // producers: thread = (16-byte channel chunk c16 of the 128-wide tile, pixel slot 0..15)
         const int c16 = tid & 15, pslot = tid >> 4;
         const int atom = c16 >> 3, jc = c16 & 7;
@@ -1112,7 +1166,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
             cp_async_arrive_noinc(&full_bar[stage]);
         }
         }
-    } else {
+    } else if (warp == kWgProd / 32) {
         // MMA issuer: the whole warp walks the loop, elect.sync picks the issuing lane
         const uint32_t idesc = make_idesc(n_cta, 1, 1);
         const uint32_t hi = desc_hi(1024);
@@ -1721,6 +1775,32 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
         }
     }
     if (!wp.p.a_tma) memset(&wp.map_a, 0, sizeof(wp.map_a));
+    memset(wp.map_x, 0, sizeof(wp.map_x));
+    wp.p.b_tma = 0;
+    if (wp.p.a_tma && p.fast && t->ld_in % 64 == 0 && ((uintptr_t)x_bf16 & 15) == 0 && !getenv("ACG_WGRAD_NO_TMA_X")) {
+        // x operand by TMA: one map per input-parity plane, box = the input pixels of one 64-pixel K slice
+        EncodeTiledFn enc = encode_tiled_fn();
+        const int S = s->OH * s->OW;
+        const cuuint32_t bw = (cuuint32_t)s->OW, bh = (cuuint32_t)(S >= BK ? BK / s->OW : s->OH),
+                         bn = (cuuint32_t)(S >= BK ? 1 : BK / S);
+        const int st = s->stride, nplanes = st * st;
+        const cuuint64_t ld = (cuuint64_t)t->ld_in;
+        bool ok = enc != nullptr;
+        for (int pl = 0; ok && pl < nplanes; ++pl) {
+            const int qy = pl / st, qx = pl % st;
+            if (qy >= s->H || qx >= s->W) { wp.map_x[pl] = wp.map_x[0]; continue; }
+            cuuint64_t dims[4] = {ld, (cuuint64_t)((s->W - qx + st - 1) / st), (cuuint64_t)((s->H - qy + st - 1) / st),
+                                  (cuuint64_t)s->B};
+            cuuint64_t strides[3] = {(cuuint64_t)st * ld * 2, (cuuint64_t)st * s->W * ld * 2, (cuuint64_t)s->H * s->W * ld * 2};
+            cuuint32_t box[4] = {64, bw, bh, bn};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            const void* base = static_cast<const __nv_bfloat16*>(x_bf16) + ((size_t)qy * s->W + qx) * t->ld_in;
+            ok = enc(&wp.map_x[pl], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+        wp.p.b_tma = ok ? 1 : 0;
+    }
     launch_pdl(conv_wgrad_tc_kernel, grid, kWgThreads, kSmemBytes, static_cast<cudaStream_t>(stream), wp);
     return check_launch("acg_conv_wgrad_tc");
 }
