@@ -23,6 +23,12 @@ class ConvShape(C.Structure):
                 ("B", "H", "W", "Cin", "OH", "OW", "Cout", "KH", "KW", "stride", "pad_t", "pad_l")]
 
 
+class PeerExchange(C.Structure):
+    """struct acg_peer_exchange"""
+    _fields_ = [("mailboxes", C.c_void_p), ("epoch", C.c_void_p), ("slot_off", C.c_longlong), ("rank", C.c_int),
+                ("world", C.c_int), ("cap", C.c_int), ("timeout_s", C.c_float)]
+
+
 class TcArgs(C.Structure):
     """struct acg_tc_args"""
     _fields_ = [("ld_in", C.c_int), ("ld_out", C.c_int), ("bias", C.c_void_p), ("out_dtype", C.c_int),
@@ -33,7 +39,7 @@ class TcArgs(C.Structure):
                 ("red_mean", C.c_void_p), ("red_rstd", C.c_void_p), ("red_shift", C.c_void_p),
                 ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_longlong), ("splitk_tickets", C.c_void_p),
                 ("splitk_n_tickets", C.c_int), ("n_limit", C.c_int), ("stats_fix", C.c_void_p),
-                ("stats_fix_len", C.c_longlong)]
+                ("stats_fix_len", C.c_longlong), ("peer", C.c_void_p)]
 
 
 class PackJob(C.Structure):
@@ -67,6 +73,7 @@ SIGNATURES = {
     "acg_bn_finalize": [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _P],
     "acg_bn_act_fwd": [_P, _I, _L, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P],
     "acg_bn_act_bwd_reduce": [_P, _P, _I, _I, _P, _I, _I, _L, _I, _I, _P, _P, _P, _I, _P, _P],
+    "acg_bn_act_bwd_reduce_sync": [_P, _P, _I, _I, _P, _I, _I, _L, _I, _P, _P, _P, _I, _P, _P, _P, _P],
     "acg_bn_act_bwd_apply": [_P, _P, _I, _I, _P, _I, _I, _L, _I, _I, _P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _L, _F,
                              _P],
     "acg_copy_channels": [_P, _I, _I, _I, _P, _I, _I, _I, _L, _I, _P],

@@ -153,7 +153,7 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
     __syncthreads();
     tc_fence_after();
     // PDL: dependents may be scheduled now that this CTA owns its tensor memory; nothing above touched global memory
-    pdl_launch_dependents();
+    if (p.px.world <= 1) pdl_launch_dependents();     // a launch that exchanges with peers must not (peer.cu)
     pdl_wait();
     const uint32_t tmem_base = tmem_base_sh;
 

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    pdl_launch_dependents();
+    if (p.px.world <= 1) pdl_launch_dependents();     // a launch that exchanges with peers must not (peer.cu)
     pdl_wait();
     const uint32_t tmem_base = tmem_base_sh;
     const int nkb_all = ntap_sh * pp.kchunks;

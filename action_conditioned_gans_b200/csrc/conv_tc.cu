@@ -136,7 +136,7 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
     __syncthreads();
     tc_fence_after();
     // PDL: dependents may be scheduled now that this CTA owns its tensor memory; nothing above touched global memory
-    pdl_launch_dependents();
+    if (p.px.world <= 1) pdl_launch_dependents();     // a launch that exchanges with peers must not (peer.cu)
     pdl_wait();
     const uint32_t tmem_base = tmem_base_sh;
     if (timing) t1 = gtime();
@@ -411,7 +411,7 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    pdl_launch_dependents();
+    if (p.px.world <= 1) pdl_launch_dependents();     // a launch that exchanges with peers must not (peer.cu)
     pdl_wait();
     const uint32_t tmem_base = tmem_base_sh;
 
@@ -661,7 +661,7 @@ conv_adj_halo_kernel(const __grid_constant__ HaloParams hp) {
     __syncthreads();
     tc_fence_after();
     // PDL: dependents may be scheduled now that this CTA owns its tensor memory; nothing above touched global memory
-    pdl_launch_dependents();
+    if (p.px.world <= 1) pdl_launch_dependents();     // a launch that exchanges with peers must not (peer.cu)
     pdl_wait();
     const uint32_t tmem_base = tmem_base_sh;
     if (timing) t1 = gtime();
@@ -1386,12 +1386,17 @@ int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char
     }
     p->stats_fix = nullptr;
     p->bn_rows = 0;
+    p->px.world = 0;
     if (t->stats && t->bn_counter) {
         // bn_rows == 0: the last CTA only completes the totals (deterministic workspace sum), the caller finalises
         ACG_REQUIRE(t->bn_rows == 0 || (t->bn_mean && t->bn_rstd && t->bn_scale && t->bn_shift && t->bn_rows > 0),
                     ACG_ERR_INVALID,
                     "%s: in-kernel batch-norm finalize needs mean/rstd/scale/shift buffers and the row count", who);
         p->counter = t->bn_counter;
+        if (t->peer && t->peer->world > 1) {
+            int prc = fill_peer_exchange(&p->px, t->peer, 2 * p->n_stat, who);
+            if (prc) return prc;
+        }
         p->beta = t->bn_beta;
         p->bn_mean = t->bn_mean; p->bn_rstd = t->bn_rstd; p->bn_scale = t->bn_scale; p->bn_shift = t->bn_shift;
         p->bn_rows = t->bn_rows;

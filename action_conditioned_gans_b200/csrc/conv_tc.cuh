@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace acg {
 namespace tc {
@@ -53,6 +54,8 @@ struct Params {
     unsigned int* tickets;
     // reproducible moments (optional): integer limb accumulators [3][2][n_stat], see fix_add / cta_stats_finish
     unsigned long long* stats_fix;
+    // data parallel (optional): the last CTA sums the totals over the ranks before finalising (peer.cuh); px.world == 0: off
+    PeerExchange px;
     int dbg_skip;               // probe library only (-DACG_PROBES, env ACG_DBG_SKIP): see ACG_DBG below
 };
 // Profiling probes (per-phase timing, pipelines with one stage switched off) exist only in libacg_b200_probe.so, which
@@ -405,6 +408,7 @@ __device__ __forceinline__ void cta_stats_finish(const Params& p, int tid, int n
         __threadfence();
         __syncthreads();
     }
+    if (p.px.world > 1) peer_exchange(p.px, p.stats, ncols, tid, nthreads, [] {});      // SyncBN: totals over all ranks
     if (p.bn_rows > 0) {
         const double inv = 1.0 / (double)p.bn_rows;
         for (int c = tid; c < p.n_bias; c += nthreads) {

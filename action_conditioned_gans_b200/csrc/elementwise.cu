@@ -6,6 +6,7 @@
 // All tensors are [rows, C] views of NHWC buffers with an explicit row stride so that producers can write
 // straight into the wider concat buffers and consumers can read a channel slice.
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace acg {
 namespace {
@@ -517,9 +518,13 @@ __global__ void __launch_bounds__(256)
 fast_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ z, int ld_z, const __nv_bfloat16* __restrict__ dA,
                        const __nv_bfloat16* __restrict__ dA2, int ld_d, long long rows, int C,
                        const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ shift,
-                       double* __restrict__ out) {
-    pdl_prologue();
+                       double* __restrict__ out, unsigned int* __restrict__ counter, PeerExchange px) {
+    // counter != NULL (data parallel): the LAST block sums `out` over the ranks itself (peer.cuh) -- no exchange launch
+    // between this pass and the apply pass.  Such a launch must not trigger its dependents early (see peer.cu).
+    if (!counter) pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sm[16][257];
+    __shared__ int last_block_sh;
     const int bx = blockDim.x, by = blockDim.y;
     const int tid = threadIdx.y * bx + threadIdx.x;
     const int nv = C >> 3;
@@ -593,6 +598,17 @@ fast_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ z, int ld_z, const __nv
             for (int y = 0; y < by; ++y) t += sm[i][y * bx + threadIdx.x];
             const int c = cv * 8 + (i & 7);
             atomicAdd(&out[(i < 8 ? 0 : C) + c], (double)t);
+        }
+    }
+    if (counter) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last_block_sh = (atomicAdd(counter, 1u) == gridDim.x * gridDim.y - 1u);
+        __syncthreads();
+        if (last_block_sh) {
+            __threadfence();
+            peer_exchange(px, out, 2 * C, tid, bx * by, [] {});
+            if (tid == 0) *counter = 0u;          // ready for the next launch
         }
     }
 }
@@ -766,12 +782,14 @@ void fast_launch_dims(long long rows, int C, int blocks_per_sm, bool atomics, di
 template <int ACT, bool HAS_Z>
 void launch_fast_reduce(dim3 grid, dim3 block, cudaStream_t st, const void* z, int ld_z, const void* dA, const void* dA2,
                         int ld_d, long long rows, int C, const float* mean, const float* rstd, const float* shift,
-                        double* red) {
+                        double* red, unsigned int* counter = nullptr, const PeerExchange* px = nullptr) {
     const __nv_bfloat16* zz = static_cast<const __nv_bfloat16*>(z);
     const __nv_bfloat16* d1 = static_cast<const __nv_bfloat16*>(dA);
     const __nv_bfloat16* d2 = static_cast<const __nv_bfloat16*>(dA2);
-    if (dA2) launch_pdl(fast_bwd_reduce_kernel<ACT, HAS_Z, true>, grid, block, 0, st, zz, ld_z, d1, d2, ld_d, rows, C, mean, rstd, shift, red);
-    else launch_pdl(fast_bwd_reduce_kernel<ACT, HAS_Z, false>, grid, block, 0, st, zz, ld_z, d1, d2, ld_d, rows, C, mean, rstd, shift, red);
+    PeerExchange x{};
+    if (px) x = *px;
+    if (dA2) launch_pdl(fast_bwd_reduce_kernel<ACT, HAS_Z, true>, grid, block, 0, st, zz, ld_z, d1, d2, ld_d, rows, C, mean, rstd, shift, red, counter, x);
+    else launch_pdl(fast_bwd_reduce_kernel<ACT, HAS_Z, false>, grid, block, 0, st, zz, ld_z, d1, d2, ld_d, rows, C, mean, rstd, shift, red, counter, x);
 }
 
 template <int ACT, bool HAS_BN>
@@ -921,6 +939,39 @@ int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d
     }
     launch_pdl(col_reduce_kernel<1>, reduce_grid(rpg, C, groups), dim3(kTX, kTY), 0, static_cast<cudaStream_t>(stream), z, z_dtype, ld_z, dA, dA2, d_dtype, ld_d, rpg, C, mean, rstd, shift, act, red);
     return check_launch("acg_bn_act_bwd_reduce");
+}
+
+int acg_bn_act_bwd_reduce_sync(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype,
+                               int ld_z, long long rows, int C, const float* mean, const float* rstd,
+                               const float* shift, int act, double* red, unsigned int* counter,
+                               const acg_peer_exchange* peer, void* stream) {
+    using namespace acg;
+    ACG_REQUIRE(dA && red && counter && peer, ACG_ERR_INVALID, "acg_bn_act_bwd_reduce_sync: null pointer");
+    ACG_REQUIRE(z || (!mean && act == ACG_ACT_NONE), ACG_ERR_INVALID,
+                "acg_bn_act_bwd_reduce_sync: z may only be NULL for a layer without batch-norm and activation");
+    ACG_REQUIRE(rows > 0 && C > 0 && ld_d >= C && (!z || ld_z >= C), ACG_ERR_INVALID, "acg_bn_act_bwd_reduce_sync: bad size");
+    PeerExchange x;
+    int rc = fill_peer_exchange(&x, peer, 2 * C, "acg_bn_act_bwd_reduce_sync");
+    if (rc) return rc;
+    const bool fast = C % 8 == 0 && ld_d % 8 == 0 && (!z || ld_z % 8 == 0) && al16(z) && al16(dA) && al16(dA2) &&
+                      al16(mean) && al16(rstd) && al16(shift) && d_dtype == ACG_BF16 && (!z || z_dtype == ACG_BF16) &&
+                      (act == ACG_ACT_NONE || act == ACG_ACT_RELU || act == ACG_ACT_LRELU) && !getenv("ACG_NO_FAST_EW") &&
+                      peer->world > 1;
+    if (!fast) {        // same result in two launches: the reduction pass, then the stand-alone exchange kernel
+        rc = acg_bn_act_bwd_reduce(dA, dA2, d_dtype, ld_d, z, z_dtype, ld_z, rows, C, 1, mean, rstd, shift, act, red, stream);
+        if (rc || peer->world <= 1) return rc;
+        return acg_peer_allreduce_f64(red, 2 * C, peer->cap, peer->slot_off, peer->rank, peer->world, peer->mailboxes,
+                                      peer->epoch, peer->timeout_s, 0, nullptr, 0, 0.f, nullptr, nullptr, nullptr, nullptr,
+                                      stream);
+    }
+    dim3 grid, block;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    fast_launch_dims(rows, C, 2, true, &grid, &block);
+    if (!z) launch_fast_reduce<ACG_ACT_NONE, false>(grid, block, st, z, ld_z, dA, dA2, ld_d, rows, C, mean, rstd, shift, red, counter, &x);
+    else if (act == ACG_ACT_RELU) launch_fast_reduce<ACG_ACT_RELU, true>(grid, block, st, z, ld_z, dA, dA2, ld_d, rows, C, mean, rstd, shift, red, counter, &x);
+    else if (act == ACG_ACT_LRELU) launch_fast_reduce<ACG_ACT_LRELU, true>(grid, block, st, z, ld_z, dA, dA2, ld_d, rows, C, mean, rstd, shift, red, counter, &x);
+    else launch_fast_reduce<ACG_ACT_NONE, true>(grid, block, st, z, ld_z, dA, dA2, ld_d, rows, C, mean, rstd, shift, red, counter, &x);
+    return check_launch("acg_bn_act_bwd_reduce_sync");
 }
 
 int acg_bn_act_bwd_apply(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype, int ld_z,

@@ -2,44 +2,24 @@
 //
 // The reference normalises over the WHOLE batch (slim.batch_norm inside one TF graph, models.py:11,32,81); with the
 // batch sharded over GPUs every batch-norm layer therefore needs the sum of a tiny fp64 vector ([2C] moments forward,
-// [2C] reduction terms backward, <= 8 KB) over all ranks -- ~66 times per training iteration.  A library all-reduce
-// costs a launch plus a multi-hop protocol each time.  Here every rank owns a MAILBOX segment that all peers map
-// (cudaIpc handles, exchanged by the host once); one single-CTA kernel per exchange
-//   1. PUSHES its vector into slot[parity][my rank] of every peer's mailbox with plain NVLink stores,
-//   2. publishes a monotonically increasing epoch flag with a system-scope release store,
-//   3. spins (bounded) on its OWN mailbox until every peer's flag reached the epoch (local memory polling),
-//   4. sums the `world` vectors in rank order (every rank gets bit-identical sums, so replicas never drift),
-//   5. optionally finalises the batch-norm coefficients (mean / rstd / scale / shift) in the same launch.
-// The epoch counter lives in device memory and is advanced by the kernel itself, so the launch can be captured in a
-// CUDA graph and replayed.  Slots are double-buffered by epoch parity: a rank can be at most one exchange ahead of a
-// peer on the same slot (it needs the peer's next flag to get further), so it never overwrites data still being read.
-#include "common.cuh"
+// [2C] reduction terms backward, <= 8 KB) over all ranks -- ~63 times per training iteration, each one a point where
+// every rank waits for the slowest.  A library all-reduce costs a launch plus a multi-hop protocol each time.  Here
+// every rank owns a MAILBOX segment that all peers map (cudaIpc handles, exchanged by the host once) and an exchange is
+//   1. PUSH: every value goes into the sender's row of every peer's mailbox as a self-validating 16-byte cell
+//      (value halves + epoch tags, plain NVLink stores: no fence, no flag, one one-way latency),
+//   2. PULL: poll the cells of the OWN mailbox (local memory) until they carry the epoch, add them in rank order (every
+//      rank gets bit-identical sums, so replicas never drift),
+//   3. optionally finalise the batch-norm coefficients (mean / rstd / scale / shift).
+// It runs either as the single-CTA kernel below or inside the LAST CTA of the kernel that produced the vector (conv
+// epilogue moments, backward reduction pass: no extra launch).  The epoch counter lives in device memory and is
+// advanced by the exchange itself, so launches can be captured in a CUDA graph and replayed.  The device code and the
+// double-buffering argument are in peer.cuh.
+#include "peer.cuh"
 
 namespace acg {
 
-struct PeerPtrs {
-    unsigned char* p[ACG_MAX_PEERS];
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-// slot layout inside a mailbox, at byte offset slot_off (256-byte aligned):
-//   flags[ACG_MAX_PEERS] u64 | pad to 128 B | data[2 parities][world][cap] fp64
 __global__ void __launch_bounds__(256)
-peer_allreduce_kernel(double* __restrict__ vec, int n, int cap, long long slot_off, int rank, int world, PeerPtrs peers,
-                      unsigned long long* __restrict__ epoch_ptr, long long timeout_ns,
+peer_allreduce_kernel(double* __restrict__ vec, int n, PeerExchange x,
                       // optional batch-norm finalisation of vec = [sum | sum of squares][C]
                       int bn_C, const float* __restrict__ beta, double inv_rows, float eps, float* __restrict__ mean,
                       float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift) {
@@ -49,44 +29,9 @@ peer_allreduce_kernel(double* __restrict__ vec, int n, int cap, long long slot_o
     // trigger comes after the flag wait instead.
     pdl_wait();
     const int tid = threadIdx.x;
-    const unsigned long long epoch = *epoch_ptr + 1ull;
-    const size_t data_off = (size_t)slot_off + 128 + (size_t)(epoch & 1ull) * world * cap * sizeof(double);
-    // 1. push
-    for (int p = 0; p < world; ++p) {
-        double* dst = reinterpret_cast<double*>(peers.p[p] + data_off) + (size_t)rank * cap;
-        for (int i = tid; i < n; i += blockDim.x) dst[i] = vec[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    // 2. publish
-    if (tid < world) {
-        unsigned long long* flag = reinterpret_cast<unsigned long long*>(peers.p[tid] + slot_off) + rank;
-        st_release_sys(flag, epoch);
-    }
-    // 3. wait for every peer (flags in MY mailbox)
-    if (tid < world) {
-        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(peers.p[rank] + slot_off) + tid;
-        const unsigned long long t0 = global_ns();
-        while (ld_acquire_sys(flag) < epoch) {
-            if ((long long)(global_ns() - t0) > timeout_ns) {
-                printf("acg: peer exchange timed out (rank %d waits for rank %d, slot offset %lld, epoch %llu)\n", rank,
-                       tid, slot_off, epoch);
-                __trap();
-            }
-        }
-    }
-    __syncthreads();
-    pdl_launch_dependents();
-    // 4. sum in rank order
-    const double* mine = reinterpret_cast<const double*>(peers.p[rank] + data_off);
-    for (int i = tid; i < n; i += blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < world; ++r) s += __ldcg(mine + (size_t)r * cap + i);
-        vec[i] = s;
-    }
-    // 5. batch-norm coefficients (same arithmetic as bn_finalize_kernel)
+    peer_exchange(x, vec, n, tid, (int)blockDim.x, [] { pdl_launch_dependents(); });
+    // batch-norm coefficients (same arithmetic as bn_finalize_kernel)
     if (bn_C > 0) {
-        __syncthreads();
         for (int c = tid; c < bn_C; c += blockDim.x) {
             const double mu = vec[c] * inv_rows;
             double var = vec[bn_C + c] * inv_rows - mu * mu;
@@ -99,7 +44,24 @@ peer_allreduce_kernel(double* __restrict__ vec, int n, int cap, long long slot_o
             shift[c] = b - (float)mu * rs;
         }
     }
-    if (tid == 0) *epoch_ptr = epoch;
+}
+
+int fill_peer_exchange(PeerExchange* x, const acg_peer_exchange* d, int n, const char* who) {
+    ACG_REQUIRE(d && d->mailboxes && d->epoch, ACG_ERR_INVALID, "%s: peer exchange: null pointer", who);
+    ACG_REQUIRE(d->world >= 1 && d->world <= ACG_MAX_PEERS && d->rank >= 0 && d->rank < d->world, ACG_ERR_INVALID,
+                "%s: peer exchange: rank %d / world %d (at most %d peers)", who, d->rank, d->world, ACG_MAX_PEERS);
+    ACG_REQUIRE(n > 0 && n <= d->cap && d->slot_off >= 0 && d->slot_off % 256 == 0, ACG_ERR_INVALID,
+                "%s: peer exchange: n %d cap %d slot offset %lld", who, n, d->cap, d->slot_off);
+    for (int i = 0; i < ACG_MAX_PEERS; ++i) x->mbox[i] = nullptr;
+    for (int i = 0; i < d->world; ++i) {
+        ACG_REQUIRE(d->mailboxes[i], ACG_ERR_INVALID, "%s: peer exchange: mailbox %d is NULL", who, i);
+        x->mbox[i] = static_cast<unsigned char*>(d->mailboxes[i]);
+    }
+    x->epoch = d->epoch;
+    x->slot_off = d->slot_off;
+    x->timeout_ns = (long long)((d->timeout_s > 0.f ? d->timeout_s : 30.f) * 1e9);
+    x->rank = d->rank; x->world = d->world; x->cap = d->cap;
+    return ACG_OK;
 }
 
 }  // namespace acg
@@ -172,7 +134,7 @@ int acg_peer_close(void* ptr) {
 
 long long acg_peer_slot_bytes(int cap, int world) {
     if (cap <= 0 || world <= 0 || world > ACG_MAX_PEERS) return -1;
-    long long b = 128 + 2ll * world * cap * (long long)sizeof(double);
+    long long b = 128 + 2ll * world * cap * 16;      // 16-byte cells: value + tags (peer.cuh)
     return (b + 255) / 256 * 256;
 }
 
@@ -188,15 +150,12 @@ int acg_peer_allreduce_f64(double* vec, int n, int cap, long long slot_off, int 
                 "acg_peer_allreduce_f64: n %d cap %d slot offset %lld", n, cap, slot_off);
     ACG_REQUIRE(bn_C == 0 || (2 * bn_C == n && bn_rows > 0 && mean && rstd && scale && shift), ACG_ERR_INVALID,
                 "acg_peer_allreduce_f64: batch-norm finalisation needs n == 2*C and the four outputs");
-    PeerPtrs pp;
-    for (int i = 0; i < ACG_MAX_PEERS; ++i) pp.p[i] = nullptr;
-    for (int i = 0; i < world; ++i) {
-        ACG_REQUIRE(host_mailboxes[i], ACG_ERR_INVALID, "acg_peer_allreduce_f64: mailbox %d is NULL", i);
-        pp.p[i] = static_cast<unsigned char*>(host_mailboxes[i]);
-    }
-    const long long timeout_ns = (long long)((timeout_s > 0.f ? timeout_s : 30.f) * 1e9);
-    launch_pdl(peer_allreduce_kernel, 1, 256, 0, static_cast<cudaStream_t>(stream), vec, n, cap, slot_off, rank, world, pp, epoch, timeout_ns, bn_C, beta, bn_C ? 1.0 / (double)bn_rows : 0.0, eps,
-        mean, rstd, scale, shift);
+    acg_peer_exchange d{host_mailboxes, epoch, slot_off, rank, world, cap, timeout_s};
+    PeerExchange x;
+    int rc = fill_peer_exchange(&x, &d, n, "acg_peer_allreduce_f64");
+    if (rc) return rc;
+    launch_pdl(peer_allreduce_kernel, 1, 256, 0, static_cast<cudaStream_t>(stream), vec, n, x, bn_C, beta,
+               bn_C ? 1.0 / (double)bn_rows : 0.0, eps, mean, rstd, scale, shift);
     return check_launch("acg_peer_allreduce_f64");
 }
 

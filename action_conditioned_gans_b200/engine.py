@@ -32,6 +32,9 @@ FUSE_BWD_REDUCE = os.environ.get("ACG_FUSE_BWD_REDUCE", "0")
 # Fused batch-norm moments through integer limb accumulators (order-independent: bitwise reproducible forward pass).
 # "0": fp64 atomics instead (order varies from run to run; kept to measure what reproducibility costs).
 DETERMINISTIC = os.environ.get("ACG_DETERMINISTIC", "1") != "0"
+# Data parallel, peer-memory exchange: the conv kernel's last CTA pushes its batch-norm totals to the peers, waits for
+# theirs and finalises over the global batch -- no exchange launch per SyncBN layer.  "0": separate exchange kernel.
+DP_FUSED = os.environ.get("ACG_DP_FUSED", "1") != "0"
 
 
 @dataclass(frozen=True)
@@ -241,7 +244,7 @@ class NetRun:
         n_stat = sum(4 * ru16(L.cout) for L in store.spec)
         self.f64 = torch.zeros(n_stat, dtype=torch.float64, device=device)   # [stats | red] per layer
         # "last CTA" tickets of the conv kernels, one per layer (layers of one network may run concurrently)
-        self.counters = torch.zeros(len(store.spec), dtype=torch.int32, device=device)
+        self.counters = torch.zeros(2 * len(store.spec), dtype=torch.int32, device=device)
         # side streams: weight gradients (no collective inside -> also with data parallelism) and a second chain
         self.branches = bool(branches)
         self.wgrad_branch = Branch(device) if self.branches else _NoBranch()
@@ -251,6 +254,7 @@ class NetRun:
             st = _LayerState()
             st.spec = L
             st.counter = self.counters[li:li + 1]
+            st.counter_b = self.counters[len(store.spec) + li:len(store.spec) + li + 1]     # backward reduction pass
             if dp is not None and getattr(dp, "peer_sync", False) and L.bn:
                 # exchange slots of this layer's forward moments / backward reduction terms (same order on every rank)
                 st.slot_f = dp.mailbox.new_slot(2 * L.cout)
@@ -327,13 +331,13 @@ class NetRun:
         self.f64.zero_()
 
     # -- convolution dispatch ------------------------------------------------------------------------------
-    def _conv_fwd(self, st, x, out, ld_out, bias=None, stats=None, bn=None):
+    def _conv_fwd(self, st, x, out, ld_out, bias=None, stats=None, bn=None, peer=None):
         L = st.spec
         if self.bf16:
             pk = self.store.packs[L.name]
             fn = K.conv_fprop_tc if L.kind == "conv" else K.conv_dgrad_tc
             fn(st.shape, x, pk[3], out, st.ld_in, ld_out, bias=bias, stats=stats, bn=bn, splitk=st.splitk_f,
-               stats_fix=st.stats_fix if stats is not None else None)
+               stats_fix=st.stats_fix if stats is not None else None, peer=peer)
         else:
             w = self.store.views[L.name + "/weights"]
             (K.conv_fprop_f32 if L.kind == "conv" else K.conv_dgrad_f32)(st.shape, x, w, out)
@@ -362,6 +366,11 @@ class NetRun:
             if self.dp is None:
                 self._conv_fwd(st, x, st.z, st.ldz, stats=st.stats,
                                bn=(st.counter, beta, st.mean, st.rstd, st.scale, st.shift, st.rows, BN_EPS))
+            elif self.dp.peer_sync and DP_FUSED and st.stats_fix is not None:
+                # SyncBN inside the conv launch: its last CTA exchanges the totals with the peers and finalises
+                self._conv_fwd(st, x, st.z, st.ldz, stats=st.stats,
+                               bn=(st.counter, beta, st.mean, st.rstd, st.scale, st.shift, st.rows * self.dp.world, BN_EPS),
+                               peer=(self.dp.mailbox, st.slot_f))
             else:
                 # the ticket alone (rows 0): this rank's totals in a fixed order, finalised after the exchange
                 self._conv_fwd(st, x, st.z, st.ldz, stats=st.stats,
@@ -434,13 +443,21 @@ class NetRun:
             # epilogue is already in st.red; the others go through the reduction pass (it accumulates as well)
             fused = getattr(st, "red_fused", set())
             todo = [d for d in (dA, dA2) if d is not None and not (None in fused or d.data_ptr() in fused)]
-            if todo:
+            sync_fused = (self.dp is not None and L.bn and self.dp.peer_sync and DP_FUSED and self.bf16
+                          and len(todo) == len([d for d in (dA, dA2) if d is not None]))
+            if todo and sync_fused:
+                # SyncBN backward: the reduction pass's last block sums the terms over the ranks itself
+                K.bn_act_bwd_reduce_sync(todo[0], todo[1] if len(todo) > 1 else None, ld_d, st.z, st.ldz, st.rows, L.cout,
+                                         mean, rstd, shift, L.act, st.red, st.counter_b, self.dp.mailbox, st.slot_b)
+            elif todo:
                 K.bn_act_bwd_reduce(todo[0], todo[1] if len(todo) > 1 else None, ld_d, st.z, st.ldz, st.rows, L.cout, 1,
                                     mean, rstd, shift, L.act, st.red)
             world = 1
             if self.dp is not None:
                 world = self.dp.world
-                if L.bn and self.dp.peer_sync:
+                if todo and sync_fused:
+                    pass
+                elif L.bn and self.dp.peer_sync:
                     self.dp.mailbox.allreduce_f64(st.red, 2 * L.cout, st.slot_b)
                 elif L.bn:
                     self.dp.allreduce_sum(st.red)

@@ -81,7 +81,7 @@ def splitk_workspace(shape, which, ld_in, device):
             torch.zeros(ntick.value, dtype=torch.int32, device=device))
 
 
-def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, splitk=None, n_limit=0, stats_fix=None):
+def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, splitk=None, n_limit=0, stats_fix=None, peer=None):
     """bn = (counter, beta, mean, rstd, scale, shift, rows, eps): finalise the moments in-kernel (single GPU); rows == 0
       with only the counter set: the last CTA completes the totals and the caller finalises (data parallel)
     red = (red_buffer, z, ldz, C, act, mean, rstd, shift): fused batch-norm backward reduction of the consumer layer
@@ -90,6 +90,9 @@ def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, s
     t.n_limit = int(n_limit)
     if stats_fix is not None:
         t.stats_fix, t.stats_fix_len = ptr(stats_fix), stats_fix.numel()
+    if peer is not None:          # (Mailbox, slot): the launch's last CTA sums the moments over the ranks itself
+        t._peer = peer[0].exchange_struct(peer[1])     # kept alive by the args object for the duration of the call
+        t.peer = C.addressof(t._peer)
     if splitk is not None:
         ws, tickets = splitk
         t.splitk_ws, t.splitk_ws_bytes = ptr(ws), ws.numel() * 4
@@ -108,14 +111,14 @@ def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, s
 
 
 def conv_fprop_tc(shape, x, w_pack, y, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None,
-                  splitk=None, n_limit=0, stats_fix=None):
-    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn, red, splitk, n_limit, stats_fix)
+                  splitk=None, n_limit=0, stats_fix=None, peer=None):
+    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn, red, splitk, n_limit, stats_fix, peer)
     call("acg_conv_fprop_tc", C.byref(shape), ptr(x), ptr(w_pack), ptr(y), C.byref(t), stream())
 
 
 def conv_dgrad_tc(shape, dy, w_pack, dx, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None,
-                  splitk=None, n_limit=0, stats_fix=None):
-    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn, red, splitk, n_limit, stats_fix)
+                  splitk=None, n_limit=0, stats_fix=None, peer=None):
+    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn, red, splitk, n_limit, stats_fix, peer)
     call("acg_conv_dgrad_tc", C.byref(shape), ptr(dy), ptr(w_pack), ptr(dx), C.byref(t), stream())
 
 
@@ -184,6 +187,14 @@ def bn_act_bwd_reduce(dA, dA2, ld_d, z, ld_z, rows, Cc, groups, mean, rstd, shif
     call("acg_bn_act_bwd_reduce", ptr(dA), ptr(dA2), dtype_id(dA), ld_d, ptr(z), dtype_id(z) if z is not None else 0,
          ld_z, rows, Cc,
          groups, ptr(mean), ptr(rstd), ptr(shift), ACT_IDS[act], ptr(red), stream())
+
+
+def bn_act_bwd_reduce_sync(dA, dA2, ld_d, z, ld_z, rows, Cc, mean, rstd, shift, act, red, counter, mailbox, slot):
+    """bn_act_bwd_reduce + the sum of red over the data-parallel ranks, in one launch where the fast path applies"""
+    px = mailbox.exchange_struct(slot)
+    call("acg_bn_act_bwd_reduce_sync", ptr(dA), ptr(dA2), dtype_id(dA), ld_d, ptr(z),
+         dtype_id(z) if z is not None else 0, ld_z, rows, Cc, ptr(mean), ptr(rstd), ptr(shift), ACT_IDS[act], ptr(red),
+         ptr(counter), C.addressof(px), stream())
 
 
 def bn_act_bwd_apply(dA, dA2, ld_d, z, ld_z, rows, Cc, groups, mean, rstd, shift, act, has_bn, red, dz, dbeta,

@@ -90,6 +90,12 @@ class Mailbox:
         off, idx = self.plan.take(cap)
         return (off, int(cap), self.epochs[idx:idx + 1])
 
+    def exchange_struct(self, slot):
+        """struct acg_peer_exchange of a slot, for launches whose last CTA does the exchange itself"""
+        off, cap, epoch = slot
+        return _lib.PeerExchange(C.cast(self.ptrs, C.c_void_p), _lib.ptr(epoch), off, self.rank, self.world, cap,
+                                 self.timeout_s)
+
     def allreduce_f64(self, vec, n, slot, bn=None):
         """vec[0:n] <- sum over ranks.  bn = (C, beta, global_rows, eps, mean, rstd, scale, shift) also finalises the
         batch-norm coefficients in the same launch."""

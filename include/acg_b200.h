@@ -97,6 +97,16 @@ int acg_conv_wgrad_f32(const acg_conv_shape* s, const float* x, const float* dy,
  *   is taps x ld).  The output is written for ru16(N) channels (pad channels come out as exact zeros) with row
  *   stride ld_out, as bf16 or f32; `bias` (real channel count entries, may be NULL) and tanh (models.py:20) are
  *   applied in the epilogue. */
+/* Data-parallel exchange slot of a launch whose last CTA sums its result over the ranks itself (see "Data parallelism"
+ * below for the mailbox protocol and acg_peer_allreduce_f64 for the meaning of the fields). */
+typedef struct acg_peer_exchange {
+    void* const* mailboxes;         /* HOST array of `world` DEVICE pointers, [rank] = own segment */
+    unsigned long long* epoch;      /* device uint64 of this slot on this rank */
+    long long slot_off;
+    int rank, world, cap;
+    float timeout_s;                /* <= 0: 30 s */
+} acg_peer_exchange;
+
 typedef struct acg_tc_args {
     int ld_in;          /* channel stride of the gathered operand */
     int ld_out;         /* channel stride of the output rows, >= ru16(output channels) */
@@ -142,6 +152,10 @@ typedef struct acg_tc_args {
      * finalises after its exchange). */
     unsigned long long* stats_fix;
     long long stats_fix_len;
+    /* optional (needs bn_counter): SyncBN without an extra launch -- the last CTA exchanges the [2C] totals with the
+     * peers through this slot (every rank must launch the same layer) and then finalises over bn_rows GLOBAL rows.
+     * Such a launch does not trigger its programmatic dependents early (see csrc/peer.cu on why). */
+    const acg_peer_exchange* peer;
 } acg_tc_args;
 
 /* y = conv(x): x [B,H,W,ld_in] -> y [B,OH,OW,ld_out]; w_pack = acg_pack_weights(which=0, ld_k=ld_in) */
@@ -208,6 +222,13 @@ int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in,
 int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype, int ld_z,
                           long long rows, int C, int groups, const float* mean, const float* rstd,
                           const float* shift, int act, double* red, void* stream);
+/* Data parallel (SyncBN): pass 1 with the sum over the ranks inside the launch -- the last block pushes red[0:2C] into the
+ * peers' mailboxes, waits for theirs and adds them in rank order (counter: zeroed uint32 in device memory, left zeroed).
+ * Shapes the one-launch form does not cover run as acg_bn_act_bwd_reduce + acg_peer_allreduce_f64: same result. */
+int acg_bn_act_bwd_reduce_sync(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype,
+                               int ld_z, long long rows, int C, const float* mean, const float* rstd,
+                               const float* shift, int act, double* red, unsigned int* counter,
+                               const acg_peer_exchange* peer, void* stream);
 /* backward, pass 2: dz = rstd*(dzh - red0/R - xhat*red1/R) when has_bn, else dz = dzh, with
  * R = norm_rows (0 -> rows/groups; data-parallel SyncBN passes the GLOBAL row count after all-reducing red).
  * dbeta[c] += dbeta_scale * sum over groups of red0 (also the bias gradient of non-BN layers).
@@ -269,8 +290,8 @@ int acg_rmsprop_step(float* p, const float* g, float* ms, long long n, float lr,
  * Data parallelism over NVLink peer memory.  The reference is single-GPU and normalises
  * over the whole batch (slim.batch_norm, models.py:11,32,81); with the batch sharded over one process per GPU the
  * [2C] fp64 moment / reduction vectors of every batch-norm layer are summed over the ranks by ONE single-CTA kernel
- * that pushes its vector into every peer's mailbox, waits on flags in its own mailbox, sums in rank order (identical
- * bits on every rank) and optionally finalises mean / rstd / scale / shift.  The flat gradient buckets stay on NCCL.
+ * that pushes its vector into every peer's mailbox as self-validating 16-byte cells (value + epoch tags), polls the
+ * cells of its own mailbox, sums in rank order (identical bits on every rank) and optionally finalises mean / rstd / scale / shift.  The flat gradient buckets stay on NCCL.
  *
  * Mailboxes are the one exception to "the caller owns all buffers": a segment that peers can map must come from
  * cudaMalloc directly, so the library allocates it.  Handles are cudaIpcMemHandle_t (64 bytes, HOST memory); the host
