@@ -950,8 +950,10 @@ struct WgradParams {
     int k_chunk;     // pixels per split (multiple of BK)
     int fast;        // 1: a 64-pixel K slice is whole rows of one image (OW | 64 | OH*OW) or whole images (OH*OW | 64)
     int a_tma;       // 1: the dy operand (a plain [pixels][ldy] matrix) arrives by TMA: two 64 x 64 boxes per K slice
-    int b_tma;       // 1: the x operand arrives by TMA too (ldx % 64 == 0, regular geometry): per 64-channel atom ONE box
+    int b_tma;       // 1: the x operand arrives by TMA too (regular geometry): per 64-channel atom ONE box
                      //    {64 channels, bw, bh, bn pixels} of the tap's input-parity plane, zero fill outside the image
+                     //    AND past the last channel (ldx = 48, 144, 272: the last atom of a tap is partly padding)
+    int ldn;         // channels per tap in the N index of the GEMM: ldx, or ldx rounded up to 64 with b_tma
 };
 struct alignas(64) WgradTmaParams {
     WgradParams p;
@@ -974,7 +976,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smemA = smem_base, smemB = smem_base + STAGES * kStageA;
 
-    const int Ntot = p.KH * p.KW * p.ldx;
+    const int Ntot = p.KH * p.KW * p.ldn;
     const int n0 = blockIdx.x * BN;
     const int n_valid = min(BN, Ntot - n0);          // multiple of 8 (ldx % 8 == 0)
     const int n_cta = (n_valid + 15) & ~15;          // MMA N: multiple of 16, columns past n_valid are zero filled
@@ -1020,8 +1022,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
                 const int nn = n0 + 64 * a;
-                const int tap = nn / p.ldx;
-                cc[a] = nn - tap * p.ldx;
+                const int tap = nn / p.ldn;
+                cc[a] = nn - tap * p.ldn;
                 const int ta = tap / p.KW, tcx = tap - ta * p.KW;
                 const int ry = ta - p.pad_t, rx = tcx - p.pad_l;
                 if (p.stride == 2) {
@@ -1201,7 +1203,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgradTmaParams wp) {
                 for (int h = 0; h < 2; ++h) {       // 8-column groups never straddle a tap (ldx % 8 == 0)
                     const int nn = n0 + cb + 8 * h;
                     if (nn >= Ntot) break;
-                    const int tap = nn / p.ldx, ci0 = nn - tap * p.ldx;
+                    const int tap = nn / p.ldn, ci0 = nn - tap * p.ldn;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int ci = ci0 + i;
@@ -1743,7 +1745,22 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
     p.B = s->B; p.H = s->H; p.W = s->W; p.OH = s->OH; p.OW = s->OW; p.KH = s->KH; p.KW = s->KW;
     p.stride = s->stride; p.pad_t = s->pad_t; p.pad_l = s->pad_l;
     p.Cin = s->Cin; p.Cout = s->Cout; p.ldx = t->ld_in; p.ldy = t->ld_out;
-    const int Ntot = s->KH * s->KW * t->ld_in;
+    // x operand by TMA (see the kernel): regular geometry, 16-byte aligned tensors, channel stride a multiple of 64.
+    // (The kernel also takes strides that leave the last 64-channel atom of a tap partly empty -- p.ldn -- but measured
+    // on B200 the padded MMA work costs more than the gather it replaces: g/tconv4 at ld 48: 115 vs 104 us, g/conv2 at
+    // ld 32: 28.8 vs 25.4 us; ACG_WGRAD_TMA_PAD=1 enables it for strides >= 32.)
+    bool x_tma = false;
+    {
+        const int S = s->OH * s->OW;
+        const bool rows_ok = S % BK == 0 && BK % s->OW == 0, imgs_ok = S < BK && BK % S == 0;
+        const long long span = (long long)(imgs_ok ? BK / S : 1) * s->H * s->W * t->ld_in;
+        x_tma = (rows_ok || imgs_ok) && span < (1ll << 30) && !getenv("ACG_WGRAD_SLOW") && !getenv("ACG_WGRAD_NO_TMA") &&
+                !getenv("ACG_WGRAD_NO_TMA_X") && (t->ld_in % 64 == 0 || (getenv("ACG_WGRAD_TMA_PAD") && t->ld_in >= 32)) &&
+                ((uintptr_t)x_bf16 & 15) == 0 &&
+                ((uintptr_t)dy_bf16 & 15) == 0 && encode_tiled_fn() != nullptr;
+    }
+    p.ldn = x_tma ? ru(t->ld_in, 64) : t->ld_in;
+    const int Ntot = s->KH * s->KW * p.ldn;
     const int gx = (Ntot + BN - 1) / BN, gy = (s->Cout + BM - 1) / BM;
     const long long Kd = (long long)s->B * s->OH * s->OW;
     // split the pixel reduction so that the CTAs fill whole waves (two CTAs are co-resident per SM; a count just above
@@ -1785,7 +1802,7 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
     if (!wp.p.a_tma) memset(&wp.map_a, 0, sizeof(wp.map_a));
     memset(wp.map_x, 0, sizeof(wp.map_x));
     wp.p.b_tma = 0;
-    if (wp.p.a_tma && p.fast && t->ld_in % 64 == 0 && ((uintptr_t)x_bf16 & 15) == 0 && !getenv("ACG_WGRAD_NO_TMA_X")) {
+    if (wp.p.a_tma && x_tma) {
         // x operand by TMA: one map per input-parity plane, box = the input pixels of one 64-pixel K slice
         EncodeTiledFn enc = encode_tiled_fn();
         const int S = s->OH * s->OW;
@@ -1807,7 +1824,10 @@ int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* d
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
         }
-        wp.p.b_tma = ok ? 1 : 0;
+        ACG_REQUIRE(ok, ACG_ERR_CUDA, "acg_conv_wgrad_tc: tensor map of the x operand failed");
+        wp.p.b_tma = 1;
+    } else {
+        ACG_REQUIRE(!x_tma, ACG_ERR_CUDA, "acg_conv_wgrad_tc: tensor map of the dy operand failed");
     }
     launch_pdl(conv_wgrad_tc_kernel, grid, kWgThreads, kSmemBytes, static_cast<cudaStream_t>(stream), wp);
     return check_launch("acg_conv_wgrad_tc");

@@ -265,6 +265,12 @@ int launch(const void* logits, const float* img, const float* dy, float* out, vo
     const int nbands = B * (H / kRows);
     int grid = num_sms() * occ;
     if (grid > nbands) grid = nbands;
+    // every CTA walks the same number of bands: 1024 bands over 296 CTAs left 136 CTAs alone on the fourth pass (a
+    // quarter of the kernel at half the memory parallelism); 256 CTAs x 4 bands finish together
+    if (!getenv("ACG_DNA_UNBALANCED")) {
+        const int passes = (nbands + grid - 1) / grid;
+        grid = (nbands + passes - 1) / passes;
+    }
     launch_pdl(kern, grid, kThreads, smem, stream, static_cast<const LT*>(logits), img, dy, out, dlogits, B, H, W);
     return check_launch(BWD ? "acg_dna_bwd" : "acg_dna_fwd");
 }

@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(256)
 fast_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ z, int ld_z, const __nv_bfloat16* __restrict__ dA,
                        const __nv_bfloat16* __restrict__ dA2, int ld_d, long long rows, int C,
                        const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ shift,
-                       double* __restrict__ out, unsigned int* __restrict__ counter, PeerExchange px) {
+                       double* __restrict__ out, unsigned int* __restrict__ counter, PeerExchange px, int rev) {
     // counter != NULL (data parallel): the LAST block sums `out` over the ranks itself (peer.cuh) -- no exchange launch
     // between this pass and the apply pass.  Such a launch must not trigger its dependents early (see peer.cu).
     if (!counter) pdl_launch_dependents();
@@ -554,12 +554,13 @@ fast_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ z, int ld_z, const __nv
 #pragma unroll
             for (int u = 0; u < kFastU; ++u) {
                 const long long r = r0 + u * rstep;
+                const long long ra = rev ? rows - 1 - r : r;      // traversal direction (see ew_rev())
                 const bool ok = r < rows;
                 zr[u] = make_uint4(0u, 0u, 0u, 0u); dr[u] = zr[u]; d2r[u] = zr[u];
                 if (ok) {
-                    if (HAS_Z) zr[u] = ldg16(z + (size_t)r * ld_z + c);
-                    dr[u] = ldg16(dA + (size_t)r * ld_d + c);
-                    if (HAS_D2) d2r[u] = ldg16(dA2 + (size_t)r * ld_d + c);
+                    if (HAS_Z) zr[u] = ldg16(z + (size_t)ra * ld_z + c);
+                    dr[u] = ldg16(dA + (size_t)ra * ld_d + c);
+                    if (HAS_D2) d2r[u] = ldg16(dA2 + (size_t)ra * ld_d + c);
                 }
             }
 #pragma unroll
@@ -619,7 +620,7 @@ fast_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16*
                       const __nv_bfloat16* __restrict__ z, int ld_z, int C, long long rows,
                       const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ shift,
                       const double* __restrict__ red, __nv_bfloat16* __restrict__ dz, int ld_dz,
-                      float* __restrict__ dbeta, long long norm_rows, float dbeta_scale) {
+                      float* __restrict__ dbeta, long long norm_rows, float dbeta_scale, int rev) {
     pdl_prologue();
     __shared__ float4 coef[256];               // this block's <= 32 vector columns x 8 channels: rs, sh, k1, k0
     const int bx = blockDim.x, by = blockDim.y;
@@ -656,16 +657,18 @@ fast_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16*
 #pragma unroll
         for (int u = 0; u < kFastU; ++u) {
             const long long r = r0 + u * rstep;
+                const long long ra = rev ? rows - 1 - r : r;      // traversal direction (see ew_rev())
             zr[u] = make_uint4(0u, 0u, 0u, 0u); dr[u] = zr[u]; d2r[u] = zr[u];
             if (r < rows) {
-                zr[u] = ldg16(z + (size_t)r * ld_z + c);
-                dr[u] = ldg16(dA + (size_t)r * ld_d + c);
-                if (HAS_D2) d2r[u] = ldg16(dA2 + (size_t)r * ld_d + c);
+                zr[u] = ldg16(z + (size_t)ra * ld_z + c);
+                dr[u] = ldg16(dA + (size_t)ra * ld_d + c);
+                if (HAS_D2) d2r[u] = ldg16(dA2 + (size_t)ra * ld_d + c);
             }
         }
 #pragma unroll
         for (int u = 0; u < kFastU; ++u) {
             const long long r = r0 + u * rstep;
+                const long long ra = rev ? rows - 1 - r : r;      // traversal direction (see ew_rev())
             if (r >= rows) break;
             float zf[8], df[8];
             unpack8(zr[u], zf);
@@ -690,7 +693,7 @@ fast_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dA, const __nv_bfloat16*
                 __nv_bfloat162 h = __floats2bfloat162_rn(o[0], o[1]);
                 w[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
             }
-            *reinterpret_cast<uint4*>(dz + (size_t)r * ld_dz + c) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(dz + (size_t)ra * ld_dz + c) = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
 }
@@ -706,7 +709,7 @@ template <int ACT>
 __global__ void __launch_bounds__(256)
 fast_bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, int ld_in, int C, long long rows,
                        const float* __restrict__ scale, const float* __restrict__ shift,
-                       __nv_bfloat16* __restrict__ out, int ld_out) {
+                       __nv_bfloat16* __restrict__ out, int ld_out, int rev) {
     pdl_prologue();
     const int bx = blockDim.x, by = blockDim.y;
     const int cv = blockIdx.x * bx + threadIdx.x;
@@ -727,12 +730,14 @@ fast_bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, int ld_in, int C, lo
 #pragma unroll
         for (int u = 0; u < kFastU; ++u) {
             const long long r = r0 + u * rstep;
+            const long long ra = rev ? rows - 1 - r : r;
             zr[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (r < rows) zr[u] = ldg16(z + (size_t)r * ld_in + c);
+            if (r < rows) zr[u] = ldg16(z + (size_t)ra * ld_in + c);
         }
 #pragma unroll
         for (int u = 0; u < kFastU; ++u) {
             const long long r = r0 + u * rstep;
+            const long long ra = rev ? rows - 1 - r : r;
             if (r >= rows) break;
             float zf[8];
             unpack8(zr[u], zf);
@@ -743,7 +748,7 @@ fast_bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, int ld_in, int C, lo
                                                          act_fwd_t<ACT>(fmaf(zf[i + 1], sc[i + 1], sh[i + 1])));
                 w[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
             }
-            *reinterpret_cast<uint4*>(out + (size_t)r * ld_out + c) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(out + (size_t)ra * ld_out + c) = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
 }
@@ -779,6 +784,14 @@ void fast_launch_dims(long long rows, int C, int blocks_per_sm, bool atomics, di
     *block = dim3(bx, by);
 }
 
+// Row traversal direction of the streaming passes (bit 1: forward apply, 2: backward reduction, 4: backward apply run
+// from the LAST row to the first).  A pass that follows a kernel which streamed the same tensors first-to-last finds the
+// most recently touched rows still in the 126 MB L2 when it starts from the end.  ACG_EW_REV overrides the default.
+int ew_rev() {
+    static const int v = [] { const char* e = getenv("ACG_EW_REV"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 template <int ACT, bool HAS_Z>
 void launch_fast_reduce(dim3 grid, dim3 block, cudaStream_t st, const void* z, int ld_z, const void* dA, const void* dA2,
                         int ld_d, long long rows, int C, const float* mean, const float* rstd, const float* shift,
@@ -788,8 +801,8 @@ void launch_fast_reduce(dim3 grid, dim3 block, cudaStream_t st, const void* z, i
     const __nv_bfloat16* d2 = static_cast<const __nv_bfloat16*>(dA2);
     PeerExchange x{};
     if (px) x = *px;
-    if (dA2) launch_pdl(fast_bwd_reduce_kernel<ACT, HAS_Z, true>, grid, block, 0, st, zz, ld_z, d1, d2, ld_d, rows, C, mean, rstd, shift, red, counter, x);
-    else launch_pdl(fast_bwd_reduce_kernel<ACT, HAS_Z, false>, grid, block, 0, st, zz, ld_z, d1, d2, ld_d, rows, C, mean, rstd, shift, red, counter, x);
+    if (dA2) launch_pdl(fast_bwd_reduce_kernel<ACT, HAS_Z, true>, grid, block, 0, st, zz, ld_z, d1, d2, ld_d, rows, C, mean, rstd, shift, red, counter, x, ew_rev() & 2);
+    else launch_pdl(fast_bwd_reduce_kernel<ACT, HAS_Z, false>, grid, block, 0, st, zz, ld_z, d1, d2, ld_d, rows, C, mean, rstd, shift, red, counter, x, ew_rev() & 2);
 }
 
 template <int ACT, bool HAS_BN>
@@ -800,8 +813,8 @@ void launch_fast_apply(dim3 grid, dim3 block, cudaStream_t st, const void* dA, c
     const __nv_bfloat16* d1 = static_cast<const __nv_bfloat16*>(dA);
     const __nv_bfloat16* d2 = static_cast<const __nv_bfloat16*>(dA2);
     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(dz);
-    if (dA2) launch_pdl(fast_bwd_apply_kernel<ACT, HAS_BN, true>, grid, block, 0, st, d1, d2, ld_d, zz, ld_z, C, rows, mean, rstd, shift, red, o, ld_dz, dbeta, norm_rows, dbeta_scale);
-    else launch_pdl(fast_bwd_apply_kernel<ACT, HAS_BN, false>, grid, block, 0, st, d1, d2, ld_d, zz, ld_z, C, rows, mean, rstd, shift, red, o, ld_dz, dbeta, norm_rows, dbeta_scale);
+    if (dA2) launch_pdl(fast_bwd_apply_kernel<ACT, HAS_BN, true>, grid, block, 0, st, d1, d2, ld_d, zz, ld_z, C, rows, mean, rstd, shift, red, o, ld_dz, dbeta, norm_rows, dbeta_scale, ew_rev() & 4);
+    else launch_pdl(fast_bwd_apply_kernel<ACT, HAS_BN, false>, grid, block, 0, st, d1, d2, ld_d, zz, ld_z, C, rows, mean, rstd, shift, red, o, ld_dz, dbeta, norm_rows, dbeta_scale, ew_rev() & 4);
 }
 
 // 2-D launch shape shared by the streaming kernels: `waves` resident blocks per SM
@@ -895,9 +908,9 @@ int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in,
             const __nv_bfloat16* zz = static_cast<const __nv_bfloat16*>(z);
             __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
             fast_launch_dims(rows, C, 4, false, &grid, &block);
-            if (act == ACG_ACT_RELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_RELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out);
-            else if (act == ACG_ACT_LRELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_LRELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out);
-            else launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_NONE>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out);
+            if (act == ACG_ACT_RELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_RELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1);
+            else if (act == ACG_ACT_LRELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_LRELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1);
+            else launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_NONE>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1);
             return check_launch("acg_bn_act_fwd");
         }
         vec_stream_launch_dims(rows / groups, C, groups, 8, &grid, &block);
