@@ -23,16 +23,17 @@ CASES = [   # (label, layer, role)  role: f = forward, d = data gradient, w = we
     ("halo2<2> CONV N=128    g/tconv3 dgrad", "g/tconv3", "d"),
     ("halo2<2> CONV N=128    d/conv2 fwd", "d/conv2", "f"),
     ("halo2<4> ADJ N=64      d/conv2 dgrad", "d/conv2", "d"),
-    ("halo2<1> CONV 8x8      g/conv3 fwd", "g/conv3", "f"),
+    ("px CONV 8x8            g/conv3 fwd", "g/conv3", "f"),
     ("halo2<1> ADJ 8x8       g/tconv2 fwd", "g/tconv2", "f"),
-    ("conv_tc<CONV,6> splitK d/conv5 fwd", "d/conv5", "f"),
-    ("conv_tc<CONV,*>        d/conv4 fwd", "d/conv4", "f"),
-    ("conv_tc<ADJ,6>         g/tconv1 fwd", "g/tconv1", "f"),
-    ("conv_tc<ADJ,*>         d/conv4 dgrad", "d/conv4", "d"),
+    ("px CONV splitK 2x2     d/conv5 fwd", "d/conv5", "f"),
+    ("px CONV 4x4            d/conv4 fwd", "d/conv4", "f"),
+    ("px ADJ 8x8             g/tconv1 fwd", "g/tconv1", "f"),
+    ("px ADJ 8x8             d/conv4 dgrad", "d/conv4", "d"),
     ("smallk_persistent<64>  d/conv1 fwd", "d/conv1", "f"),
-    ("wgrad                  g/tconv3 wgrad", "g/tconv3", "w"),
-    ("wgrad                  g/tconv4 wgrad", "g/tconv4", "w"),
-    ("wgrad                  d/conv2 wgrad", "d/conv2", "w"),
+    ("wgrad (x by TMA)       g/tconv3 wgrad", "g/tconv3", "w"),
+    ("wgrad (x gathered)     g/tconv4 wgrad", "g/tconv4", "w"),
+    ("wgrad (x by TMA)       d/conv2 wgrad", "d/conv2", "w"),
+    ("wgrad (x by TMA) 4x4   d/conv5 wgrad", "d/conv5", "w"),
 ]
 
 
