@@ -709,7 +709,8 @@ template <int ACT>
 __global__ void __launch_bounds__(256)
 fast_bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, int ld_in, int C, long long rows,
                        const float* __restrict__ scale, const float* __restrict__ shift,
-                       __nv_bfloat16* __restrict__ out, int ld_out, int rev) {
+                       __nv_bfloat16* __restrict__ out, int ld_out, int rev,
+                       const float* __restrict__ acts, int n_act, int hw, int act_off) {
     pdl_prologue();
     const int bx = blockDim.x, by = blockDim.y;
     const int cv = blockIdx.x * bx + threadIdx.x;
@@ -749,6 +750,13 @@ fast_bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, int ld_in, int C, lo
                 w[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
             }
             *reinterpret_cast<uint4*>(out + (size_t)ra * ld_out + c) = make_uint4(w[0], w[1], w[2], w[3]);
+            // concat of the tiled action vector (models.py:16,38,84): the thread that owns the row's first channel
+            // vector also writes the n_act action channels behind the features -- no acg_tile_actions launch
+            if (acts && cv == 0) {
+                const float* a = acts + (size_t)(ra / hw) * n_act;
+                __nv_bfloat16* o = out + (size_t)ra * ld_out + act_off;
+                for (int j = 0; j < n_act; ++j) o[j] = __float2bfloat16_rn(a[j]);
+            }
         }
     }
 }
@@ -893,13 +901,17 @@ int acg_bn_finalize(const double* stats, const float* beta, long long rows_per_g
     return check_launch("acg_bn_finalize");
 }
 
-int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in, int groups, const float* scale,
-                   const float* shift, int act, void* out, int out_dtype, int ld_out, void* stream) {
+static int bn_act_fwd_impl(const void* z, int z_dtype, long long rows, int C, int ld_in, int groups, const float* scale,
+                           const float* shift, int act, void* out, int out_dtype, int ld_out, const float* acts,
+                           int n_act, int hw, int act_off, void* stream, const char* who) {
     using namespace acg;
-    ACG_REQUIRE(z && out, ACG_ERR_INVALID, "acg_bn_act_fwd: null pointer");
+    ACG_REQUIRE(z && out, ACG_ERR_INVALID, "%s: null pointer", who);
     ACG_REQUIRE(rows > 0 && C > 0 && ld_in >= C && ld_out >= C && groups > 0 && rows % groups == 0,
-                ACG_ERR_INVALID, "acg_bn_act_fwd: bad size");
-    ACG_REQUIRE(dt_ok(z_dtype) && dt_ok(out_dtype), ACG_ERR_UNSUPPORTED, "acg_bn_act_fwd: dtype");
+                ACG_ERR_INVALID, "%s: bad size", who);
+    ACG_REQUIRE(dt_ok(z_dtype) && dt_ok(out_dtype), ACG_ERR_UNSUPPORTED, "%s: dtype", who);
+    ACG_REQUIRE(!acts || (n_act > 0 && hw > 0 && rows % hw == 0 && act_off >= C && act_off + n_act <= ld_out),
+                ACG_ERR_INVALID, "%s: action concat: %d channels at offset %d of %d, %d pixels per image", who, n_act,
+                act_off, ld_out, hw);
     if (C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && al16(z) && al16(out) && al16(scale) && al16(shift)) {
         dim3 grid, block;
         if (groups == 1 && z_dtype == ACG_BF16 && out_dtype == ACG_BF16 &&
@@ -908,17 +920,34 @@ int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in,
             const __nv_bfloat16* zz = static_cast<const __nv_bfloat16*>(z);
             __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
             fast_launch_dims(rows, C, 4, false, &grid, &block);
-            if (act == ACG_ACT_RELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_RELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1);
-            else if (act == ACG_ACT_LRELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_LRELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1);
-            else launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_NONE>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1);
-            return check_launch("acg_bn_act_fwd");
+            if (act == ACG_ACT_RELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_RELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1, acts, n_act, hw, act_off);
+            else if (act == ACG_ACT_LRELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_LRELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1, acts, n_act, hw, act_off);
+            else launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_NONE>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1, acts, n_act, hw, act_off);
+            return check_launch(who);
         }
         vec_stream_launch_dims(rows / groups, C, groups, 8, &grid, &block);
         launch_pdl(vec_bn_act_fwd_kernel, grid, block, 0, static_cast<cudaStream_t>(stream), z, z_dtype, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
-        return check_launch("acg_bn_act_fwd");
+    } else {
+        launch_pdl(bn_act_fwd_kernel, ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream), z, z_dtype, rows, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
     }
-    launch_pdl(bn_act_fwd_kernel, ew_grid(rows * C), 256, 0, static_cast<cudaStream_t>(stream), z, z_dtype, rows, C, ld_in, rows / groups, scale, shift, act, out, out_dtype, ld_out);
-    return check_launch("acg_bn_act_fwd");
+    int rc = check_launch(who);
+    if (rc || !acts) return rc;
+    // shapes outside the fast path: the concat as its own launch, same result
+    return acg_tile_actions(acts, (int)(rows / hw), hw, n_act, out, out_dtype, ld_out, act_off, stream);
+}
+
+int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in, int groups, const float* scale,
+                   const float* shift, int act, void* out, int out_dtype, int ld_out, void* stream) {
+    return bn_act_fwd_impl(z, z_dtype, rows, C, ld_in, groups, scale, shift, act, out, out_dtype, ld_out, nullptr, 0, 1, 0,
+                           stream, "acg_bn_act_fwd");
+}
+
+int acg_bn_act_fwd_cat(const void* z, int z_dtype, long long rows, int C, int ld_in, const float* scale,
+                       const float* shift, int act, void* out, int out_dtype, int ld_out, const float* actions,
+                       int n_act, int hw, int act_off, void* stream) {
+    ACG_REQUIRE(actions, ACG_ERR_INVALID, "acg_bn_act_fwd_cat: null actions");
+    return bn_act_fwd_impl(z, z_dtype, rows, C, ld_in, 1, scale, shift, act, out, out_dtype, ld_out, actions, n_act, hw,
+                           act_off, stream, "acg_bn_act_fwd_cat");
 }
 
 int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype, int ld_z,

@@ -353,7 +353,9 @@ class NetRun:
             K.bn_finalize(st.stats, beta, st.rows * dp.world, L.cout, 1, st.mean, st.rstd, st.scale, st.shift, BN_EPS)
 
     # -- one layer forward: conv -> (bias | batch-norm) -> activation --------------------------------------
-    def layer_fwd(self, name, x, out, ld_out):
+    def layer_fwd(self, name, x, out, ld_out, cat=None):
+        """cat = (actions [B, A], channel offset): `out` is a concat buffer whose channels behind the layer's features
+        hold the tiled action vector (models.py:16,38,84); written by the activation pass itself on the bf16 path."""
         st = self.layers[name]
         L = st.spec
         st.x = x
@@ -376,7 +378,11 @@ class NetRun:
                 self._conv_fwd(st, x, st.z, st.ldz, stats=st.stats,
                                bn=(st.counter, None, None, None, None, None, 0, BN_EPS) if st.stats_fix is not None else None)
                 self._sync_moments(st, beta)           # SyncBN: statistics over the GLOBAL batch
-            K.bn_act_fwd(st.z, st.rows, L.cout, st.ldz, 1, st.scale, st.shift, L.act, out, ld_out)
+            if cat is not None:
+                K.bn_act_fwd_cat(st.z, st.rows, L.cout, st.ldz, st.scale, st.shift, L.act, out, ld_out, cat[0],
+                                 st.out_hw[0] * st.out_hw[1], cat[1])
+            else:
+                K.bn_act_fwd(st.z, st.rows, L.cout, st.ldz, 1, st.scale, st.shift, L.act, out, ld_out)
             return
         self._conv_fwd(st, x, st.z, st.ldz)
         if L.bn:
@@ -561,9 +567,11 @@ class GeneratorRun(NetRun):
             self.layer_fwd(n, x, Ls[n].a, Ls[n].a.shape[3])
             x = Ls[n].a
         ld = self.cat.shape[3]
-        self.layer_fwd("g/conv4", x, self.cat, ld)
-        hw = self.cat.shape[1] * self.cat.shape[2]
-        K.tile_actions(actions, self.B, hw, self.cat, ld, self.cat_c)            # train.py:48-49
+        if self.bf16:       # concat([conv4, tile(action)], 3) (train.py:48-49): written by conv4's activation pass
+            self.layer_fwd("g/conv4", x, self.cat, ld, cat=(actions, self.cat_c))
+        else:
+            self.layer_fwd("g/conv4", x, self.cat, ld)
+            K.tile_actions(actions, self.B, self.cat.shape[1] * self.cat.shape[2], self.cat, ld, self.cat_c)
         self.layer_fwd("g/tconv1", self.cat, Ls["g/tconv1"].a, Ls["g/tconv1"].a.shape[3])
         self.layer_fwd("g/tconv2", Ls["g/tconv1"].a, Ls["g/tconv2"].a, Ls["g/tconv2"].a.shape[3])
         t2 = Ls["g/tconv2"].a
@@ -647,8 +655,11 @@ class DiscriminatorRun(NetRun):
         Ls = self.layers
         self.layer_fwd("d/conv1", self.d_in, Ls["d/conv1"].a, Ls["d/conv1"].a.shape[3])
         ld = self.cat.shape[3]
-        self.layer_fwd("d/conv2", Ls["d/conv1"].a, self.cat, ld)
-        K.tile_actions(actions, self.B, self.cat.shape[1] * self.cat.shape[2], self.cat, ld, 128)
+        if self.bf16:       # concat([conv2, tile(action)], 3) (models.py:84): written by conv2's activation pass
+            self.layer_fwd("d/conv2", Ls["d/conv1"].a, self.cat, ld, cat=(actions, 128))
+        else:
+            self.layer_fwd("d/conv2", Ls["d/conv1"].a, self.cat, ld)
+            K.tile_actions(actions, self.B, self.cat.shape[1] * self.cat.shape[2], self.cat, ld, 128)
         x = self.cat
         for n in ["d/conv3", "d/conv4", "d/conv5"]:
             self.layer_fwd(n, x, Ls[n].a, Ls[n].a.shape[3])

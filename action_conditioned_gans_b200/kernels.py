@@ -183,6 +183,12 @@ def bn_act_fwd(z, rows, Cc, ld_in, groups, scale, shift, act, out, ld_out):
          ptr(out), dtype_id(out), ld_out, stream())
 
 
+def bn_act_fwd_cat(z, rows, Cc, ld_in, scale, shift, act, out, ld_out, actions, hw, act_off):
+    """bn_act_fwd into a concat buffer + the tiled action vector behind the features, one launch"""
+    call("acg_bn_act_fwd_cat", ptr(z), dtype_id(z), rows, Cc, ld_in, ptr(scale), ptr(shift), ACT_IDS[act], ptr(out),
+         dtype_id(out), ld_out, ptr(actions), actions.shape[1], hw, act_off, stream())
+
+
 def bn_act_bwd_reduce(dA, dA2, ld_d, z, ld_z, rows, Cc, groups, mean, rstd, shift, act, red):
     call("acg_bn_act_bwd_reduce", ptr(dA), ptr(dA2), dtype_id(dA), ld_d, ptr(z), dtype_id(z) if z is not None else 0,
          ld_z, rows, Cc,

@@ -216,6 +216,12 @@ int acg_bn_finalize(const double* stats, const float* beta, long long rows_per_g
 int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in, int groups,
                    const float* scale, const float* shift, int act, void* out, int out_dtype,
                    int ld_out, void* stream);
+/* The same pass writing into a CONCAT buffer: besides out[r][0:C] = act(z*scale+shift) it fills out[r][act_off : act_off +
+ * n_act] with actions[r / hw][0:n_act] -- tf.concat([features, tf.tile(action)], 3) of models.py:16,38,84 without a
+ * launch of its own (acg_tile_actions remains for callers that build the buffer separately). */
+int acg_bn_act_fwd_cat(const void* z, int z_dtype, long long rows, int C, int ld_in, const float* scale,
+                       const float* shift, int act, void* out, int out_dtype, int ld_out, const float* actions,
+                       int n_act, int hw, int act_off, void* stream);
 /* backward, pass 1: dzh = (dA + dA2) * act'(z*scale+shift)   (dA2 may be NULL; it is the second consumer's
  * gradient where the graph forks -- g/tconv2 feeds both g/tconv3 and g/sconv3, models.py:40-53); red[0:C] += sum dzh, red[C:2C] += sum dzh*xhat
  * (xhat = (z-mean)*rstd; fp64, caller zeroes; [groups][2][C]). */

@@ -35,11 +35,11 @@ def measure(skip_calls=(), skip_layers=(), branches=True, iters=10):
             return
         orig_call(name, *a)
 
-    def layer_fwd(self, name, x, out, ld_out):
+    def layer_fwd(self, name, x, out, ld_out, cat=None):
         if name in skip_layers:
             self.layers[name].x = x
             return
-        return orig_fwd(self, name, x, out, ld_out)
+        return orig_fwd(self, name, x, out, ld_out, cat=cat)
 
     def layer_bwd(self, name, dA, ld_d, **kw):
         if name in skip_layers:

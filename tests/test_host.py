@@ -141,9 +141,9 @@ def test_peer_slot_plan_is_symmetric(built_lib):
     for (off, idx), c in zip(offs[0], caps):
         assert off % 256 == 0 and off >= prev_end
         prev_end = off + peer.slot_bytes(c, 8)
-        assert peer.slot_bytes(c, 8) >= 128 + 2 * 8 * c * 8
+        assert peer.slot_bytes(c, 8) >= 128 + 2 * 8 * c * 16          # 16-byte cells: value halves + epoch tags
     assert built_lib.acg_peer_slot_bytes(16, 9) == -1          # more than ACG_MAX_PEERS ranks
-    small = peer.SlotPlan(2, segment_bytes=4096)
+    small = peer.SlotPlan(2, segment_bytes=8192)
     small.take(64)
     with pytest.raises(RuntimeError, match="exhausted"):
         small.take(1024)

@@ -256,3 +256,30 @@ def test_pack_frames(cuda):
             if second is not None:
                 ref[..., 3:6] = second
             assert torch.equal(out, ref.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("case", [(256, 4, 4, 256, 272, "relu"), (6, 16, 16, 128, 144, "lrelu"), (3, 5, 7, 24, 40, "none")])
+def test_activation_pass_writes_the_action_concat(cuda, case):
+    """acg_bn_act_fwd_cat == acg_bn_act_fwd + acg_tile_actions (tf.concat([features, tf.tile(action)], 3) of
+    models.py:16,38,84) on the bf16 fast path and, for a shape outside it (C % 8 != 0 is impossible with padded buffers,
+    so: fp32 output), through the two-launch form."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    B, H, W, Cc, ld, act = case
+    g = torch.Generator(device=cuda).manual_seed(B + Cc)
+    rows = B * H * W
+    z = torch.randn(rows, Cc, device=cuda, generator=g).to(torch.bfloat16)
+    scale = torch.rand(Cc, device=cuda, generator=g) + 0.5
+    shift = torch.randn(Cc, device=cuda, generator=g)
+    actions = torch.randn(B, 10, device=cuda, generator=g)
+    for dt in (torch.bfloat16, torch.float32):
+        zz = z if dt == torch.bfloat16 else z.float()
+        want = torch.full((rows, ld), 7.0, dtype=dt, device=cuda)
+        Kn.bn_act_fwd(zz, rows, Cc, Cc, 1, scale, shift, act, want, ld)
+        Kn.tile_actions(actions, B, H * W, want, ld, Cc)
+        got = torch.full((rows, ld), 7.0, dtype=dt, device=cuda)
+        Kn.bn_act_fwd_cat(zz, rows, Cc, Cc, scale, shift, act, got, ld, actions, H * W, Cc)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want)
+        assert bool((got[:, Cc + 10:] == 7.0).all())                  # beyond the concat: untouched
+        ref = actions.to(dt).repeat_interleave(H * W, dim=0)
+        assert torch.equal(got[:, Cc:Cc + 10], ref)
