@@ -39,7 +39,7 @@ class TcArgs(C.Structure):
                 ("red_mean", C.c_void_p), ("red_rstd", C.c_void_p), ("red_shift", C.c_void_p),
                 ("splitk_ws", C.c_void_p), ("splitk_ws_bytes", C.c_longlong), ("splitk_tickets", C.c_void_p),
                 ("splitk_n_tickets", C.c_int), ("n_limit", C.c_int), ("stats_fix", C.c_void_p),
-                ("stats_fix_len", C.c_longlong), ("peer", C.c_void_p)]
+                ("stats_fix_len", C.c_longlong), ("peer", C.c_void_p), ("pair_x", C.c_int)]
 
 
 class PackJob(C.Structure):
@@ -67,6 +67,7 @@ SIGNATURES = {
     "acg_pack_weights": [_SP, _P, _I, _I, _P, _P],
     "acg_pack_weights_batched": [_P, _I, _P, _I, _P],
     "acg_conv_tc_supported": [_SP, _I],
+    "acg_conv_pair_ok": [_SP, _I],
     "acg_conv_kernel_kind": [_SP, _I, _I, _I],
     "acg_conv_splitk_plan": [_SP, _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_longlong), C.POINTER(C.c_int)],
     "acg_bn_stats": [_P, _I, _L, _I, _I, _I, _P, _P],

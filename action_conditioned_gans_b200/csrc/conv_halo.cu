@@ -60,6 +60,7 @@ struct alignas(64) Halo2Params {
                                   // each) keep ONE stride although they come from different images
     int nkc, nk16_last;           // 64-channel blocks; K=16 steps of the last block (lda % 64 != 0 -> fewer MMAs)
     int out_H, out_W;             // spatial size of the output tensor
+    int npg;                      // CONV form: staged planes per tile (4 parity planes; 2 row planes in the pixel-pair mode)
 };
 
 struct H2Tile {
@@ -78,7 +79,7 @@ __device__ __forceinline__ H2Tile h2_tile(const Halo2Params& hp, int t) {
     } else {
         h.cls = 0;
         h.pg0 = 0;
-        h.npg = 4;
+        h.npg = hp.npg;
     }
     const int tiles_x = hp.il ? 1 : hp.Ws / hp.TW, tiles_y = hp.il ? 1 : hp.Hs >> 4;
     const int per_img = tiles_x * tiles_y;
@@ -424,9 +425,48 @@ bool halo2_conv_ok(const acg_conv_shape* s, const acg_tc_args* t, int N) {
     return pick_tile(s->B, s->OH, s->OW, N, &nacc, &TW, &TB, &il);
 }
 
-// form 0: dx / deconv output [B,H,W,N] from dy [B,OH,OW,lda] (ADJ);  form 1: y [B,OH,OW,N] from x [B,H,W,lda] (CONV)
+// Pixel-pair mode of the CONV form, for the FIRST layers (8-channel frame operands: K = 8 per tap is half an MMA step and
+// the small-K kernel's 16-byte gather is LSU bound).  x [B,H,W,8] is read as [B,H,W/2,16]: two horizontally adjacent
+// pixels are one 16-channel "pixel".  Output column ox reads input columns 2 ox + c - pad_l = pair ox + q, half h with
+// q = floor((c - pad_l) / 2), h = (c - pad_l) & 1: along x the stride-2 filter becomes a STRIDE-1 filter of nq <= 3 pair
+// taps (zero weights where a half has no tap), along y nothing changes (two row-parity planes).  Every tap is again a
+// pure shift of a staged dense patch and one K=16 MMA step: 15 steps per accumulator for a 5x5 filter instead of 13, no
+// gather at all.  The weights come as the pair pack (acg_pack_weights which = 2): [N][KH * nq][16].
+void pair_taps(const acg_conv_shape* s, int* qmin, int* nq) {
+    int lo = 1 << 20, hi = -(1 << 20);
+    for (int c = 0; c < s->KW; ++c) {
+        const int r = c - s->pad_l, h = ((r % 2) + 2) % 2, q = (r - h) / 2;
+        lo = q < lo ? q : lo;
+        hi = q > hi ? q : hi;
+    }
+    *qmin = lo;
+    *nq = hi - lo + 1;
+}
+bool halo2_pair_ok(const acg_conv_shape* s, const acg_tc_args* t, int N) {
+    if (getenv("ACG_NO_HALO") || getenv("ACG_NO_PAIR")) return false;
+    if (s->stride != 2 || s->KH > 6 || s->KW > 6 || s->KH < 2 || s->KW < 2 || t->ld_in != 8 || t->red_z) return false;
+    if (s->OH != s->H / 2 || s->OW != s->W / 2 || (s->H & 1) || (s->W & 1)) return false;
+    int qmin, nq;
+    pair_taps(s, &qmin, &nq);
+    if (nq > 3) return false;
+    for (int par = 0; par < 2; ++par) {          // row taps of a parity plane must fit the 3-row window of the halo
+        int dmin = 1 << 20, dmax = -(1 << 20);
+        for (int a = 0; a < s->KH; ++a) {
+            const int r = a - s->pad_t, pi = ((r % 2) + 2) % 2, d = (r - pi) / 2;
+            if (pi != par) continue;
+            dmin = d < dmin ? d : dmin;
+            dmax = d > dmax ? d : dmax;
+        }
+        if (dmax >= dmin && dmax - dmin > 2) return false;
+    }
+    int nacc, TW, TB, il;
+    return pick_tile(s->B, s->OH, s->OW, N, &nacc, &TW, &TB, &il) && !il;
+}
+
+// form 0: dx / deconv output [B,H,W,N] from dy [B,OH,OW,lda] (ADJ);  form 1: y [B,OH,OW,N] from x [B,H,W,lda] (CONV);
+// pair: form 1 in the pixel-pair mode (lda == 8, weights = the pair pack)
 int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const Params& p_in, const void* src,
-                 const void* w_pack, int N, cudaStream_t stream, const char* who) {
+                 const void* w_pack, int N, cudaStream_t stream, const char* who, bool pair) {
     Halo2Params hp;
     memset(&hp, 0, sizeof(hp));
     hp.p = p_in;
@@ -438,7 +478,8 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
         set_error("%s: shape not covered by the halo kernel", who);
         return ACG_ERR_UNSUPPORTED;
     }
-    const int lda = t->ld_in;
+    const int lda = pair ? 2 * t->ld_in : t->ld_in;       // pixel-pair mode: 16-channel pair pixels
+    hp.npg = pair ? 2 : 4;
     hp.nkc = (lda + 63) / 64;
     hp.nk16_last = ((lda - (hp.nkc - 1) * 64) + 15) / 16;
     hp.out_H = form == 0 ? s->H : s->OH;
@@ -482,6 +523,46 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
             rc = encode_map(&hp.map_b[cls], base, 2, wd, ws, wb, who);
             if (rc) return rc;
         }
+    } else if (pair) {
+        const int Hp = s->H / 2, Wp = s->W / 2;           // plane rows; pixel PAIRS per row
+        int qmin, nq;
+        pair_taps(s, &qmin, &nq);
+        for (int pi = 0; pi < 2; ++pi) {
+            TapProg& pr = hp.prog[pi];
+            int dmin_i = 1 << 20;
+            for (int a = 0; a < s->KH; ++a) {
+                const int r = a - s->pad_t, q = ((r % 2) + 2) % 2;
+                if (q == pi && (r - q) / 2 < dmin_i) dmin_i = (r - q) / 2;
+            }
+            int n = 0;
+            for (int a = 0; a < s->KH; ++a) {
+                const int ra = a - s->pad_t, qa = ((ra % 2) + 2) % 2;
+                if (qa != pi) continue;
+                for (int qi = 0; qi < nq; ++qi) {
+                    ACG_REQUIRE(n < kMaxTaps, ACG_ERR_UNSUPPORTED, "%s: more than %d taps per plane", who, kMaxTaps);
+                    pr.a_off[n] = (((ra - qa) / 2 - dmin_i) * ystep + qi) * 8;
+                    pr.w_off[n] = (a * nq + qi) * lda;
+                    ++n;
+                }
+            }
+            pr.ntaps = n;
+            pr.oy = n ? dmin_i : 0;
+            pr.ox = qmin;
+            // row plane pi of the pair view xp [B,H,Wp,16]: xp_p[b][i][j][k] = xp[b][2i+pi][j][k]
+            const cuuint64_t dims[4] = {(cuuint64_t)lda, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)s->B};
+            const cuuint64_t strides[3] = {(cuuint64_t)lda * 2, (cuuint64_t)2 * Wp * lda * 2, (cuuint64_t)s->H * Wp * lda * 2};
+            const void* base = static_cast<const __nv_bfloat16*>(src) + (size_t)pi * Wp * lda;
+            rc = encode_map(&hp.map_a[pi], base, 4, dims, strides, box_a, who);
+            if (rc) return rc;
+        }
+        hp.map_a[2] = hp.map_a[0]; hp.map_a[3] = hp.map_a[1];
+        const cuuint64_t Kt = (cuuint64_t)s->KH * nq * lda;
+        const cuuint64_t wd[2] = {Kt, (cuuint64_t)N};
+        const cuuint64_t ws[1] = {Kt * 2};
+        const cuuint32_t wb[2] = {64, (cuuint32_t)N};
+        rc = encode_map(&hp.map_b[0], w_pack, 2, wd, ws, wb, who);
+        if (rc) return rc;
+        for (int c = 1; c < 4; ++c) hp.map_b[c] = hp.map_b[0];
     } else {
         const int Hp = s->H / 2, Wp = s->W / 2;
         for (int pl = 0; pl < 4; ++pl) {

@@ -29,8 +29,10 @@ namespace tc {
 // persistent halo-tile kernel in both gather forms (conv_halo.cu)
 bool halo2_adj_ok(const acg_conv_shape* s, const acg_tc_args* t, int N);
 bool halo2_conv_ok(const acg_conv_shape* s, const acg_tc_args* t, int N);
+bool halo2_pair_ok(const acg_conv_shape* s, const acg_tc_args* t, int N);
+void pair_taps(const acg_conv_shape* s, int* qmin, int* nq);
 int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const Params& p_in, const void* src,
-                 const void* w_pack, int N, cudaStream_t stream, const char* who);
+                 const void* w_pack, int N, cudaStream_t stream, const char* who, bool pair = false);
 
 constexpr int HALO_ACC = 4;
 constexpr int HALO_H = 18;    // staged halo rows per image: 16 output rows + (na-1) <= 2
@@ -841,6 +843,17 @@ pack_tiles_kernel(const acg_pack_job* __restrict__ jobs, const int4* __restrict_
                 if (n < j.N && ci < ld) out[((size_t)n * taps + tap) * ld + ci] = __float2bfloat16_rn(sm[tx][ty + 8 * k]);
             }
             __syncthreads();
+        } else if (j.which == 2) {           // pixel-pair CONV pack: out[(n*nt + t)*16 + c0 + ci] = w[(tap*Cin + ci)*Cout + n]
+            if (tx < 8) {                    // c0 = 8 * half; tap 255: this half of the pair has no filter tap (zeros)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int n = n0 + ty + 8 * k;
+                    if (n < j.N) {
+                        const float v = (tap != 255 && tx < j.Cin && n < j.Cout) ? w[((size_t)tap * j.Cin + tx) * j.Cout + n] : 0.f;
+                        out[((size_t)n * nt + t) * ld + c0 + tx] = __float2bfloat16_rn(v);
+                    }
+                }
+            }
         } else {                             // out[class offset + (n*nt + t)*ld + co] = w[(tap*Cin + n)*Cout + co]
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -1239,6 +1252,24 @@ pack_conv_kernel(const float* __restrict__ w, int taps, int Cin, int Cout, int C
         out[idx] = __float2bfloat16_rn(v);
     }
 }
+// HWIO fp32 -> pixel-pair CONV pack (conv_halo.cu, pair mode): Wp[n][a * nq + qi][half * 8 + ci] = w[a][c][ci][n] with
+// c = 2 (qmin + qi) + half + pad_l; zeros where that c is outside the filter or ci >= Cin
+__global__ void __launch_bounds__(256)
+pack_pair_kernel(const float* __restrict__ w, int KH, int KW, int Cin, int Cout, int N, int pad_l, int qmin, int nq,
+                 __nv_bfloat16* __restrict__ out) {
+    pdl_prologue();
+    const long long total = (long long)N * KH * nq * 16;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int k = (int)(idx % 16), half = k >> 3, ci = k & 7;
+    const long long r = idx / 16;
+    const int t = (int)(r % (KH * nq)), n = (int)(r / (KH * nq));
+    const int a = t / nq, qi = t - a * nq;
+    const int c = 2 * (qmin + qi) + half + pad_l;
+    float v = 0.f;
+    if (c >= 0 && c < KW && ci < Cin && n < Cout) v = w[((size_t)(a * KW + c) * Cin + ci) * Cout + n];
+    out[idx] = __float2bfloat16_rn(v);
+}
 // HWIO fp32 -> ADJ pack: per parity class Wb[class][n = ci (N rows)][class tap][cos (zero padded)]
 __global__ void __launch_bounds__(256)
 pack_adj_kernel(const float* __restrict__ w, int KH, int KW, int Cin, int Cout, int Cos, int N, int stride, int pad_t,
@@ -1454,6 +1485,11 @@ long long acg_pack_size(const acg_conv_shape* s, int which, int ld_k) {
     using namespace acg::tc;
     if (!s || ld_k <= 0) return -1;
     if (which == 0) return (long long)ru(s->Cout, 16) * s->KH * s->KW * ld_k;      // CONV pack
+    if (which == 2) {                                                              // pixel-pair CONV pack (ld_k == 16)
+        int qmin, nq;
+        pair_taps(s, &qmin, &nq);
+        return ld_k == 16 ? (long long)ru(s->Cout, 16) * s->KH * nq * 16 : -1;
+    }
     long long tot = 0;
     for (int cls = 0; cls < s->stride * s->stride; ++cls) {
         int na, nc;
@@ -1467,6 +1503,16 @@ int acg_pack_weights(const acg_conv_shape* s, const float* w, int which, int ld_
     using namespace acg;
     using namespace acg::tc;
     ACG_REQUIRE(s && w && pack, ACG_ERR_INVALID, "acg_pack_weights: null pointer");
+    if (which == 2) {
+        ACG_REQUIRE(ld_k == 16 && s->Cin <= 8, ACG_ERR_INVALID, "acg_pack_weights: the pixel-pair pack needs ld_k == 16, Cin <= 8");
+        int qmin, nq;
+        pair_taps(s, &qmin, &nq);
+        const int N = ru(s->Cout, 16);
+        const long long total = (long long)N * s->KH * nq * 16;
+        launch_pdl(pack_pair_kernel, (int)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream), w, s->KH, s->KW,
+                   s->Cin, s->Cout, N, s->pad_l, qmin, nq, static_cast<__nv_bfloat16*>(pack));
+        return check_launch("acg_pack_weights");
+    }
     ACG_REQUIRE(ld_k % 8 == 0 && ld_k >= (which == 0 ? s->Cin : s->Cout), ACG_ERR_INVALID,
                 "acg_pack_weights: ld_k=%d", ld_k);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1515,6 +1561,20 @@ long long acg_pack_plan(const acg_pack_job* host_jobs, int njobs, int* host_tile
             for (int tap = 0; tap < j.KH * j.KW; ++tap)
                 for (int n0 = 0; n0 < j.N; n0 += 32)
                     for (int c0 = 0; c0 < j.ld_k; c0 += 32) emit(ji, tap, n0, c0, 0);
+        } else if (j.which == 2) {
+            if (j.ld_k != 16 || j.Cin > 8 || j.stride != 2) return -1;
+            acg_conv_shape sh{};
+            sh.KW = j.KW; sh.pad_l = j.pad_l;
+            int qmin, nq;
+            pair_taps(&sh, &qmin, &nq);
+            for (int a = 0; a < j.KH; ++a)
+                for (int qi = 0; qi < nq; ++qi)
+                    for (int half = 0; half < 2; ++half) {
+                        const int c = 2 * (qmin + qi) + half + j.pad_l;
+                        const int tap = (c >= 0 && c < j.KW) ? a * j.KW + c : 255;
+                        for (int n0 = 0; n0 < j.N; n0 += 32)
+                            emit(ji, tap | ((a * nq + qi) << 8) | ((j.KH * nq) << 16), n0, 8 * half, 0);
+                    }
         } else {
             long long off = 0;
             for (int cls = 0; cls < j.stride * j.stride; ++cls) {
@@ -1569,6 +1629,14 @@ int acg_conv_kernel_kind(const acg_conv_shape* s, int which, int ld_in, int n_li
     return halo2_adj_ok(s, &t, N) ? 1 : 0;
 }
 
+int acg_conv_pair_ok(const acg_conv_shape* s, int ld_in) {
+    using namespace acg::tc;
+    if (!s) return 0;
+    acg_tc_args t{};
+    t.ld_in = ld_in;
+    return halo2_pair_ok(s, &t, ru(s->Cout, 16)) ? 1 : 0;
+}
+
 int acg_conv_tc_supported(const acg_conv_shape* s, int which) {
     if (!s) return 0;
     if (s->stride != 1 && s->stride != 2) return 0;
@@ -1599,6 +1667,13 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
     dim3 grid((unsigned)((M + BM - 1) / BM), (N + BN - 1) / BN, 1);
     rc = fill_bn(&p, t, grid.x * grid.y, "acg_conv_fprop_tc");
     if (rc) return rc;
+    if (t->pair_x) {
+        // first layers, pixel-pair mode of the halo kernel (w_pack = the pair pack, which = 2)
+        ACG_REQUIRE(N == ru(s->Cout, 16) && halo2_pair_ok(s, t, N), ACG_ERR_UNSUPPORTED,
+                    "acg_conv_fprop_tc: the pixel-pair mode does not cover this shape (acg_conv_pair_ok)");
+        return launch_halo2(1, s, t, p, x_bf16, w_pack, N, static_cast<cudaStream_t>(stream),
+                            "acg_conv_fprop_tc(halo, pixel pairs)", true);
+    }
     {   // first layers (tiny K, many tiles of 4 whole 32-pixel output rows, N = 32 / 64, plain bias-free epilogue)
         const int nkb = (s->KH * s->KW * t->ld_in + BK - 1) / BK;
         const long long tiles = (M + BM - 1) / BM;

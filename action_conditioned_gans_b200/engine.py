@@ -35,6 +35,12 @@ DETERMINISTIC = os.environ.get("ACG_DETERMINISTIC", "1") != "0"
 # Data parallel, peer-memory exchange: the conv kernel's last CTA pushes its batch-norm totals to the peers, waits for
 # theirs and finalises over the global batch -- no exchange launch per SyncBN layer.  "0": separate exchange kernel.
 DP_FUSED = os.environ.get("ACG_DP_FUSED", "1") != "0"
+# First layers (g/conv1, d/conv1: 8-channel frame operands): "1" sends their forward through the halo kernel's pixel-pair
+# mode instead of the small-K gather kernel.  Built, parity-tested (tests/test_conv_halo_gpu.py) and measured: no gather,
+# but no faster either (B=256: g/conv1 30.9 vs 29.9 us, d/conv1 42.5 vs 36.7 us) -- with 16-channel pair pixels in
+# 128-byte-swizzled rows the halo kernel streams an 8 KB weight slice and waits on one mbarrier round trip per K=16 step;
+# the knock-out probe (scripts/pair_bench.py probe) shows 20-28 us with MMAs and epilogue switched off.  Default off.
+PAIR_FIRST = os.environ.get("ACG_PAIR_FIRST", "0") != "0"
 
 
 @dataclass(frozen=True)
@@ -136,6 +142,7 @@ class ParamStore:
         self.gviews = {n: self.grad[o:o + k].view(shape) for n, (o, k, shape) in self.offsets.items()}
         self._pack_table = None
         self.packs = {}      # layer name -> (shape, fwd_which, fwd_ld, fwd_pack, bwd_which, bwd_ld, bwd_pack)
+        self.pair_packs = {}  # first layers: layer name -> (shape, pixel-pair forward pack)
         if init is not None:
             self.load(init)
 
@@ -144,13 +151,16 @@ class ParamStore:
         every pack of the store in ONE launch through a device-side job table."""
         if not self.packs:
             return
-        if self._pack_table is None or self._pack_table[4] != len(self.packs):
+        npk = len(self.packs) + len(self.pair_packs)
+        if self._pack_table is None or self._pack_table[4] != npk:
             entries = []
             for name, (shape, fw, fld, pf, bw, bld, pb) in self.packs.items():
                 w = self.views[name + "/weights"]
                 entries.append((shape, w, fw, fld, pf))
                 entries.append((shape, w, bw, bld, pb))
-            self._pack_table = K.make_pack_jobs(entries, self.device) + (len(self.packs),)
+            for name, (shape, pp) in self.pair_packs.items():     # first layers: pixel-pair forward pack
+                entries.append((shape, self.views[name + "/weights"], 2, 16, pp))
+            self._pack_table = K.make_pack_jobs(entries, self.device) + (npk,)
         K.pack_weights_batched(*self._pack_table[:4])
 
     def load(self, arrays):
@@ -325,6 +335,11 @@ class NetRun:
             pf = torch.empty(K.pack_size(st.shape, fwd_which, ld_in), dtype=torch.bfloat16, device=self.device)
             pb = torch.empty(K.pack_size(st.shape, bwd_which, st.ldz), dtype=torch.bfloat16, device=self.device)
             self.store.packs[name] = (st.shape, fwd_which, ld_in, pf, bwd_which, st.ldz, pb)
+        # first layers (8-channel frame operands): forward through the halo kernel's pixel-pair mode
+        st.pair = bool(self.bf16 and PAIR_FIRST and L.kind == "conv" and ld_in == 8 and K.pair_ok(st.shape, ld_in))
+        if st.pair and name not in self.store.pair_packs:
+            self.store.pair_packs[name] = (st.shape, torch.empty(K.pack_size(st.shape, 2, 16), dtype=torch.bfloat16,
+                                                                 device=self.device))
         return oh, ow
 
     def zero_reductions(self):
@@ -336,8 +351,10 @@ class NetRun:
         if self.bf16:
             pk = self.store.packs[L.name]
             fn = K.conv_fprop_tc if L.kind == "conv" else K.conv_dgrad_tc
-            fn(st.shape, x, pk[3], out, st.ld_in, ld_out, bias=bias, stats=stats, bn=bn, splitk=st.splitk_f,
-               stats_fix=st.stats_fix if stats is not None else None, peer=peer)
+            pair = getattr(st, "pair", False)
+            fn(st.shape, x, self.store.pair_packs[L.name][1] if pair else pk[3], out, st.ld_in, ld_out, bias=bias,
+               stats=stats, bn=bn, splitk=st.splitk_f, stats_fix=st.stats_fix if stats is not None else None, peer=peer,
+               pair_x=pair)
         else:
             w = self.store.views[L.name + "/weights"]
             (K.conv_fprop_f32 if L.kind == "conv" else K.conv_dgrad_f32)(st.shape, x, w, out)

@@ -70,6 +70,11 @@ def kernel_kind(shape, which, ld_in, n_limit=0):
     return int(_lib.load().acg_conv_kernel_kind(C.byref(shape), which, ld_in, int(n_limit)))
 
 
+def pair_ok(shape, ld_in):
+    """True when conv_fprop_tc(..., pair_x=True) covers the shape (first layers: 8-channel frames read as pixel pairs)"""
+    return bool(_lib.load().acg_conv_pair_ok(C.byref(shape), ld_in))
+
+
 def splitk_workspace(shape, which, ld_in, device):
     """(workspace, tickets) tensors a conv_fprop_tc (which=0) / conv_dgrad_tc (which=1) launch of this shape wants for
     split-K, or None when it never splits (acg_conv_splitk_plan)."""
@@ -81,7 +86,7 @@ def splitk_workspace(shape, which, ld_in, device):
             torch.zeros(ntick.value, dtype=torch.int32, device=device))
 
 
-def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, splitk=None, n_limit=0, stats_fix=None, peer=None):
+def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, splitk=None, n_limit=0, stats_fix=None, peer=None, pair_x=False):
     """bn = (counter, beta, mean, rstd, scale, shift, rows, eps): finalise the moments in-kernel (single GPU); rows == 0
       with only the counter set: the last CTA completes the totals and the caller finalises (data parallel)
     red = (red_buffer, z, ldz, C, act, mean, rstd, shift): fused batch-norm backward reduction of the consumer layer
@@ -90,6 +95,7 @@ def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, s
     t.n_limit = int(n_limit)
     if stats_fix is not None:
         t.stats_fix, t.stats_fix_len = ptr(stats_fix), stats_fix.numel()
+    t.pair_x = int(bool(pair_x))
     if peer is not None:          # (Mailbox, slot): the launch's last CTA sums the moments over the ranks itself
         t._peer = peer[0].exchange_struct(peer[1])     # kept alive by the args object for the duration of the call
         t.peer = C.addressof(t._peer)
@@ -111,14 +117,14 @@ def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, s
 
 
 def conv_fprop_tc(shape, x, w_pack, y, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None,
-                  splitk=None, n_limit=0, stats_fix=None, peer=None):
-    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn, red, splitk, n_limit, stats_fix, peer)
+                  splitk=None, n_limit=0, stats_fix=None, peer=None, pair_x=False):
+    t = _tc_args(ld_in, ld_out, bias, y, out_act, stats, bn, red, splitk, n_limit, stats_fix, peer, pair_x)
     call("acg_conv_fprop_tc", C.byref(shape), ptr(x), ptr(w_pack), ptr(y), C.byref(t), stream())
 
 
 def conv_dgrad_tc(shape, dy, w_pack, dx, ld_in, ld_out, bias=None, out_act=None, stats=None, bn=None, red=None,
-                  splitk=None, n_limit=0, stats_fix=None, peer=None):
-    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn, red, splitk, n_limit, stats_fix, peer)
+                  splitk=None, n_limit=0, stats_fix=None, peer=None, pair_x=False):
+    t = _tc_args(ld_in, ld_out, bias, dx, out_act, stats, bn, red, splitk, n_limit, stats_fix, peer, pair_x)
     call("acg_conv_dgrad_tc", C.byref(shape), ptr(dy), ptr(w_pack), ptr(dx), C.byref(t), stream())
 
 
@@ -144,7 +150,7 @@ def make_pack_jobs(entries, device):
     jobs = (_lib.PackJob * len(entries))()
     first = 0
     for i, (shape, w, which, ld_k, pack) in enumerate(entries):
-        n_rows = (shape.Cout + 15) // 16 * 16 if which == 0 else (shape.Cin + 15) // 16 * 16
+        n_rows = (shape.Cout + 15) // 16 * 16 if which in (0, 2) else (shape.Cin + 15) // 16 * 16
         jobs[i] = _lib.PackJob(ptr(w), ptr(pack), first, which, ld_k, shape.KH, shape.KW, shape.Cin, shape.Cout,
                                shape.stride, shape.pad_t, shape.pad_l, n_rows)
         first += pack_size(shape, which, ld_k)

@@ -156,6 +156,11 @@ typedef struct acg_tc_args {
      * peers through this slot (every rank must launch the same layer) and then finalises over bn_rows GLOBAL rows.
      * Such a launch does not trigger its programmatic dependents early (see csrc/peer.cu on why). */
     const acg_peer_exchange* peer;
+    /* optional (acg_conv_fprop_tc, first layers): pixel-pair mode.  x [B,H,W,8] is read as [B,H,W/2,16] (two neighbouring
+     * pixels = one 16-channel pixel), which turns the stride-2 filter into stride 1 along x: every tap is a pure shift
+     * of a staged tile, no gather.  w_pack must then be the PAIR pack (acg_pack_weights which = 2, ld_k = 16);
+     * acg_conv_pair_ok says whether a shape qualifies. */
+    int pair_x;
 } acg_tc_args;
 
 /* y = conv(x): x [B,H,W,ld_in] -> y [B,OH,OW,ld_out]; w_pack = acg_pack_weights(which=0, ld_k=ld_in) */
@@ -167,7 +172,8 @@ int acg_conv_dgrad_tc(const acg_conv_shape* s, const void* dy_bf16, const void* 
 /* dw[a,c,ci,co] += sum x*dy over the batch: x [B,H,W,ld_in], dy [B,OH,OW,ld_out] (both bf16); dw fp32 HWIO */
 int acg_conv_wgrad_tc(const acg_conv_shape* s, const void* x_bf16, const void* dy_bf16, float* dw,
                       const acg_tc_args* t, void* stream);
-/* fp32 HWIO weights -> bf16 pack.  which=0: fprop pack [ru16(Cout)][tap][ld_k>=Cin]; which=1: dgrad pack, one
+/* fp32 HWIO weights -> bf16 pack.  which=2: pixel-pair fprop pack [ru16(Cout)][KH * pair taps][16] (acg_tc_args.pair_x);
+ * which=0: fprop pack [ru16(Cout)][tap][ld_k>=Cin]; which=1: dgrad pack, one
  * [ru16(Cin)][class taps][ld_k>=Cout] matrix per output-parity class.  acg_pack_size gives the element count. */
 long long acg_pack_size(const acg_conv_shape* s, int which, int ld_k);
 int acg_pack_weights(const acg_conv_shape* s, const float* w, int which, int ld_k, void* pack, void* stream);
@@ -196,6 +202,8 @@ int acg_conv_splitk_plan(const acg_conv_shape* s, int which, int ld_in, int* spl
  * halo-tile kernel (dedicated epilogue warps), 0 = the generic kernel, -1 = bad argument.  Host only. */
 int acg_conv_kernel_kind(const acg_conv_shape* s, int which, int ld_in, int n_limit);
 int acg_conv_tc_supported(const acg_conv_shape* s, int which);
+/* 1 when acg_conv_fprop_tc accepts acg_tc_args.pair_x for this shape (stride 2, ld_in == 8, even extents, <= 3 pair taps) */
+int acg_conv_pair_ok(const acg_conv_shape* s, int ld_in);
 
 /* ------------------------------------------------------------------------------------------
  * Batch-norm (slim.batch_norm defaults: batch statistics always, biased variance, eps 1e-3, beta

@@ -129,3 +129,58 @@ def test_halo_kernel_is_the_one_that_runs(cuda):
     ref = torch.nn.functional.conv2d(torch.nn.functional.pad(x.float().permute(0, 3, 1, 2), (1, 2, 1, 2)),
                                      w.to(torch.bfloat16).float().permute(3, 2, 0, 1), stride=2).permute(0, 2, 3, 1)
     assert (y - ref).abs().max() <= 2e-3 * ref.abs().max()
+
+
+@pytest.mark.parametrize("case", [(6, 64, 64, 3, 32, 5), (4, 64, 64, 6, 64, 5), (4, 32, 32, 8, 16, 5), (2, 64, 32, 5, 48, 3),
+                                  (5, 32, 64, 6, 64, 4)])
+def test_pixel_pair_first_layers(cuda, case, monkeypatch):
+    """First layers in the halo kernel's pixel-pair mode (x [B,H,W,8] read as [B,H,W/2,16], pair pack): against the fp32
+    SIMT convolution, bit-identical to... no other kernel (the K grouping differs), so: the small-K / generic tcgen05
+    kernel within one bf16 ulp, fused moments + finalize, batched pack == single pack."""
+    from action_conditioned_gans_b200 import kernels as Kn
+    B, H, W, Cin, Cout, k = case
+    g = torch.Generator(device=cuda).manual_seed(B * 7 + Cout)
+    shape = Kn.conv_shape(B, H, W, Cin, Cout, k, 2, "SAME")
+    assert Kn.pair_ok(shape, 8)
+    x = torch.zeros(B, H, W, 8, dtype=torch.bfloat16, device=cuda)
+    x[..., :Cin] = (torch.rand(B, H, W, Cin, device=cuda, generator=g) * 2 - 1).to(torch.bfloat16)
+    w = (torch.randn(k, k, Cin, Cout, device=cuda, generator=g) / (k * Cin ** 0.5)).to(torch.bfloat16).float()
+    ref = torch.empty(B, shape.OH, shape.OW, Cout, device=cuda)
+    Kn.conv_fprop_f32(shape, x[..., :Cin].float().contiguous(), w, ref)
+    pp = torch.full((Kn.pack_size(shape, 2, 16),), float("nan"), dtype=torch.bfloat16, device=cuda)
+    Kn.pack_weights(shape, w, 2, 16, pp)
+    pp2 = torch.full_like(pp, float("nan"))
+    Kn.pack_weights_batched(*Kn.make_pack_jobs([(shape, w, 2, 16, pp2)], cuda))
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(pp.float()).all()) and torch.equal(pp, pp2)
+    pf = torch.empty(Kn.pack_size(shape, 0, 8), dtype=torch.bfloat16, device=cuda)
+    Kn.pack_weights(shape, w, 0, 8, pf)
+    rows, ldo = B * shape.OH * shape.OW, (Cout + 15) // 16 * 16
+    beta = torch.randn(Cout, device=cuda, generator=g)
+    res = []
+    for pair in (True, False):
+        out = torch.full((rows, ldo), 7.0, dtype=torch.bfloat16, device=cuda)
+        stats = torch.zeros(2 * Cout, dtype=torch.float64, device=cuda)
+        fix = Kn.stats_accumulators(Cout, cuda)
+        counter = torch.zeros(1, dtype=torch.int32, device=cuda)
+        mean, rstd, scale, shift = (torch.zeros(Cout, device=cuda) for _ in range(4))
+        for rep in range(2):
+            stats.zero_()
+            Kn.conv_fprop_tc(shape, x, pp if pair else pf, out, 8, ldo, stats=stats,
+                             bn=(counter, beta, mean, rstd, scale, shift, rows, 1e-3), stats_fix=fix, pair_x=pair)
+        torch.cuda.synchronize()
+        assert int(counter.item()) == 0 and int(fix.abs().sum()) == 0
+        res.append((out.float(), stats.clone(), torch.stack([mean, rstd, shift])))
+    sc = max(1.0, float(ref.abs().max()))
+    for out, stats, fin in res:
+        got = out.view(B, shape.OH, shape.OW, ldo)
+        assert float((got[..., :Cout] - ref).abs().max()) <= 1.2e-2 * sc
+        o = out[:, :Cout].double()
+        tot = torch.cat([o.sum(0), (o * o).sum(0)])
+        assert float((stats - tot).abs().max()) <= 2e-6 * max(1.0, float(tot.abs().max()))
+    a, b = res[0][0], res[1][0]
+    assert float((a - b).abs().max()) <= 1e-2 * sc and float((a != b).float().mean()) < 0.02
+    assert float((res[0][2] - res[1][2]).abs().max()) <= 1e-3 * max(1.0, float(res[1][2].abs().max()))
+    # what the mode refuses
+    assert not Kn.pair_ok(Kn.conv_shape(B, H, W, Cin, Cout, k, 2, "SAME"), 16)
+    assert not Kn.pair_ok(Kn.conv_shape(B, 63, 64, Cin, Cout, k, 2, "SAME"), 8)
