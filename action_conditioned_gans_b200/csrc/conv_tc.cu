@@ -372,14 +372,30 @@ conv_tc_kernel(const __grid_constant__ ConvParams cp) {
 //   * the batch-norm moments are kept PER THREAD in registers across all tiles of the CTA (2 x N accumulators) and
 //     reduced over the 32 rows of a warp once at the end, instead of two 16-shuffle butterflies per 16-column chunk
 //     (epilogue ~75 instead of ~250 instructions per chunk).
-constexpr int kSmallKRing = 8;
 constexpr int kSmallKMaxKb = 4;
-constexpr int kSmallKSmem = kSmallKMaxKb * kStageB + kSmallKRing * kStageA + 1024;
-constexpr int kSmallKThreads = 288;      // warps 0-3 epilogue, warp 4 MMA issue + TMEM, warps 5-8 gather producers
+// warps 0-3 epilogue, warp 4 MMA issue + TMEM, warps 5.. gather producers.  N = 32: EIGHT producer warps (with four --
+// one per scheduler -- the ~300 dependent instructions a tile costs a producer thread issue at one per ~6 clk: 25.5 ->
+// 23.3 us for g/conv1).  N = 64 keeps four: its epilogue threads hold 2 x 64 moment accumulators, and the 128-register
+// cap of a 416-thread CTA spilled them (32 -> 45 us).
+// Knock-out probe (scripts/smallk_knockout.py): with gather, MMAs and epilogue all switched off the launch still takes
+// ~16 us of its 23 / 32 us -- and neither one arrival per warp instead of per thread, nor plain arrivals instead of
+// tcgen05.commit, nor a deeper ring, nor dropping the 3 padding MMAs of the last K block changed that.
+template <int NT> struct SmallK {
+    static constexpr int kProd = NT == 32 ? 256 : 128;
+    static constexpr int kRows = kProd / 8;               // tile rows covered by one pass of the producer threads
+    static constexpr int kPass = BM / kRows;              // passes (rows per producer thread) per K slice
+    static constexpr int kThreads = 160 + kProd;
+    static constexpr int kStageBN = kStageB;              // one resident weight slice (N rows x 128 B used)
+    static constexpr int kStatic = 6 * 1024;              // static shared memory of the kernel, rounded up
+    static constexpr int kRing = 8;
+    static constexpr int kSmem = kSmallKMaxKb * kStageBN + kRing * kStageA + 4 * kEpiStageBytes + 1024;
+};
 
 template <int NT>
-__global__ void __launch_bounds__(kSmallKThreads, 1)
+__global__ void __launch_bounds__(SmallK<NT>::kThreads, 1)
 conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles) {
+    constexpr int kSmallKRing = SmallK<NT>::kRing, kSmallKProd = SmallK<NT>::kProd, kSmallKRows = SmallK<NT>::kRows,
+                  kSmallKPass = SmallK<NT>::kPass, kSmallKThreads = SmallK<NT>::kThreads, kStageBN = SmallK<NT>::kStageBN;
     const Params& p = cp.p;
     extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[kSmallKRing], empty_bar[kSmallKRing], b_full, acc_full[2], acc_empty[2];
@@ -389,7 +405,8 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t smemB = smem_base, smemA = smem_base + kSmallKMaxKb * kStageB;
+    const uint32_t smemB = smem_base, smemA = smem_base + kSmallKMaxKb * kStageBN;
+    const uint32_t smemE = smemA + kSmallKRing * kStageA;      // per epilogue warp: staging tile of the transposed stores
     for (int i = tid; i < 4 * 2 * BN; i += kSmallKThreads) (&sm_stats[0][0][0])[i] = 0.f;
 
     const int s = p.stride;
@@ -399,7 +416,11 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
     constexpr uint32_t tmem_cols = 2 * NT < 32 ? 32 : 2 * NT;
 
     if (tid == 0) {
-        for (int i = 0; i < kSmallKRing; ++i) { mbar_init(&full_bar[i], kProducers); mbar_init(&empty_bar[i], 1); }
+        // probe bit 64 (only together with bit 1): one plain arrival per producer warp instead of one per thread
+        for (int i = 0; i < kSmallKRing; ++i) {
+            mbar_init(&full_bar[i], ACG_DBG(p, 64) ? kSmallKProd / 32 : kSmallKProd);
+            mbar_init(&empty_bar[i], 1);
+        }
         mbar_init(&b_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
         fence_mbar_init();
@@ -422,7 +443,7 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
         const int ptid = tid - 160;
         if (ptid == 0) {     // resident weights: one TMA slice per K block, all on one barrier
             mbar_expect_tx(&b_full, (uint32_t)(nkb * NT) * 128u);
-            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smemB + kb * kStageB, &cp.map_b[0], kb * BK, 0, &b_full);
+            for (int kb = 0; kb < nkb; ++kb) tma_load_2d(smemB + kb * kStageBN, &cp.map_b[0], kb * BK, 0, &b_full);
         }
         const int j = ptid & 7, rslot = ptid >> 3;
         // per K slice (kernel constants): tap bit and source offset of this thread's 16-byte column
@@ -440,13 +461,13 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
             }
         }
         // per row slot (kernel constants; OW == 32: a tile is 4 whole output rows): row delta, column mask, offset
-        int doh[8], xoff[8];
-        uint32_t cmask[8];
+        int doh[kSmallKPass], xoff[kSmallKPass];
+        uint32_t cmask[kSmallKPass];
         uint32_t fullsel = 0;
         for (int a = 0; a < p.KH; ++a) fullsel |= 1u << (a * p.KW);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int q = rslot + 16 * i;
+        for (int i = 0; i < kSmallKPass; ++i) {
+            const int q = rslot + kSmallKRows * i;
             doh[i] = q >> 5;
             const int x0 = (q & 31) * s - p.pad_l;
             const int c_lo = max(0, -x0), c_hi = min(p.KW, p.W - x0);
@@ -457,10 +478,10 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
         int cnt = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int b = tile / tiles_per_img, oh0 = (tile - b * tiles_per_img) << 2;
-            long long row_off[8];
-            uint32_t row_mask[8];
+            long long row_off[kSmallKPass];
+            uint32_t row_mask[kSmallKPass];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < kSmallKPass; ++i) {
                 const int y0 = (oh0 + doh[i]) * s - p.pad_t;
                 const int a_lo = max(0, -y0), a_hi = min(p.KH, p.H - y0);
                 const uint32_t rowsel = fullsel & ((1u << (a_hi * p.KW)) - 1u) & ~((1u << (a_lo * p.KW)) - 1u);
@@ -474,12 +495,18 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
                     if (use >= 1) mbar_wait(&empty_bar[stage], (uint32_t)((use - 1) & 1));
                     const uint32_t dstA = (smemA + stage * kStageA + (rslot * 128) + (j << 4)) ^ ((uint32_t)(rslot & 7) << 4);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < kSmallKPass; ++i) {
+                        if (ACG_DBG(p, 1)) break;                                  // probe: no gather traffic
                         const bool ok = (row_mask[i] & tbit[kb]) != 0;
-                        cp_async16(dstA + i * 2048, ok ? (const void*)(p.a_src + row_off[i] + koff[kb]) : (const void*)p.a_src,
+                        cp_async16(dstA + i * (kSmallKRows * 128), ok ? (const void*)(p.a_src + row_off[i] + koff[kb]) : (const void*)p.a_src,
                                    ok ? 16u : 0u);
                     }
-                    cp_async_arrive_noinc(&full_bar[stage]);
+                    if (ACG_DBG(p, 64)) {
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full_bar[stage]);
+                    } else {
+                        cp_async_arrive_noinc(&full_bar[stage]);
+                    }
                     ++cnt;
                 }
             }
@@ -490,6 +517,10 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
 #pragma unroll
         for (int i = 0; i < NT; ++i) { q1[i] = 0.f; q2[i] = 0.f; }
         const bool bf16_out = p.out_dtype == ACG_BF16;
+        // bf16 rows of NT columns = 64 (NT = 32) or 128 (NT = 64) bytes go out through the warp's staging tile
+        constexpr int RB = NT * 2;
+        const bool staged = bf16_out && (p.ldo & 7) == 0 && !p.direct_store;
+        const uint32_t stile = smemE + (uint32_t)warp * kEpiStageBytes;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int abuf = it & 1;
@@ -501,8 +532,10 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
             const uint32_t tacc = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(abuf * NT);
 #pragma unroll
             for (int cb = 0; cb < NT; cb += 16) {
+                if (ACG_DBG(p, 32)) break;                                         // probe: no epilogue work
                 uint32_t v[16];
                 tmem_ld16(tacc + cb, v);
+                if (ACG_DBG(p, 16)) continue;                                      // probe: TMEM loads only
                 if (bf16_out) {
                     uint32_t w[8];
 #pragma unroll
@@ -517,9 +550,15 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
                             q1[cb + 2 * i] += lo; q2[cb + 2 * i] = fmaf(lo, lo, q2[cb + 2 * i]);
                             q1[cb + 2 * i + 1] += hi; q2[cb + 2 * i + 1] = fmaf(hi, hi, q2[cb + 2 * i + 1]);
                         }
-                        uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + cb);
-                        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        if (!staged) {
+                            uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out) + row_off + cb);
+                            o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        }
+                    }
+                    if (staged) {
+                        epi_stage_put<RB>(stile, lane, cb >> 3, w[0], w[1], w[2], w[3]);
+                        epi_stage_put<RB>(stile, lane, (cb >> 3) + 1, w[4], w[5], w[6], w[7]);
                     }
                 } else if (row_ok) {
 #pragma unroll
@@ -537,6 +576,9 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[abuf]);
+            // (after the arrive: the MMAs of the tile after next may start while the rows leave)
+            if (staged && !ACG_DBG(p, 16 | 32))
+                epi_stage_flush<RB>(stile, lane, static_cast<unsigned char*>(p.out), (unsigned long long)row_off * 2ull, row_ok);
         }
         if (p.stats) {      // one reduction over the warp's 32 rows per 16-column chunk, for the whole kernel
 #pragma unroll
@@ -569,12 +611,15 @@ conv_smallk_persistent_kernel(const __grid_constant__ ConvParams cp, int ntiles)
                 const int stage = cnt % kSmallKRing;
                 mbar_wait(&full_bar[stage], (uint32_t)((cnt / kSmallKRing) & 1));
                 tc_fence_after();
-                const uint32_t alo = alo0 + stage * (kStageA >> 4), blo = blo0 + kb * (kStageB >> 4);
+                const uint32_t alo = alo0 + stage * (kStageA >> 4), blo = blo0 + kb * (kStageBN >> 4);
                 if (elect_one()) {
+                    if (!ACG_DBG(p, 4)) {                                          // probe: no MMAs
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        tc_mma2(tacc, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc_commit(&empty_bar[stage]);
+                        for (int k = 0; k < BK / 16; ++k)
+                            tc_mma2(tacc, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if (ACG_DBG(p, 128)) mbar_arrive(&empty_bar[stage]);   // probe (with bit 4): plain arrive, no commit
+                    else tc_commit(&empty_bar[stage]);
                 }
                 __syncwarp();
             }
@@ -1388,6 +1433,7 @@ int apply_split(Params* p, const acg_tc_args* t, const SplitPlan& pl) {
 
 int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char* who) {
     p->dbg_skip = 0;
+    p->direct_store = getenv("ACG_EPI_DIRECT") ? 1 : 0;
 #ifdef ACG_PROBES
     {
         const char* e = getenv("ACG_DBG_SKIP");
@@ -1682,8 +1728,8 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
         const bool epi_ok = !t->bias && t->out_act == ACG_ACT_NONE && !t->red_z && t->ld_out % 8 == 0 &&
                             ((uintptr_t)y & 15) == 0;
         if (nkb <= kSmallKMaxKb && shape_ok && epi_ok && tiles >= 2ll * num_sms() && !getenv("ACG_NO_SMALLK")) {
-            rc = set_smem((const void*)conv_smallk_persistent_kernel<32>, kSmallKSmem);
-            if (!rc) rc = set_smem((const void*)conv_smallk_persistent_kernel<64>, kSmallKSmem);
+            rc = set_smem((const void*)conv_smallk_persistent_kernel<32>, SmallK<32>::kSmem);
+            if (!rc) rc = set_smem((const void*)conv_smallk_persistent_kernel<64>, SmallK<64>::kSmem);
             if (rc) return rc;
             p.splits = 1;
             p.total_ctas = (unsigned int)num_sms();
@@ -1693,10 +1739,10 @@ int acg_conv_fprop_tc(const acg_conv_shape* s, const void* x_bf16, const void* w
             rc = encode_weight_map(&scp.map_b[0], w_pack, (long long)s->KH * s->KW * t->ld_in, N, "acg_conv_fprop_tc");
             if (rc) return rc;
             if (N == 32)
-                launch_pdl(conv_smallk_persistent_kernel<32>, num_sms(), kSmallKThreads, kSmallKSmem,
+                launch_pdl(conv_smallk_persistent_kernel<32>, num_sms(), SmallK<32>::kThreads, SmallK<32>::kSmem,
                            static_cast<cudaStream_t>(stream), scp, (int)tiles);
             else
-                launch_pdl(conv_smallk_persistent_kernel<64>, num_sms(), kSmallKThreads, kSmallKSmem,
+                launch_pdl(conv_smallk_persistent_kernel<64>, num_sms(), SmallK<64>::kThreads, SmallK<64>::kSmem,
                            static_cast<cudaStream_t>(stream), scp, (int)tiles);
             return check_launch("acg_conv_fprop_tc(small K, persistent)");
         }

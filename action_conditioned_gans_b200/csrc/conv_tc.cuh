@@ -57,6 +57,7 @@ struct Params {
     // data parallel (optional): the last CTA sums the totals over the ranks before finalising (peer.cuh); px.world == 0: off
     PeerExchange px;
     int dbg_skip;               // probe library only (-DACG_PROBES, env ACG_DBG_SKIP): see ACG_DBG below
+    int direct_store;           // A/B switch ACG_EPI_DIRECT: every thread stores its own row (no warp-local transposition)
 };
 // Profiling probes (per-phase timing, pipelines with one stage switched off) exist only in libacg_b200_probe.so, which
 // scripts/ load explicitly; in the product library ACG_DBG() is a compile-time false and the code below it vanishes.
@@ -97,6 +98,44 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
     }
     z += __shfl_xor_sync(0xffffffffu, z, 1);
     return z;
+}
+
+// ---- warp-local transposed stores ----------------------------------------------------------------------------------
+// In every epilogue one THREAD owns one output row (tcgen05.ld 32x32b), so a warp-wide 16-byte store touches 32 different
+// 128-byte lines and the L1 tag stage -- shared with the cp.async gather of the same SM -- takes ~2 clk per line: the
+// 33 MB of d/conv1's output cost ~15 us of it.  Here every lane first parks the 16-byte chunks of ITS row in a per-warp
+// shared-memory tile (32 rows x RB bytes, RB = 64 or 128; chunk index XOR-ed with row bits so that both the row-wise
+// writes and the chunk-wise reads are bank-conflict free), then the warp stores the tile so that RB/16 consecutive lanes
+// write the RB contiguous bytes of one row: 4 (RB = 128) or 8 (RB = 64) lines per instruction instead of 32.
+constexpr int kEpiStageBytes = 32 * 128;           // per epilogue warp
+template <int RB> __device__ __forceinline__ uint32_t epi_stage_addr(uint32_t tile, int row, int chunk) {
+    static_assert(RB == 64 || RB == 128, "staging rows are 64 or 128 bytes");
+    if (RB == 128) return tile + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+    return tile + (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4);
+}
+template <int RB> __device__ __forceinline__ void epi_stage_put(uint32_t tile, int lane, int chunk, uint32_t a, uint32_t b,
+                                                                uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(epi_stage_addr<RB>(tile, lane, chunk)), "r"(a), "r"(b),
+                 "r"(c), "r"(d) : "memory");
+}
+// out_bytes: the tensor's base + the byte offset of the tile's first column; row_off_bytes: byte offset of THIS lane's row
+// (any value when !row_ok).  All 32 lanes must call.
+template <int RB> __device__ __forceinline__ void epi_stage_flush(uint32_t tile, int lane, unsigned char* out_bytes,
+                                                                  unsigned long long row_off_bytes, bool row_ok) {
+    constexpr int LPR = RB / 16, RPI = 32 / LPR;        // lanes per row, rows per store instruction
+    const unsigned long long mine = row_ok ? row_off_bytes : ~0ull;
+    __syncwarp();
+    const int sub = lane / LPR, c = lane % LPR;
+#pragma unroll
+    for (int i = 0; i < 32 / RPI; ++i) {
+        const int r = i * RPI + sub;
+        const unsigned long long ro = __shfl_sync(0xffffffffu, mine, r);
+        uint32_t v0, v1, v2, v3;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(epi_stage_addr<RB>(tile, r, c)));
+        if (ro != ~0ull) *reinterpret_cast<uint4*>(out_bytes + ro + c * 16) = make_uint4(v0, v1, v2, v3);
+    }
+    __syncwarp();       // the tile may be refilled
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {

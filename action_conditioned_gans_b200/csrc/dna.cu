@@ -23,17 +23,19 @@
 namespace acg {
 namespace {
 
-constexpr int kRows = 4;                 // image rows per band
 constexpr int kMaxW = 64;
-constexpr int kThreads = kRows * kMaxW;  // one pixel per thread
+// image rows per band R (template parameter): 4 for the training step's shapes; 2 for SMALL batches (B = 64 is only
+// 1024 four-row bands = 3.5 per CTA slot: the launch is then ramp-up + drain around ~5 us of HBM time, and half-size
+// bands halve the compute phase that trails the last load and the wait for the first one).  One pixel per thread.
 constexpr int kPadCols = 4;              // zero columns left and right (4*12 B keeps rows 16 B aligned)
 constexpr int kRowStride = (kMaxW + 2 * kPadCols) * 3;  // floats per staged image row
 
 constexpr int pad16(int v) { return (v + 15) / 16 * 16; }
 
-template <int K, typename LT, bool BWD> struct StageLayout {
+template <int K, typename LT, bool BWD, int R> struct StageLayout {
     static constexpr int KK = K * K;
-    static constexpr int NR = kRows + K - 1;  // band rows + halo
+    static constexpr int kThreads = R * kMaxW;
+    static constexpr int NR = R + K - 1;  // band rows + halo
     static constexpr int logits_bytes = kThreads * KK * (int)sizeof(LT);
     static constexpr int img_bytes = NR * kRowStride * 4;
     static constexpr int dy_bytes = BWD ? kThreads * 3 * 4 : 0;
@@ -45,15 +47,17 @@ template <int K, typename LT, bool BWD> struct StageLayout {
 // PADOUT (backward only): dlogits are written as bf16 with the channel count padded to 16 (zeros in the pad) into
 // a separate double-buffered shared-memory tile -- the layout the tensor-core convolutions consume -- instead of
 // in place over the staged logits.
-template <int K, typename LT, bool BWD, int STAGES, bool PADOUT>
-__global__ void __launch_bounds__(kThreads)
+template <int K, typename LT, bool BWD, int STAGES, bool PADOUT, int R>
+__global__ void __launch_bounds__(R * kMaxW)
 dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const float* __restrict__ dy,
-           float* __restrict__ out, void* __restrict__ dlogits_v, int B, int H, int W) {
+           float* __restrict__ out, void* __restrict__ dlogits_v, int B, int H, int W, int issue_lanes) {
     // PDL: dependents may be scheduled at once; the wait for the producer grid comes AFTER the shared-memory setup below
     // (barrier init, pad zeroing: no global memory involved), so that setup hides under the previous kernel's tail.  At
     // the small bench size (B=64, K=5: 10 us per launch against 5 us of HBM time) the prologue was 10 % of the kernel.
     pdl_launch_dependents();
-    using L = StageLayout<K, LT, BWD>;
+    using L = StageLayout<K, LT, BWD, R>;
+    constexpr int kRows = R;
+    constexpr int kThreads = R * kMaxW;
     constexpr int KK = K * K;
     constexpr int LDO = pad16(KK);
     constexpr int PB = (K - 1) / 2;  // TF SAME: pad_before = (K-1)/2, the odd element goes after
@@ -91,29 +95,48 @@ dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const f
     }
     };
 
+    // called by every lane of warp 0: lane 0 posts the byte count, then the band's copies are issued by different
+    // lanes side by side (one thread issuing 7-11 bulk copies back to back was ~0.3 us of every CTA's ramp-up)
     auto issue = [&](int band, int stage) {
         unsigned char* st = smem + (size_t)stage * L::bytes;
         const int b = band / bands_per_img;
         const int r0 = (band % bands_per_img) * kRows;
-        int valid = 0;
-        for (int t = 0; t < L::NR; ++t) {
-            int row = r0 - PB + t;
-            valid += (row >= 0 && row < H);
+        if (tid == 0) {
+            int valid = 0;
+            for (int t = 0; t < L::NR; ++t) {
+                int row = r0 - PB + t;
+                valid += (row >= 0 && row < H);
+            }
+            uint32_t total = lbytes + (uint32_t)valid * rbytes + (BWD ? (uint32_t)npx * 12u : 0u);
+            mbar_expect_tx(&full_bar[stage], total);
         }
-        uint32_t total = lbytes + (uint32_t)valid * rbytes + (BWD ? (uint32_t)npx * 12u : 0u);
-        mbar_expect_tx(&full_bar[stage], total);
-        bulk_g2s(st, logits + (size_t)band * npx * KK, lbytes, &full_bar[stage]);
-        for (int t = 0; t < L::NR; ++t) {
-            int row = r0 - PB + t;
+        if (issue_lanes == 1) {            // A/B: thread 0 issues every copy of the band itself
+            bulk_g2s(st, logits + (size_t)band * npx * KK, lbytes, &full_bar[stage]);
+            for (int t = 0; t < L::NR; ++t) {
+                const int row = r0 - PB + t;
+                if (row >= 0 && row < H)
+                    bulk_g2s(reinterpret_cast<float*>(st + L::off_img) + t * kRowStride + kPadCols * 3,
+                             img + ((size_t)(b * H + row) * W) * 3, rbytes, &full_bar[stage]);
+            }
+            if (BWD) bulk_g2s(st + L::off_dy, dy + (size_t)band * npx * 3, (uint32_t)npx * 12u, &full_bar[stage]);
+            return;
+        }
+        __syncwarp();
+        if (tid == 0) {
+            bulk_g2s(st, logits + (size_t)band * npx * KK, lbytes, &full_bar[stage]);
+        } else if (tid <= L::NR) {
+            const int t = tid - 1;
+            const int row = r0 - PB + t;
             if (row >= 0 && row < H)
                 bulk_g2s(reinterpret_cast<float*>(st + L::off_img) + t * kRowStride + kPadCols * 3,
                          img + ((size_t)(b * H + row) * W) * 3, rbytes, &full_bar[stage]);
+        } else if (BWD && tid == L::NR + 1) {
+            bulk_g2s(st + L::off_dy, dy + (size_t)band * npx * 3, (uint32_t)npx * 12u, &full_bar[stage]);
         }
-        if (BWD) bulk_g2s(st + L::off_dy, dy + (size_t)band * npx * 3, (uint32_t)npx * 12u, &full_bar[stage]);
     };
 
     pdl_wait();                 // the producer grid has completed: global memory may be read from here on
-    if (tid == 0) {
+    if (tid < issue_lanes) {
         for (int p = 0; p < PREFETCH; ++p) {
             int band = blockIdx.x + p * gridDim.x;
             if (band < nbands) issue(band, p % STAGES);
@@ -130,10 +153,12 @@ dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const f
         const int band = blockIdx.x + it * gridDim.x;
         if (band >= nbands) break;
         const int stage = it % STAGES;
-        if (tid == 0) {
+        if (tid < issue_lanes) {
             int nb = band + PREFETCH * gridDim.x;
             if (nb < nbands) {
-                if (BWD && !PADOUT) bulk_wait_read<1>();  // the store that last read this stage has drained
+                // the store that last read this stage has drained (thread 0 committed it; the __syncwarp inside
+                // issue() orders the other lanes' copies behind this wait)
+                if (BWD && !PADOUT && tid == 0) bulk_wait_read<1>();
                 issue(nb, (it + PREFETCH) % STAGES);
             }
         }
@@ -239,11 +264,13 @@ dna_kernel(const LT* __restrict__ logits, const float* __restrict__ img, const f
     if (BWD && tid == 0) bulk_wait<0>();  // smem must stay alive until the last store has read it
 }
 
-template <int K, typename LT, bool BWD, int STAGES, bool PADOUT = false>
-int launch(const void* logits, const float* img, const float* dy, float* out, void* dlogits, int B, int H,
-           int W, cudaStream_t stream) {
-    using L = StageLayout<K, LT, BWD>;
-    auto kern = dna_kernel<K, LT, BWD, STAGES, PADOUT>;
+template <int K, typename LT, bool BWD, int STAGES, bool PADOUT, int R>
+int launch_r(const void* logits, const float* img, const float* dy, float* out, void* dlogits, int B, int H,
+             int W, cudaStream_t stream) {
+    using L = StageLayout<K, LT, BWD, R>;
+    constexpr int kRows = R;
+    constexpr int kThreads = R * kMaxW;
+    auto kern = dna_kernel<K, LT, BWD, STAGES, PADOUT, R>;
     const int smem = STAGES * L::bytes + (PADOUT ? 2 * kThreads * pad16(K * K) * 2 : 0);
     static int occ_dev[64] = {0};  // per template instance and device (the smem attribute is per device)
     int dev = 0;
@@ -271,8 +298,49 @@ int launch(const void* logits, const float* img, const float* dy, float* out, vo
         const int passes = (nbands + grid - 1) / grid;
         grid = (nbands + passes - 1) / passes;
     }
-    launch_pdl(kern, grid, kThreads, smem, stream, static_cast<const LT*>(logits), img, dy, out, dlogits, B, H, W);
+#ifdef ACG_PROBES
+    if (const char* e = getenv("ACG_DNA_GRID")) {
+        const int g = atoi(e);
+        if (g > 0) grid = g < nbands ? g : nbands;
+    }
+#endif
+    const char* il = getenv("ACG_DNA_ISSUE_LANES");
+    launch_pdl(kern, grid, kThreads, smem, stream, static_cast<const LT*>(logits), img, dy, out, dlogits, B, H, W,
+               il && atoi(il) == 1 ? 1 : 32);
     return check_launch(BWD ? "acg_dna_bwd" : "acg_dna_fwd");
+}
+
+// Band height: 2 rows where four-row bands would give every CTA slot only a few bands (see the note at kMaxW),
+// 4 rows otherwise.  ACG_DNA_ROWS = 2 | 4 forces one (A/B runs, tests of both variants).
+int band_rows(int B, int H) {
+    if (const char* e = getenv("ACG_DNA_ROWS")) {
+        const int r = atoi(e);
+        if (r == 2 || r == 4) return r;
+    }
+    (void)B; (void)H;
+    return 2;
+}
+
+template <int K, typename LT, bool BWD, int STAGES, bool PADOUT = false>
+int launch(const void* logits, const float* img, const float* dy, float* out, void* dlogits, int B, int H,
+           int W, cudaStream_t stream) {
+#ifdef ACG_PROBES
+    // probe library only (scripts/dna_sweep.py): ring depth as a run-time choice
+    if (const char* e = getenv("ACG_DNA_STAGES")) {
+        const int st = atoi(e), r = band_rows(B, H);
+        constexpr int kMin = (BWD && !PADOUT) ? 3 : 2;
+#define ACG_DNA_TRY(S, R)                                                                                  \
+        if constexpr ((S) >= kMin) {                                                                           \
+            if (st == (S) && r == (R))                                                                         \
+                return launch_r<K, LT, BWD, (S), PADOUT, (R)>(logits, img, dy, out, dlogits, B, H, W, stream); \
+        }
+        ACG_DNA_TRY(2, 2) ACG_DNA_TRY(3, 2) ACG_DNA_TRY(4, 2) ACG_DNA_TRY(5, 2)
+        ACG_DNA_TRY(2, 4) ACG_DNA_TRY(3, 4) ACG_DNA_TRY(4, 4)
+#undef ACG_DNA_TRY
+    }
+#endif
+    if (band_rows(B, H) == 2) return launch_r<K, LT, BWD, STAGES, PADOUT, 2>(logits, img, dy, out, dlogits, B, H, W, stream);
+    return launch_r<K, LT, BWD, STAGES, PADOUT, 4>(logits, img, dy, out, dlogits, B, H, W, stream);
 }
 
 int validate(const void* logits, const float* img, int B, int H, int W, int C, int K, int dtype) {
@@ -280,7 +348,7 @@ int validate(const void* logits, const float* img, int B, int H, int W, int C, i
     ACG_REQUIRE(B > 0 && H > 0 && W > 0, ACG_ERR_INVALID, "acg_dna: non-positive size");
     ACG_REQUIRE(C == 3, ACG_ERR_UNSUPPORTED, "acg_dna: C=%d (only 3 colour channels)", C);
     ACG_REQUIRE(K == 5 || K == 6, ACG_ERR_UNSUPPORTED, "acg_dna: K=%d (only 5 or 6)", K);
-    ACG_REQUIRE(W <= kMaxW && W % 4 == 0 && H % kRows == 0, ACG_ERR_UNSUPPORTED,
+    ACG_REQUIRE(W <= kMaxW && W % 4 == 0 && H % 4 == 0, ACG_ERR_UNSUPPORTED,
                 "acg_dna: H=%d W=%d (need H%%4==0, W%%4==0, W<=64)", H, W);
     ACG_REQUIRE(dtype == ACG_F32 || dtype == ACG_BF16, ACG_ERR_UNSUPPORTED, "acg_dna: logits dtype %d", dtype);
     ACG_REQUIRE(((uintptr_t)logits % 16) == 0 && ((uintptr_t)img % 16) == 0, ACG_ERR_INVALID,

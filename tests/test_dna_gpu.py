@@ -16,10 +16,12 @@ def _inputs(B, H, W, K, seed, scale=3.0):
     return logits, img, dy
 
 
+@pytest.mark.parametrize("rows", ["2", "4"])     # both band heights of the kernel (ACG_DNA_ROWS; default: by batch size)
 @pytest.mark.parametrize("K", [5, 6])
 @pytest.mark.parametrize("B,H,W", [(1, 4, 4), (2, 8, 16), (3, 64, 64), (5, 12, 64)])
-def test_dna_fwd_bwd_vs_oracle(cuda, K, B, H, W):
+def test_dna_fwd_bwd_vs_oracle(cuda, monkeypatch, rows, K, B, H, W):
     from action_conditioned_gans_b200 import kernels as Kn
+    monkeypatch.setenv("ACG_DNA_ROWS", rows)
     logits, img, dy = _inputs(B, H, W, K, seed=100 + K + B)
     ref = np_ref.dna_forward(logits.astype(np.float64), img.astype(np.float64), K)
     ref_b = np_ref.dna_backward(logits.astype(np.float64), img.astype(np.float64), dy.astype(np.float64), K)
@@ -124,10 +126,12 @@ def test_dna_rejects_bad_arguments(cuda):
         Kn.dna_fwd(lg.cpu(), img, out, 5)                # no CPU path
 
 
+@pytest.mark.parametrize("rows", ["2", "4"])
 @pytest.mark.parametrize("K", [5, 6])
-def test_dna_bwd_padded_bf16_output(cuda, K):
+def test_dna_bwd_padded_bf16_output(cuda, monkeypatch, rows, K):
     """dlogits written as bf16 rows of ru16(K*K) channels with zero pad channels (the dz operand of g/tconv4)."""
     from action_conditioned_gans_b200 import kernels as Kn
+    monkeypatch.setenv("ACG_DNA_ROWS", rows)
     B, H, W = 3, 16, 64
     logits, img, dy = _inputs(B, H, W, K, seed=21)
     ref_b = np_ref.dna_backward(logits.astype(np.float64), img.astype(np.float64), dy.astype(np.float64), K)
