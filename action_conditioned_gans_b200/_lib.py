@@ -74,6 +74,8 @@ SIGNATURES = {
     "acg_bn_finalize": [_P, _P, _L, _I, _I, _F, _P, _P, _P, _P, _P],
     "acg_bn_act_fwd": [_P, _I, _L, _I, _I, _I, _P, _P, _I, _P, _I, _I, _P],
     "acg_bn_act_fwd_cat": [_P, _I, _L, _I, _I, _P, _P, _I, _P, _I, _I, _P, _I, _I, _I, _P],
+    "acg_bn_finalize_act_fwd_ok": [_I, _I, _I, _I],
+    "acg_bn_finalize_act_fwd": [_P, _L, _I, _I, _P, _P, _P, _L, _F, _P, _P, _P, _P, _I, _P, _I, _P, _I, _I, _I, _P],
     "acg_bn_act_bwd_reduce": [_P, _P, _I, _I, _P, _I, _I, _L, _I, _I, _P, _P, _P, _I, _P, _P],
     "acg_bn_act_bwd_reduce_sync": [_P, _P, _I, _I, _P, _I, _I, _L, _I, _P, _P, _P, _I, _P, _P, _P, _P],
     "acg_bn_act_bwd_apply": [_P, _P, _I, _I, _P, _I, _I, _L, _I, _I, _P, _P, _P, _I, _I, _P, _P, _I, _I, _P, _L, _F,

@@ -81,6 +81,22 @@ __device__ __forceinline__ void pdl_prologue() {
     pdl_launch_dependents();
     pdl_wait();
 }
+// slim.batch_norm (scale=False, eps inside the sqrt, biased variance) from the per-channel totals; ONE definition so that
+// the in-kernel finalize of the convolutions and the finalize inside the activation pass give the same bits.
+__device__ __forceinline__ void bn_finalize_channel(double sum, double sumsq, double inv_rows, float eps, float beta,
+                                                    float* mean, float* rstd, float* shift) {
+    const double mu = sum * inv_rows;
+    double var = sumsq * inv_rows - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float rs = (float)(1.0 / sqrt(var + (double)eps));
+    *mean = (float)mu;
+    *rstd = rs;
+    *shift = beta - (float)mu * rs;
+}
+// value of one integer-limb accumulator triple (conv_tc.cuh fix_add): H * 2^24 + M * 2^-8 + L * 2^-40
+__device__ __forceinline__ double limbs_to_double(unsigned long long h, unsigned long long m, unsigned long long l) {
+    return (double)(long long)h * 0x1p24 + ((double)m * 0x1p-8 + (double)l * 0x1p-40);
+}
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>

@@ -118,9 +118,12 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
             const int stage = kb % kPxStages;
             if (kb >= kPxStages) mbar_wait(&empty_bar[stage], (uint32_t)(((kb / kPxStages) - 1) & 1));
             if (elect_one()) {
-                mbar_expect_tx(&full_bar[stage], tx);
-                tma_load_4d(smemA + stage * kStageA, &pp.map_a, ch * BK, tap_x[t], tap_y[t], b0, &full_bar[stage]);
-                tma_load_2d(smemB + stage * kStageB, bmap, tap_k[t] + ch * BK, n0, &full_bar[stage]);
+                // probe bits 1 / 2: no activation / no weight traffic
+                const uint32_t txa = ACG_DBG(p, 1) ? 0u : (uint32_t)kStageA, txb = ACG_DBG(p, 2) ? 0u : tx - (uint32_t)kStageA;
+                if (txa + txb == 0u) mbar_arrive(&full_bar[stage]);
+                else mbar_expect_tx(&full_bar[stage], txa + txb);
+                if (txa) tma_load_4d(smemA + stage * kStageA, &pp.map_a, ch * BK, tap_x[t], tap_y[t], b0, &full_bar[stage]);
+                if (txb) tma_load_2d(smemB + stage * kStageB, bmap, tap_k[t] + ch * BK, n0, &full_bar[stage]);
             }
             __syncwarp();
             if (++ch == pp.kchunks) { ch = 0; ++t; }
@@ -139,8 +142,9 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
             const uint32_t alo = alo0 + stage * (kStageA >> 4), blo = blo0 + stage * (kStageB >> 4);
             const int nk = ch == pp.kchunks - 1 ? pp.nk16_last : BK / 16;
             if (elect_one()) {
-                for (int k = 0; k < nk; ++k)
-                    tc_mma2(tmem_u, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                if (!ACG_DBG(p, 4))                                                // probe: no MMAs
+                    for (int k = 0; k < nk; ++k)
+                        tc_mma2(tmem_u, alo + 2 * k, hi, blo + 2 * k, hi, idesc, (kb | k) != 0 ? 1u : 0u);
                 tc_commit(&empty_bar[stage]);
             }
             __syncwarp();

@@ -1486,11 +1486,12 @@ int fill_bn(Params* p, const acg_tc_args* t, unsigned int total_ctas, const char
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: remember (kernel, device) pairs, so a
 // process that drives several GPUs sets it on each of them.
-// reproducible moments: use the caller's limb accumulators when a ticket exists (the last CTA converts them)
+// reproducible moments: the caller's limb accumulators.  With a ticket the last CTA converts them into `stats` and
+// leaves them zeroed; WITHOUT one the launch only adds its limbs (fire and forget: no fence, no ticket, no last-CTA
+// pass) and whoever consumes the moments completes them (acg_bn_finalize_act_fwd) and zeroes the accumulators.
 void set_stats_fix(Params* p, const acg_tc_args* t) {
     p->stats_fix = nullptr;
-    if (p->stats && p->counter && !p->rz && t->stats_fix && t->stats_fix_len >= 6LL * p->n_stat &&
-        ((uintptr_t)t->stats_fix & 7) == 0)
+    if (p->stats && !p->rz && t->stats_fix && t->stats_fix_len >= 6LL * p->n_stat && ((uintptr_t)t->stats_fix & 7) == 0)
         p->stats_fix = t->stats_fix;
 }
 

@@ -438,11 +438,10 @@ __device__ __forceinline__ void cta_stats_finish(const Params& p, int tid, int n
     if (p.stats_fix) {
         for (int c = tid; c < ncols; c += nthreads) {
             unsigned long long* a = p.stats_fix + c;
-            const long long H = (long long)__ldcg(a);
-            const unsigned long long M = __ldcg(a + ncols), L = __ldcg(a + 2 * ncols);
+            const unsigned long long H = __ldcg(a), M = __ldcg(a + ncols), L = __ldcg(a + 2 * ncols);
             a[0] = 0ull; a[ncols] = 0ull; a[2 * ncols] = 0ull;
             // p.stats[c] is zero on entry unless a non-finite value was added to it
-            p.stats[c] = __ldcg(&p.stats[c]) + ((double)H * 0x1p24 + ((double)M * 0x1p-8 + (double)L * 0x1p-40));
+            p.stats[c] = __ldcg(&p.stats[c]) + limbs_to_double(H, M, L);
         }
         __threadfence();
         __syncthreads();
@@ -451,15 +450,13 @@ __device__ __forceinline__ void cta_stats_finish(const Params& p, int tid, int n
     if (p.bn_rows > 0) {
         const double inv = 1.0 / (double)p.bn_rows;
         for (int c = tid; c < p.n_bias; c += nthreads) {
-            const double mu = __ldcg(&p.stats[c]) * inv;
-            double var = __ldcg(&p.stats[p.n_bias + c]) * inv - mu * mu;
-            if (var < 0.0) var = 0.0;
-            const float rs = (float)(1.0 / sqrt(var + (double)p.bn_eps));
-            const float b = p.beta ? p.beta[c] : 0.f;
-            p.bn_mean[c] = (float)mu;
+            float mu, rs, sh;
+            bn_finalize_channel(__ldcg(&p.stats[c]), __ldcg(&p.stats[p.n_bias + c]), inv, p.bn_eps,
+                                p.beta ? p.beta[c] : 0.f, &mu, &rs, &sh);
+            p.bn_mean[c] = mu;
             p.bn_rstd[c] = rs;
             p.bn_scale[c] = rs;
-            p.bn_shift[c] = b - (float)mu * rs;
+            p.bn_shift[c] = sh;
         }
     }
     if (tid == 0) *p.counter = 0u;   // ready for the next launch

@@ -704,27 +704,65 @@ template <int ACT> __device__ __forceinline__ float act_fwd_t(float u) {
     return u;
 }
 
+// RAW moments of a convolution launch (acg_bn_finalize_act_fwd): fp64 totals [2][C] (+ optional integer limb accumulators
+// [3][2][C], conv_tc.cuh fix_add) that NO kernel has completed yet.  Every block of the activation pass completes the
+// totals of ITS channels itself (<= 256 channels: one thread each) -- that replaces the convolution's tail of fence,
+// ticket atomic, last-CTA conversion and finalize (~2-3 us at the end of every launch with fused moments), and the
+// blocks of the first row block export mean / rstd / scale / shift for the backward pass.
+struct RawMoments {
+    const double* stats;                 // [2][C]; zero unless a non-finite value was added
+    const unsigned long long* fix;       // [3][2][C] or NULL
+    const float* beta;                   // [C] or NULL
+    double inv_rows;
+    float eps;
+    float* mean; float* rstd; float* scale; float* shift;     // exported [C]
+};
+
 // a[r] = act(z[r]*scale + shift), bf16 -> bf16, same thread map / row pipelining as the backward kernels
-template <int ACT>
+template <int ACT, bool RAW>
 __global__ void __launch_bounds__(256)
 fast_bn_act_fwd_kernel(const __nv_bfloat16* __restrict__ z, int ld_in, int C, long long rows,
                        const float* __restrict__ scale, const float* __restrict__ shift,
                        __nv_bfloat16* __restrict__ out, int ld_out, int rev,
-                       const float* __restrict__ acts, int n_act, int hw, int act_off) {
+                       const float* __restrict__ acts, int n_act, int hw, int act_off, RawMoments rm) {
     pdl_prologue();
     const int bx = blockDim.x, by = blockDim.y;
     const int cv = blockIdx.x * bx + threadIdx.x;
+    __shared__ float s_sc[RAW ? 256 : 1], s_sh[RAW ? 256 : 1];
+    if (RAW) {
+        const int tid = threadIdx.y * bx + threadIdx.x;
+        const int ch = blockIdx.x * bx * 8 + tid;
+        if (tid < bx * 8 && ch < C) {
+            double s0 = __ldcg(rm.stats + ch), s1 = __ldcg(rm.stats + C + ch);
+            if (rm.fix) {
+                const unsigned long long* a = rm.fix + ch;
+                s0 += limbs_to_double(__ldcg(a), __ldcg(a + 2 * C), __ldcg(a + 4 * C));
+                s1 += limbs_to_double(__ldcg(a + C), __ldcg(a + 3 * C), __ldcg(a + 5 * C));
+            }
+            float mu, rs, sh_;
+            bn_finalize_channel(s0, s1, rm.inv_rows, rm.eps, rm.beta ? rm.beta[ch] : 0.f, &mu, &rs, &sh_);
+            s_sc[tid] = rs;
+            s_sh[tid] = sh_;
+            if (blockIdx.y == 0) { rm.mean[ch] = mu; rm.rstd[ch] = rs; rm.scale[ch] = rs; rm.shift[ch] = sh_; }
+        }
+        __syncthreads();
+    }
     if (cv >= (C >> 3)) return;
     const int c = cv * 8;
     float sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { sc[i] = 1.f; sh[i] = 0.f; }
+    if (RAW) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sc[i] = s_sc[threadIdx.x * 8 + i]; sh[i] = s_sh[threadIdx.x * 8 + i]; }
+    } else {
     if (scale) { const F8 t = load8f(scale, c);
 #pragma unroll
         for (int i = 0; i < 8; ++i) sc[i] = t.v[i]; }
     if (shift) { const F8 t = load8f(shift, c);
 #pragma unroll
         for (int i = 0; i < 8; ++i) sh[i] = t.v[i]; }
+    }
     const long long rstep = (long long)gridDim.y * by;
     for (long long r0 = (long long)blockIdx.y * by + threadIdx.y; r0 < rows; r0 += rstep * kFastU) {
         uint4 zr[kFastU];
@@ -920,9 +958,10 @@ static int bn_act_fwd_impl(const void* z, int z_dtype, long long rows, int C, in
             const __nv_bfloat16* zz = static_cast<const __nv_bfloat16*>(z);
             __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
             fast_launch_dims(rows, C, 4, false, &grid, &block);
-            if (act == ACG_ACT_RELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_RELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1, acts, n_act, hw, act_off);
-            else if (act == ACG_ACT_LRELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_LRELU>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1, acts, n_act, hw, act_off);
-            else launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_NONE>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1, acts, n_act, hw, act_off);
+            const RawMoments none{};
+            if (act == ACG_ACT_RELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_RELU, false>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1, acts, n_act, hw, act_off, none);
+            else if (act == ACG_ACT_LRELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_LRELU, false>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1, acts, n_act, hw, act_off, none);
+            else launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_NONE, false>, grid, block, 0, st, zz, ld_in, C, rows, scale, shift, oo, ld_out, ew_rev() & 1, acts, n_act, hw, act_off, none);
             return check_launch(who);
         }
         vec_stream_launch_dims(rows / groups, C, groups, 8, &grid, &block);
@@ -948,6 +987,41 @@ int acg_bn_act_fwd_cat(const void* z, int z_dtype, long long rows, int C, int ld
     ACG_REQUIRE(actions, ACG_ERR_INVALID, "acg_bn_act_fwd_cat: null actions");
     return bn_act_fwd_impl(z, z_dtype, rows, C, ld_in, 1, scale, shift, act, out, out_dtype, ld_out, actions, n_act, hw,
                            act_off, stream, "acg_bn_act_fwd_cat");
+}
+
+int acg_bn_finalize_act_fwd_ok(int C, int ld_in, int ld_out, int act) {
+    return C > 0 && C % 8 == 0 && ld_in % 8 == 0 && ld_out % 8 == 0 && ld_in >= C && ld_out >= C &&
+           (act == ACG_ACT_NONE || act == ACG_ACT_RELU || act == ACG_ACT_LRELU) && !getenv("ACG_NO_FAST_EW");
+}
+
+int acg_bn_finalize_act_fwd(const void* z, long long rows, int C, int ld_in, const double* stats,
+                            const unsigned long long* stats_fix, const float* beta, long long norm_rows, float eps,
+                            float* mean, float* rstd, float* scale, float* shift, int act, void* out, int ld_out,
+                            const float* actions, int n_act, int hw, int act_off, void* stream) {
+    using namespace acg;
+    const char* who = "acg_bn_finalize_act_fwd";
+    ACG_REQUIRE(z && out && stats && mean && rstd && scale && shift, ACG_ERR_INVALID, "%s: null pointer", who);
+    ACG_REQUIRE(rows > 0 && norm_rows > 0, ACG_ERR_INVALID, "%s: bad size", who);
+    ACG_REQUIRE(acg_bn_finalize_act_fwd_ok(C, ld_in, ld_out, act), ACG_ERR_UNSUPPORTED,
+                "%s: C=%d ld_in=%d ld_out=%d act=%d (bf16 rows, channel counts in multiples of 8, relu / lrelu / none)", who, C,
+                ld_in, ld_out, act);
+    ACG_REQUIRE(al16(z) && al16(out) && ((uintptr_t)stats & 7) == 0 && ((uintptr_t)stats_fix & 7) == 0, ACG_ERR_INVALID,
+                "%s: misaligned buffer", who);
+    ACG_REQUIRE(!actions || (n_act > 0 && hw > 0 && rows % hw == 0 && act_off >= C && act_off + n_act <= ld_out),
+                ACG_ERR_INVALID, "%s: action concat: %d channels at offset %d of %d, %d pixels per image", who, n_act,
+                act_off, ld_out, hw);
+    dim3 grid, block;
+    fast_launch_dims(rows, C, 4, false, &grid, &block);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const __nv_bfloat16* zz = static_cast<const __nv_bfloat16*>(z);
+    __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
+    RawMoments rm{stats, stats_fix, beta, 1.0 / (double)norm_rows, eps, mean, rstd, scale, shift};
+    const float* nof = nullptr;
+    if (!actions) { n_act = 0; hw = 1; act_off = 0; }
+    if (act == ACG_ACT_RELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_RELU, true>, grid, block, 0, st, zz, ld_in, C, rows, nof, nof, oo, ld_out, ew_rev() & 1, actions, n_act, hw, act_off, rm);
+    else if (act == ACG_ACT_LRELU) launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_LRELU, true>, grid, block, 0, st, zz, ld_in, C, rows, nof, nof, oo, ld_out, ew_rev() & 1, actions, n_act, hw, act_off, rm);
+    else launch_pdl(fast_bn_act_fwd_kernel<ACG_ACT_NONE, true>, grid, block, 0, st, zz, ld_in, C, rows, nof, nof, oo, ld_out, ew_rev() & 1, actions, n_act, hw, act_off, rm);
+    return check_launch(who);
 }
 
 int acg_bn_act_bwd_reduce(const void* dA, const void* dA2, int d_dtype, int ld_d, const void* z, int z_dtype, int ld_z,

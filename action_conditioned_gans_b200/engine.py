@@ -32,6 +32,8 @@ FUSE_BWD_REDUCE = os.environ.get("ACG_FUSE_BWD_REDUCE", "0")
 # Fused batch-norm moments through integer limb accumulators (order-independent: bitwise reproducible forward pass).
 # "0": fp64 atomics instead (order varies from run to run; kept to measure what reproducibility costs).
 DETERMINISTIC = os.environ.get("ACG_DETERMINISTIC", "1") != "0"
+# single GPU: batch-norm finalize inside the activation pass instead of the conv launch's last CTA (A/B switch)
+RAW_MOMENTS = os.environ.get("ACG_RAW_MOMENTS", "1") != "0"
 # Data parallel, peer-memory exchange: the conv kernel's last CTA pushes its batch-norm totals to the peers, waits for
 # theirs and finalises over the global batch -- no exchange launch per SyncBN layer.  "0": separate exchange kernel.
 DP_FUSED = os.environ.get("ACG_DP_FUSED", "1") != "0"
@@ -251,8 +253,10 @@ class NetRun:
         self.bf16 = precision == "bf16"
         self.adt = torch.bfloat16 if self.bf16 else torch.float32
         self.layers = {}
-        n_stat = sum(4 * ru16(L.cout) for L in store.spec)
-        self.f64 = torch.zeros(n_stat, dtype=torch.float64, device=device)   # [stats | red] per layer
+        # per layer [stats 2C | red 2C | integer limb accumulators of the fused moments 6C]: ONE buffer, zeroed by one
+        # launch at the start of every forward pass (zero_reductions)
+        n_stat = sum(10 * ru16(L.cout) for L in store.spec)
+        self.f64 = torch.zeros(n_stat, dtype=torch.float64, device=device)
         # "last CTA" tickets of the conv kernels, one per layer (layers of one network may run concurrently)
         self.counters = torch.zeros(2 * len(store.spec), dtype=torch.int32, device=device)
         # side streams: weight gradients (no collective inside -> also with data parallelism) and a second chain
@@ -272,7 +276,8 @@ class NetRun:
             cp = ru16(L.cout)
             st.stats = self.f64[soff:soff + 2 * cp]
             st.red = self.f64[soff + 2 * cp:soff + 4 * cp]
-            soff += 4 * cp
+            st.fix_view = self.f64[soff + 4 * cp:soff + 10 * cp].view(torch.int64)
+            soff += 10 * cp
             st.mean = torch.zeros(L.cout, device=device)
             st.rstd = torch.ones(L.cout, device=device)
             st.scale = torch.ones(L.cout, device=device)
@@ -328,7 +333,7 @@ class NetRun:
             st.splitk_b = K.splitk_workspace(st.shape, bwd_w, st.ldz, self.device) if dx else None
             # integer limb accumulators of the fused batch-norm moments (order-independent atomics): the forward pass
             # is bitwise reproducible (ACG_DETERMINISTIC=0: fp64 atomics, for A/B timing only)
-            st.stats_fix = K.stats_accumulators(ru16(L.cout), self.device) if L.bn and DETERMINISTIC else None
+            st.stats_fix = st.fix_view if L.bn and DETERMINISTIC else None
         if self.bf16 and name not in self.store.packs:
             # forward / backward-data packs; conv2d_transpose swaps the roles (see include/acg_b200.h)
             fwd_which, bwd_which = (0, 1) if L.kind == "conv" else (1, 0)
@@ -382,6 +387,14 @@ class NetRun:
         if L.bn and self.bf16:
             # moments in the conv epilogue; on one GPU the last CTA also finalises mean / rstd / scale / shift
             beta = self.store.views[name + "/BatchNorm/beta"]
+            if self.dp is None and RAW_MOMENTS and K.bn_finalize_act_fwd_ok(L.cout, st.ldz, ld_out, L.act):
+                # the conv launch only ADDS its moments (no ticket, no last-CTA pass at its end); the activation pass
+                # completes and finalises them per block (~2.8 us less per layer than the in-kernel finalize below)
+                self._conv_fwd(st, x, st.z, st.ldz, stats=st.stats)
+                K.bn_finalize_act_fwd(st.z, st.rows, L.cout, st.ldz, st.stats, st.stats_fix, beta, st.rows, BN_EPS,
+                                      st.mean, st.rstd, st.scale, st.shift, L.act, out, ld_out, cat=cat,
+                                      hw=st.out_hw[0] * st.out_hw[1])
+                return
             if self.dp is None:
                 self._conv_fwd(st, x, st.z, st.ldz, stats=st.stats,
                                bn=(st.counter, beta, st.mean, st.rstd, st.scale, st.shift, st.rows, BN_EPS))

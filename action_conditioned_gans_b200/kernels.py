@@ -195,6 +195,19 @@ def bn_act_fwd_cat(z, rows, Cc, ld_in, scale, shift, act, out, ld_out, actions, 
          dtype_id(out), ld_out, ptr(actions), actions.shape[1], hw, act_off, stream())
 
 
+def bn_finalize_act_fwd_ok(Cc, ld_in, ld_out, act):
+    return bool(_lib.load().acg_bn_finalize_act_fwd_ok(Cc, ld_in, ld_out, ACT_IDS[act]))
+
+
+def bn_finalize_act_fwd(z, rows, Cc, ld_in, stats, stats_fix, beta, norm_rows, eps, mean, rstd, scale, shift, act, out,
+                        ld_out, cat=None, hw=1):
+    """batch-norm finalize + activation from the RAW moments of a conv launch without a ticket; cat = (actions, offset)"""
+    acts, off = cat if cat is not None else (None, 0)
+    call("acg_bn_finalize_act_fwd", ptr(z), rows, Cc, ld_in, ptr(stats), ptr(stats_fix), ptr(beta), norm_rows, eps,
+         ptr(mean), ptr(rstd), ptr(scale), ptr(shift), ACT_IDS[act], ptr(out), ld_out, ptr(acts),
+         acts.shape[1] if acts is not None else 0, hw, off, stream())
+
+
 def bn_act_bwd_reduce(dA, dA2, ld_d, z, ld_z, rows, Cc, groups, mean, rstd, shift, act, red):
     call("acg_bn_act_bwd_reduce", ptr(dA), ptr(dA2), dtype_id(dA), ld_d, ptr(z), dtype_id(z) if z is not None else 0,
          ld_z, rows, Cc,

@@ -144,7 +144,9 @@ typedef struct acg_tc_args {
     /* optional: compute only the first n_limit output channels (0 = all).  The data gradient w.r.t. a concat buffer
      * whose tail is the tiled action map (models.py:16,38,84) is only needed for the feature channels. */
     int n_limit;
-    /* optional: run-to-run reproducible moments.  With a ticket (bn_counter) AND stats_fix -- 6*C uint64 integer
+    /* optional: run-to-run reproducible moments.  stats_fix WITHOUT a ticket: the launch only adds its limbs and
+     * acg_bn_finalize_act_fwd completes them (caller zeroes the accumulators before the launch).
+     * With a ticket (bn_counter) AND stats_fix -- 6*C uint64 integer
      * accumulators (stats_fix_len elements >= 6*C), zeroed once by the caller and left zeroed by every launch -- the
      * per-CTA column totals are added as fixed-point limbs with integer atomics (associative: the CTA arrival order
      * does not matter) and the last CTA converts them into `stats` (which must be zero on entry).  Without it: fp64
@@ -230,6 +232,19 @@ int acg_bn_act_fwd(const void* z, int z_dtype, long long rows, int C, int ld_in,
 int acg_bn_act_fwd_cat(const void* z, int z_dtype, long long rows, int C, int ld_in, const float* scale,
                        const float* shift, int act, void* out, int out_dtype, int ld_out, const float* actions,
                        int n_act, int hw, int act_off, void* stream);
+/* slim.batch_norm + activation straight from the RAW moments a convolution launch left behind (models.py:10-11,31-32,
+ * 80-81): `stats` [2][C] fp64 and, optionally, the integer limb accumulators `stats_fix` [3][2][C] of a launch that got
+ * acg_tc_args.stats / stats_fix but NO ticket (bn_counter == NULL: such a launch only adds its limbs -- no fence, no
+ * ticket, no last-CTA pass at its end).  Every block completes the totals of its own channels, finalises them over
+ * norm_rows rows (beta may be NULL), exports mean / rstd / scale / shift [C] for the backward pass and applies
+ * out = act(z*scale + shift); actions != NULL additionally writes the action concat like acg_bn_act_fwd_cat.
+ * bf16 z / out, C % 8 == 0, act in {none, relu, lrelu} (acg_bn_finalize_act_fwd_ok).  The caller zeroes stats AND
+ * stats_fix before the convolution launch (one memset covers every layer of a network). */
+int acg_bn_finalize_act_fwd_ok(int C, int ld_in, int ld_out, int act);
+int acg_bn_finalize_act_fwd(const void* z, long long rows, int C, int ld_in, const double* stats,
+                            const unsigned long long* stats_fix, const float* beta, long long norm_rows, float eps,
+                            float* mean, float* rstd, float* scale, float* shift, int act, void* out, int ld_out,
+                            const float* actions, int n_act, int hw, int act_off, void* stream);
 /* backward, pass 1: dzh = (dA + dA2) * act'(z*scale+shift)   (dA2 may be NULL; it is the second consumer's
  * gradient where the graph forks -- g/tconv2 feeds both g/tconv3 and g/sconv3, models.py:40-53); red[0:C] += sum dzh, red[C:2C] += sum dzh*xhat
  * (xhat = (z-mean)*rstd; fp64, caller zeroes; [groups][2][C]). */

@@ -92,6 +92,21 @@ def test_fused_moments_are_bitwise_reproducible(cuda, case):
        splitk=wsp, stats_fix=short)
     assert float((stats4 - stats).abs().max()) <= 1e-9 * max(1.0, float(stats.abs().max()))
     assert int(counter.item()) == 0 and int(short.abs().sum()) == 0
+    # the same moments WITHOUT a ticket: the launch only adds its limbs (no fence / ticket / last-CTA pass) and the
+    # activation pass completes, finalises and applies them -- same bits as the in-kernel finalize + plain activation pass
+    for act in ("relu", "lrelu", "none"):
+        stats6 = torch.zeros(2 * n_out, dtype=torch.float64, device=cuda)
+        ws.zero_()
+        fin6 = [torch.zeros(n_out, device=cuda) for _ in range(4)]
+        fn(shape, src, pack, out, ld_in, ld_out, stats=stats6, splitk=wsp, stats_fix=ws)
+        assert int(ws.abs().sum()) != 0 and float(stats6.abs().sum()) == 0.0     # limbs only, nobody converted them
+        a = torch.zeros(rows, ld_out, dtype=torch.bfloat16, device=cuda)
+        assert Kn.bn_finalize_act_fwd_ok(n_out, ld_out, ld_out, act)
+        Kn.bn_finalize_act_fwd(out, rows, n_out, ld_out, stats6, ws, beta, rows, 1e-3, *fin6, act, a, ld_out)
+        a_ref = torch.zeros(rows, ld_out, dtype=torch.bfloat16, device=cuda)
+        Kn.bn_act_fwd(out, rows, n_out, ld_out, 1, fin[2], fin[3], act, a_ref, ld_out)
+        assert torch.equal(torch.stack(fin6), fin) and torch.equal(a.view(torch.int16), a_ref.view(torch.int16))
+    ws.zero_()
     # a diverged layer still reads as diverged: inf in the input -> non-finite totals
     bad = src.clone()
     bad.view(-1)[0] = float("inf")
