@@ -61,6 +61,8 @@ struct alignas(64) Halo2Params {
     int nkc, nk16_last;           // 64-channel blocks; K=16 steps of the last block (lda % 64 != 0 -> fewer MMAs)
     int out_H, out_W;             // spatial size of the output tensor
     int npg;                      // CONV form: staged planes per tile (4 parity planes; 2 row planes in the pixel-pair mode)
+    int nbs_cap;                  // weight-ring depth cap (kH2MaxBStages; the probe library reads ACG_H2_NBS)
+    int staged_rb;                // staged epilogue: bytes per staging row (128 / 64), 0 = off
 };
 
 struct H2Tile {
@@ -101,6 +103,29 @@ __device__ __forceinline__ void issue_tap(uint32_t tacc, int N, uint32_t alo_t, 
             tc_mma2(tacc + q * N, alo_t + acc_row8[q] + 2 * k, ahi, blo + 2 * k, bhi, idesc, first | (uint32_t)k);
 }
 
+// Epilogue of one accumulator for the batch-norm layers (bf16 output, moments, no bias / activation) through the warp's
+// staging tile: see epi_stage_put_chunk / epi_stage_moments_flush (conv_tc.cuh).
+template <int RB>
+__device__ __forceinline__ void epilogue_acc_staged(const Params& p, uint32_t tacc_q, int N, uint32_t stile, int lane,
+                                                    size_t row_off, float* sm_sum, float* sm_sq) {
+    constexpr int GC = RB / 2, NCH = GC / 16;           // columns / 16-column chunks per group
+    unsigned char* out = static_cast<unsigned char*>(p.out);
+    for (int g0 = 0; g0 < N; g0 += GC) {
+#pragma unroll
+        for (int i0 = 0; i0 < NCH; i0 += 2) {           // two 16-column TMEM loads in flight per wait
+            uint32_t v[2][16];
+            tmem_ld16_nowait(tacc_q + g0 + 16 * i0, v[0]);
+            tmem_ld16_nowait(tacc_q + g0 + 16 * i0 + 16, v[1]);
+            tmem_ld_wait();
+            epi_stage_put_chunk<RB>(stile, lane, i0, v[0], true);
+            epi_stage_put_chunk<RB>(stile, lane, i0 + 1, v[1], true);
+        }
+        if (ACG_DBG(p, 16)) continue;                                     // probe bit 16: TMEM loads and staging only
+        epi_stage_moments_flush<RB>(stile, lane, out + (size_t)g0 * 2, (unsigned long long)row_off * 2ull, true, true,
+                                    sm_sum + g0, sm_sq + g0);
+    }
+}
+
 template <int NACC>
 __global__ void __launch_bounds__(kH2Threads, 1)
 conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
@@ -130,8 +155,14 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
     // per tap -- so the ring must hold ~8 taps or the tensor pipe idles (3 stages: 1032-1296 clk per tap measured).
     const uint32_t smemB = smemH + NH * halo_stride;
     const uint32_t b_stride = ((uint32_t)N * 128u + 1023u) & ~1023u;
-    int NBS = (int)(((uint32_t)kH2Data - NH * halo_stride) / b_stride);
-    NBS = NBS > kH2MaxBStages ? kH2MaxBStages : NBS;
+    // staged epilogue (batch-norm layers): 8 staging tiles of 32 rows x 128 B (N = 128) or x 64 B at the END of the
+    // operand area.  The ring gives them up for free: a sweep of its depth (scripts/halo_ring_sweep.py) showed no layer
+    // slower at 4 stages than at 8 (g/tconv4's data gradient excepted: +1 us at 5).
+    const uint32_t stage_rb = hp.staged_rb;                    // 0: every thread stores its own row
+    const uint32_t stage_bytes = 8u * 32u * stage_rb;
+    const uint32_t smemE = smem_base + (uint32_t)kH2Data - stage_bytes;
+    int NBS = (int)(((uint32_t)kH2Data - stage_bytes - NH * halo_stride) / b_stride);
+    NBS = NBS > hp.nbs_cap ? hp.nbs_cap : NBS;
     const int NB = (2 * NACC * N <= 512) ? 2 : 1;            // accumulator buffers in tensor memory
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(NB * NACC * N)) tmem_cols <<= 1;
@@ -307,6 +338,14 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
                 if (hp.form == 0) { oy = (oy << 1) + (h.cls >> 1); ox = (ox << 1) + (h.cls & 1); }
                 const size_t pix = (size_t)((h.b0 + tb) * hp.out_H + oy) * hp.out_W + ox;
                 const size_t row_off = pix * p.ldo;
+                if (stage_rb) {
+                    const uint32_t stile = smemE + (uint32_t)ew * 32u * stage_rb;
+                    if (stage_rb == 128u)
+                        epilogue_acc_staged<128>(p, tacc + q * N, N, stile, lane, row_off, &sm_stats[ew][0][0], &sm_stats[ew][1][0]);
+                    else
+                        epilogue_acc_staged<64>(p, tacc + q * N, N, stile, lane, row_off, &sm_stats[ew][0][0], &sm_stats[ew][1][0]);
+                    continue;
+                }
                 // fused batch-norm backward reduction of the layer that consumes this gradient: its pre-activation row
                 const __nv_bfloat16* zrow = p.rz ? p.rz + pix * p.rz_ld : nullptr;
                 for (int cb0 = 0; cb0 < N; cb0 += 16 * kEpiBatch) {
@@ -480,6 +519,13 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
     }
     const int lda = pair ? 2 * t->ld_in : t->ld_in;       // pixel-pair mode: 16-channel pair pixels
     hp.npg = pair ? 2 : 4;
+    hp.nbs_cap = kH2MaxBStages;
+#ifdef ACG_PROBES
+    if (const char* e = getenv("ACG_H2_NBS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= kH2MaxBStages) hp.nbs_cap = v;
+    }
+#endif
     hp.nkc = (lda + 63) / 64;
     hp.nk16_last = ((lda - (hp.nkc - 1) * 64) + 15) / 16;
     hp.out_H = form == 0 ? s->H : s->OH;
@@ -616,6 +662,19 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
     rc = fill_bn(&hp.p, t, (unsigned int)ctas, who);
     if (rc) return rc;
     set_stats_fix(&hp.p, t);
+    // staged epilogue with column-wise moments for the batch-norm layers (ACG_EPI_DIRECT switches it off); the ring keeps
+    // at least 4 stages
+    hp.staged_rb = 0;
+    {
+        const Params& q = hp.p;
+        const bool ok = q.stats && !q.rz && !q.bias && q.out_act == ACG_ACT_NONE && q.out_dtype == ACG_BF16 &&
+                        (q.ldo & 7) == 0 && q.n_store >= N && q.n_stat == N && ((uintptr_t)q.out & 15) == 0 &&
+                        !q.direct_store && !pair;
+        const long long halo_stride = (((long long)hp.TB * hp.rows * (hp.TW + 2) * 128) + 1023) / 1024 * 1024;
+        const long long b_stride = ((long long)N * 128 + 1023) / 1024 * 1024;
+        for (int rb = 128; ok && rb >= 64 && !hp.staged_rb; rb >>= 1)
+            if (N % (rb / 2) == 0 && (kH2Data - 8LL * 32 * rb - 2 * halo_stride) / b_stride >= 4) hp.staged_rb = rb;
+    }
     if (nacc == 1) {
         rc = set_smem((const void*)conv_halo2_kernel<1>, kH2Smem);
         if (rc) return rc;

@@ -23,7 +23,7 @@ namespace tc {
 
 constexpr int kPxStages = 6;
 constexpr int kPxThreads = 192;
-constexpr int kPxSmem = kPxStages * (kStageA + kStageB) + 1024;
+constexpr int kPxSmem = kPxStages * (kStageA + kStageB) + 4 * kEpiStageBytes + 1024;   // + 4 epilogue staging tiles
 constexpr int kPxMaxTaps = 32;
 constexpr int kPxMaxSplits = 4;
 
@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smemA = smem_base, smemB = smem_base + kPxStages * kStageA;
+    const uint32_t smemE = smemB + kPxStages * kStageB;        // per epilogue warp: 32 rows x 128 B staging tile
     for (int i = tid; i < 4 * 2 * BN; i += kPxThreads) (&sm_stats[0][0][0])[i] = 0.f;
 
     // ---- geometry of this CTA: output pixel (py, px), images [b0, b0 + 128), columns [n0, n0 + n_cta) ----
@@ -196,6 +197,24 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
         const int b = b0 + warp * 32 + lane;
         const bool row_ok = b < p.B;
         const size_t row_off = ((size_t)((size_t)b * pp.DY + py) * pp.DX + px) * p.ldo;
+        // full 128-column bf16 tiles without bias / activation go out through the warp's staging tile: column-wise
+        // moments instead of butterflies, full-line stores (conv_tc.cuh, epi_stage_*)
+        const bool staged = p.out_dtype == ACG_BF16 && !p.bias && p.out_act == ACG_ACT_NONE && (p.ldo & 7) == 0 &&
+                            n_cta == BN && n0 + BN <= p.n_store && (!p.stats || n0 + BN <= p.n_stat) && !p.direct_store &&
+                            (reinterpret_cast<uintptr_t>(p.out) & 15) == 0;
+        const uint32_t stile = smemE + (uint32_t)warp * kEpiStageBytes;
+        unsigned char* out_tile = static_cast<unsigned char*>(p.out) + (size_t)n0 * 2;
+        auto emit = [&](const uint32_t (&v)[16], int cb) {      // one 16-column chunk of this lane's row
+            if (!staged) {
+                epilogue_chunk(p, v, n0 + cb, row_ok, row_off, 0u, lane, &sm_stats[warp][0][cb], &sm_stats[warp][1][cb]);
+                return;
+            }
+            const int ch = (cb >> 4) & 3;
+            epi_stage_put_chunk<128>(stile, lane, ch, v, row_ok);
+            if (ch == 3)
+                epi_stage_moments_flush<128>(stile, lane, out_tile + (size_t)(cb - 48) * 2, (unsigned long long)row_off * 2ull,
+                                             row_ok, p.stats != nullptr, &sm_stats[warp][0][cb - 48], &sm_stats[warp][1][cb - 48]);
+        };
         if (p.splits > 1) {
             // all partial tiles in split order (this CTA's own one included: the sum does not depend on which CTA came
             // last).  The 16-column chunk after the current one is already in flight while this one goes through the
@@ -235,7 +254,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
                 uint32_t v[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(f[i]);
-                epilogue_chunk(p, v, n0 + cb, row_ok, row_off, 0u, lane, &sm_stats[warp][0][cb], &sm_stats[warp][1][cb]);
+                emit(v, cb);
             }
         } else {
             for (int cb = 0; cb < n_cta; cb += 16) {
@@ -245,7 +264,7 @@ __global__ void __launch_bounds__(kPxThreads, 1) conv_px_kernel(const __grid_con
 #pragma unroll
                     for (int i = 0; i < 16; ++i) v[i] = 0u;
                 }
-                epilogue_chunk(p, v, n0 + cb, row_ok, row_off, 0u, lane, &sm_stats[warp][0][cb], &sm_stats[warp][1][cb]);
+                emit(v, cb);
             }
         }
     }

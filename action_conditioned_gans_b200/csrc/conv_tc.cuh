@@ -138,6 +138,60 @@ template <int RB> __device__ __forceinline__ void epi_stage_flush(uint32_t tile,
     __syncwarp();       // the tile may be refilled
 }
 
+// Staged epilogue of the batch-norm layers: chunk by chunk the fp32 accumulator values of a lane's row are rounded to
+// bf16 and parked in the warp's staging tile (zeros for rows outside the tensor) ...
+template <int RB> __device__ __forceinline__ void epi_stage_put_chunk(uint32_t tile, int lane, int chunk, const uint32_t (&v)[16],
+                                                                      bool row_ok) {
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+        w[k] = row_ok ? *reinterpret_cast<uint32_t*>(&h) : 0u;
+    }
+    epi_stage_put<RB>(tile, lane, 2 * chunk, w[0], w[1], w[2], w[3]);
+    epi_stage_put<RB>(tile, lane, 2 * chunk + 1, w[4], w[5], w[6], w[7]);
+}
+// ... then the column moments of the group are read DOWN the tile -- lane L sums the 32 rows of its bf16 column pair
+// (RB = 128: 64 columns per group) or column (RB = 64: 32 columns), ~7 instructions per row, instead of two 16-shuffle
+// butterflies per 16-column chunk (~160 instructions per chunk: with moments the epilogue, not the MMAs, bounded
+// g/tconv3's forward, 55 -> 66 us) -- and the tile leaves with full-line stores.  The sums are over exactly the values
+// stored, rows in a fixed order.  sm_sum / sm_sq: THIS warp's slots of the group's first column; do_stats is warp-uniform.
+template <int RB> __device__ __forceinline__ void epi_stage_moments_flush(uint32_t tile, int lane, unsigned char* out_group,
+                                                                          unsigned long long row_off_bytes, bool row_ok,
+                                                                          bool do_stats, float* sm_sum, float* sm_sq) {
+    __syncwarp();
+    if (do_stats) {
+        if (RB == 128) {        // lane owns the bf16 pair (columns 2 L, 2 L + 1) = 32-bit word L of every row
+            float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                uint32_t wv;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv)
+                             : "r"(epi_stage_addr<RB>(tile, r, lane >> 2) + (uint32_t)((lane & 3) << 2)));
+                const float lo = __uint_as_float(wv << 16), hi = __uint_as_float(wv & 0xffff0000u);
+                s0a += lo; s0b += hi;
+                s1a = fmaf(lo, lo, s1a); s1b = fmaf(hi, hi, s1b);
+            }
+            sm_sum[2 * lane] += s0a; sm_sum[2 * lane + 1] += s0b;
+            sm_sq[2 * lane] += s1a; sm_sq[2 * lane + 1] += s1b;
+        } else {                // lane owns column L = 16-bit word L of every row
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                uint16_t hv;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv)
+                             : "r"(epi_stage_addr<RB>(tile, r, lane >> 3) + (uint32_t)((lane & 7) << 1)));
+                const float x = __uint_as_float((uint32_t)hv << 16);
+                s0 += x;
+                s1 = fmaf(x, x, s1);
+            }
+            sm_sum[lane] += s0;
+            sm_sq[lane] += s1;
+        }
+    }
+    epi_stage_flush<RB>(tile, lane, out_group, row_off_bytes, row_ok);
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }

@@ -6,13 +6,8 @@ import numpy as np
 
 
 def build_all_mask(num_frame):
-    """util.py:10-16: one-hot rows selecting frame i, for i in [0, num_frame-1)."""
-    masks = []
-    for i in range(num_frame - 1):
-        m = [0] * num_frame
-        m[i] = 1
-        masks.append(m)
-    return np.array(masks).astype(bool)
+    """util.py:10-16: boolean [num_frame-1, num_frame]; row i selects frame i (the last frame has no successor)."""
+    return np.eye(num_frame, dtype=bool)[:num_frame - 1]
 
 
 def _to_uint8(a):
