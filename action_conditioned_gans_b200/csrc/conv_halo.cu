@@ -121,8 +121,8 @@ __device__ __forceinline__ void epilogue_acc_staged(const Params& p, uint32_t ta
             epi_stage_put_chunk<RB>(stile, lane, i0 + 1, v[1], true);
         }
         if (ACG_DBG(p, 16)) continue;                                     // probe bit 16: TMEM loads and staging only
-        epi_stage_moments_flush<RB>(stile, lane, out + (size_t)g0 * 2, (unsigned long long)row_off * 2ull, true, true,
-                                    sm_sum + g0, sm_sq + g0);
+        epi_stage_moments_flush<RB>(stile, lane, out + (size_t)g0 * 2, (unsigned long long)row_off * 2ull, true,
+                                    p.stats != nullptr, sm_sum + g0, sm_sq + g0);
     }
 }
 
@@ -662,13 +662,13 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
     rc = fill_bn(&hp.p, t, (unsigned int)ctas, who);
     if (rc) return rc;
     set_stats_fix(&hp.p, t);
-    // staged epilogue with column-wise moments for the batch-norm layers (ACG_EPI_DIRECT switches it off); the ring keeps
-    // at least 4 stages
+    // staged epilogue (column-wise moments, full-line stores) for every bf16 output without bias / activation
+    // (ACG_EPI_DIRECT switches it off); the ring keeps at least 4 stages
     hp.staged_rb = 0;
     {
         const Params& q = hp.p;
-        const bool ok = q.stats && !q.rz && !q.bias && q.out_act == ACG_ACT_NONE && q.out_dtype == ACG_BF16 &&
-                        (q.ldo & 7) == 0 && q.n_store >= N && q.n_stat == N && ((uintptr_t)q.out & 15) == 0 &&
+        const bool ok = !q.rz && !q.bias && q.out_act == ACG_ACT_NONE && q.out_dtype == ACG_BF16 &&
+                        (q.ldo & 7) == 0 && q.n_store >= N && (!q.stats || q.n_stat == N) && ((uintptr_t)q.out & 15) == 0 &&
                         !q.direct_store && !pair;
         const long long halo_stride = (((long long)hp.TB * hp.rows * (hp.TW + 2) * 128) + 1023) / 1024 * 1024;
         const long long b_stride = ((long long)N * 128 + 1023) / 1024 * 1024;
