@@ -106,10 +106,11 @@ __device__ __forceinline__ void issue_tap(uint32_t tacc, int N, uint32_t alo_t, 
 // Epilogue of one accumulator for the batch-norm layers (bf16 output, moments, no bias / activation) through the warp's
 // staging tile: see epi_stage_put_chunk / epi_stage_moments_flush (conv_tc.cuh).
 template <int RB>
-__device__ __forceinline__ void epilogue_acc_staged(const Params& p, uint32_t tacc_q, int N, uint32_t stile, int lane,
-                                                    size_t row_off, float* sm_sum, float* sm_sq) {
+__device__ __forceinline__ void epilogue_acc_staged(const Params& p, uint32_t tacc_q, int N, uint32_t stile, uint32_t rowtab,
+                                                    int lane, size_t row_off, size_t pix, float* sm_sum, float* sm_sq) {
     constexpr int GC = RB / 2, NCH = GC / 16;           // columns / 16-column chunks per group
     unsigned char* out = static_cast<unsigned char*>(p.out);
+    if (p.rz) epi_stage_rowtab(rowtab, lane, (unsigned long long)pix * (unsigned long long)p.rz_ld * 2ull);
     for (int g0 = 0; g0 < N; g0 += GC) {
 #pragma unroll
         for (int i0 = 0; i0 < NCH; i0 += 2) {           // two 16-column TMEM loads in flight per wait
@@ -121,8 +122,12 @@ __device__ __forceinline__ void epilogue_acc_staged(const Params& p, uint32_t ta
             epi_stage_put_chunk<RB>(stile, lane, i0 + 1, v[1], true);
         }
         if (ACG_DBG(p, 16)) continue;                                     // probe bit 16: TMEM loads and staging only
-        epi_stage_moments_flush<RB>(stile, lane, out + (size_t)g0 * 2, (unsigned long long)row_off * 2ull, true,
-                                    p.stats != nullptr, sm_sum + g0, sm_sq + g0);
+        if (p.rz)
+            epi_stage_redux_flush<RB>(p, stile, rowtab, lane, g0, out + (size_t)g0 * 2, (unsigned long long)row_off * 2ull, true,
+                                      sm_sum + g0, sm_sq + g0);
+        else
+            epi_stage_moments_flush<RB>(stile, lane, out + (size_t)g0 * 2, (unsigned long long)row_off * 2ull, true,
+                                        p.stats != nullptr, sm_sum + g0, sm_sq + g0);
     }
 }
 
@@ -159,7 +164,7 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
     // operand area.  The ring gives them up for free: a sweep of its depth (scripts/halo_ring_sweep.py) showed no layer
     // slower at 4 stages than at 8 (g/tconv4's data gradient excepted: +1 us at 5).
     const uint32_t stage_rb = hp.staged_rb;                    // 0: every thread stores its own row
-    const uint32_t stage_bytes = 8u * 32u * stage_rb;
+    const uint32_t stage_bytes = stage_rb ? 8u * 32u * stage_rb + 8u * 256u : 0u;     // tiles + per-warp row tables
     const uint32_t smemE = smem_base + (uint32_t)kH2Data - stage_bytes;
     int NBS = (int)(((uint32_t)kH2Data - stage_bytes - NH * halo_stride) / b_stride);
     NBS = NBS > hp.nbs_cap ? hp.nbs_cap : NBS;
@@ -340,10 +345,13 @@ conv_halo2_kernel(const __grid_constant__ Halo2Params hp, int ntiles) {
                 const size_t row_off = pix * p.ldo;
                 if (stage_rb) {
                     const uint32_t stile = smemE + (uint32_t)ew * 32u * stage_rb;
+                    const uint32_t rowtab = smemE + 8u * 32u * stage_rb + (uint32_t)ew * 256u;
                     if (stage_rb == 128u)
-                        epilogue_acc_staged<128>(p, tacc + q * N, N, stile, lane, row_off, &sm_stats[ew][0][0], &sm_stats[ew][1][0]);
+                        epilogue_acc_staged<128>(p, tacc + q * N, N, stile, rowtab, lane, row_off, pix, &sm_stats[ew][0][0],
+                                                 &sm_stats[ew][1][0]);
                     else
-                        epilogue_acc_staged<64>(p, tacc + q * N, N, stile, lane, row_off, &sm_stats[ew][0][0], &sm_stats[ew][1][0]);
+                        epilogue_acc_staged<64>(p, tacc + q * N, N, stile, rowtab, lane, row_off, pix, &sm_stats[ew][0][0],
+                                                &sm_stats[ew][1][0]);
                     continue;
                 }
                 // fused batch-norm backward reduction of the layer that consumes this gradient: its pre-activation row
@@ -667,13 +675,13 @@ int launch_halo2(int form, const acg_conv_shape* s, const acg_tc_args* t, const 
     hp.staged_rb = 0;
     {
         const Params& q = hp.p;
-        const bool ok = !q.rz && !q.bias && q.out_act == ACG_ACT_NONE && q.out_dtype == ACG_BF16 &&
+        const bool ok = !q.bias && q.out_act == ACG_ACT_NONE && q.out_dtype == ACG_BF16 &&
                         (q.ldo & 7) == 0 && q.n_store >= N && (!q.stats || q.n_stat == N) && ((uintptr_t)q.out & 15) == 0 &&
                         !q.direct_store && !pair;
         const long long halo_stride = (((long long)hp.TB * hp.rows * (hp.TW + 2) * 128) + 1023) / 1024 * 1024;
         const long long b_stride = ((long long)N * 128 + 1023) / 1024 * 1024;
         for (int rb = 128; ok && rb >= 64 && !hp.staged_rb; rb >>= 1)
-            if (N % (rb / 2) == 0 && (kH2Data - 8LL * 32 * rb - 2 * halo_stride) / b_stride >= 4) hp.staged_rb = rb;
+            if (N % (rb / 2) == 0 && (kH2Data - 8LL * 32 * rb - 8 * 256 - 2 * halo_stride) / b_stride >= 4) hp.staged_rb = rb;
     }
     if (nacc == 1) {
         rc = set_smem((const void*)conv_halo2_kernel<1>, kH2Smem);

@@ -70,7 +70,7 @@ def measure(skip_calls=(), skip_layers=(), branches=True, iters=10):
 base = measure()
 print("baseline (branches)      %.3f ms" % base)
 print("baseline (one stream)    %.3f ms" % measure(branches=False))
-fams = ["acg_conv_fprop_tc", "acg_conv_dgrad_tc", "acg_conv_wgrad_tc", "acg_bn_act_fwd", "acg_bn_act_bwd_reduce",
+fams = ["acg_conv_fprop_tc", "acg_conv_dgrad_tc", "acg_conv_wgrad_tc", "acg_bn_finalize_act_fwd", "acg_bn_act_fwd", "acg_bn_act_bwd_reduce",
         "acg_bn_act_bwd_apply", "acg_pack_weights_batched", "acg_copy_channels", "acg_tile_actions", "acg_dna_fwd",
         "acg_dna_bwd", "acg_frame_losses", "acg_adam_step"]
 for f in fams:
