@@ -196,34 +196,35 @@ template <int RB> __device__ __forceinline__ void epi_stage_moments_flush(uint32
 // the backward reduction terms  sum_r dzh  and  sum_r dzh * xhat  (dzh = dA * act'(z * rstd + shift), xhat = (z - mean) * rstd,
 // dA as stored) are read down the staged tile, the consumer's pre-activation z straight from global memory -- the 32
 // lanes of a row read 128 (RB = 128) or 64 contiguous bytes.  rowtab: shared-memory table of this warp's 32 rows' BYTE
-// offsets into z (written by epi_stage_rowtab).  Replaces a whole acg_bn_act_bwd_reduce pass over dA and z.
+// offsets into z (written by epi_stage_rowtab; rows outside the tensor pass 0: their staged dA is zero, they add nothing).
+// Replaces a whole acg_bn_act_bwd_reduce pass over dA and z.
 __device__ __forceinline__ void epi_stage_rowtab(uint32_t rowtab, int lane, unsigned long long z_row_bytes) {
     __syncwarp();
     asm volatile("st.shared.u64 [%0], %1;" ::"r"(rowtab + (uint32_t)lane * 8u), "l"(z_row_bytes) : "memory");
     __syncwarp();
 }
-template <int RB> __device__ __forceinline__ void epi_stage_redux_flush(const Params& p, uint32_t tile, uint32_t rowtab, int lane,
-                                                                        int col0, unsigned char* out_group,
-                                                                        unsigned long long row_off_bytes, bool row_ok,
-                                                                        float* sm_sum, float* sm_sq) {
-    __syncwarp();
-    const unsigned char* zb = reinterpret_cast<const unsigned char*>(p.rz) + (size_t)col0 * 2;
+template <int ACT> __device__ __forceinline__ float act_bwd_ct(float u, int act_rt) {
+    if (ACT == ACG_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+    if (ACT == ACG_ACT_LRELU) return 0.6f + 0.4f * (u > 0.f ? 1.f : (u < 0.f ? -1.f : 0.f));
+    return act_bwd(u, act_rt);
+}
+// column sums of one group; ACT is a compile-time activation (or -1: run-time switch)
+template <int RB, int ACT> __device__ __forceinline__ void epi_stage_redux_cols(const Params& p, const unsigned char* tb,
+                                                                              const unsigned long long* rt,
+                                                                              const unsigned char* zb, int lane, int col0,
+                                                                              float* sm_sum, float* sm_sq) {
     if (RB == 128) {
         const int c = col0 + 2 * lane;
         const float mu0 = p.r_mean[c], mu1 = p.r_mean[c + 1], rs0 = p.r_rstd[c], rs1 = p.r_rstd[c + 1];
         const float sh0 = p.r_shift[c], sh1 = p.r_shift[c + 1];
         float s0a = 0.f, s0b = 0.f, s1a = 0.f, s1b = 0.f;
-#pragma unroll 8
+#pragma unroll 16
         for (int r = 0; r < 32; ++r) {
-            unsigned long long zo;
-            uint32_t wv;
-            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(zo) : "r"(rowtab + (uint32_t)r * 8u));
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wv)
-                         : "r"(epi_stage_addr<RB>(tile, r, lane >> 2) + (uint32_t)((lane & 3) << 2)));
-            const uint32_t zw = zo != ~0ull ? __ldg(reinterpret_cast<const uint32_t*>(zb + zo) + lane) : 0u;
+            const uint32_t zw = __ldg(reinterpret_cast<const uint32_t*>(zb + rt[r]) + lane);
+            const uint32_t wv = *reinterpret_cast<const uint32_t*>(tb + (epi_stage_addr<RB>(0u, r, lane >> 2) + ((lane & 3) << 2)));
             const float dl = __uint_as_float(wv << 16), dh = __uint_as_float(wv & 0xffff0000u);
             const float zl = __uint_as_float(zw << 16), zh = __uint_as_float(zw & 0xffff0000u);
-            const float ql = dl * act_bwd(fmaf(zl, rs0, sh0), p.r_act), qh = dh * act_bwd(fmaf(zh, rs1, sh1), p.r_act);
+            const float ql = dl * act_bwd_ct<ACT>(fmaf(zl, rs0, sh0), p.r_act), qh = dh * act_bwd_ct<ACT>(fmaf(zh, rs1, sh1), p.r_act);
             s0a += ql; s0b += qh;
             s1a = fmaf(ql, (zl - mu0) * rs0, s1a); s1b = fmaf(qh, (zh - mu1) * rs1, s1b);
         }
@@ -233,22 +234,34 @@ template <int RB> __device__ __forceinline__ void epi_stage_redux_flush(const Pa
         const int c = col0 + lane;
         const float mu = p.r_mean[c], rs = p.r_rstd[c], sh = p.r_shift[c];
         float s0 = 0.f, s1 = 0.f;
-#pragma unroll 8
+#pragma unroll 16
         for (int r = 0; r < 32; ++r) {
-            unsigned long long zo;
-            uint16_t hv;
-            asm volatile("ld.shared.u64 %0, [%1];" : "=l"(zo) : "r"(rowtab + (uint32_t)r * 8u));
-            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv)
-                         : "r"(epi_stage_addr<RB>(tile, r, lane >> 3) + (uint32_t)((lane & 7) << 1)));
-            const uint16_t zv = zo != ~0ull ? __ldg(reinterpret_cast<const uint16_t*>(zb + zo) + lane) : (uint16_t)0;
+            const uint16_t zv = __ldg(reinterpret_cast<const uint16_t*>(zb + rt[r]) + lane);
+            const uint16_t hv = *reinterpret_cast<const uint16_t*>(tb + (epi_stage_addr<RB>(0u, r, lane >> 3) + ((lane & 7) << 1)));
             const float d = __uint_as_float((uint32_t)hv << 16), z = __uint_as_float((uint32_t)zv << 16);
-            const float q = d * act_bwd(fmaf(z, rs, sh), p.r_act);
+            const float q = d * act_bwd_ct<ACT>(fmaf(z, rs, sh), p.r_act);
             s0 += q;
             s1 = fmaf(q, (z - mu) * rs, s1);
         }
         sm_sum[lane] += s0;
         sm_sq[lane] += s1;
     }
+}
+template <int RB> __device__ __forceinline__ void epi_stage_redux_flush(const Params& p, uint32_t tile, uint32_t rowtab, int lane,
+                                                                        int col0, unsigned char* out_group,
+                                                                        unsigned long long row_off_bytes, bool row_ok,
+                                                                        float* sm_sum, float* sm_sq) {
+    __syncwarp();
+    // Plain C++ loads through generic pointers (not volatile asm), an UNCONDITIONAL global load per row and the activation
+    // as a compile-time parameter (one switch per group, none per element), so that the row loop is ONE basic block and
+    // the compiler keeps the z loads of 16 rows in flight: earlier versions paid one full memory latency per ROW
+    // (g/tconv4's data gradient 77 -> 257 us) -- first behind a predicated load, then behind the branches of act_bwd().
+    const unsigned char* zb = reinterpret_cast<const unsigned char*>(p.rz) + (size_t)col0 * 2;
+    const unsigned long long* rt = reinterpret_cast<const unsigned long long*>(__cvta_shared_to_generic((size_t)rowtab));
+    const unsigned char* tb = reinterpret_cast<const unsigned char*>(__cvta_shared_to_generic((size_t)tile));
+    if (p.r_act == ACG_ACT_RELU) epi_stage_redux_cols<RB, ACG_ACT_RELU>(p, tb, rt, zb, lane, col0, sm_sum, sm_sq);
+    else if (p.r_act == ACG_ACT_LRELU) epi_stage_redux_cols<RB, ACG_ACT_LRELU>(p, tb, rt, zb, lane, col0, sm_sum, sm_sq);
+    else epi_stage_redux_cols<RB, -1>(p, tb, rt, zb, lane, col0, sm_sum, sm_sq);
     epi_stage_flush<RB>(tile, lane, out_group, row_off_bytes, row_ok);
 }
 

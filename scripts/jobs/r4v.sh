@@ -1,0 +1,11 @@
+#!/bin/bash
+# round 2, session 3, GPU call V: fused backward reduction, row loop as one basic block -- per launch, parity, step time
+mkdir -p gpurun_out
+timeout 200 python scripts/fused_red_cost.py 256 > gpurun_out/r4v_fused_red.log 2>&1
+tail -n 7 gpurun_out/r4v_fused_red.log
+timeout 120 python scripts/step_time.py 256 30 2>&1 | tail -n 1
+ACG_FUSE_BWD_REDUCE=halo timeout 120 python scripts/step_time.py 256 30 2>&1 | tail -n 1
+timeout 200 python -m pytest tests/test_conv_tc_gpu.py -m gpu -q -x -k "fused_bwd" > gpurun_out/r4v_tests.log 2>&1
+echo "tests rc=$?" >> gpurun_out/r4v_tests.log
+tail -n 2 gpurun_out/r4v_tests.log
+exit 0
