@@ -386,7 +386,6 @@ template <int NT> struct SmallK {
     static constexpr int kPass = BM / kRows;              // passes (rows per producer thread) per K slice
     static constexpr int kThreads = 160 + kProd;
     static constexpr int kStageBN = kStageB;              // one resident weight slice (N rows x 128 B used)
-    static constexpr int kStatic = 6 * 1024;              // static shared memory of the kernel, rounded up
     static constexpr int kRing = 8;
     static constexpr int kSmem = kSmallKMaxKb * kStageBN + kRing * kStageA + 4 * kEpiStageBytes + 1024;
 };

@@ -4,12 +4,12 @@
 // tf.extract_image_patches of the input frame with SAME zero padding, stack/multiply/reduce_sum)
 // and TF's autodiff of that sub-graph.  The reference materialises the [B,64,64,K*K,3] patch tensor
 // and a 3x stacked softmax in HBM (~15x the algorithmic traffic); here one persistent kernel streams
-// each band of 4 image rows exactly once:
+// each band of R image rows (R = 2; 4 behind ACG_DNA_ROWS) exactly once:
 //
-//   * thread 0 of the CTA is the producer: per band it issues ONE bulk-copy (TMA engine, SASS UBLKCP)
-//     for the band's contiguous logits and one per image row of the band + halo into a padded
-//     shared-memory tile, all completing on the stage's mbarrier (expect_tx byte counting);
-//   * 256 consumer threads (one pixel each) read their K*K logits from shared memory (stride K*K words
+//   * warp 0 of the CTA is the producer: per band ONE bulk-copy (TMA engine, SASS UBLKCP) for the band's
+//     contiguous logits and one per image row of the band + halo into a padded shared-memory tile, issued
+//     by different lanes side by side, all completing on the stage's mbarrier (expect_tx byte counting);
+//   * R x 64 consumer threads (one pixel each) read their K*K logits from shared memory (stride K*K words
 //     -> conflict free for K=5), do max / exp / sum in registers, accumulate the K*K x 3 weighted
 //     neighbourhood from the padded image tile (stride-3 words -> conflict free) and normalise once;
 //   * the backward kernel recomputes the softmax, forms g_p = <dy, x_p>, writes
@@ -310,8 +310,9 @@ int launch_r(const void* logits, const float* img, const float* dy, float* out, 
     return check_launch(BWD ? "acg_dna_bwd" : "acg_dna_fwd");
 }
 
-// Band height: 2 rows where four-row bands would give every CTA slot only a few bands (see the note at kMaxW),
-// 4 rows otherwise.  ACG_DNA_ROWS = 2 | 4 forces one (A/B runs, tests of both variants).
+// Band height: 2 rows at every batch size (measured equal or better than 4 from B = 16 to 256: the half-size bands
+// shorten ramp-up and drain, and 3-4 CTAs of 128 threads per SM overlap better than 2 of 256).  ACG_DNA_ROWS = 2 | 4
+// forces one (A/B runs, tests of both variants).
 int band_rows(int B, int H) {
     if (const char* e = getenv("ACG_DNA_ROWS")) {
         const int r = atoi(e);
