@@ -67,6 +67,33 @@ def test_argument_validation_without_a_device(built_lib):
         _lib.call("acg_dna_fwd", None, 0, None, None, 1, 8, 8, 3, 5, None)
 
 
+def test_bn_finalize_act_fwd_host_checks(built_lib):
+    """acg_bn_finalize_act_fwd (batch-norm finalize + activation from the raw moments of a conv launch): the shape gate
+    is a host function and the argument checks reject before any CUDA call."""
+    from action_conditioned_gans_b200 import _lib
+    from action_conditioned_gans_b200 import kernels as K
+    lib = built_lib
+    relu, lrelu, none_, tanh = (_lib.ACT_IDS[a] for a in ("relu", "lrelu", "none", "tanh"))
+    assert lib.acg_bn_finalize_act_fwd_ok(128, 128, 128, relu) == 1
+    assert lib.acg_bn_finalize_act_fwd_ok(256, 256, 272, lrelu) == 1         # into a concat buffer
+    assert lib.acg_bn_finalize_act_fwd_ok(16, 16, 16, none_) == 1
+    assert lib.acg_bn_finalize_act_fwd_ok(1, 16, 16, relu) == 0              # d/conv6: C not a multiple of 8
+    assert lib.acg_bn_finalize_act_fwd_ok(128, 128, 128, tanh) == 0
+    assert lib.acg_bn_finalize_act_fwd_ok(128, 120, 128, relu) == 0          # row stride shorter than C
+    assert K.bn_finalize_act_fwd_ok(64, 64, 64, "lrelu") and not K.bn_finalize_act_fwd_ok(12, 16, 16, "relu")
+    buf = C.create_string_buffer(8192)
+    p = C.cast(C.addressof(buf) + (-C.addressof(buf)) % 16, C.c_void_p)
+    args = [p, 64, 16, 16, p, None, None, 64, 1e-3, p, p, p, p, relu, p, 16, None, 0, 1, 0, None]
+    bad = list(args); bad[4] = None                                          # no moments
+    assert lib.acg_bn_finalize_act_fwd(*bad) == -1 and b"null" in lib.acg_last_error()
+    bad = list(args); bad[2] = 12                                            # C = 12
+    assert lib.acg_bn_finalize_act_fwd(*bad) == -2
+    bad = list(args); bad[7] = 0                                             # no rows to normalise over
+    assert lib.acg_bn_finalize_act_fwd(*bad) == -1
+    bad = list(args); bad[16], bad[17], bad[18], bad[19] = p, 10, 7, 16      # concat: 64 rows are not whole images of 7
+    assert lib.acg_bn_finalize_act_fwd(*bad) == -1 and b"concat" in lib.acg_last_error()
+
+
 def test_pack_size_is_host_only(built_lib):
     from action_conditioned_gans_b200 import kernels as K
     s = K.conv_shape(4, 16, 16, 64, 128, 5, 2, "SAME")
