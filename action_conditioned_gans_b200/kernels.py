@@ -90,7 +90,9 @@ def _tc_args(ld_in, ld_out, bias, out, out_act, stats=None, bn=None, red=None, s
     """bn = (counter, beta, mean, rstd, scale, shift, rows, eps): finalise the moments in-kernel (single GPU); rows == 0
       with only the counter set: the last CTA completes the totals and the caller finalises (data parallel)
     red = (red_buffer, z, ldz, C, act, mean, rstd, shift): fused batch-norm backward reduction of the consumer layer
-    stats_fix: int64 tensor of >= 6*C zeros: reproducible moments (integer limb accumulators; needs bn's ticket)"""
+    stats_fix: int64 tensor of >= 6*C zeros: reproducible moments (integer limb accumulators).  With bn's ticket the last
+      CTA converts them into `stats` and leaves them zeroed; without bn the launch only adds its limbs and
+      bn_finalize_act_fwd completes them (the caller zeroes the accumulators before the next launch)"""
     t = TcArgs(ld_in, ld_out, ptr(bias), dtype_id(out), ACT_IDS[out_act], ptr(stats))
     t.n_limit = int(n_limit)
     if stats_fix is not None:
